@@ -1,0 +1,170 @@
+/*
+ * sma_b200.h - C ABI of the B200-native per-driving-frame talking-head path.
+ *
+ * Drop-in boundary.  The reference is a PyTorch program whose hot path is
+ * stock ATen ops; its only native-op slot is basicsr/ops/ (pybind module per op, caller-allocated
+ * outputs, errors surfaced as exceptions, launches on the caller's current stream:
+ * basicsr/ops/dcn/src/deform_conv_ext.cpp:150-164, basicsr/ops/dcn/deform_conv.py:51-64).  This
+ * library occupies that slot: every entry point takes raw device pointers, explicit
+ * dims/strides, a cudaStream_t and caller-provided workspaces, and returns an int status.
+ * It never allocates, never synchronises, never aborts, and keeps no global mutable state.
+ *
+ * All activations are fp32, channels-last (NHWC): element (b,y,x,c) of a tensor with pixel
+ * stride `ld` floats and batch stride `bstride` floats lives at  p[b*bstride + (y*W+x)*ld + c].
+ * A batch stride of 0 means "shared by every frame of the batch" (per-source cached tensors).
+ * Each function's comment cites the reference code it replaces (paths relative to
+ * /root/reference/basicsr/).
+ */
+#ifndef SMA_B200_H
+#define SMA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* sma_stream_t; /* cudaStream_t */
+
+enum {
+  SMA_OK = 0,
+  SMA_ERR_BAD_ARG = -1,      /* null pointer, non-positive dim, misaligned pointer            */
+  SMA_ERR_UNSUPPORTED = -2,  /* shape outside what the kernels implement                      */
+  SMA_ERR_CUDA = -3,         /* launch failed; see cudaGetLastError in the caller             */
+  SMA_ERR_NO_DEVICE = -4     /* device is not sm_100                                          */
+};
+
+enum { SMA_ACT_NONE = 0, SMA_ACT_RELU = 1, SMA_ACT_LEAKY02 = 2, SMA_ACT_GELU = 3, SMA_ACT_SIGMOID = 4,
+       SMA_ACT_SWISH = 5 };
+
+/* library / device info */
+int sma_abi_version(void);                 /* bumps when a signature changes */
+const char* sma_status_string(int status);
+int sma_device_check(int device);          /* SMA_OK iff compute capability 10.x */
+int sma_kernel_launch_count(void);         /* launches issued by this library in this process (monotonic, relaxed atomic) */
+
+/* ---------------------------------------------------------------------------------------------
+ * Convolution as implicit GEMM (replaces every nn.Conv2d / nn.Linear on the path:
+ * archs/vqgan_arch.py:144-191, archs/appmotioncodebook_arch.py:28-52,72-74,129-168,219-240,
+ * utils/motion_estimator_util.py:214-231,363-380, archs/dense_motion_arch.py:26,56,
+ * archs/keypoint_detector_arch.py:27-31).
+ *   out[b,oy,ox,n] = act( bias[n] + sum_{ky,kx,c} W[(ky*kw+kx)*Cin+c][n] * pre(in[b, iy, ix, c]) ) (+ res)
+ *   iy = oy*stride - pad_t + ky, ix = ox*stride - pad_l + kx on the (optionally nearest-x2
+ *   upsampled) input; out-of-range taps contribute 0 AFTER the prologue (zero padding of the
+ *   normalised tensor, as F.conv2d(pad=..) after GroupNorm does).
+ *   pre(v) = act_pre(v * pre_scale[b*Cin+c] + pre_shift[b*Cin+c])  (GroupNorm-apply + swish fused
+ *   into the operand load; pre_scale == NULL disables it).
+ * Weights are pre-packed by sma_pack_conv_weight: row k=(ky*kw+kx)*Cin+c, `ldw` floats per row.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct sma_conv_desc {
+  const float* x;  int B, Hi, Wi, Cin;  int64_t in_bstride;  int in_ld;
+  const float* w;  int ldw;  const float* bias;
+  int Cout, kh, kw, stride, pad_t, pad_l;
+  int upsample2;                 /* 1: conv runs on nearest-x2 upsampled input (Hi,Wi are the stored dims) */
+  const float* pre_scale; const float* pre_shift; int pre_act;
+  float* y;  int Ho, Wo;  int64_t out_bstride;  int out_ld;
+  int act;
+  const float* res;  int64_t res_bstride;  int res_ld;   /* added after the activation; may be NULL */
+  int d2s;                       /* depth-to-space factor p (<=1 off): column n=(p1*p+p2)*C+c goes to pixel
+                                    (oy*p+p1, ox*p+p2) channel c of a (B,Ho*p,Wo*p,C) tensor (un-patchify,
+                                    appmotioncodebook_arch.py:223,230,237) */
+  int out_nchw;                  /* 1: y is (B,Cout,Ho,Wo) contiguous (API-facing final image) */
+  int tf32x3;                    /* 1: use the tcgen05 3xTF32 tensor-core kernel when the shape allows */
+} sma_conv_desc;
+
+int sma_conv2d_fwd(const sma_conv_desc* d, sma_stream_t stream);
+/* OIHW (or (N,K) Linear) fp32 weight on the device -> packed [kh*kw*Cin][ldw] ; optional BatchNorm(eval)
+ * fold: w' = w*g/sqrt(var+eps), b' = (b-mean)*g/sqrt(var+eps)+beta (sync_batchnorm/batchnorm.py:48-53). */
+int sma_pack_conv_weight(const float* w_oihw, const float* bias, int Cout, int Cin, int kh, int kw,
+                         const float* bn_gamma, const float* bn_beta, const float* bn_mean, const float* bn_var,
+                         float bn_eps, float* w_packed, int ldw, float* bias_out, sma_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * GroupNorm(32, eps) statistics -> per-(b,c) scale/shift consumed by the conv prologue
+ * (archs/vqgan_arch.py:14-15).  partial: workspace of B*nchunk*C*2 floats, nchunk = ceil(HW/256).
+ * ------------------------------------------------------------------------------------------- */
+int sma_groupnorm_stats(const float* x, int B, int HW, int C, int64_t bstride, int ld, int groups, float eps,
+                        const float* gamma, const float* beta, float* partial, float* scale, float* shift,
+                        sma_stream_t stream);
+/* y = act(x*scale[b,c]+shift[b,c]) elementwise (used where no conv follows, e.g. AttnBlock input) */
+int sma_affine_act(const float* x, int B, int HW, int C, int64_t bstride, int ld, const float* scale,
+                   const float* shift, int act, float* y, int64_t y_bstride, int y_ld, sma_stream_t stream);
+/* LayerNorm over the last dim of (rows,E) tokens; y = LN(x)*g+b ; yq = y + pos[row % pos_rows] (optional)
+ * (archs/appmotioncodebook_arch.py:76-78,97-99,109-113,119). */
+int sma_layernorm(const float* x, int rows, int E, const float* gamma, const float* beta, float eps,
+                  const float* pos, int pos_rows, float* y, float* yq, sma_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Stage 2: bilinear warp fused with the occlusion multiply (deform_input + occlude_input,
+ * archs/appmotioncodebook_arch.py:349-362).  flow (B,hf,wf,2) and occ (B,hf,wf) are resized to
+ * (H,W) on the fly (bilinear, align_corners=True); sampling is grid_sample bilinear / zeros /
+ * align_corners=True.  occ may be NULL (query warp).  feat batch stride may be 0.
+ * ------------------------------------------------------------------------------------------- */
+int sma_warp_occlude_fwd(const float* feat, int64_t feat_bstride, int B, int H, int W, int C,
+                         const float* flow, const float* occ, int hf, int wf, float* out, sma_stream_t stream);
+/* bilinear align_corners=True resize of an NHWC tensor (F.interpolate call sites :390,414,418,571,671) */
+int sma_resize_bilinear_ac(const float* x, int B, int Hi, int Wi, int C, int64_t in_bstride, int in_ld,
+                           float* y, int Ho, int Wo, int64_t out_bstride, int out_ld, sma_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Stage 3: multi-head attention core softmax(Q K^T * scale [+mask]) V on projected tensors
+ * (nn.MultiheadAttention inside TransformerLayer, appmotioncodebook_arch.py:97-116, and the
+ * single-head AttnBlock, archs/vqgan_arch.py:233-248).  q:(B,L,*) k,v:(B or shared,S,*) ;
+ * head h occupies columns [h*D,(h+1)*D).  key_mask (B,S) uint8, 1 = ignore (may be NULL).
+ * D in {4,32,256}.
+ * ------------------------------------------------------------------------------------------- */
+int sma_mha_fwd(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv,
+                int64_t kv_bstride, int B, int L, int S, int heads, int D, float scale,
+                const uint8_t* key_mask, float* out, int ldo, sma_stream_t stream);
+
+/* VectorQuantizer lookup (archs/vqgan_arch.py:33-73): d = fl(fl(|z|^2+|e|^2) - 2 z.e), argmin with
+ * lowest-index ties -> idx (int64), zq = e[idx].  z:(N,E) row-major, codebook (n_codes,E). */
+int sma_vq_lookup_fwd(const float* z, int N, int E, const float* codebook, int n_codes, int64_t* idx,
+                      float* zq, float* min_dist, sma_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Motion-estimator heads and glue
+ * ------------------------------------------------------------------------------------------- */
+/* AntiAliasInterpolation2d (utils/motion_estimator_util.py:599-645): x (B,3,H,W) NCHW -> y (B,H/4,W/4,3) NHWC */
+int sma_antialias_down4(const float* x_nchw, int B, int C, int H, int W, const float* kernel13, float* y_nhwc,
+                        int y_ld, sma_stream_t stream);
+int sma_avgpool2(const float* x, int B, int H, int W, int C, float* y, int y_ld, sma_stream_t stream);
+/* KPDetector tail (archs/keypoint_detector_arch.py:48-86): pred (B,h,w,ld>=5K) with columns [0,K) = kp logits,
+ * [K,5K) = jacobian maps -> value (B,K,2), jacobian (B,K,2,2) */
+int sma_kp_head_fwd(const float* pred, int B, int h, int w, int ld, int K, float temperature, float* value,
+                    float* jacobian, sma_stream_t stream);
+/* normalize_kp relative mode (demo.py:24-44): value = kp_src + s*(kp_drv-kp_drv0); jac = J_drv J_drv0^-1 J_src */
+int sma_normalize_kp(const float* src_v, const float* src_j, const float* drv_v, const float* drv_j,
+                     const float* drv0_v, const float* drv0_j, int B, int K, float scale, int relative,
+                     float* out_v, float* out_j, sma_stream_t stream);
+/* DenseMotionNetwork input (archs/dense_motion_arch.py:65-130): heat-map differences, sparse motions and the
+ * 16 warped copies of the down-sampled source (grid_sample align_corners=False) interleaved k-major into
+ * hg_in (B,h,w,4*(K+1)); also the driving heat-maps drv_heat (B,h,w,K). src64 is (h,w,3) NHWC shared. */
+int sma_dense_motion_prep(const float* src64, int h, int w, const float* kp_src_v, const float* kp_src_j,
+                          const float* kp_drv_v, const float* kp_drv_j, int B, int K, float kp_variance,
+                          float* hg_in, int hg_ld, float* drv_heat, sma_stream_t stream);
+/* DenseMotionNetwork head (:134-159): logits (B,h,w,ld>=K+2): softmax over first K+1 columns, deformation =
+ * sum mask_k * sparse_motion_k (recomputed), occlusion = sigmoid(column K+1). */
+int sma_dense_motion_head(const float* logits, int ld, int h, int w, const float* kp_src_v, const float* kp_src_j,
+                          const float* kp_drv_v, const float* kp_drv_j, int B, int K, float* deformation,
+                          float* occlusion, float* mask_out, sma_stream_t stream);
+/* flow glue of AppMotionCompFormer.forward (archs/appmotioncodebook_arch.py:562-601,689-710) */
+int sma_flow_to_px(const float* m, int B, int h, int w, float* flow_px, int out_ld, sma_stream_t stream);
+/* res: (B,h,w,res_ld) with columns 0,1 = delta-flow in pixels, 2 = delta-occlusion logit */
+int sma_flow_update(const float* m_prev, const float* occ_prev, const float* res, int res_ld, int B, int h, int w,
+                    float* m_new, float* occ_new, sma_stream_t stream);
+/* key-padding mask of app_codebook_compensation (:487-492): m (B,h,w,2) resized to 32x32, 1 where |.|>1 */
+int sma_motion_ignore_mask(const float* m, int B, int h, int w, int ht, int wt, uint8_t* mask, sma_stream_t stream);
+/* Fuse_sft_block tail (:50-51): out = dec + w*(dec*scale + shift) */
+int sma_sft_combine(const float* dec, const float* scale, const float* shift, float w, int64_t n, float* out,
+                    sma_stream_t stream);
+/* tensor2img (utils/img_util.py:42-98): NHWC fp32 in [-1,1] -> HWC uint8 (round half even), optional BGR */
+int sma_to_uint8(const float* x_nhwc, int B, int H, int W, int C, int ld, int bgr, uint8_t* out, sma_stream_t stream);
+/* (B,C,H,W) <-> (B,H,W,C) */
+int sma_nchw_to_nhwc(const float* x, int B, int C, int H, int W, float* y, int y_ld, sma_stream_t stream);
+int sma_nhwc_to_nchw(const float* x, int B, int C, int H, int W, int x_ld, float* y, sma_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SMA_B200_H */

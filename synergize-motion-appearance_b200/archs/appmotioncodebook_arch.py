@@ -1,0 +1,497 @@
+"""AppMotionCompFormer on B200 kernels.
+
+Drop-in for basicsr/archs/appmotioncodebook_arch.py:170-764 (generator of options/test.yml:8-45, built
+on the VQGAN blocks of basicsr/archs/vqgan_arch.py): same constructor kwargs, same 472 state_dict keys,
+same call `net_g(source, dense_motion, w=1, inference=True) -> dict` with the keys callers read
+(`out`, `lq_feat`, `out_occ`, `deformation_list`, `res_deform_list`), plus `encode_driving`.  Inference only.
+
+Design (B200-first, not a module-for-module port):
+  * everything NHWC fp32; torch only allocates buffers; every op is a kernel from csrc/;
+  * per-source work is hoisted and cached: the 19 encoder blocks run once per source, the codebook K/V
+    projections of all cross-attentions once per weight load (the reference redoes both every frame,
+    appmotioncodebook_arch.py:549-554,405,514);
+  * B driving frames share one source: source features are passed with batch stride 0;
+  * GroupNorm = statistics kernel + normalise/swish fused into the consuming conv's operand load;
+    residual adds, activations, biases, nearest upsampling, (un)patchify fused into the conv kernel;
+    torch.cat is replaced by writing producers into channel slices of one buffer;
+  * the third (duplicate) warp per scale that only feeds `deform_feat_list` is not computed.
+"""
+import math
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+from .. import ops
+from ..registry import ARCH_REGISTRY
+from .params import ParamModule
+
+# block kinds for nf=64, ch_mult=[1,2,2,4], res_blocks=2, attn_resolutions=[32] (vqgan_arch.py:256-350)
+
+
+def _encoder_layout(nf, ch_mult, res_blocks, resolution, attn_res) -> List[Tuple[str, int, int]]:
+    blocks = [('conv', 3, nf)]
+    cur = resolution
+    in_mult = (1,) + tuple(ch_mult)
+    cin = nf
+    for i in range(len(ch_mult)):
+        cin, cout = nf * in_mult[i], nf * ch_mult[i]
+        for _ in range(res_blocks):
+            blocks.append(('res', cin, cout))
+            cin = cout
+            if cur in attn_res:
+                blocks.append(('attn', cin, cin))
+        if i != len(ch_mult) - 1:
+            blocks.append(('down', cin, cin))
+            cur //= 2
+    blocks += [('res', cin, cin), ('attn', cin, cin), ('res', cin, cin), ('norm', cin, cin)]
+    return blocks, cin
+
+
+def _generator_layout(nf, ch_mult, res_blocks, resolution, attn_res, emb_dim):
+    cin = nf * ch_mult[-1]
+    cur = resolution // 2 ** (len(ch_mult) - 1)
+    blocks = [('conv', emb_dim, cin), ('res', cin, cin), ('attn', cin, cin), ('res', cin, cin)]
+    for i in reversed(range(len(ch_mult))):
+        cout = nf * ch_mult[i]
+        for _ in range(res_blocks):
+            blocks.append(('res', cin, cout))
+            cin = cout
+            if cur in attn_res:
+                blocks.append(('attn', cin, cin))
+        if i != 0:
+            blocks.append(('up', cin, cin))
+            cur *= 2
+    blocks += [('norm', cin, cin), ('conv', cin, 3)]
+    return blocks
+
+
+@ARCH_REGISTRY.register()
+class AppMotionCompFormer(ParamModule):
+    SCALES = (32, 64, 128, 256)
+
+    def __init__(self, img_size=256, nf=64, ch_mult=[1, 2, 2, 4], res_blocks=2, attn_resolutions=[32],
+                 quantizer_type='nearest', beta=0.25, codebook_size_motion=1024, embed_dim_motion=32,
+                 codebook_size_app=1024, embed_dim_app=256, n_head=8, dim_embd_motion=32, n_layers_motion=2,
+                 dim_embd_app=256, n_layers_app=2, split=1, num_kp=15, with_position_emb=True, warp_s_d_kp_query=True,
+                 MRFA_motion_enc=True, motion_codebook_split=True, detach_motion_query=True,
+                 multiscale_feature_fusion=True, multiscale_sft=True, app_codebook_split=True,
+                 wo_motion_cdbk_share=False, wo_app_cdbk_share=False, connect_list=['64', '128', '256'],
+                 connect_app_list=['32', '64', '128', '256'], fix_modules=[], ae_path=None):
+        super().__init__()
+        supported = (img_size == 256 and nf == 64 and list(ch_mult) == [1, 2, 2, 4] and res_blocks == 2 and
+                     list(attn_resolutions) == [32] and quantizer_type == 'nearest' and split == 1 and with_position_emb and
+                     warp_s_d_kp_query and MRFA_motion_enc and motion_codebook_split and multiscale_feature_fusion and
+                     multiscale_sft and app_codebook_split and not wo_motion_cdbk_share and not wo_app_cdbk_share and
+                     list(connect_list) == ['64', '128', '256'] and list(connect_app_list) == ['32', '64', '128', '256'] and
+                     embed_dim_motion == dim_embd_motion and embed_dim_app == dim_embd_app and n_layers_motion == 2 and
+                     n_layers_app == 2 and dim_embd_app == 256 and dim_embd_motion == 32 and n_head == 8)
+        if not supported:
+            raise NotImplementedError('B200 AppMotionCompFormer implements the options/test.yml configuration only')
+        self.beta, self.n_head, self.num_kp = beta, n_head, num_kp
+        self.Ea, self.Em = dim_embd_app, dim_embd_motion
+        self.n_codes_app, self.n_codes_motion = codebook_size_app, codebook_size_motion
+        self.channels = {32: 256, 64: 128, 128: 128, 256: 64}
+        self.connect_list, self.connect_app_list = list(connect_list), list(connect_app_list)
+        self.fuse_encoder_block = {'256': 2, '128': 5, '64': 8, '32': 11}
+        self.fuse_generator_block = {'32': 6, '64': 9, '128': 12, '256': 15}
+        self.enc_layout, latent_c = _encoder_layout(nf, ch_mult, res_blocks, img_size, attn_resolutions)
+        self.enc_layout.append(('conv', latent_c, 256))
+        self.gen_layout = _generator_layout(nf, ch_mult, res_blocks, img_size, attn_resolutions, 256)
+        self._declare_all()
+        self._src_cache = None
+        if ae_path is not None:
+            self.load_state_dict(torch.load(ae_path, map_location='cpu')['params_ema'])
+        for module in (fix_modules or []):
+            for n, p in self.named_parameters():
+                if n == module or n.startswith(module + '.'):
+                    p.requires_grad = False
+
+    # ------------------------------------------------------------------------------------------
+    # parameter inventory
+    # ------------------------------------------------------------------------------------------
+    def _declare_res(self, name, cin, cout):
+        self.declare_norm(name + '.norm1', cin)
+        self.declare_conv(name + '.conv1', cout, cin, 3)
+        self.declare_norm(name + '.norm2', cout)
+        self.declare_conv(name + '.conv2', cout, cout, 3)
+        if cin != cout:
+            self.declare_conv(name + '.conv_out', cout, cin, 1)
+
+    def _declare_blocks(self, prefix, layout):
+        for i, (kind, cin, cout) in enumerate(layout):
+            n = f'{prefix}.blocks.{i}'
+            if kind == 'conv':
+                self.declare_conv(n, cout, cin, 3)
+            elif kind == 'res':
+                self._declare_res(n, cin, cout)
+            elif kind == 'attn':
+                self.declare_norm(n + '.norm', cin)
+                for k in ('q', 'k', 'v', 'proj_out'):
+                    self.declare_conv(f'{n}.{k}', cin, cin, 1)
+            elif kind in ('down', 'up'):
+                self.declare_conv(n + '.conv', cin, cin, 3)
+            elif kind == 'norm':
+                self.declare_norm(n, cin)
+
+    def _declare_transformer(self, name, E):
+        for a in ('self_attn', 'cross_attn'):
+            b = 1.0 / math.sqrt(E)
+            self.declare(f'{name}.{a}.in_proj_weight', (3 * E, E), lambda t: t.uniform_(-b, b))
+            self.declare(f'{name}.{a}.in_proj_bias', (3 * E,), lambda t: t.zero_())
+            self.declare_linear(f'{name}.{a}.out_proj', E, E)
+        self.declare_conv(name + '.conv1', 2 * E, E, 3)
+        self.declare_conv(name + '.conv2', E, 2 * E, 3)
+        for k in ('norm1', 'norm2', 'norm3'):
+            self.declare_norm(f'{name}.{k}', E)
+
+    def _declare_all(self):
+        Ea, Em = self.Ea, self.Em
+        self._declare_blocks('encoder', self.enc_layout)
+        self._declare_blocks('generator', self.gen_layout)
+        self.declare_conv('app_feat_emb_32', Ea, 256, 1)
+        self.declare_conv('to_app_feat_32', 256, Ea, 1)
+        for s in (64, 128, 256):
+            p, c = s // 32, self.channels[s]
+            self.declare_linear(f'app_feat_emb_{s}.1', Ea, c * p * p)
+            self.declare_linear(f'to_app_feat_{s}.0', c * p * p, Ea)
+        self.declare('quantize_app.embedding.weight', (self.n_codes_app, Ea),
+                     lambda t: t.uniform_(-1.0 / self.n_codes_app, 1.0 / self.n_codes_app))   # vqgan_arch.py:31
+        for s in (64, 128, 256):
+            c = self.channels[s]
+            self._declare_res(f'fuse_convs_dict.{s}.encode_enc', 2 * c, c)
+            for br in ('scale', 'shift'):
+                self.declare_conv(f'fuse_convs_dict.{s}.{br}.0', c, c, 3)
+                self.declare_conv(f'fuse_convs_dict.{s}.{br}.2', c, c, 3)
+            self.declare_conv(f'fuse_ms_dict.{s}', c, c, 3)
+        self.declare('position_emb_app', (1024, Ea), lambda t: t.zero_())                      # :266-267
+        self.declare('position_emb_motion', (1024, Em), lambda t: t.zero_())
+        self.declare('quantize_motion.embedding.weight', (self.n_codes_motion, Em),
+                     lambda t: t.uniform_(-1.0 / self.n_codes_motion, 1.0 / self.n_codes_motion))
+        self.declare_conv('motion_emb.0', Em, 2, 3)
+        self.declare_conv('motion_emb.1.conv', Em, Em, 3)
+        self._declare_res('motion_emb.2', Em, Em)
+        for i in range(2):
+            self._declare_transformer(f'motion_block.{i}', Em)
+        self.declare_conv('to_motion.0.conv', Em, Em, 3)        # training-only head (:290-292); kept for strict loading
+        self._declare_res('to_motion.1', Em, Em)
+        self.declare_norm('to_motion.2', Em)
+        self.declare_conv('to_motion.3', 2, Em, 3)
+        self.declare_conv('BasicMotionEncoder.convc1', 128, Em, 1)
+        self.declare_conv('BasicMotionEncoder.convc2', 96, 128, 3)
+        self.declare_conv('BasicMotionEncoder.convf1', 128, 2, 7)
+        self.declare_conv('BasicMotionEncoder.convf2', 64, 128, 3)
+        self.declare_conv('BasicMotionEncoder.conv', 126, 160, 3)
+        for i, s in enumerate(self.SCALES):
+            self.declare_conv(f'to_context.{i}', 192, self.channels[s], 1)
+        self.declare_conv('refine.convc1', 128, 192, 3)
+        self.declare_conv('refine.conv1', 128, 256, 3)
+        self.declare_conv('refine.conv2', 2, 128, 3)
+        self.declare_conv('refine.convo1', 128, 256, 3)
+        self.declare_conv('refine.convo2', 1, 128, 3)
+        for i in range(2):
+            self._declare_transformer(f'app_block.{i}', Ea)
+        for s in self.SCALES:
+            self.declare_conv(f'warped_source_enc_{s}', Em, self.channels[s], 1)
+        self.declare_conv('driving_kp_enc', Em, self.num_kp, 1)
+        self.declare_conv('motion_query_enc_1', Em, 2 * Em, 1)
+        self.declare_conv('motion_query_enc_2', Em, 2 * Em, 1)
+
+    # ------------------------------------------------------------------------------------------
+    # weight packing (once per load): kernel layouts, fused siblings, constant codebook K/V
+    # ------------------------------------------------------------------------------------------
+    def _weights(self) -> dict:
+        if self._packed is not None:
+            return self._packed
+        T = self.tensors()
+        W: Dict[str, object] = {}
+
+        def pc(name):
+            W[name] = ops.pack_conv(T[name + '.weight'], T[name + '.bias'])
+
+        def pres(name, cin, cout):
+            pc(name + '.conv1'); pc(name + '.conv2')
+            if cin != cout:
+                pc(name + '.conv_out')
+
+        for prefix, layout in (('encoder', self.enc_layout), ('generator', self.gen_layout)):
+            for i, (kind, cin, cout) in enumerate(layout):
+                n = f'{prefix}.blocks.{i}'
+                if kind == 'conv':
+                    pc(n)
+                elif kind == 'res':
+                    pres(n, cin, cout)
+                elif kind == 'attn':
+                    W[n + '.qkv'] = ops.pack_conv_cat([T[f'{n}.{k}.weight'] for k in 'qkv'], [T[f'{n}.{k}.bias'] for k in 'qkv'])
+                    pc(n + '.proj_out')
+                elif kind in ('down', 'up'):
+                    pc(n + '.conv')
+        pc('app_feat_emb_32'); pc('to_app_feat_32')
+        for s in (64, 128, 256):
+            pc(f'app_feat_emb_{s}.1'); pc(f'to_app_feat_{s}.0')
+            W[f'app_feat_emb_{s}.1'] = W[f'app_feat_emb_{s}.1'].as_patch(s // 32)
+            c = self.channels[s]
+            pres(f'fuse_convs_dict.{s}.encode_enc', 2 * c, c)
+            W[f'fuse_convs_dict.{s}.ss0'] = ops.pack_conv_cat(
+                [T[f'fuse_convs_dict.{s}.{b}.0.weight'] for b in ('scale', 'shift')],
+                [T[f'fuse_convs_dict.{s}.{b}.0.bias'] for b in ('scale', 'shift')])
+            pc(f'fuse_convs_dict.{s}.scale.2'); pc(f'fuse_convs_dict.{s}.shift.2'); pc(f'fuse_ms_dict.{s}')
+        pc('motion_emb.0'); pc('motion_emb.1.conv'); pres('motion_emb.2', self.Em, self.Em)
+        for n in ('BasicMotionEncoder.convc1', 'BasicMotionEncoder.convc2', 'BasicMotionEncoder.convf1',
+                  'BasicMotionEncoder.convf2', 'BasicMotionEncoder.conv', 'refine.convc1', 'refine.conv2', 'refine.convo2',
+                  'driving_kp_enc', 'motion_query_enc_1', 'motion_query_enc_2'):
+            pc(n)
+        W['refine.conv1o1'] = ops.pack_conv_cat([T['refine.conv1.weight'], T['refine.convo1.weight']],
+                                                [T['refine.conv1.bias'], T['refine.convo1.bias']])
+        for i, s in enumerate(self.SCALES):
+            pc(f'to_context.{i}'); pc(f'warped_source_enc_{s}')
+        for blk, E, cb in (('motion_block', self.Em, 'quantize_motion.embedding.weight'), ('app_block', self.Ea, 'quantize_app.embedding.weight')):
+            codes = T[cb].float().contiguous()
+            for i in range(2):
+                n = f'{blk}.{i}'
+                W[n + '.self_in'] = ops.pack_conv(T[n + '.self_attn.in_proj_weight'], T[n + '.self_attn.in_proj_bias'])
+                W[n + '.cross_in'] = ops.pack_conv(T[n + '.cross_attn.in_proj_weight'], T[n + '.cross_attn.in_proj_bias'])
+                W[n + '.self_out'] = ops.pack_conv(T[n + '.self_attn.out_proj.weight'], T[n + '.self_attn.out_proj.bias'])
+                W[n + '.cross_out'] = ops.pack_conv(T[n + '.cross_attn.out_proj.weight'], T[n + '.cross_attn.out_proj.bias'])
+                pc(n + '.conv1'); pc(n + '.conv2')
+                # codebook keys/values are frame-invariant: project all rows once (prefix-sliceable for the split)
+                kv = ops.linear(codes.view(1, -1, E), W[n + '.cross_in'].cols(E, 2 * E), exact=True)
+                W[n + '.ctx_kv'] = kv[0]                              # (n_codes, 2E): K | V
+        self._packed = W
+        self._T = T
+        self._src_cache = None
+        return W
+
+    # ------------------------------------------------------------------------------------------
+    # VQGAN blocks
+    # ------------------------------------------------------------------------------------------
+    def _gn(self, name, x):
+        return ops.groupnorm_stats(x, self._T[name + '.weight'], self._T[name + '.bias'], 32, 1e-6)
+
+    def _res(self, name, x, cin, cout, out=None):
+        W = self._packed
+        s1, h1 = self._gn(name + '.norm1', x)
+        h = ops.conv2d(x, W[name + '.conv1'], pad=1, pre=(s1, h1, 'swish'))
+        s2, h2 = self._gn(name + '.norm2', h)
+        skip = x if cin == cout else ops.conv2d(x, W[name + '.conv_out'])
+        return ops.conv2d(h, W[name + '.conv2'], pad=1, pre=(s2, h2, 'swish'), res=skip, out=out)
+
+    def _attn(self, name, x, out=None):
+        W = self._packed
+        B, H, Wd, Cc = x.shape
+        s, h = self._gn(name + '.norm', x)
+        qkv = ops.conv2d(x, W[name + '.qkv'], pre=(s, h, 'none')).view(B, H * Wd, 3 * Cc)
+        o = ops.mha(qkv[..., :Cc], qkv[..., Cc:2 * Cc], qkv[..., 2 * Cc:], heads=1, scale=float(int(Cc) ** (-0.5)))
+        return ops.conv2d(o.view(B, H, Wd, Cc), W[name + '.proj_out'], res=x, out=out)
+
+    def _block(self, prefix, i, layout, x, out=None):
+        kind, cin, cout = layout[i]
+        n = f'{prefix}.blocks.{i}'
+        W = self._packed
+        if kind == 'conv':
+            pre = None
+            if i > 0 and layout[i - 1][0] == 'norm':          # GroupNorm (no activation) feeding the last conv
+                s, h = self._gn(f'{prefix}.blocks.{i - 1}', x)
+                pre = (s, h, 'none')
+            return ops.conv2d(x, W[n], pad=1, pre=pre, out=out)
+        if kind == 'res':
+            return self._res(n, x, cin, cout, out=out)
+        if kind == 'attn':
+            return self._attn(n, x, out=out)
+        if kind == 'down':      # pad right/bottom by one, stride 2 (vqgan_arch.py:149-152)
+            return ops.conv2d(x, W[n + '.conv'], stride=2, pad_tl=(0, 0), out_hw=(x.shape[1] // 2, x.shape[2] // 2), out=out)
+        if kind == 'up':
+            return ops.conv2d(x, W[n + '.conv'], pad=1, upsample2=True, out=out)
+        if kind == 'norm':
+            return x              # folded into the next conv's operand load
+        raise ValueError(kind)
+
+    # ------------------------------------------------------------------------------------------
+    # per-source work: encoder features (cached)
+    # ------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def encode_source(self, x: torch.Tensor) -> Dict[int, torch.Tensor]:
+        """x (N,3,256,256) NCHW -> {256,128,64,32: NHWC features}.  Cached on the tensor identity."""
+        self._weights()
+        key = (x.data_ptr(), x._version, tuple(x.shape))
+        if self._src_cache is not None and self._src_cache[0] == key:
+            return self._src_cache[1]
+        h = ops.nchw_to_nhwc(x.contiguous().float())
+        feats = {}
+        for i in range(len(self.enc_layout)):
+            h = self._block('encoder', i, self.enc_layout, h)
+            if i in (2, 5, 8):
+                feats[h.shape[2]] = h
+        feats[32] = h
+        self._src_cache = (key, feats)
+        return feats
+
+    def encode_driving(self, x):
+        """Reference API (appmotioncodebook_arch.py:364-371): NCHW feature dict keyed by resolution string."""
+        f = self.encode_source(x)
+        return {str(s): ops.nhwc_to_nchw(t) for s, t in f.items()}
+
+    # ------------------------------------------------------------------------------------------
+    # codebook transformer layer (appmotioncodebook_arch.py:88-126) on (B,1024,E) tokens
+    # ------------------------------------------------------------------------------------------
+    def _transformer(self, name, t, E, n_ctx, pos, key_mask=None):
+        W, T = self._packed, self._T
+        B = t.shape[0]
+        u, uq = ops.layernorm(t, T[name + '.norm1.weight'], T[name + '.norm1.bias'], pos)
+        qkv = torch.empty((B, 1024, 3 * E), device=t.device, dtype=torch.float32)
+        ops.linear(uq, W[name + '.self_in'].cols(0, 2 * E), out=qkv[..., :2 * E])
+        ops.linear(u, W[name + '.self_in'].cols(2 * E, E), out=qkv[..., 2 * E:])
+        a = ops.mha(qkv[..., :E], qkv[..., E:2 * E], qkv[..., 2 * E:], heads=self.n_head, key_mask=key_mask)
+        t = ops.linear(a, W[name + '.self_out'], res=t)
+        _, uq = ops.layernorm(t, T[name + '.norm2.weight'], T[name + '.norm2.bias'], pos, want_y=False)
+        qc = ops.linear(uq, W[name + '.cross_in'].cols(0, E))
+        kv = W[name + '.ctx_kv']
+        a = ops.mha(qc, kv[:n_ctx, :E], kv[:n_ctx, E:], heads=self.n_head)
+        t = ops.linear(a, W[name + '.cross_out'], res=t)
+        u, _ = ops.layernorm(t, T[name + '.norm3.weight'], T[name + '.norm3.bias'])
+        f = ops.conv2d(u.view(B, 32, 32, E), W[name + '.conv1'], pad=1, act='gelu')
+        return ops.conv2d(f, W[name + '.conv2'], pad=1, res=t.view(B, 32, 32, E)).view(B, 1024, E)
+
+    # ------------------------------------------------------------------------------------------
+    # stage 3m: motion codebook compensation (appmotioncodebook_arch.py:373-427, 129-168)
+    # ------------------------------------------------------------------------------------------
+    def _motion_comp(self, m_prev, occ_prev, warp0, qcat, s):
+        W, T = self._packed, self._T
+        B = m_prev.shape[0]
+        dev = m_prev.device
+        Em = self.Em
+        z = torch.empty((B, 64, 64, 256), device=dev, dtype=torch.float32)        # [BME out 126 | flow_px 2 | refine.convc1 128]
+        flow_px = ops.flow_to_px(m_prev, z[..., 126:128])
+        mf = ops.conv2d(flow_px, W['motion_emb.0'], pad=1)
+        mf = ops.conv2d(mf, W['motion_emb.1.conv'], stride=2, pad_tl=(0, 0), out_hw=(32, 32))
+        ops_out = qcat[..., :Em]
+        self._res('motion_emb.2', mf, Em, Em, out=ops_out)                        # qcat = [m_feat | query_feat]
+        t = ops.conv2d(qcat, W['motion_query_enc_2']).view(B, 1024, Em)
+        for i in range(2):
+            t = self._transformer(f'motion_block.{i}', t, Em, 256 * (int(math.log2(s)) - 4), T['position_emb_motion'])
+        mfeat = ops.resize_ac(t.view(B, 32, 32, Em), (64, 64))
+        cf = torch.empty((B, 64, 64, 160), device=dev, dtype=torch.float32)       # [cor 96 | flo 64]
+        cor = ops.conv2d(mfeat, W['BasicMotionEncoder.convc1'], act='relu')
+        ops.conv2d(cor, W['BasicMotionEncoder.convc2'], pad=1, act='relu', out=cf[..., :96])
+        flo = ops.conv2d(flow_px, W['BasicMotionEncoder.convf1'], pad=3, act='relu')
+        ops.conv2d(flo, W['BasicMotionEncoder.convf2'], pad=1, act='relu', out=cf[..., 96:])
+        ops.conv2d(cf, W['BasicMotionEncoder.conv'], pad=1, act='relu', out=z[..., :126])
+        ctx = ops.conv2d(warp0, W[f'to_context.{int(math.log2(s)) - 5}'], act='relu')
+        if s != 64:
+            ctx = ops.resize_ac(ctx, (64, 64))
+        ops.conv2d(ctx, W['refine.convc1'], pad=1, act='relu', out=z[..., 128:])
+        f = ops.conv2d(z, W['refine.conv1o1'], pad=1, act='relu')                 # [flow branch 128 | occlusion branch 128]
+        r = torch.empty((B, 64, 64, 4), device=dev, dtype=torch.float32)
+        ops.conv2d(f[..., :128], W['refine.conv2'], pad=1, out=r[..., 0:2])
+        ops.conv2d(f[..., 128:], W['refine.convo2'], pad=1, out=r[..., 2:3])
+        return ops.flow_update(m_prev, occ_prev, r) + (r,)
+
+    # ------------------------------------------------------------------------------------------
+    # stage 3a: appearance codebook compensation (appmotioncodebook_arch.py:472-544)
+    # ------------------------------------------------------------------------------------------
+    def _app_comp(self, feat, m_com, s, out=None):
+        W, T = self._packed, self._T
+        B = feat.shape[0]
+        mask = ops.motion_ignore_mask(m_com, (32, 32))
+        if s == 32:
+            tok = ops.conv2d(feat, W['app_feat_emb_32'])
+        else:
+            p = s // 32
+            tok = ops.conv2d(feat, W[f'app_feat_emb_{s}.1'], stride=p)
+        tok = tok.view(B, 1024, self.Ea)
+        n_ctx = 256 * (int(math.log2(s)) - 4)
+        tok = self._transformer('app_block.0', tok, self.Ea, n_ctx, T['position_emb_app'], key_mask=mask)
+        tok = self._transformer('app_block.1', tok, self.Ea, n_ctx, T['position_emb_app'])
+        tok = tok.view(B, 32, 32, self.Ea)
+        if s == 32:
+            return ops.conv2d(tok, W['to_app_feat_32'], out=out)
+        return ops.conv2d(tok, W[f'to_app_feat_{s}.0'], d2s=s // 32, out=out)
+
+    # ------------------------------------------------------------------------------------------
+    # the per-driving-frame body (appmotioncodebook_arch.py:556-764, inference=True)
+    # ------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def generate(self, feats: Dict[int, torch.Tensor], deformation: torch.Tensor, occlusion: torch.Tensor,
+                 kp_heat_nhwc: torch.Tensor, w: float = 1.0, collect: Optional[dict] = None) -> dict:
+        """feats: encode_source() output (batch 1 = shared by all frames, or batch B).
+        deformation (B,64,64,2), occlusion (B,64,64) post-sigmoid, kp_heat_nhwc (B,64,64,15).
+        Returns NHWC tensors: out (B,256,256,3), lq_feat (B,32,32,256), lists of motions / occlusions."""
+        W = self._weights()
+        B = deformation.shape[0]
+        dev = deformation.device
+        Em = self.Em
+
+        def src(s):
+            f = feats[s]
+            return f if f.shape[0] == B else f.expand(B, -1, -1, -1)
+
+        motions, occs, residuals = [deformation.contiguous()], [], []
+        occ_prev = occlusion.contiguous().view(B, 64, 64)
+        qk = torch.empty((B, 32, 32, 2 * Em), device=dev, dtype=torch.float32)     # [warped-source query | driving kp feat]
+        qcat = torch.empty((B, 32, 32, 2 * Em), device=dev, dtype=torch.float32)   # [motion feat | query feat]
+        ops.conv2d(ops.resize_ac(kp_heat_nhwc, (32, 32)), W['driving_kp_enc'], act='relu', out=qk[..., Em:])
+
+        def compensate(s, out=None):
+            nonlocal occ_prev
+            f = src(s)
+            warp0 = ops.warp_occlude(f, motions[-1], None)
+            w32 = warp0 if s == 32 else ops.resize_ac(warp0, (32, 32))
+            ops.conv2d(w32, W[f'warped_source_enc_{s}'], act='relu', out=qk[..., :Em])
+            ops.conv2d(qk, W['motion_query_enc_1'], out=qcat[..., Em:])
+            m_com, occ, r = self._motion_comp(motions[-1], occ_prev, warp0, qcat, s)
+            motions.append(m_com); occs.append(occ); residuals.append(r)
+            occ_prev = occ
+            warped = ops.warp_occlude(f, m_com, occ)
+            enc = self._app_comp(warped, m_com, s, out=out)
+            if collect is not None:
+                collect[f'warp0_{s}'], collect[f'warped_{s}'], collect[f'app_{s}'] = warp0, warped, enc
+            return enc
+
+        x = compensate(32)
+        lq_feat = x
+        fuse_at = {9: 64, 12: 128, 15: 256}
+        cat = None
+        for i in range(len(self.gen_layout)):
+            if i in fuse_at and w > 0:
+                s = fuse_at[i]
+                c = self.channels[s]
+                cat = torch.empty((B, s, s, 2 * c), device=dev, dtype=torch.float32)   # [enc | dec] for Fuse_sft_block
+                x = self._block('generator', i, self.gen_layout, x, out=cat[..., c:])
+                enc = compensate(s, out=cat[..., :c])
+                n = f'fuse_convs_dict.{s}'
+                e = self._res(n + '.encode_enc', cat, 2 * c, c)
+                ss = ops.conv2d(e, W[n + '.ss0'], pad=1, act='leaky')                  # [scale.0 | shift.0]
+                scale = ops.conv2d(ss[..., :c], W[n + '.scale.2'], pad=1)
+                shift = ops.conv2d(ss[..., c:], W[n + '.shift.2'], pad=1)
+                xd = ops.affine_act(x, None, None)                                     # dense copy of the decoder half
+                xf = ops.sft_combine(xd, scale, shift, float(w))
+                x = ops.conv2d(enc, W[f'fuse_ms_dict.{s}'], pad=1, res=xf, out=xf)
+            else:
+                x = self._block('generator', i, self.gen_layout, x)
+        return {'out': x, 'lq_feat': lq_feat, 'out_occ': occs, 'deformation_list': motions, 'residuals': residuals}
+
+    # ------------------------------------------------------------------------------------------
+    # reference call surface
+    # ------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def forward(self, x, dense_motion, w=1, inference=False, vis_app_before_comp=False, gt=None, visualize_app_feat=False):
+        if not inference:
+            raise NotImplementedError('the B200 path implements inference=True only (training losses are out of scope)')
+        if isinstance(dense_motion['occlusion_map'], list):
+            raise NotImplementedError('multi-mask occlusion lists are not part of options/test.yml')
+        feats = self.encode_source(x)
+        deformation = dense_motion['deformation'].float()
+        B = deformation.shape[0]
+        heat = dense_motion.get('_driving_kp_heatmap_nhwc')
+        if heat is None:
+            heat = ops.nchw_to_nhwc(dense_motion['driving_kp_heatmap'].contiguous().float())
+        occ = dense_motion['occlusion_map'].contiguous().float().view(B, 64, 64)
+        r = self.generate(feats, deformation, occ, heat, float(w))
+        half = (deformation.shape[1] - 1.0) / 2.0
+        return {
+            'out': ops.nhwc_to_nchw(r['out']),
+            '_out_nhwc': r['out'],
+            'lq_feat': ops.nhwc_to_nchw(r['lq_feat']),
+            'out_occ': [o.view(B, 1, 64, 64) for o in r['out_occ']],
+            'deformation_list': r['deformation_list'],
+            'res_deform_list': [q[..., 0:2] / half for q in r['residuals']],
+        }

@@ -1,0 +1,341 @@
+// Motion-estimator heads and the small glue kernels of the per-frame path (all HBM/latency-bound,
+// CUDA-core work; none of it is a dense contraction).
+#include "sma_common.cuh"
+#include <math_constants.h>
+
+namespace {
+
+// 2*(i/(n-1))-1 exactly as make_coordinate_grid evaluates it (utils/motion_estimator_util.py:63-64)
+__device__ __forceinline__ float grid_coord(int i, int n) { return 2.f * ((float)i / (float)(n - 1)) - 1.f; }
+
+__global__ void antialias_down4_kernel(const float* __restrict__ x, int B, int C, int H, int W, const float* __restrict__ k13,
+                                       float* __restrict__ y, int yld) {
+  __shared__ float ks[169];
+  for (int i = threadIdx.x; i < 169; i += blockDim.x) ks[i] = k13[i];
+  __syncthreads();
+  const int Ho = H / 4, Wo = W / 4;
+  long long total = (long long)B * Ho * Wo * C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % C); long long pp = i / C; int ox = (int)(pp % Wo); long long t = pp / Wo; int oy = (int)(t % Ho); int b = (int)(t / Ho);
+    const float* xc = x + ((long long)b * C + c) * H * W;
+    float acc = 0.f;
+    for (int ky = 0; ky < 13; ky++) {
+      int iy = oy * 4 + ky - 6; if ((unsigned)iy >= (unsigned)H) continue;
+      for (int kx = 0; kx < 13; kx++) {
+        int ix = ox * 4 + kx - 6; if ((unsigned)ix >= (unsigned)W) continue;
+        acc = fmaf(ks[ky * 13 + kx], __ldg(xc + (long long)iy * W + ix), acc);
+      }
+    }
+    y[pp * yld + c] = acc;
+  }
+}
+
+__global__ void avgpool2_kernel(const float* __restrict__ x, int B, int H, int W, int C, float* __restrict__ y, int yld) {
+  const int Ho = H / 2, Wo = W / 2, C4 = C / 4;
+  long long total = (long long)B * Ho * Wo * C4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int c4 = (int)(i % C4); long long pp = i / C4; int ox = (int)(pp % Wo); long long t = pp / Wo; int oy = (int)(t % Ho); int b = (int)(t / Ho);
+    const float* p = x + (((long long)b * H + oy * 2) * W + ox * 2) * C + c4 * 4;
+    float4 a = __ldg(reinterpret_cast<const float4*>(p)), bq = __ldg(reinterpret_cast<const float4*>(p + C));
+    float4 c = __ldg(reinterpret_cast<const float4*>(p + (long long)W * C)), d = __ldg(reinterpret_cast<const float4*>(p + (long long)W * C + C));
+    float4 o = make_float4((a.x + bq.x + c.x + d.x) * 0.25f, (a.y + bq.y + c.y + d.y) * 0.25f, (a.z + bq.z + c.z + d.z) * 0.25f, (a.w + bq.w + c.w + d.w) * 0.25f);
+    *reinterpret_cast<float4*>(y + pp * yld + c4 * 4) = o;
+  }
+}
+
+__device__ __forceinline__ float block_reduce(float v, float* sh, bool is_max) {
+  v = is_max ? warp_max(v) : warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float r = is_max ? -CUDART_INF_F : 0.f;
+  for (int i = 0; i < (int)(blockDim.x >> 5); i++) r = is_max ? fmaxf(r, sh[i]) : r + sh[i];
+  return r;
+}
+
+// one block per (k, b): softmax(logit / T) over h*w, expectation of the grid and of the 4 jacobian maps
+__global__ void kp_head_kernel(const float* __restrict__ pred, int h, int w, int ld, int K, float T, float* __restrict__ value, float* __restrict__ jac) {
+  __shared__ float sh[32];
+  const int k = blockIdx.x, b = blockIdx.y, n = h * w;
+  const float* pb = pred + (long long)b * n * ld;
+  float mx = -CUDART_INF_F;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) mx = fmaxf(mx, __ldg(pb + (long long)i * ld + k) / T);
+  mx = block_reduce(mx, sh, true);
+  float s = 0.f, sx = 0.f, sy = 0.f, j0 = 0.f, j1 = 0.f, j2 = 0.f, j3 = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float* px = pb + (long long)i * ld;
+    float e = expf(__ldg(px + k) / T - mx);
+    int yy = i / w, xx = i - yy * w;
+    s += e; sx = fmaf(e, grid_coord(xx, w), sx); sy = fmaf(e, grid_coord(yy, h), sy);
+    if (jac) {
+      const float* pj = px + K + k * 4;
+      j0 = fmaf(e, __ldg(pj), j0); j1 = fmaf(e, __ldg(pj + 1), j1); j2 = fmaf(e, __ldg(pj + 2), j2); j3 = fmaf(e, __ldg(pj + 3), j3);
+    }
+  }
+  s = block_reduce(s, sh, false); sx = block_reduce(sx, sh, false); sy = block_reduce(sy, sh, false);
+  if (jac) { j0 = block_reduce(j0, sh, false); j1 = block_reduce(j1, sh, false); j2 = block_reduce(j2, sh, false); j3 = block_reduce(j3, sh, false); }
+  if (threadIdx.x == 0) {
+    float inv = 1.f / s;
+    float* v = value + ((long long)b * K + k) * 2; v[0] = sx * inv; v[1] = sy * inv;
+    if (jac) { float* j = jac + ((long long)b * K + k) * 4; j[0] = j0 * inv; j[1] = j1 * inv; j[2] = j2 * inv; j[3] = j3 * inv; }
+  }
+}
+
+__device__ __forceinline__ void inv2(const float* a, float* o) {
+  float det = a[0] * a[3] - a[1] * a[2]; float r = 1.f / det;
+  o[0] = a[3] * r; o[1] = -a[1] * r; o[2] = -a[2] * r; o[3] = a[0] * r;
+}
+__device__ __forceinline__ void mm2(const float* a, const float* b, float* o) {
+  o[0] = a[0] * b[0] + a[1] * b[2]; o[1] = a[0] * b[1] + a[1] * b[3];
+  o[2] = a[2] * b[0] + a[3] * b[2]; o[3] = a[2] * b[1] + a[3] * b[3];
+}
+
+__global__ void normalize_kp_kernel(const float* src_v, const float* src_j, const float* drv_v, const float* drv_j, const float* drv0_v,
+                                    const float* drv0_j, int B, int K, float scale, int relative, float* out_v, float* out_j) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * K) return;
+  int k = i % K;
+  if (!relative) {
+    out_v[i * 2] = drv_v[i * 2]; out_v[i * 2 + 1] = drv_v[i * 2 + 1];
+    for (int j = 0; j < 4; j++) out_j[i * 4 + j] = drv_j[i * 4 + j];
+    return;
+  }
+  out_v[i * 2] = (drv_v[i * 2] - drv0_v[k * 2]) * scale + src_v[k * 2];
+  out_v[i * 2 + 1] = (drv_v[i * 2 + 1] - drv0_v[k * 2 + 1]) * scale + src_v[k * 2 + 1];
+  float inv0[4], t[4], o[4];
+  inv2(drv0_j + k * 4, inv0); mm2(drv_j + i * 4, inv0, t); mm2(t, src_j + k * 4, o);
+  for (int j = 0; j < 4; j++) out_j[i * 4 + j] = o[j];
+}
+
+// sparse motion k (1..K) at grid point (gx,gy):  J_s J_d^-1 (g - kp_d) + kp_s   (dense_motion_arch.py:84-104)
+struct KpXform { float a[4]; float dx, dy, sx, sy; };
+__device__ __forceinline__ KpXform make_xform(const float* sv, const float* sj, const float* dv, const float* dj) {
+  KpXform t; float inv[4]; inv2(dj, inv); mm2(sj, inv, t.a); t.dx = dv[0]; t.dy = dv[1]; t.sx = sv[0]; t.sy = sv[1]; return t;
+}
+__device__ __forceinline__ void apply_xform(const KpXform& t, float gx, float gy, float& ox, float& oy) {
+  float zx = gx - t.dx, zy = gy - t.dy;
+  ox = t.a[0] * zx + t.a[1] * zy + t.sx; oy = t.a[2] * zx + t.a[3] * zy + t.sy;
+}
+
+// thread per (b, pixel, k)
+__global__ void dense_motion_prep_kernel(const float* __restrict__ src, int h, int w, const float* __restrict__ sv, const float* __restrict__ sj,
+                                         const float* __restrict__ dv, const float* __restrict__ dj, int B, int K, float var,
+                                         float* __restrict__ hg, int hg_ld, float* __restrict__ heat_out) {
+  const int K1 = K + 1;
+  long long total = (long long)B * h * w * K1;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int k = (int)(i % K1); long long pp = i / K1; int x = (int)(pp % w); long long t = pp / w; int y = (int)(t % h); int b = (int)(t / h);
+    float gx = grid_coord(x, w), gy = grid_coord(y, h);
+    float heat = 0.f, mx = gx, my = gy;
+    if (k > 0) {
+      const float* dvk = dv + ((long long)b * K + k - 1) * 2; const float* svk = sv + (k - 1) * 2;
+      float ddx = gx - dvk[0], ddy = gy - dvk[1], sdx = gx - svk[0], sdy = gy - svk[1];
+      float gd = expf(-0.5f * (ddx * ddx + ddy * ddy) / var), gs = expf(-0.5f * (sdx * sdx + sdy * sdy) / var);
+      heat = gd - gs;
+      if (heat_out) heat_out[pp * K + (k - 1)] = gd;
+      KpXform xf = make_xform(svk, sj + (k - 1) * 4, dvk, dj + ((long long)b * K + k - 1) * 4);
+      apply_xform(xf, gx, gy, mx, my);
+    }
+    // grid_sample bilinear / zeros / align_corners=False on the (h,w,3) source
+    float ix = ((mx + 1.f) * (float)w - 1.f) * 0.5f, iy = ((my + 1.f) * (float)h - 1.f) * 0.5f;
+    float fx = floorf(ix), fy = floorf(iy);
+    int x0 = (int)fx, y0 = (int)fy, x1 = x0 + 1, y1 = y0 + 1;
+    float wx1 = ix - fx, wy1 = iy - fy, wx0 = 1.f - wx1, wy0 = 1.f - wy1;
+    float r = 0.f, g = 0.f, bl = 0.f;
+    bool vx0 = (unsigned)x0 < (unsigned)w, vx1 = (unsigned)x1 < (unsigned)w, vy0 = (unsigned)y0 < (unsigned)h, vy1 = (unsigned)y1 < (unsigned)h;
+    if (vy0 && vx0) { const float* p = src + ((long long)y0 * w + x0) * 3; float ww = wy0 * wx0; r = fmaf(ww, p[0], r); g = fmaf(ww, p[1], g); bl = fmaf(ww, p[2], bl); }
+    if (vy0 && vx1) { const float* p = src + ((long long)y0 * w + x1) * 3; float ww = wy0 * wx1; r = fmaf(ww, p[0], r); g = fmaf(ww, p[1], g); bl = fmaf(ww, p[2], bl); }
+    if (vy1 && vx0) { const float* p = src + ((long long)y1 * w + x0) * 3; float ww = wy1 * wx0; r = fmaf(ww, p[0], r); g = fmaf(ww, p[1], g); bl = fmaf(ww, p[2], bl); }
+    if (vy1 && vx1) { const float* p = src + ((long long)y1 * w + x1) * 3; float ww = wy1 * wx1; r = fmaf(ww, p[0], r); g = fmaf(ww, p[1], g); bl = fmaf(ww, p[2], bl); }
+    *reinterpret_cast<float4*>(hg + pp * hg_ld + k * 4) = make_float4(heat, r, g, bl);
+  }
+}
+
+// thread per (b, pixel); K+1 <= 32
+__global__ void dense_motion_head_kernel(const float* __restrict__ logits, int ld, int h, int w, const float* __restrict__ sv, const float* __restrict__ sj,
+                                         const float* __restrict__ dv, const float* __restrict__ dj, int B, int K, float* __restrict__ deform,
+                                         float* __restrict__ occ, float* __restrict__ mask_out) {
+  const int K1 = K + 1;
+  long long total = (long long)B * h * w;
+  for (long long pp = blockIdx.x * (long long)blockDim.x + threadIdx.x; pp < total; pp += (long long)gridDim.x * blockDim.x) {
+    int x = (int)(pp % w); long long t = pp / w; int y = (int)(t % h); int b = (int)(t / h);
+    const float* lg = logits + pp * ld;
+    float mx = -CUDART_INF_F;
+    for (int k = 0; k < K1; k++) mx = fmaxf(mx, __ldg(lg + k));
+    float s = 0.f;
+    for (int k = 0; k < K1; k++) s += expf(__ldg(lg + k) - mx);
+    float inv = 1.f / s;
+    float gx = grid_coord(x, w), gy = grid_coord(y, h);
+    float ax = 0.f, ay = 0.f;
+    for (int k = 0; k < K1; k++) {
+      float m = expf(__ldg(lg + k) - mx) * inv;
+      if (mask_out) mask_out[pp * K1 + k] = m;
+      float px = gx, py = gy;
+      if (k > 0) {
+        KpXform xf = make_xform(sv + (k - 1) * 2, sj + (k - 1) * 4, dv + ((long long)b * K + k - 1) * 2, dj + ((long long)b * K + k - 1) * 4);
+        apply_xform(xf, gx, gy, px, py);
+      }
+      ax = fmaf(m, px, ax); ay = fmaf(m, py, ay);
+    }
+    deform[pp * 2] = ax; deform[pp * 2 + 1] = ay;
+    if (occ) occ[pp] = 1.f / (1.f + expf(-__ldg(lg + K1)));
+  }
+}
+
+// torch.linspace(-1, 1, n)[i] as ATen evaluates it (symmetric two-sided formula)
+__device__ __forceinline__ float linspace_pm1(int i, int n) {
+  float step = 2.f / (float)(n - 1);
+  return i < n / 2 ? -1.f + step * (float)i : 1.f - step * (float)(n - 1 - i);
+}
+
+__global__ void flow_to_px_kernel(const float* __restrict__ m, int B, int h, int w, float* __restrict__ o, int ld) {
+  long long total = (long long)B * h * w;
+  const float hx = ((float)h - 1.f) * 0.5f;   // the reference scales both components by (shape[1]-1)/2
+  for (long long pp = blockIdx.x * (long long)blockDim.x + threadIdx.x; pp < total; pp += (long long)gridDim.x * blockDim.x) {
+    int x = (int)(pp % w); int y = (int)((pp / w) % h);
+    o[pp * ld] = (m[pp * 2] - linspace_pm1(x, h)) * hx;
+    o[pp * ld + 1] = (m[pp * 2 + 1] - linspace_pm1(y, w)) * hx;
+  }
+}
+
+__global__ void flow_update_kernel(const float* __restrict__ m, const float* __restrict__ occ, const float* __restrict__ res, int ld, int B, int h,
+                                   int w, float* __restrict__ mo, float* __restrict__ oo) {
+  long long total = (long long)B * h * w;
+  const float hx = ((float)h - 1.f) * 0.5f;
+  for (long long pp = blockIdx.x * (long long)blockDim.x + threadIdx.x; pp < total; pp += (long long)gridDim.x * blockDim.x) {
+    const float* r = res + pp * ld;
+    mo[pp * 2] = m[pp * 2] + r[0] / hx; mo[pp * 2 + 1] = m[pp * 2 + 1] + r[1] / hx;
+    oo[pp] = 1.f / (1.f + expf(-(occ[pp] + r[2])));
+  }
+}
+
+__global__ void ignore_mask_kernel(const float* __restrict__ m, int B, int h, int w, int ht, int wt, uint8_t* __restrict__ mask) {
+  long long total = (long long)B * ht * wt;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int ox = (int)(i % wt); int oy = (int)((i / wt) % ht); int b = (int)(i / ((long long)wt * ht));
+    float sy = (ht > 1 ? (float)(h - 1) / (float)(ht - 1) : 0.f) * oy, sx = (wt > 1 ? (float)(w - 1) / (float)(wt - 1) : 0.f) * ox;
+    int y0 = min((int)sy, h - 1), x0 = min((int)sx, w - 1); int y1 = y0 + (y0 < h - 1), x1 = x0 + (x0 < w - 1);
+    float ly = sy - y0, lx = sx - x0;
+    const float* mb = m + (long long)b * h * w * 2;
+    bool ig = false;
+    for (int c = 0; c < 2; c++) {
+      float v = (1.f - ly) * ((1.f - lx) * mb[(y0 * w + x0) * 2 + c] + lx * mb[(y0 * w + x1) * 2 + c]) +
+                ly * ((1.f - lx) * mb[(y1 * w + x0) * 2 + c] + lx * mb[(y1 * w + x1) * 2 + c]);
+      ig = ig || v > 1.f || v < -1.f;
+    }
+    mask[i] = ig ? 1 : 0;
+  }
+}
+
+__global__ void sft_combine_kernel(const float4* __restrict__ dec, const float4* __restrict__ sc, const float4* __restrict__ sh, float w, long long n4,
+                                   float4* __restrict__ out) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 d = __ldg(dec + i), s = __ldg(sc + i), h = __ldg(sh + i), o;
+    o.x = d.x + w * (d.x * s.x + h.x); o.y = d.y + w * (d.y * s.y + h.y); o.z = d.z + w * (d.z * s.z + h.z); o.w = d.w + w * (d.w * s.w + h.w);
+    out[i] = o;
+  }
+}
+
+__global__ void to_uint8_kernel(const float* __restrict__ x, long long npix, int C, int ld, int bgr, uint8_t* __restrict__ out) {
+  long long total = npix * C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % C); long long pp = i / C;
+    float v = x[pp * ld + (bgr ? C - 1 - c : c)];
+    v = fminf(fmaxf(v, -1.f), 1.f);
+    v = (v + 1.f) / 2.f;
+    out[i] = (uint8_t)rintf(v * 255.f);
+  }
+}
+
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, int B, int C, int HW, float* __restrict__ y, int yld) {
+  long long total = (long long)B * HW * C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % C); long long pp = i / C; int p = (int)(pp % HW); int b = (int)(pp / HW);
+    y[pp * yld + c] = x[((long long)b * C + c) * HW + p];
+  }
+}
+__global__ void nhwc_to_nchw_kernel(const float* __restrict__ x, int B, int C, int HW, int xld, float* __restrict__ y) {
+  long long total = (long long)B * HW * C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int p = (int)(i % HW); long long t = i / HW; int c = (int)(t % C); int b = (int)(t / C);
+    y[i] = x[((long long)b * HW + p) * xld + c];
+  }
+}
+
+inline int nblocks(long long total, int per = 256) { long long b = (total + per - 1) / per; if (b > kNumSMs * 32) b = kNumSMs * 32; if (b < 1) b = 1; return (int)b; }
+
+}  // namespace
+
+extern "C" int sma_antialias_down4(const float* x, int B, int C, int H, int W, const float* k13, float* y, int yld, sma_stream_t s) {
+  if (!x || !k13 || !y || B <= 0 || C <= 0 || H < 4 || W < 4 || (H & 3) || (W & 3) || yld < C) return SMA_ERR_BAD_ARG;
+  antialias_down4_kernel<<<nblocks((long long)B * (H / 4) * (W / 4) * C), 256, 0, as_stream(s)>>>(x, B, C, H, W, k13, y, yld);
+  SMA_LAUNCH_CHECK(); return SMA_OK;
+}
+extern "C" int sma_avgpool2(const float* x, int B, int H, int W, int C, float* y, int yld, sma_stream_t s) {
+  if (!x || !y || B <= 0 || H < 2 || W < 2 || (H & 1) || (W & 1)) return SMA_ERR_BAD_ARG;
+  if ((C & 3) || (yld & 3) || yld < C) return SMA_ERR_UNSUPPORTED;
+  avgpool2_kernel<<<nblocks((long long)B * (H / 2) * (W / 2) * (C / 4)), 256, 0, as_stream(s)>>>(x, B, H, W, C, y, yld);
+  SMA_LAUNCH_CHECK(); return SMA_OK;
+}
+extern "C" int sma_kp_head_fwd(const float* pred, int B, int h, int w, int ld, int K, float T, float* value, float* jac, sma_stream_t s) {
+  if (!pred || !value || B <= 0 || h <= 1 || w <= 1 || K <= 0 || ld < (jac ? 5 * K : K) || T <= 0.f) return SMA_ERR_BAD_ARG;
+  kp_head_kernel<<<dim3(K, B), 256, 0, as_stream(s)>>>(pred, h, w, ld, K, T, value, jac);
+  SMA_LAUNCH_CHECK(); return SMA_OK;
+}
+extern "C" int sma_normalize_kp(const float* sv, const float* sj, const float* dv, const float* dj, const float* d0v, const float* d0j, int B,
+                                int K, float scale, int relative, float* ov, float* oj, sma_stream_t s) {
+  if (!sv || !sj || !dv || !dj || !d0v || !d0j || !ov || !oj || B <= 0 || K <= 0) return SMA_ERR_BAD_ARG;
+  normalize_kp_kernel<<<cdiv(B * K, 128), 128, 0, as_stream(s)>>>(sv, sj, dv, dj, d0v, d0j, B, K, scale, relative, ov, oj);
+  SMA_LAUNCH_CHECK(); return SMA_OK;
+}
+extern "C" int sma_dense_motion_prep(const float* src64, int h, int w, const float* sv, const float* sj, const float* dv, const float* dj, int B,
+                                     int K, float var, float* hg, int hg_ld, float* heat, sma_stream_t s) {
+  if (!src64 || !sv || !sj || !dv || !dj || !hg || B <= 0 || K <= 0 || h <= 1 || w <= 1 || var <= 0.f) return SMA_ERR_BAD_ARG;
+  if ((reinterpret_cast<uintptr_t>(hg) & 15) || (hg_ld & 3) || hg_ld < 4 * (K + 1)) return SMA_ERR_UNSUPPORTED;
+  dense_motion_prep_kernel<<<nblocks((long long)B * h * w * (K + 1)), 256, 0, as_stream(s)>>>(src64, h, w, sv, sj, dv, dj, B, K, var, hg, hg_ld, heat);
+  SMA_LAUNCH_CHECK(); return SMA_OK;
+}
+extern "C" int sma_dense_motion_head(const float* logits, int ld, int h, int w, const float* sv, const float* sj, const float* dv, const float* dj,
+                                     int B, int K, float* deform, float* occ, float* mask_out, sma_stream_t s) {
+  if (!logits || !sv || !sj || !dv || !dj || !deform || B <= 0 || K <= 0 || ld < K + (occ ? 2 : 1)) return SMA_ERR_BAD_ARG;
+  dense_motion_head_kernel<<<nblocks((long long)B * h * w, 128), 128, 0, as_stream(s)>>>(logits, ld, h, w, sv, sj, dv, dj, B, K, deform, occ, mask_out);
+  SMA_LAUNCH_CHECK(); return SMA_OK;
+}
+extern "C" int sma_flow_to_px(const float* m, int B, int h, int w, float* o, int ld, sma_stream_t s) {
+  if (!m || !o || B <= 0 || h <= 1 || w <= 1 || ld < 2) return SMA_ERR_BAD_ARG;
+  flow_to_px_kernel<<<nblocks((long long)B * h * w), 256, 0, as_stream(s)>>>(m, B, h, w, o, ld);
+  SMA_LAUNCH_CHECK(); return SMA_OK;
+}
+extern "C" int sma_flow_update(const float* m, const float* occ, const float* res, int ld, int B, int h, int w, float* mo, float* oo, sma_stream_t s) {
+  if (!m || !occ || !res || !mo || !oo || B <= 0 || h <= 1 || w <= 1 || ld < 3) return SMA_ERR_BAD_ARG;
+  flow_update_kernel<<<nblocks((long long)B * h * w), 256, 0, as_stream(s)>>>(m, occ, res, ld, B, h, w, mo, oo);
+  SMA_LAUNCH_CHECK(); return SMA_OK;
+}
+extern "C" int sma_motion_ignore_mask(const float* m, int B, int h, int w, int ht, int wt, uint8_t* mask, sma_stream_t s) {
+  if (!m || !mask || B <= 0 || h <= 0 || w <= 0 || ht <= 0 || wt <= 0) return SMA_ERR_BAD_ARG;
+  ignore_mask_kernel<<<nblocks((long long)B * ht * wt), 256, 0, as_stream(s)>>>(m, B, h, w, ht, wt, mask);
+  SMA_LAUNCH_CHECK(); return SMA_OK;
+}
+extern "C" int sma_sft_combine(const float* dec, const float* sc, const float* sh, float w, int64_t n, float* out, sma_stream_t s) {
+  if (!dec || !sc || !sh || !out || n <= 0) return SMA_ERR_BAD_ARG;
+  if ((n & 3) || ((reinterpret_cast<uintptr_t>(dec) | reinterpret_cast<uintptr_t>(sc) | reinterpret_cast<uintptr_t>(sh) | reinterpret_cast<uintptr_t>(out)) & 15))
+    return SMA_ERR_UNSUPPORTED;
+  sft_combine_kernel<<<nblocks(n / 4), 256, 0, as_stream(s)>>>(reinterpret_cast<const float4*>(dec), reinterpret_cast<const float4*>(sc),
+                                                               reinterpret_cast<const float4*>(sh), w, n / 4, reinterpret_cast<float4*>(out));
+  SMA_LAUNCH_CHECK(); return SMA_OK;
+}
+extern "C" int sma_to_uint8(const float* x, int B, int H, int W, int C, int ld, int bgr, uint8_t* out, sma_stream_t s) {
+  if (!x || !out || B <= 0 || H <= 0 || W <= 0 || C <= 0 || ld < C) return SMA_ERR_BAD_ARG;
+  to_uint8_kernel<<<nblocks((long long)B * H * W * C), 256, 0, as_stream(s)>>>(x, (long long)B * H * W, C, ld, bgr, out);
+  SMA_LAUNCH_CHECK(); return SMA_OK;
+}
+extern "C" int sma_nchw_to_nhwc(const float* x, int B, int C, int H, int W, float* y, int yld, sma_stream_t s) {
+  if (!x || !y || B <= 0 || C <= 0 || H <= 0 || W <= 0 || yld < C) return SMA_ERR_BAD_ARG;
+  nchw_to_nhwc_kernel<<<nblocks((long long)B * C * H * W), 256, 0, as_stream(s)>>>(x, B, C, H * W, y, yld);
+  SMA_LAUNCH_CHECK(); return SMA_OK;
+}
+extern "C" int sma_nhwc_to_nchw(const float* x, int B, int C, int H, int W, int xld, float* y, sma_stream_t s) {
+  if (!x || !y || B <= 0 || C <= 0 || H <= 0 || W <= 0 || xld < C) return SMA_ERR_BAD_ARG;
+  nhwc_to_nchw_kernel<<<nblocks((long long)B * C * H * W), 256, 0, as_stream(s)>>>(x, B, C, H * W, xld, y);
+  SMA_LAUNCH_CHECK(); return SMA_OK;
+}

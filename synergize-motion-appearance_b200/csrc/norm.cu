@@ -1,0 +1,141 @@
+// GroupNorm statistics (-> per-(b,c) scale/shift for the conv prologue), affine+activation, LayerNorm.
+#include "sma_common.cuh"
+
+namespace {
+
+constexpr int GN_CHUNK = 256;   // pixels per partial block
+
+// partial[(b*nchunk+chunk)*C*2 + c*2 + {0,1}] = sum, sum of squares over the chunk's pixels for channel c
+__global__ void gn_partial_kernel(const float* __restrict__ x, int HW, int C, long long bstride, int ld, float* __restrict__ partial, int nchunk) {
+  const int chunk = blockIdx.x, b = blockIdx.y;
+  const int p0 = chunk * GN_CHUNK, p1 = min(HW, p0 + GN_CHUNK);
+  extern __shared__ float sm[];          // [2][rows][C] reduction scratch
+  const int tid = threadIdx.x;           // 256 threads: lane -> channel (coalesced), row groups -> pixels
+  const int cpt = min(C, 256);           // channels covered per pass
+  const int rows = 256 / cpt;            // pixel rows processed concurrently
+  const int c_in = tid % cpt, r_in = tid / cpt;
+  for (int cb = 0; cb < C; cb += cpt) {
+    float s = 0.f, q = 0.f;
+    int c = cb + c_in;
+    if (r_in < rows && c < C) {
+      const float* px = x + (long long)b * bstride + c;
+      for (int p = p0 + r_in; p < p1; p += rows) { float v = __ldg(px + (long long)p * ld); s += v; q = fmaf(v, v, q); }
+    }
+    sm[tid] = s; sm[256 + tid] = q;
+    __syncthreads();
+    if (tid < cpt && cb + tid < C) {
+      float ss = 0.f, qq = 0.f;
+      for (int r = 0; r < rows; r++) { ss += sm[r * cpt + tid]; qq += sm[256 + r * cpt + tid]; }
+      float* o = partial + (((long long)b * nchunk + chunk) * C + cb + tid) * 2;
+      o[0] = ss; o[1] = qq;
+    }
+    __syncthreads();
+  }
+}
+
+// one block per (b, group): combine chunk partials in fp64, emit scale/shift per channel
+__global__ void gn_finalize_kernel(const float* __restrict__ partial, int nchunk, int C, int groups, int HW, float eps,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ scale, float* __restrict__ shift) {
+  const int g = blockIdx.x, b = blockIdx.y;
+  const int cg = C / groups;
+  double s = 0.0, q = 0.0;
+  for (int i = threadIdx.x; i < nchunk * cg; i += blockDim.x) {
+    int chunk = i / cg, c = g * cg + i % cg;
+    const float* o = partial + (((long long)b * nchunk + chunk) * C + c) * 2;
+    s += (double)o[0]; q += (double)o[1];
+  }
+  __shared__ double sh[2][32];
+  for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); q += __shfl_xor_sync(0xffffffffu, q, o); }
+  if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = s; sh[1][threadIdx.x >> 5] = q; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double ss = 0, qq = 0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); i++) { ss += sh[0][i]; qq += sh[1][i]; }
+    double n = (double)HW * cg; double mean = ss / n; double var = qq / n - mean * mean; if (var < 0) var = 0;
+    sh[0][0] = mean; sh[1][0] = 1.0 / sqrt(var + (double)eps);
+  }
+  __syncthreads();
+  float mean = (float)sh[0][0], rstd = (float)sh[1][0];
+  for (int i = threadIdx.x; i < cg; i += blockDim.x) {
+    int c = g * cg + i;
+    float ga = gamma ? gamma[c] : 1.f, be = beta ? beta[c] : 0.f;
+    float sc = ga * rstd;
+    scale[(long long)b * C + c] = sc; shift[(long long)b * C + c] = be - mean * sc;
+  }
+}
+
+__global__ void affine_act_kernel(const float* __restrict__ x, int HW, int C, long long bstride, int ld, const float* __restrict__ scale,
+                                  const float* __restrict__ shift, int act, float* __restrict__ y, long long ybs, int yld, long long total4) {
+  const int C4 = C >> 2;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
+    int c4 = (int)(i % C4); long long pp = i / C4; int p = (int)(pp % HW); int b = (int)(pp / HW);
+    float4 v = __ldg(reinterpret_cast<const float4*>(x + (long long)b * bstride + (long long)p * ld + c4 * 4));
+    float4 s = make_float4(1.f, 1.f, 1.f, 1.f), h = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (scale) { s = __ldg(reinterpret_cast<const float4*>(scale + (long long)b * C + c4 * 4)); h = __ldg(reinterpret_cast<const float4*>(shift + (long long)b * C + c4 * 4)); }
+    v.x = sma_act(fmaf(v.x, s.x, h.x), act); v.y = sma_act(fmaf(v.y, s.y, h.y), act);
+    v.z = sma_act(fmaf(v.z, s.z, h.z), act); v.w = sma_act(fmaf(v.w, s.w, h.w), act);
+    *reinterpret_cast<float4*>(y + (long long)b * ybs + (long long)p * yld + c4 * 4) = v;
+  }
+}
+
+// one warp per token row; E in {32,...,1024}, E % 32 == 0; two-pass mean/variance in registers
+template <int EPL>   // elements per lane
+__global__ void layernorm_kernel(const float* __restrict__ x, int rows, const float* __restrict__ g, const float* __restrict__ be, float eps,
+                                 const float* __restrict__ pos, int pos_rows, float* __restrict__ y, float* __restrict__ yq) {
+  constexpr int E = EPL * 32;
+  int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  float v[EPL]; float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < EPL; i++) { v[i] = __ldg(x + (long long)row * E + lane + i * 32); s += v[i]; }
+  float mean = warp_sum(s) / E; float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < EPL; i++) { float d = v[i] - mean; q = fmaf(d, d, q); }
+  float rstd = 1.f / sqrtf(warp_sum(q) / E + eps);
+#pragma unroll
+  for (int i = 0; i < EPL; i++) {
+    int c = lane + i * 32;
+    float o = (v[i] - mean) * rstd * __ldg(g + c) + __ldg(be + c);
+    if (y) y[(long long)row * E + c] = o;
+    if (yq) yq[(long long)row * E + c] = o + __ldg(pos + (long long)(row % pos_rows) * E + c);
+  }
+}
+
+}  // namespace
+
+extern "C" int sma_groupnorm_stats(const float* x, int B, int HW, int C, int64_t bstride, int ld, int groups, float eps, const float* gamma,
+                                   const float* beta, float* partial, float* scale, float* shift, sma_stream_t stream) {
+  if (!x || !partial || !scale || !shift || B <= 0 || HW <= 0 || C <= 0 || groups <= 0 || C % groups) return SMA_ERR_BAD_ARG;
+  int nchunk = cdiv(HW, GN_CHUNK);
+  gn_partial_kernel<<<dim3(nchunk, B), 256, 512 * sizeof(float), as_stream(stream)>>>(x, HW, C, bstride, ld, partial, nchunk);
+  SMA_LAUNCH_CHECK();
+  gn_finalize_kernel<<<dim3(groups, B), 128, 0, as_stream(stream)>>>(partial, nchunk, C, groups, HW, eps, gamma, beta, scale, shift);
+  SMA_LAUNCH_CHECK();
+  return SMA_OK;
+}
+
+extern "C" int sma_affine_act(const float* x, int B, int HW, int C, int64_t bstride, int ld, const float* scale, const float* shift, int act,
+                              float* y, int64_t ybs, int yld, sma_stream_t stream) {
+  if (!x || !y || B <= 0 || HW <= 0 || C <= 0) return SMA_ERR_BAD_ARG;
+  if ((C & 3) || (ld & 3) || (yld & 3) || (bstride & 3) || (ybs & 3)) return SMA_ERR_UNSUPPORTED;
+  if ((scale == nullptr) != (shift == nullptr)) return SMA_ERR_BAD_ARG;
+  long long total4 = (long long)B * HW * (C >> 2);
+  int blocks = (int)((total4 + 255) / 256); if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+  affine_act_kernel<<<blocks, 256, 0, as_stream(stream)>>>(x, HW, C, bstride, ld, scale, shift, act, y, ybs, yld, total4);
+  SMA_LAUNCH_CHECK();
+  return SMA_OK;
+}
+
+extern "C" int sma_layernorm(const float* x, int rows, int E, const float* gamma, const float* beta, float eps, const float* pos, int pos_rows,
+                             float* y, float* yq, sma_stream_t stream) {
+  if (!x || !gamma || !beta || rows <= 0 || (!y && !yq) || (yq && (!pos || pos_rows <= 0))) return SMA_ERR_BAD_ARG;
+  dim3 grid(cdiv(rows, 8));
+  cudaStream_t st = as_stream(stream);
+  if (!pos_rows) pos_rows = 1;
+  if (E == 32) layernorm_kernel<1><<<grid, 256, 0, st>>>(x, rows, gamma, beta, eps, pos, pos_rows, y, yq);
+  else if (E == 256) layernorm_kernel<8><<<grid, 256, 0, st>>>(x, rows, gamma, beta, eps, pos, pos_rows, y, yq);
+  else return SMA_ERR_UNSUPPORTED;
+  SMA_LAUNCH_CHECK();
+  return SMA_OK;
+}

@@ -1,0 +1,398 @@
+"""Tensor-level wrappers over the C ABI (include/sma_b200.h).
+
+PyTorch is plumbing here: it owns device memory and the current stream; every computation is a
+hand-written kernel in csrc/.  Tensors are fp32 CUDA, channels-last *views* `(B,H,W,C)` whose
+strides satisfy stride(3)==1 and stride(1)==W*stride(2) (so channel slices of concat buffers and
+batch-expanded per-source tensors are passed without copies).  The caller-allocates convention
+follows the reference's native-op slot (basicsr/ops/dcn/deform_conv.py:51-64); CPU tensors raise
+(no fallback, as deform_conv.py:55-56).
+"""
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import ConvDesc, check
+
+ACT = {'none': 0, 'relu': 1, 'leaky': 2, 'gelu': 3, 'sigmoid': 4, 'swish': 5}
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _nhwc(t: torch.Tensor) -> Tuple[int, int, int, int, int, int]:
+    """-> (B,H,W,C,bstride,ld) of a channels-last view; raises for anything the kernels cannot address."""
+    if not t.is_cuda:
+        raise _lib.SmaError('sma_b200 ops need CUDA tensors (no CPU fallback)')
+    if t.dtype != torch.float32 or t.dim() != 4:
+        raise _lib.SmaError(f'expected fp32 (B,H,W,C) view, got {t.dtype} {tuple(t.shape)}')
+    B, H, W, Cc = t.shape
+    sb, sh, sw, sc = t.stride()
+    if Cc > 1 and sc != 1:
+        raise _lib.SmaError('channel stride must be 1')
+    if H > 1 and sh != W * sw:
+        raise _lib.SmaError(f'row stride {sh} != W*ld {W * sw}')
+    if B == 1:
+        sb = 0 if sb == 0 else sb
+    return B, H, W, Cc, sb, sw
+
+
+@dataclass
+class ConvW:
+    """Packed conv / linear weight: w[(ky*kw+kx)*Cin+c][ldw], bias[Cout]."""
+    w: torch.Tensor
+    bias: Optional[torch.Tensor]
+    Cout: int
+    Cin: int
+    kh: int
+    kw: int
+
+    def cols(self, start: int, n: int) -> 'ConvW':
+        """Output-column slice (free: the packed weight is row-major [K][ldw])."""
+        assert start % 4 == 0
+        return ConvW(self.w[:, start:], None if self.bias is None else self.bias[start:start + n], n, self.Cin, self.kh, self.kw)
+
+    def as_patch(self, p: int) -> 'ConvW':
+        """View a Linear(C*p*p -> N) whose features are ordered (p1 p2 c) as a pxp stride-p conv
+        (appmotioncodebook_arch.py:222,229,236)."""
+        assert self.kh == 1 and self.kw == 1 and self.Cin % (p * p) == 0
+        return ConvW(self.w, self.bias, self.Cout, self.Cin // (p * p), p, p)
+
+
+def pack_conv(weight: torch.Tensor, bias: Optional[torch.Tensor], bn: Optional[dict] = None) -> ConvW:
+    """OIHW conv weight or (N,K) linear weight -> ConvW, optionally folding an eval-mode BatchNorm."""
+    lib = _lib.load()
+    w = weight.detach().float().contiguous()
+    if w.dim() == 2:
+        w = w.view(w.shape[0], w.shape[1], 1, 1)
+    Cout, Cin, kh, kw = w.shape
+    ldw = (Cout + 3) // 4 * 4
+    wp = torch.empty((kh * kw * Cin, ldw), device=w.device, dtype=torch.float32)
+    need_bias = bias is not None or bn is not None
+    bo = torch.empty((ldw,), device=w.device, dtype=torch.float32).zero_() if need_bias else None
+    b = None if bias is None else bias.detach().float().contiguous()
+    g = be = mu = var = None
+    eps = 0.0
+    if bn is not None:
+        g, be, mu, var = (bn[k].detach().float().contiguous() for k in ('weight', 'bias', 'running_mean', 'running_var'))
+        eps = float(bn.get('eps', 1e-5))
+    check(lib.sma_pack_conv_weight(_ptr(w), _ptr(b), Cout, Cin, kh, kw, _ptr(g), _ptr(be), _ptr(mu), _ptr(var), eps,
+                                   _ptr(wp), ldw, _ptr(bo), _stream()), 'sma_pack_conv_weight')
+    return ConvW(wp, None if bo is None else bo[:Cout], Cout, Cin, kh, kw)
+
+
+def pack_conv_cat(weights, biases) -> ConvW:
+    """Several convs over the same input fused along the output dim (q|k|v, scale.0|shift.0, kp|jacobian ...)."""
+    w = torch.cat([x.detach().float() for x in weights], dim=0)
+    b = torch.cat([x.detach().float() for x in biases], dim=0)
+    return pack_conv(w, b)
+
+
+USE_TF32X3 = True   # let sma_conv2d_fwd pick the tcgen05 3xTF32 kernel where the shape allows
+
+
+def conv2d(x: torch.Tensor, cw: ConvW, *, stride: int = 1, pad: int = 0, pad_tl: Optional[Tuple[int, int]] = None,
+           out: Optional[torch.Tensor] = None, out_hw: Optional[Tuple[int, int]] = None, act: str = 'none',
+           pre: Optional[Tuple[torch.Tensor, torch.Tensor, str]] = None, res: Optional[torch.Tensor] = None,
+           upsample2: bool = False, d2s: int = 0, out_nchw: bool = False, exact: bool = False) -> torch.Tensor:
+    lib = _lib.load()
+    B, Hi, Wi, Cin, ibs, ild = _nhwc(x)
+    if Cin != cw.Cin:
+        raise _lib.SmaError(f'conv2d: input has {Cin} channels, weight expects {cw.Cin}')
+    pt, pl = (pad, pad) if pad_tl is None else pad_tl
+    Hv, Wv = (Hi * 2, Wi * 2) if upsample2 else (Hi, Wi)
+    if out_hw is None:
+        Ho = (Hv + 2 * pt - cw.kh) // stride + 1
+        Wo = (Wv + 2 * pl - cw.kw) // stride + 1
+    else:
+        Ho, Wo = out_hw
+    d = ConvDesc()
+    d.x, d.B, d.Hi, d.Wi, d.Cin, d.in_bstride, d.in_ld = x.data_ptr(), B, Hi, Wi, Cin, ibs, ild
+    d.w, d.ldw, d.bias = cw.w.data_ptr(), cw.w.stride(0), _ptr(cw.bias)
+    d.Cout, d.kh, d.kw, d.stride, d.pad_t, d.pad_l = cw.Cout, cw.kh, cw.kw, stride, pt, pl
+    d.upsample2 = 1 if upsample2 else 0
+    if pre is not None:
+        d.pre_scale, d.pre_shift, d.pre_act = pre[0].data_ptr(), pre[1].data_ptr(), ACT[pre[2]]
+    if out_nchw:
+        if out is None:
+            out = torch.empty((B, cw.Cout, Ho, Wo), device=x.device, dtype=torch.float32)
+        d.y, d.out_bstride, d.out_ld = out.data_ptr(), cw.Cout * Ho * Wo, 0
+    elif d2s > 1:
+        Cq = cw.Cout // (d2s * d2s)
+        if out is None:
+            out = torch.empty((B, Ho * d2s, Wo * d2s, Cq), device=x.device, dtype=torch.float32)
+        oB, oH, oW, oC, obs, old = _nhwc(out)
+        assert (oB, oH, oW, oC) == (B, Ho * d2s, Wo * d2s, Cq), (out.shape, (B, Ho * d2s, Wo * d2s, Cq))
+        d.y, d.out_bstride, d.out_ld = out.data_ptr(), obs, old
+    else:
+        if out is None:
+            out = torch.empty((B, Ho, Wo, cw.Cout), device=x.device, dtype=torch.float32)
+        oB, oH, oW, oC, obs, old = _nhwc(out)
+        assert (oB, oH, oW, oC) == (B, Ho, Wo, cw.Cout), (tuple(out.shape), (B, Ho, Wo, cw.Cout))
+        d.y, d.out_bstride, d.out_ld = out.data_ptr(), obs, old
+    d.Ho, d.Wo, d.act = Ho, Wo, ACT[act]
+    if res is not None:
+        rB, rH, rW, rC, rbs, rld = _nhwc(res)
+        assert (rB, rH, rW, rC) == (B, Ho, Wo, cw.Cout), (tuple(res.shape), (B, Ho, Wo, cw.Cout))
+        d.res, d.res_bstride, d.res_ld = res.data_ptr(), rbs, rld
+    d.d2s, d.out_nchw = d2s, 1 if out_nchw else 0
+    d.tf32x3 = 1 if (USE_TF32X3 and not exact) else 0
+    check(lib.sma_conv2d_fwd(C.byref(d), _stream()), f'sma_conv2d_fwd Cin={Cin} Cout={cw.Cout} k={cw.kh}x{cw.kw}')
+    return out
+
+
+def linear(x: torch.Tensor, cw: ConvW, **kw) -> torch.Tensor:
+    """Linear over the last dim of a (B,L,E) token tensor == 1x1 conv over (B,1,L,E)."""
+    y = conv2d(x.unsqueeze(1), cw, **{k: (v.unsqueeze(1) if isinstance(v, torch.Tensor) else v) for k, v in kw.items()})
+    return y.squeeze(1)
+
+
+def groupnorm_stats(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, groups: int = 32, eps: float = 1e-6):
+    """-> (scale, shift) of shape (B,C) such that GN(x)[b,:,c] = x*scale[b,c]+shift[b,c]."""
+    lib = _lib.load()
+    B, H, W, Cc, bs, ld = _nhwc(x)
+    HW = H * W
+    nchunk = (HW + 255) // 256
+    partial = torch.empty((B * nchunk * Cc * 2,), device=x.device, dtype=torch.float32)
+    scale = torch.empty((B, Cc), device=x.device, dtype=torch.float32)
+    shift = torch.empty((B, Cc), device=x.device, dtype=torch.float32)
+    check(lib.sma_groupnorm_stats(x.data_ptr(), B, HW, Cc, bs, ld, groups, eps, gamma.data_ptr(), beta.data_ptr(),
+                                  partial.data_ptr(), scale.data_ptr(), shift.data_ptr(), _stream()), 'sma_groupnorm_stats')
+    return scale, shift
+
+
+def affine_act(x: torch.Tensor, scale: Optional[torch.Tensor], shift: Optional[torch.Tensor], act: str = 'none',
+               out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    lib = _lib.load()
+    B, H, W, Cc, bs, ld = _nhwc(x)
+    if out is None:
+        out = torch.empty((B, H, W, Cc), device=x.device, dtype=torch.float32)
+    _, _, _, _, obs, old = _nhwc(out)
+    check(lib.sma_affine_act(x.data_ptr(), B, H * W, Cc, bs, ld, _ptr(scale), _ptr(shift), ACT[act], out.data_ptr(), obs, old,
+                             _stream()), 'sma_affine_act')
+    return out
+
+
+def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, pos: Optional[torch.Tensor] = None,
+              want_y: bool = True, eps: float = 1e-5):
+    """x (B,L,E) contiguous -> (LN(x), LN(x)+pos) ; either may be skipped (None)."""
+    lib = _lib.load()
+    assert x.is_contiguous() and x.is_cuda
+    E = x.shape[-1]
+    rows = x.numel() // E
+    y = torch.empty_like(x) if want_y else None
+    yq = torch.empty_like(x) if pos is not None else None
+    check(lib.sma_layernorm(x.data_ptr(), rows, E, gamma.data_ptr(), beta.data_ptr(), eps, _ptr(pos),
+                            0 if pos is None else pos.shape[0], _ptr(y), _ptr(yq), _stream()), 'sma_layernorm')
+    return y, yq
+
+
+def warp_occlude(feat: torch.Tensor, flow: torch.Tensor, occ: Optional[torch.Tensor], out: Optional[torch.Tensor] = None):
+    """feat (B or 1-expanded,H,W,C) NHWC contiguous per frame; flow (B,hf,wf,2); occ (B,hf,wf) or None."""
+    lib = _lib.load()
+    B, H, W, Cc, bs, ld = _nhwc(feat)
+    assert ld == Cc, 'warp source must be dense NHWC'
+    assert flow.is_contiguous() and flow.shape[0] == B and flow.shape[3] == 2
+    hf, wf = flow.shape[1], flow.shape[2]
+    if occ is not None:
+        assert occ.is_contiguous() and occ.numel() == B * hf * wf
+    if out is None:
+        out = torch.empty((B, H, W, Cc), device=feat.device, dtype=torch.float32)
+    assert out.is_contiguous()
+    check(lib.sma_warp_occlude_fwd(feat.data_ptr(), bs, B, H, W, Cc, flow.data_ptr(), _ptr(occ), hf, wf, out.data_ptr(), _stream()),
+          'sma_warp_occlude_fwd')
+    return out
+
+
+def resize_ac(x: torch.Tensor, size: Tuple[int, int], out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    lib = _lib.load()
+    B, Hi, Wi, Cc, ibs, ild = _nhwc(x)
+    Ho, Wo = size
+    if out is None:
+        out = torch.empty((B, Ho, Wo, Cc), device=x.device, dtype=torch.float32)
+    _, _, _, _, obs, old = _nhwc(out)
+    check(lib.sma_resize_bilinear_ac(x.data_ptr(), B, Hi, Wi, Cc, ibs, ild, out.data_ptr(), Ho, Wo, obs, old, _stream()),
+          'sma_resize_bilinear_ac')
+    return out
+
+
+def mha(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, key_mask: Optional[torch.Tensor] = None,
+        scale: Optional[float] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """q (B,L,E-view) ; k,v (B,S,E-view) or (S,E-view) shared by all frames.  Views may be column slices."""
+    lib = _lib.load()
+    B, L, E = q.shape
+    D = E // heads
+    if k.dim() == 2:
+        S, kvbs = k.shape[0], 0
+        ldk, ldv = k.stride(0), v.stride(0)
+    else:
+        S, kvbs = k.shape[1], k.stride(0)
+        ldk, ldv = k.stride(1), v.stride(1)
+        assert v.stride(0) == kvbs
+    assert q.stride(2) == 1 and k.stride(-1) == 1 and v.stride(-1) == 1 and q.stride(0) == L * q.stride(1)
+    if out is None:
+        out = torch.empty((B, L, E), device=q.device, dtype=torch.float32)
+    if scale is None:
+        scale = float(D) ** -0.5
+    if key_mask is not None:
+        assert key_mask.dtype == torch.uint8 and key_mask.is_contiguous() and key_mask.numel() == B * S
+    check(lib.sma_mha_fwd(q.data_ptr(), q.stride(1), k.data_ptr(), ldk, v.data_ptr(), ldv, kvbs, B, L, S, heads, D, scale,
+                          _ptr(key_mask), out.data_ptr(), out.stride(1), _stream()), f'sma_mha_fwd D={D}')
+    return out
+
+
+def vq_lookup(z: torch.Tensor, codebook: torch.Tensor, n_codes: Optional[int] = None):
+    """z (N,E) contiguous -> (idx int64 (N,), zq (N,E), min_dist (N,))"""
+    lib = _lib.load()
+    assert z.is_cuda and z.is_contiguous() and codebook.is_contiguous()
+    N, E = z.shape
+    n = codebook.shape[0] if n_codes is None else n_codes
+    idx = torch.empty((N,), device=z.device, dtype=torch.int64)
+    zq = torch.empty_like(z)
+    md = torch.empty((N,), device=z.device, dtype=torch.float32)
+    check(lib.sma_vq_lookup_fwd(z.data_ptr(), N, E, codebook.data_ptr(), n, idx.data_ptr(), zq.data_ptr(), md.data_ptr(), _stream()),
+          'sma_vq_lookup_fwd')
+    return idx, zq, md
+
+
+def antialias_down4(x_nchw: torch.Tensor, kernel13: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    lib = _lib.load()
+    assert x_nchw.is_cuda and x_nchw.is_contiguous() and x_nchw.dtype == torch.float32
+    B, Cc, H, W = x_nchw.shape
+    if out is None:
+        out = torch.empty((B, H // 4, W // 4, Cc), device=x_nchw.device, dtype=torch.float32)
+    _, _, _, _, obs, old = _nhwc(out)
+    assert obs == (H // 4) * (W // 4) * old or B == 1
+    check(lib.sma_antialias_down4(x_nchw.data_ptr(), B, Cc, H, W, kernel13.data_ptr(), out.data_ptr(), old, _stream()),
+          'sma_antialias_down4')
+    return out
+
+
+def avgpool2(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    lib = _lib.load()
+    assert x.is_contiguous()
+    B, H, W, Cc = x.shape
+    if out is None:
+        out = torch.empty((B, H // 2, W // 2, Cc), device=x.device, dtype=torch.float32)
+    _, _, _, _, obs, old = _nhwc(out)
+    assert obs == (H // 2) * (W // 2) * old or B == 1
+    check(lib.sma_avgpool2(x.data_ptr(), B, H, W, Cc, out.data_ptr(), old, _stream()), 'sma_avgpool2')
+    return out
+
+
+def kp_head(pred: torch.Tensor, K: int, temperature: float):
+    lib = _lib.load()
+    B, h, w, Cc, bs, ld = _nhwc(pred)
+    value = torch.empty((B, K, 2), device=pred.device, dtype=torch.float32)
+    jac = torch.empty((B, K, 2, 2), device=pred.device, dtype=torch.float32)
+    check(lib.sma_kp_head_fwd(pred.data_ptr(), B, h, w, ld, K, temperature, value.data_ptr(), jac.data_ptr(), _stream()), 'sma_kp_head_fwd')
+    return value, jac
+
+
+def normalize_kp(src_v, src_j, drv_v, drv_j, drv0_v, drv0_j, scale: float, relative: bool):
+    lib = _lib.load()
+    B, K, _ = drv_v.shape
+    ov, oj = torch.empty_like(drv_v), torch.empty_like(drv_j)
+    check(lib.sma_normalize_kp(src_v.data_ptr(), src_j.data_ptr(), drv_v.data_ptr(), drv_j.data_ptr(), drv0_v.data_ptr(),
+                               drv0_j.data_ptr(), B, K, scale, 1 if relative else 0, ov.data_ptr(), oj.data_ptr(), _stream()),
+          'sma_normalize_kp')
+    return ov, oj
+
+
+def dense_motion_prep(src64: torch.Tensor, kp_src_v, kp_src_j, kp_drv_v, kp_drv_j, hg_in: torch.Tensor, var: float = 0.01):
+    lib = _lib.load()
+    h, w = src64.shape[-3], src64.shape[-2]
+    B, K, _ = kp_drv_v.shape
+    _, _, _, _, hbs, hld = _nhwc(hg_in)
+    heat = torch.empty((B, h, w, K), device=hg_in.device, dtype=torch.float32)
+    check(lib.sma_dense_motion_prep(src64.data_ptr(), h, w, kp_src_v.data_ptr(), kp_src_j.data_ptr(), kp_drv_v.data_ptr(),
+                                    kp_drv_j.data_ptr(), B, K, var, hg_in.data_ptr(), hld, heat.data_ptr(), _stream()),
+          'sma_dense_motion_prep')
+    return heat
+
+
+def dense_motion_head(logits: torch.Tensor, kp_src_v, kp_src_j, kp_drv_v, kp_drv_j, want_mask: bool = False):
+    lib = _lib.load()
+    B, h, w, Cc, bs, ld = _nhwc(logits)
+    K = kp_drv_v.shape[1]
+    deform = torch.empty((B, h, w, 2), device=logits.device, dtype=torch.float32)
+    occ = torch.empty((B, h, w), device=logits.device, dtype=torch.float32)
+    mask = torch.empty((B, h, w, K + 1), device=logits.device, dtype=torch.float32) if want_mask else None
+    check(lib.sma_dense_motion_head(logits.data_ptr(), ld, h, w, kp_src_v.data_ptr(), kp_src_j.data_ptr(), kp_drv_v.data_ptr(),
+                                    kp_drv_j.data_ptr(), B, K, deform.data_ptr(), occ.data_ptr(), _ptr(mask), _stream()),
+          'sma_dense_motion_head')
+    return deform, occ, mask
+
+
+def flow_to_px(m: torch.Tensor, out: torch.Tensor):
+    lib = _lib.load()
+    B, h, w, _ = m.shape
+    assert m.is_contiguous()
+    _, _, _, _, obs, old = _nhwc(out)
+    check(lib.sma_flow_to_px(m.data_ptr(), B, h, w, out.data_ptr(), old, _stream()), 'sma_flow_to_px')
+    return out
+
+
+def flow_update(m_prev: torch.Tensor, occ_prev: torch.Tensor, res: torch.Tensor):
+    lib = _lib.load()
+    B, h, w, _ = m_prev.shape
+    assert m_prev.is_contiguous() and occ_prev.is_contiguous() and res.is_contiguous()
+    m_new, occ_new = torch.empty_like(m_prev), torch.empty_like(occ_prev)
+    check(lib.sma_flow_update(m_prev.data_ptr(), occ_prev.data_ptr(), res.data_ptr(), res.shape[-1], B, h, w, m_new.data_ptr(),
+                              occ_new.data_ptr(), _stream()), 'sma_flow_update')
+    return m_new, occ_new
+
+
+def motion_ignore_mask(m: torch.Tensor, size=(32, 32)) -> torch.Tensor:
+    lib = _lib.load()
+    B, h, w, _ = m.shape
+    mask = torch.empty((B, size[0] * size[1]), device=m.device, dtype=torch.uint8)
+    check(lib.sma_motion_ignore_mask(m.data_ptr(), B, h, w, size[0], size[1], mask.data_ptr(), _stream()), 'sma_motion_ignore_mask')
+    return mask
+
+
+def sft_combine(dec: torch.Tensor, scale: torch.Tensor, shift: torch.Tensor, w: float, out: Optional[torch.Tensor] = None):
+    lib = _lib.load()
+    assert dec.is_contiguous() and scale.is_contiguous() and shift.is_contiguous()
+    if out is None:
+        out = torch.empty_like(dec)
+    check(lib.sma_sft_combine(dec.data_ptr(), scale.data_ptr(), shift.data_ptr(), w, dec.numel(), out.data_ptr(), _stream()), 'sma_sft_combine')
+    return out
+
+
+def to_uint8(x: torch.Tensor, bgr: bool = False) -> torch.Tensor:
+    lib = _lib.load()
+    B, H, W, Cc, bs, ld = _nhwc(x)
+    out = torch.empty((B, H, W, Cc), device=x.device, dtype=torch.uint8)
+    check(lib.sma_to_uint8(x.data_ptr(), B, H, W, Cc, ld, 1 if bgr else 0, out.data_ptr(), _stream()), 'sma_to_uint8')
+    return out
+
+
+def nchw_to_nhwc(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    lib = _lib.load()
+    assert x.is_cuda and x.is_contiguous() and x.dtype == torch.float32
+    B, Cc, H, W = x.shape
+    if out is None:
+        out = torch.empty((B, H, W, Cc), device=x.device, dtype=torch.float32)
+    _, _, _, _, obs, old = _nhwc(out)
+    check(lib.sma_nchw_to_nhwc(x.data_ptr(), B, Cc, H, W, out.data_ptr(), old, _stream()), 'sma_nchw_to_nhwc')
+    return out
+
+
+def nhwc_to_nchw(x: torch.Tensor) -> torch.Tensor:
+    lib = _lib.load()
+    B, H, W, Cc, bs, ld = _nhwc(x)
+    out = torch.empty((B, Cc, H, W), device=x.device, dtype=torch.float32)
+    check(lib.sma_nhwc_to_nchw(x.data_ptr(), B, Cc, H, W, ld, out.data_ptr(), _stream()), 'sma_nhwc_to_nchw')
+    return out
+
+
+def launch_count() -> int:
+    return _lib.load().sma_kernel_launch_count()

@@ -1,0 +1,101 @@
+"""CPU: host-side logic - registry semantics, parameter inventory, C-ABI exports, loud failure without CUDA."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import sma_b200 as S
+from conftest import CFG, ROOT
+
+
+def test_registry_semantics():
+    from importlib import import_module
+    reg = import_module('synergize-motion-appearance_b200.registry')
+    r = reg.Registry('t')
+
+    @r.register()
+    class A:
+        pass
+    assert r.get('A') is A and 'A' in r
+    with pytest.raises(AssertionError):
+        r.register(A)                      # duplicate names assert (basicsr/utils/registry.py:38-41)
+    with pytest.raises(KeyError):
+        r.get('missing')                   # (:62-66)
+    for name in ('AppMotionCompFormer', 'Motion_Estimator_keypoint_aware', 'KPDetector', 'DenseMotionNetwork'):
+        assert name in S.ARCH_REGISTRY
+    opt = dict(CFG['network_motion_estimator'])
+    net = S.build_network(opt)
+    assert 'type' in opt                   # build_network deep-copies (basicsr/archs/__init__.py:20)
+    assert type(net).__name__ == 'Motion_Estimator_keypoint_aware'
+    assert hasattr(net, 'kp_detector') and hasattr(net, 'dense_motion_network')
+
+
+def test_state_dict_inventory_and_strict_load(inventory, weights):
+    g = S.build_network(CFG['network_g'])
+    me = S.build_network(CFG['network_motion_estimator'])
+    for net, ref, w in ((g, inventory['net_g'], weights[0]), (me, inventory['motion_estimator'], weights[1])):
+        sd = {k: list(v.shape) for k, v in net.state_dict().items()}
+        assert sd == {k: list(v) for k, v in ref.items()}
+        net.load_state_dict(w, strict=True)
+        with pytest.raises(RuntimeError):
+            bad = dict(w); bad.pop(next(iter(bad)))
+            net.load_state_dict(bad, strict=True)
+    # reference init conventions (fresh, unloaded networks)
+    g = S.build_network(CFG['network_g'])
+    me = S.build_network(CFG['network_motion_estimator'])
+    assert float(g.state_dict()['position_emb_app'].abs().max()) == 0.0
+    assert float(g.state_dict()['quantize_app.embedding.weight'].abs().max()) <= 1.0 / 1024
+    assert float(me.state_dict()['kp_detector.jacobian.weight'].abs().max()) == 0.0
+    assert torch.equal(me.state_dict()['kp_detector.jacobian.bias'][:4], torch.tensor([1., 0., 0., 1.]))
+    assert torch.allclose(me.state_dict()['kp_detector.down.weight'], weights[1]['kp_detector.down.weight'], atol=1e-8)
+
+
+def test_unsupported_configs_raise():
+    bad = dict(CFG['network_g']); bad['img_size'] = 512
+    with pytest.raises(NotImplementedError):
+        S.build_network(bad)
+
+
+def test_c_abi_exports_every_declared_symbol():
+    lib_path = os.path.join(ROOT, 'synergize-motion-appearance_b200', 'csrc', 'libsma_b200.so')
+    assert os.path.exists(lib_path), 'run __graft_entry__.build() first'
+    header = open(os.path.join(ROOT, 'include', 'sma_b200.h')).read()
+    header = re.sub(r'/\*.*?\*/', '', header, flags=re.S)
+    names = sorted(set(re.findall(r'\b(sma_[a-z0-9_]+)\s*\(', header)))
+    assert len(names) >= 25
+    lib = ctypes.CDLL(lib_path)
+    for n in names:
+        assert hasattr(lib, n), n
+    lib.sma_abi_version.restype = ctypes.c_int
+    assert lib.sma_abi_version() == 1
+    from importlib import import_module
+    _lib = import_module('synergize-motion-appearance_b200._lib')
+    assert sorted(_lib.SIGNATURES) == names       # the ctypes table binds exactly the declared ABI
+    _lib.load()
+
+
+def test_cpu_tensors_fail_loudly(weights):
+    me = S.build_network(CFG['network_motion_estimator'])
+    me.load_state_dict(weights[1])
+    with pytest.raises(RuntimeError):
+        me.estimate_kp(torch.zeros(1, 3, 256, 256))
+
+
+def test_hull_area_and_shard_ranges():
+    from scipy.spatial import ConvexHull
+    from importlib import import_module
+    an = import_module('synergize-motion-appearance_b200.animate')
+    di = import_module('synergize-motion-appearance_b200.dist')
+    rng = np.random.default_rng(1)
+    for _ in range(10):
+        p = rng.normal(size=(15, 2))
+        assert abs(an.hull_area(p) - ConvexHull(p).volume) < 1e-9
+    for n in (0, 1, 7, 64, 1024, 1025):
+        for world in (1, 2, 3, 8):
+            spans = [di.shard_range(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            assert sum(h - l for l, h in spans) == n
