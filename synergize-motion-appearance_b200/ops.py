@@ -18,6 +18,31 @@ from ._lib import ConvDesc, check
 
 ACT = {'none': 0, 'relu': 1, 'leaky': 2, 'gelu': 3, 'sigmoid': 4, 'swish': 5}
 
+# Per-launch timing hook used by bench.py's roofline leg: when PROFILE is a list, the wrappers of the dominant
+# kernels append (kind, algorithmic_flops, algorithmic_bytes, start_event, end_event) with CUDA events recorded on
+# the launching (current) stream.  None (the default) costs nothing.
+PROFILE = None
+
+
+class _Prof:
+    __slots__ = ('kind', 'flops', 'nbytes', 'e0')
+
+    def __init__(self, kind, flops, nbytes):
+        self.kind, self.flops, self.nbytes = kind, flops, nbytes
+
+    def __enter__(self):
+        if PROFILE is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *a):
+        if PROFILE is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            PROFILE.append((self.kind, self.flops, self.nbytes, self.e0, e1))
+        return False
+
 
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
@@ -144,7 +169,10 @@ def conv2d(x: torch.Tensor, cw: ConvW, *, stride: int = 1, pad: int = 0, pad_tl:
         d.res, d.res_bstride, d.res_ld = res.data_ptr(), rbs, rld
     d.d2s, d.out_nchw = d2s, 1 if out_nchw else 0
     d.tf32x3 = 1 if (USE_TF32X3 and not exact) else 0
-    check(lib.sma_conv2d_fwd(C.byref(d), _stream()), f'sma_conv2d_fwd Cin={Cin} Cout={cw.Cout} k={cw.kh}x{cw.kw}')
+    K = cw.kh * cw.kw * Cin
+    with _Prof('conv', 2.0 * B * Ho * Wo * K * cw.Cout,
+               4.0 * (B * Hi * Wi * Cin + B * Ho * Wo * cw.Cout * (2 if res is not None else 1) + K * cw.Cout)):
+        check(lib.sma_conv2d_fwd(C.byref(d), _stream()), f'sma_conv2d_fwd Cin={Cin} Cout={cw.Cout} k={cw.kh}x{cw.kw}')
     return out
 
 
@@ -206,8 +234,9 @@ def warp_occlude(feat: torch.Tensor, flow: torch.Tensor, occ: Optional[torch.Ten
     if out is None:
         out = torch.empty((B, H, W, Cc), device=feat.device, dtype=torch.float32)
     assert out.is_contiguous()
-    check(lib.sma_warp_occlude_fwd(feat.data_ptr(), bs, B, H, W, Cc, flow.data_ptr(), _ptr(occ), hf, wf, out.data_ptr(), _stream()),
-          'sma_warp_occlude_fwd')
+    with _Prof('warp', 11.0 * B * H * W * Cc, 8.0 * B * H * W * Cc):       # read every feature once + write it once
+        check(lib.sma_warp_occlude_fwd(feat.data_ptr(), bs, B, H, W, Cc, flow.data_ptr(), _ptr(occ), hf, wf, out.data_ptr(), _stream()),
+              'sma_warp_occlude_fwd')
     return out
 
 
@@ -243,8 +272,9 @@ def mha(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, key_mask:
         scale = float(D) ** -0.5
     if key_mask is not None:
         assert key_mask.dtype == torch.uint8 and key_mask.is_contiguous() and key_mask.numel() == B * S
-    check(lib.sma_mha_fwd(q.data_ptr(), q.stride(1), k.data_ptr(), ldk, v.data_ptr(), ldv, kvbs, B, L, S, heads, D, scale,
-                          _ptr(key_mask), out.data_ptr(), out.stride(1), _stream()), f'sma_mha_fwd D={D}')
+    with _Prof('mha', 4.0 * B * L * S * E, 4.0 * (2 * B * L * E + 2 * (B if kvbs else 1) * S * E)):
+        check(lib.sma_mha_fwd(q.data_ptr(), q.stride(1), k.data_ptr(), ldk, v.data_ptr(), ldv, kvbs, B, L, S, heads, D, scale,
+                              _ptr(key_mask), out.data_ptr(), out.stride(1), _stream()), f'sma_mha_fwd D={D}')
     return out
 
 
