@@ -69,7 +69,10 @@ typedef struct sma_conv_desc {
                                     (oy*p+p1, ox*p+p2) channel c of a (B,Ho*p,Wo*p,C) tensor (un-patchify,
                                     appmotioncodebook_arch.py:223,230,237) */
   int out_nchw;                  /* 1: y is (B,Cout,Ho,Wo) contiguous (API-facing final image) */
-  int tf32x3;                    /* 1: use the tcgen05 3xTF32 tensor-core kernel when the shape allows */
+  int tf32x3;                    /* 0: exact fp32 CUDA-core kernel; 1: tcgen05 3xTF32 (fp32-faithful) when the shape allows;
+                                    2: tcgen05 single-pass TF32 (only where the 1e-3 parity budget allows it) */
+  const float* w_tc;             /* tensor-core weight image from sma_pack_conv_weight_tc (NULL: CUDA-core kernel only) */
+  int tc_variant;                /* 0: library picks (persistent halo kernel for stride-1, gather kernel otherwise); 1: force the gather kernel */
 } sma_conv_desc;
 
 int sma_conv2d_fwd(const sma_conv_desc* d, sma_stream_t stream);
@@ -78,6 +81,13 @@ int sma_conv2d_fwd(const sma_conv_desc* d, sma_stream_t stream);
 int sma_pack_conv_weight(const float* w_oihw, const float* bias, int Cout, int Cin, int kh, int kw,
                          const float* bn_gamma, const float* bn_beta, const float* bn_mean, const float* bn_var,
                          float bn_eps, float* w_packed, int ldw, float* bias_out, sma_stream_t stream);
+
+/* Tensor-core weight image: per (N-tile, 32-wide K-chunk) the tf32 "hi" part and the fp32 residual "lo" part of the
+ * packed weight, each laid out as the K-major SWIZZLE_128B shared-memory tile tcgen05.mma reads, so that the kernel
+ * fetches it with one bulk copy per chunk.  Needs Cin % 32 == 0.  sma_conv_weight_tc_floats gives the buffer size
+ * in floats (0 when the shape is not eligible). */
+int64_t sma_conv_weight_tc_floats(int Cout, int Cin, int kh, int kw);
+int sma_pack_conv_weight_tc(const float* w_packed, int ldw, int Cout, int Cin, int kh, int kw, float* w_tc, sma_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * GroupNorm(32, eps) statistics -> per-(b,c) scale/shift consumed by the conv prologue

@@ -1,3 +1,694 @@
-// tcgen05 3xTF32 implicit-GEMM convolution (placeholder until the tensor-core kernel lands).
+// tcgen05 implicit-GEMM convolution, NHWC fp32 in / fp32 out, fp32-faithful through a 3xTF32 split
+// (a*b ~= a_hi*b_hi + a_hi*b_lo + a_lo*b_hi with fp32 accumulation in TMEM), or single-pass TF32.
+//
+// GEMM view (same as conv_simt.cu): M = B*Ho*Wo output pixels, N = Cout, K = kh*kw*Cin, k = tap*Cin + c.
+// One CTA = one 128 x NT output tile (NT <= 256, a multiple of 16); 6 warps:
+//   warps 0-3  A producers, then the epilogue.  Per 32-channel K-chunk they gather the 128 pixel rows of the tap
+//              from global memory with coalesced 128-bit loads (8 lanes cover the 128 contiguous bytes of one pixel),
+//              apply the fused prologue (GroupNorm scale/shift + swish, nearest-x2 upsample, zero padding after the
+//              normalisation), split every value into tf32 hi / fp32 residual lo, and store both into shared memory in
+//              the canonical K-major SWIZZLE_128B UMMA layout (row = 128 B, 8-row atoms of 1 KB, 16-byte chunk index
+//              XOR row%8).  After the last chunk they read the accumulator back with tcgen05.ld (warp w owns TMEM
+//              lanes 32w..32w+31 = tile rows) and run the fused epilogue (bias, activation, residual, depth-to-space).
+//   warp 4     TMEM allocation + the single MMA-issuing thread: per chunk 4 k-steps (K=8 each) x 3 products.
+//   warp 5     weight loader: one cp.async.bulk (TMA bulk copy, no tensor map) per chunk brings the pre-swizzled
+//              hi|lo weight image of this (N-tile, chunk) - packed once per weight load by sma_pack_conv_weight_tc -
+//              straight into its stage slot, completing on the stage's mbarrier.
+// Stages form an mbarrier ring: full[s] (128 producer arrivals + 1 expect_tx arrival + the bulk-copy bytes) and
+// empty[s] (tcgen05.commit of the MMAs that read the slot).
 #include "sma_common.cuh"
-int sma_conv2d_tc_try(const sma_conv_desc* d, cudaStream_t st) { (void)d; (void)st; return SMA_ERR_UNSUPPORTED; }
+
+namespace {
+
+constexpr int BM = 128;          // tile rows (UMMA M, cta_group::1)
+constexpr int KC = 32;           // fp32 per K-chunk = one 128-byte swizzle row
+constexpr int A_BYTES = BM * KC * 4;   // 16 KB per A image (hi or lo)
+constexpr int MAX_STAGES = 4;
+constexpr int SMEM_DYN_MAX = 232448 - 2048;  // 227 KB opt-in limit minus room for static shared memory (barriers, bias)
+constexpr int SMEM_LIMIT = SMEM_DYN_MAX - 1024;  // minus 1 KB alignment slack
+
+struct TcP {
+  const float* x; const float* wtc; const float* bias; const float* pre_scale; const float* pre_shift; const float* res; float* y;
+  long long in_bs, out_bs, res_bs;
+  int Hi, Wi, Cin, in_ld, Cout, kh, kw, stride, pad_t, pad_l, up, pre_act;
+  int Ho, Wo, out_ld, act, res_ld, d2s;
+  int M, HoWo, nchunks, cpt /* chunks per tap */, NT, stages, passes, tmem_cols;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t a, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint32_t a) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(a) : "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t a, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(a), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t a, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+// one lane of a converged warp (ptxas keeps the guarded region on the uniform datapath: no per-lane replay loops around UTCHMMA)
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred = 0;
+  asm volatile("{\n.reg .b32 %%rx;\n.reg .pred %%px;\nelect.sync %%rx|%%px, %1;\n@%%px mov.s32 %0, 1;\n}" : "+r"(pred) : "r"(0xffffffffu));
+  return pred != 0;
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc),
+               "r"(idesc), "r"(accumulate)
+               : "memory");
+}
+// K-major, SWIZZLE_128B shared-memory matrix descriptor: start>>4 | LBO(16B units)=1 | SBO = 1024 B (8-row atom pitch) | version 1 | layout 2
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFF) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ float tf32_rna(float v) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return __uint_as_float(r);
+}
+__device__ __forceinline__ void sts128(uint32_t a, float x, float y, float z, float w) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
+}
+
+__global__ void __launch_bounds__(192, 1) conv_tc_kernel(const TcP p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[2 * MAX_STAGES + 1];
+  __shared__ uint32_t tmem_slot;
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t sbase = (raw + 1023u) & ~1023u;           // SWIZZLE_128B atoms need 1 KB alignment
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b_bytes = p.NT * KC * 4;                       // one B image (hi or lo)
+  const int stage_bytes = 2 * A_BYTES + 2 * b_bytes;
+  const int m0 = blockIdx.x * BM, nt = blockIdx.y;
+  const uint32_t bar0 = smem_u32(bars);
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (MAX_STAGES + s); };
+  const uint32_t accum_bar = bar0 + 8u * (2 * MAX_STAGES);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; s++) { mbar_init(full_bar(s), 128 + 1); mbar_init(empty_bar(s), 1); }
+    mbar_init(accum_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(p.tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+
+  if (warp < 4) {
+    // =============================== A producers ===============================
+    const int cq = lane & 7;                     // 16-byte chunk of the 128-byte row
+    const int rsub = lane >> 3;                  // 4 rows per warp instruction
+    int iy0[8], ix0[8]; long long boff[8]; int bidx[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      int m = m0 + warp * 32 + j * 4 + rsub;
+      bool ok = m < p.M;
+      int mm = ok ? m : 0;
+      int b = mm / p.HoWo; int r = mm - b * p.HoWo; int oy = r / p.Wo; int ox = r - oy * p.Wo;
+      bidx[j] = b; boff[j] = (long long)b * p.in_bs;
+      iy0[j] = ok ? oy * p.stride - p.pad_t : -0x40000000;   // invalid rows never pass the range test
+      ix0[j] = ox * p.stride - p.pad_l;
+    }
+    const int Hv = p.Hi << p.up, Wv = p.Wi << p.up;
+    int cc = 0, ky = 0, kx = 0;
+    for (int kc = 0; kc < p.nchunks; kc++) {
+      const int s = kc % p.stages; const uint32_t ph = (kc / p.stages) & 1;
+      const int c = cc * KC + cq * 4;
+      float4 v[8]; bool ok[8];
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        int iy = iy0[j] + ky, ix = ix0[j] + kx;
+        ok[j] = (unsigned)iy < (unsigned)Hv && (unsigned)ix < (unsigned)Wv;
+        v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ok[j]) v[j] = __ldg(reinterpret_cast<const float4*>(p.x + boff[j] + ((long long)(iy >> p.up) * p.Wi + (ix >> p.up)) * p.in_ld + c));
+      }
+      if (p.pre_scale) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          if (ok[j]) {
+            float4 sc = __ldg(reinterpret_cast<const float4*>(p.pre_scale + (long long)bidx[j] * p.Cin + c));
+            float4 sh = __ldg(reinterpret_cast<const float4*>(p.pre_shift + (long long)bidx[j] * p.Cin + c));
+            v[j].x = sma_act(fmaf(v[j].x, sc.x, sh.x), p.pre_act); v[j].y = sma_act(fmaf(v[j].y, sc.y, sh.y), p.pre_act);
+            v[j].z = sma_act(fmaf(v[j].z, sc.z, sh.z), p.pre_act); v[j].w = sma_act(fmaf(v[j].w, sc.w, sh.w), p.pre_act);
+          }
+        }
+      }
+      mbar_wait(empty_bar(s), ph ^ 1u);          // slot free (its previous MMAs have completed)
+      const uint32_t a_hi = sbase + (uint32_t)s * stage_bytes, a_lo = a_hi + A_BYTES;
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        const int r = warp * 32 + j * 4 + rsub;
+        const uint32_t off = (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u + (uint32_t)((cq ^ (r & 7)) << 4);
+        float hx = tf32_rna(v[j].x), hy = tf32_rna(v[j].y), hz = tf32_rna(v[j].z), hw = tf32_rna(v[j].w);
+        sts128(a_hi + off, hx, hy, hz, hw);
+        if (p.passes == 3) sts128(a_lo + off, v[j].x - hx, v[j].y - hy, v[j].z - hz, v[j].w - hw);
+      }
+      fence_async_smem();                        // generic-proxy stores -> visible to the tensor core (async proxy)
+      mbar_arrive(full_bar(s));
+      if (++kx == p.kw) { kx = 0; if (++ky == p.kh) { ky = 0; ++cc; } }     // chunk order: channel chunk outer, tap inner
+    }
+    // =============================== epilogue ===============================
+    mbar_wait(accum_bar, 0);
+    tc_fence_after();
+    const int m = m0 + warp * 32 + lane;
+    const bool mok = m < p.M;
+    const int mm = mok ? m : 0;
+    const int b = mm / p.HoWo; const int r = mm - b * p.HoWo; const int oy = r / p.Wo; const int ox = r - oy * p.Wo;
+    const int nbase = nt * p.NT;
+    const bool vec_ok = (p.out_ld & 3) == 0 && (p.out_bs & 3) == 0 && ((reinterpret_cast<uintptr_t>(p.y) & 15) == 0) &&
+                        (!p.res || ((p.res_ld & 3) == 0 && (p.res_bs & 3) == 0 && (reinterpret_cast<uintptr_t>(p.res) & 15) == 0));
+    const int Cq = p.d2s > 1 ? p.Cout / (p.d2s * p.d2s) : p.Cout;     // channels of the depth-to-space output
+    for (int n0 = 0; n0 < p.NT && nbase + n0 < p.Cout; n0 += 32) {
+      uint32_t a[32];
+      const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)n0;
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, "
+          "%20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+          : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]), "=r"(a[4]), "=r"(a[5]), "=r"(a[6]), "=r"(a[7]), "=r"(a[8]), "=r"(a[9]), "=r"(a[10]),
+            "=r"(a[11]), "=r"(a[12]), "=r"(a[13]), "=r"(a[14]), "=r"(a[15]), "=r"(a[16]), "=r"(a[17]), "=r"(a[18]), "=r"(a[19]), "=r"(a[20]),
+            "=r"(a[21]), "=r"(a[22]), "=r"(a[23]), "=r"(a[24]), "=r"(a[25]), "=r"(a[26]), "=r"(a[27]), "=r"(a[28]), "=r"(a[29]), "=r"(a[30]),
+            "=r"(a[31])
+          : "r"(taddr)
+          : "memory");
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      if (mok) {
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+          const int n = nbase + n0 + q * 4;
+          if (n >= p.Cout) break;
+          float o[4];
+#pragma unroll
+          for (int t = 0; t < 4; t++) {
+            float acc = __uint_as_float(a[q * 4 + t]);
+            if (p.bias && n + t < p.Cout) acc += __ldg(p.bias + n + t);
+            o[t] = sma_act(acc, p.act);
+          }
+          // destination of column n for this pixel
+          float* dst; int cval = n;
+          if (p.d2s > 1) {
+            int qd = n / Cq; cval = n - qd * Cq; int p1 = qd / p.d2s, p2 = qd - p1 * p.d2s;
+            long long pix = (long long)(oy * p.d2s + p1) * (p.Wo * p.d2s) + (ox * p.d2s + p2);
+            dst = p.y + (long long)b * p.out_bs + pix * p.out_ld + cval;
+          } else {
+            dst = p.y + (long long)b * p.out_bs + (long long)r * p.out_ld + n;
+          }
+          if (vec_ok && n + 4 <= p.Cout && (Cq & 3) == 0) {
+            if (p.res) {
+              float4 rr = __ldg(reinterpret_cast<const float4*>(p.res + (long long)b * p.res_bs + (long long)r * p.res_ld + n));
+              o[0] += rr.x; o[1] += rr.y; o[2] += rr.z; o[3] += rr.w;
+            }
+            *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+          } else {
+#pragma unroll
+            for (int t = 0; t < 4; t++) {
+              if (n + t >= p.Cout) break;
+              float val = o[t];
+              if (p.res) val += __ldg(p.res + (long long)b * p.res_bs + (long long)r * p.res_ld + n + t);
+              if (p.d2s > 1) {
+                int nn = n + t; int qd = nn / Cq; int c2 = nn - qd * Cq; int p1 = qd / p.d2s, p2 = qd - p1 * p.d2s;
+                long long pix = (long long)(oy * p.d2s + p1) * (p.Wo * p.d2s) + (ox * p.d2s + p2);
+                p.y[(long long)b * p.out_bs + pix * p.out_ld + c2] = val;
+              } else {
+                dst[t] = val;
+              }
+            }
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  } else if (warp == 4) {
+    // =============================== MMA issuer (whole warp converged, one elected lane issues) ===============================
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.NT >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    for (int kc = 0; kc < p.nchunks; kc++) {
+      const int s = kc % p.stages; const uint32_t ph = (kc / p.stages) & 1;
+      mbar_wait(full_bar(s), ph);
+      tc_fence_after();
+      const uint32_t a_hi = sbase + (uint32_t)s * stage_bytes;
+      const uint64_t dah = make_desc(a_hi), dal = make_desc(a_hi + A_BYTES);
+      const uint64_t dbh = make_desc(a_hi + 2 * A_BYTES), dbl = make_desc(a_hi + 2 * A_BYTES + b_bytes);
+      if (elect_one_sync()) {
+#pragma unroll
+        for (int k4 = 0; k4 < KC / 8; k4++) {
+          const uint64_t ko = (uint64_t)(k4 * 2);          // 8 tf32 = 32 bytes = 2 x 16-byte units along K inside the swizzle row
+          if (p.passes == 3) {
+            tc_mma_tf32(tmem_base, dal + ko, dbh + ko, idesc, (kc | k4) != 0);
+            tc_mma_tf32(tmem_base, dah + ko, dbl + ko, idesc, 1u);
+            tc_mma_tf32(tmem_base, dah + ko, dbh + ko, idesc, 1u);
+          } else {
+            tc_mma_tf32(tmem_base, dah + ko, dbh + ko, idesc, (kc | k4) != 0);
+          }
+        }
+        tc_commit(empty_bar(s));                           // frees the slot when these MMAs retire
+        if (kc == p.nchunks - 1) tc_commit(accum_bar);     // accumulator complete -> epilogue
+      }
+      __syncwarp();
+    }
+  } else {
+    // =============================== weight loader ===============================
+    if (lane == 0) {
+      const uint32_t bytes = (uint32_t)(p.passes == 3 ? 2 * b_bytes : b_bytes);
+      const char* src = reinterpret_cast<const char*>(p.wtc) + (long long)nt * p.nchunks * (2 * b_bytes);
+      for (int kc = 0; kc < p.nchunks; kc++) {
+        const int s = kc % p.stages; const uint32_t ph = (kc / p.stages) & 1;
+        mbar_wait(empty_bar(s), ph ^ 1u);
+        mbar_expect_tx(full_bar(s), bytes);
+        bulk_g2s(sbase + (uint32_t)s * stage_bytes + 2 * A_BYTES, src + (long long)kc * (2 * b_bytes), bytes, full_bar(s));
+      }
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+  }
+}
+
+
+// =================================================================================================================
+// v2: persistent, halo-resident kernel for stride-1 convolutions (1x1, 3x3, 7x7; optional fused nearest-x2 upsample).
+//
+// One CTA per SM loops over output tiles of 8 (x) by 16 (y) pixels (1x1: 128 consecutive pixels).  For every 32-channel
+// chunk the producers load the (8+kw-1) x (16+kh-1) input halo ONCE, apply the prologue and the tf32 split ONCE per
+// element, and store one 128-byte row per halo pixel (SWIZZLE_128B keyed on the absolute shared-memory address).
+// The im2col for tap (ky,kx) is then done by the tensor core itself: the A descriptor starts at halo row
+// ky*HALO_W+kx and uses the halo row pitch HALO_W*128 B as the 8-row-atom stride (an 8-pixel output row segment is 8
+// consecutive halo rows), so the kh*kw taps re-read shared memory instead of L2 and cost no producer work.
+// Weights stream through their own ring, one (channel chunk, tap) image per bulk copy.  Two TMEM accumulators let the
+// 4 epilogue warps drain tile t while the MMA thread works on tile t+1.
+//   warps 0-3 epilogue | warp 4 MMA issue + TMEM alloc | warp 5 weight loader | warps 6-13 halo producers
+// =================================================================================================================
+constexpr int V2_PROD_WARPS = 8;                       // halo producers: enough loads in flight to cover HBM latency
+constexpr int V2_THREADS = 192 + 32 * V2_PROD_WARPS;
+constexpr int V2_PROWS = 4 * V2_PROD_WARPS;            // halo rows per producer pass (8 lanes per 128-byte row)
+constexpr int V2_UNROLL = 6;                           // loads in flight per producer thread
+constexpr int MAX_SA = 3, MAX_SB = 8;
+
+struct Tc2P {
+  const float* x; const float* wtc; const float* bias; const float* pre_scale; const float* pre_shift; const float* res; float* y;
+  long long in_bs, out_bs, res_bs;
+  int Hi, Wi, Cin, in_ld, Cout, kh, kw, pad_t, pad_l, up, pre_act;
+  int Ho, Wo, out_ld, act, res_ld, d2s;
+  int HoWo, cpt, taps, NT, ntiles_n, passes, tmem_cols;
+  int flat, tiles_x, tiles_per_img, total_tiles;
+  int halo_w, HP, a_img_bytes, a_stage_bytes, b_img_bytes, SA, SB;
+};
+
+__global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const Tc2P p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[2 * MAX_SA + 2 * MAX_SB + 4];
+  __shared__ uint32_t tmem_slot;
+  __shared__ __align__(16) float s_bias[256];              // bias of the current N tile (epilogue warps only)
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t bar0 = smem_u32(bars);
+  auto a_full = [&](int s) { return bar0 + 8u * s; };
+  auto a_empty = [&](int s) { return bar0 + 8u * (MAX_SA + s); };
+  auto b_full = [&](int s) { return bar0 + 8u * (2 * MAX_SA + s); };
+  auto b_empty = [&](int s) { return bar0 + 8u * (2 * MAX_SA + MAX_SB + s); };
+  auto acc_full = [&](int s) { return bar0 + 8u * (2 * MAX_SA + 2 * MAX_SB + s); };
+  auto acc_empty = [&](int s) { return bar0 + 8u * (2 * MAX_SA + 2 * MAX_SB + 2 + s); };
+  const uint32_t a_ring = sbase, b_ring = sbase + (uint32_t)p.SA * p.a_stage_bytes;
+  const int b_stage_bytes = 2 * p.b_img_bytes;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.SA; s++) { mbar_init(a_full(s), 32 * V2_PROD_WARPS); mbar_init(a_empty(s), 1); }
+    for (int s = 0; s < p.SB; s++) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
+    for (int s = 0; s < 2; s++) { mbar_init(acc_full(s), 1); mbar_init(acc_empty(s), 128); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(p.tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+
+  // tile -> (image b, first output row / column or first flat pixel, N tile)
+  auto decode = [&](int tile, int& b, int& ty0, int& tx0, int& nt) {
+    nt = tile % p.ntiles_n; int mt = tile / p.ntiles_n;
+    b = mt / p.tiles_per_img; int t = mt - b * p.tiles_per_img;
+    if (p.flat) { ty0 = t * BM; tx0 = 0; } else { int tyi = t / p.tiles_x; ty0 = tyi * 16; tx0 = (t - tyi * p.tiles_x) * 8; }
+  };
+
+  if (warp < 4) {
+    // =============================== epilogue ===============================
+    const int m = warp * 32 + lane;
+    const bool vec_ok = (p.out_ld & 3) == 0 && (p.out_bs & 3) == 0 && ((reinterpret_cast<uintptr_t>(p.y) & 15) == 0) &&
+                        (!p.res || ((p.res_ld & 3) == 0 && (p.res_bs & 3) == 0 && (reinterpret_cast<uintptr_t>(p.res) & 15) == 0));
+    const int Cq = p.d2s > 1 ? p.Cout / (p.d2s * p.d2s) : p.Cout;
+    int tcount = 0, cur_nt = -1;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tcount) {
+      int b, ty0, tx0, nt; decode(tile, b, ty0, tx0, nt);
+      const int ab = tcount & 1; const uint32_t aph = (tcount >> 1) & 1;
+      if (nt != cur_nt) {                           // (re)stage the bias slice of this N tile; named barrier 1 = the 4 epilogue warps
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        for (int i = m; i < p.NT; i += 128) { int n = nt * p.NT + i; s_bias[i] = (p.bias && n < p.Cout) ? __ldg(p.bias + n) : 0.f; }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        cur_nt = nt;
+      }
+      int oy, ox, r; bool mok;
+      if (p.flat) { r = ty0 + m; mok = r < p.HoWo; oy = r / p.Wo; ox = r - oy * p.Wo; }
+      else { oy = ty0 + (m >> 3); ox = tx0 + (m & 7); mok = oy < p.Ho && ox < p.Wo; r = oy * p.Wo + ox; }
+      const int nbase = nt * p.NT;
+      mbar_wait(acc_full(ab), aph);
+      tc_fence_after();
+      for (int n0 = 0; n0 < p.NT && nbase + n0 < p.Cout; n0 += 32) {
+        uint32_t a[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(ab * p.NT + n0);
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, "
+            "%20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]), "=r"(a[4]), "=r"(a[5]), "=r"(a[6]), "=r"(a[7]), "=r"(a[8]), "=r"(a[9]), "=r"(a[10]),
+              "=r"(a[11]), "=r"(a[12]), "=r"(a[13]), "=r"(a[14]), "=r"(a[15]), "=r"(a[16]), "=r"(a[17]), "=r"(a[18]), "=r"(a[19]), "=r"(a[20]),
+              "=r"(a[21]), "=r"(a[22]), "=r"(a[23]), "=r"(a[24]), "=r"(a[25]), "=r"(a[26]), "=r"(a[27]), "=r"(a[28]), "=r"(a[29]), "=r"(a[30]),
+              "=r"(a[31])
+            : "r"(taddr)
+            : "memory");
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (mok) {
+#pragma unroll
+          for (int q = 0; q < 8; q++) {
+            const int n = nbase + n0 + q * 4;
+            if (n >= p.Cout) break;
+            float o[4];
+#pragma unroll
+            for (int t = 0; t < 4; t++) {
+              o[t] = sma_act(__uint_as_float(a[q * 4 + t]) + s_bias[n0 + q * 4 + t], p.act);
+            }
+            if (vec_ok && n + 4 <= p.Cout && (Cq & 3) == 0) {
+              float* dst;
+              if (p.d2s > 1) {
+                int qd = n / Cq; int cval = n - qd * Cq; int p1 = qd / p.d2s, p2 = qd - p1 * p.d2s;
+                long long pix = (long long)(oy * p.d2s + p1) * (p.Wo * p.d2s) + (ox * p.d2s + p2);
+                dst = p.y + (long long)b * p.out_bs + pix * p.out_ld + cval;
+              } else {
+                dst = p.y + (long long)b * p.out_bs + (long long)r * p.out_ld + n;
+              }
+              if (p.res) {
+                float4 rr = __ldg(reinterpret_cast<const float4*>(p.res + (long long)b * p.res_bs + (long long)r * p.res_ld + n));
+                o[0] += rr.x; o[1] += rr.y; o[2] += rr.z; o[3] += rr.w;
+              }
+              *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+            } else {
+#pragma unroll
+              for (int t = 0; t < 4; t++) {
+                if (n + t >= p.Cout) break;
+                float val = o[t];
+                if (p.res) val += __ldg(p.res + (long long)b * p.res_bs + (long long)r * p.res_ld + n + t);
+                if (p.d2s > 1) {
+                  int nn = n + t; int qd = nn / Cq; int c2 = nn - qd * Cq; int p1 = qd / p.d2s, p2 = qd - p1 * p.d2s;
+                  long long pix = (long long)(oy * p.d2s + p1) * (p.Wo * p.d2s) + (ox * p.d2s + p2);
+                  p.y[(long long)b * p.out_bs + pix * p.out_ld + c2] = val;
+                } else {
+                  p.y[(long long)b * p.out_bs + (long long)r * p.out_ld + n + t] = val;
+                }
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(acc_empty(ab));                 // this thread's TMEM reads of accumulator `ab` are complete
+    }
+  } else if (warp == 4) {
+    // =============================== MMA issuer (whole warp converged, one elected lane issues) ===============================
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.NT >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    // A: 8-row atoms are 8 consecutive halo rows; next atom = next output row = halo row pitch
+    const uint64_t a_desc_hi_bits = (1ull << 16) | ((uint64_t)((p.halo_w * 128) >> 4) << 32) | (1ull << 46) | (2ull << 61);
+    int it = 0, jt = 0, tcount = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tcount) {
+      const int ab = tcount & 1; const uint32_t aph = (tcount >> 1) & 1;
+      mbar_wait(acc_empty(ab), aph ^ 1u);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(ab * p.NT);
+      for (int cc = 0; cc < p.cpt; cc++, it++) {
+        const int sa = it % p.SA; const uint32_t pha = (it / p.SA) & 1;
+        mbar_wait(a_full(sa), pha);
+        const uint32_t a_hi = a_ring + (uint32_t)sa * p.a_stage_bytes, a_lo = a_hi + p.a_img_bytes;
+        int ky = 0, kx = 0;
+        for (int tap = 0; tap < p.taps; tap++, jt++) {
+          const int sb = jt % p.SB; const uint32_t phb = (jt / p.SB) & 1;
+          mbar_wait(b_full(sb), phb);
+          tc_fence_after();
+          const uint32_t aoff = (uint32_t)(ky * p.halo_w + kx) * 128u;
+          const uint64_t dah = a_desc_hi_bits | (uint64_t)(((a_hi + aoff) & 0x3FFFF) >> 4);
+          const uint64_t dal = a_desc_hi_bits | (uint64_t)(((a_lo + aoff) & 0x3FFFF) >> 4);
+          const uint32_t b_hi = b_ring + (uint32_t)sb * b_stage_bytes;
+          const uint64_t dbh = make_desc(b_hi), dbl = make_desc(b_hi + p.b_img_bytes);
+          const bool last_tap = tap == p.taps - 1;
+          if (elect_one_sync()) {
+#pragma unroll
+            for (int k4 = 0; k4 < KC / 8; k4++) {
+              const uint64_t ko = (uint64_t)(k4 * 2);
+              const uint32_t first = (cc | tap | k4) != 0;
+              if (p.passes == 3) {
+                tc_mma_tf32(d_tmem, dal + ko, dbh + ko, idesc, first);
+                tc_mma_tf32(d_tmem, dah + ko, dbl + ko, idesc, 1u);
+                tc_mma_tf32(d_tmem, dah + ko, dbh + ko, idesc, 1u);
+              } else {
+                tc_mma_tf32(d_tmem, dah + ko, dbh + ko, idesc, first);
+              }
+            }
+            tc_commit(b_empty(sb));
+            if (last_tap) {
+              tc_commit(a_empty(sa));
+              if (cc == p.cpt - 1) tc_commit(acc_full(ab));
+            }
+          }
+          __syncwarp();
+          if (++kx == p.kw) { kx = 0; ++ky; }
+        }
+      }
+    }
+  } else if (warp == 5) {
+    // =============================== weight loader ===============================
+    if (lane == 0) {
+      const uint32_t bytes = (uint32_t)(p.passes == 3 ? b_stage_bytes : p.b_img_bytes);
+      int jt = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const int nt = tile % p.ntiles_n;
+        const char* src = reinterpret_cast<const char*>(p.wtc) + (long long)nt * p.cpt * p.taps * b_stage_bytes;
+        const int nblob = p.cpt * p.taps;
+        for (int j = 0; j < nblob; j++, jt++) {
+          const int sb = jt % p.SB; const uint32_t phb = (jt / p.SB) & 1;
+          mbar_wait(b_empty(sb), phb ^ 1u);
+          mbar_expect_tx(b_full(sb), bytes);
+          bulk_g2s(b_ring + (uint32_t)sb * b_stage_bytes, src + (long long)j * b_stage_bytes, bytes, b_full(sb));
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // =============================== halo producers ===============================
+    const int ptid = threadIdx.x - 192; const int cq = ptid & 7; const int prow = ptid >> 3;   // V2_PROWS halo rows per pass
+    const int Hv = p.Hi << p.up, Wv = p.Wi << p.up;
+    const int npass = (p.HP + V2_PROWS - 1) / V2_PROWS;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      int b, ty0, tx0, nt; decode(tile, b, ty0, tx0, nt);
+      const float* xb = p.x + (long long)b * p.in_bs;
+      for (int cc = 0; cc < p.cpt; cc++, it++) {
+        const int sa = it % p.SA; const uint32_t pha = (it / p.SA) & 1;
+        const int c = cc * KC + cq * 4;
+        float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.pre_scale) {
+          sc = __ldg(reinterpret_cast<const float4*>(p.pre_scale + (long long)b * p.Cin + c));
+          sh = __ldg(reinterpret_cast<const float4*>(p.pre_shift + (long long)b * p.Cin + c));
+        }
+        const uint32_t a_hi = a_ring + (uint32_t)sa * p.a_stage_bytes, a_lo = a_hi + p.a_img_bytes;
+        bool waited = false;
+        for (int pass0 = 0; pass0 < npass; pass0 += V2_UNROLL) {
+          float4 v[V2_UNROLL]; bool ok[V2_UNROLL];
+#pragma unroll
+          for (int u = 0; u < V2_UNROLL; u++) {
+            const int hp = (pass0 + u) * V2_PROWS + prow;
+            ok[u] = false; v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (hp < p.HP) {
+              long long pix;
+              if (p.flat) { int r = ty0 + hp; ok[u] = r < p.HoWo; pix = r; }
+              else {
+                int hy = hp / p.halo_w; int hx = hp - hy * p.halo_w;
+                int iy = ty0 + hy - p.pad_t, ix = tx0 + hx - p.pad_l;
+                ok[u] = (unsigned)iy < (unsigned)Hv && (unsigned)ix < (unsigned)Wv;
+                pix = (long long)(iy >> p.up) * p.Wi + (ix >> p.up);
+              }
+              if (ok[u]) v[u] = __ldg(reinterpret_cast<const float4*>(xb + pix * p.in_ld + c));
+            }
+          }
+          if (!waited) { mbar_wait(a_empty(sa), pha ^ 1u); waited = true; }     // first loads are in flight while we wait
+#pragma unroll
+          for (int u = 0; u < V2_UNROLL; u++) {
+            const int hp = (pass0 + u) * V2_PROWS + prow;
+            if (hp >= p.HP) continue;
+            float4 t = v[u];
+            if (p.pre_scale && ok[u]) {
+              t.x = sma_act(fmaf(t.x, sc.x, sh.x), p.pre_act); t.y = sma_act(fmaf(t.y, sc.y, sh.y), p.pre_act);
+              t.z = sma_act(fmaf(t.z, sc.z, sh.z), p.pre_act); t.w = sma_act(fmaf(t.w, sc.w, sh.w), p.pre_act);
+            }
+            const uint32_t off = (uint32_t)hp * 128u + (uint32_t)((cq ^ (hp & 7)) << 4);
+            float hx_ = tf32_rna(t.x), hy_ = tf32_rna(t.y), hz_ = tf32_rna(t.z), hw_ = tf32_rna(t.w);
+            sts128(a_hi + off, hx_, hy_, hz_, hw_);
+            if (p.passes == 3) sts128(a_lo + off, t.x - hx_, t.y - hy_, t.z - hz_, t.w - hw_);
+          }
+        }
+        fence_async_smem();
+        mbar_arrive(a_full(sa));
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+  }
+}
+
+// packed [K][ldw] fp32 weight -> per (N-tile, chunk) image: [hi: NT rows x 128 B, SWIZZLE_128B][lo: same]
+__global__ void pack_tc_kernel(const float* __restrict__ wp, int ldw, int Cin, int taps, int Cout, int NT, int ntiles, float* __restrict__ out) {
+  const int nchunks = taps * Cin / KC;
+  const long long total = (long long)ntiles * nchunks * NT * KC;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int kk = (int)(i % KC); long long t = i / KC; int n = (int)(t % NT); t /= NT; int kc = (int)(t % nchunks); int nt = (int)(t / nchunks);
+    const int cc = kc / taps, tap = kc - cc * taps;              // image chunk order: channel chunk outer, tap inner
+    int col = nt * NT + n, k = tap * Cin + cc * KC + kk;         // row of the [K][ldw] packed weight (k = tap*Cin + c)
+    float w = col < Cout ? wp[(long long)k * ldw + col] : 0.f;
+    uint32_t hb; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(w));
+    float hi = __uint_as_float(hb), lo = w - hi;
+    long long blob = ((long long)nt * nchunks + kc) * (2LL * NT * KC);
+    int phys = (n >> 3) * 256 + (n & 7) * 32 + ((((kk >> 2) ^ (n & 7)) << 2) | (kk & 3));   // float index inside the image
+    out[blob + phys] = hi;
+    out[blob + (long long)NT * KC + phys] = lo;
+  }
+}
+
+int tc_ntile(int Cout) { return Cout <= 256 ? ((Cout + 15) & ~15) : 256; }
+
+}  // namespace
+
+extern "C" int64_t sma_conv_weight_tc_floats(int Cout, int Cin, int kh, int kw) {
+  if (Cout <= 0 || Cin <= 0 || kh <= 0 || kw <= 0 || (Cin % KC)) return 0;
+  int NT = tc_ntile(Cout); int ntiles = (Cout + NT - 1) / NT;
+  return (int64_t)ntiles * (kh * kw * Cin / KC) * 2 * NT * KC;
+}
+
+extern "C" int sma_pack_conv_weight_tc(const float* w_packed, int ldw, int Cout, int Cin, int kh, int kw, float* w_tc, sma_stream_t stream) {
+  if (!w_packed || !w_tc || Cout <= 0 || Cin <= 0 || kh <= 0 || kw <= 0 || ldw < Cout) return SMA_ERR_BAD_ARG;
+  if (Cin % KC) return SMA_ERR_UNSUPPORTED;
+  if (reinterpret_cast<uintptr_t>(w_tc) & 15) return SMA_ERR_BAD_ARG;
+  int NT = tc_ntile(Cout); int ntiles = (Cout + NT - 1) / NT; int K = kh * kw * Cin;
+  long long total = (long long)ntiles * (K / KC) * NT * KC;
+  int blocks = (int)((total + 255) / 256); if (blocks > 8192) blocks = 8192;
+  pack_tc_kernel<<<blocks, 256, 0, as_stream(stream)>>>(w_packed, ldw, Cin, kh * kw, Cout, NT, ntiles, w_tc);
+  SMA_LAUNCH_CHECK();
+  return SMA_OK;
+}
+
+
+static int g_num_sms = 0;
+
+// persistent halo kernel (stride 1); returns SMA_ERR_UNSUPPORTED when not eligible
+static int conv_tc2_try(const sma_conv_desc* d, cudaStream_t st) {
+  if (d->stride != 1 || (d->kh != d->kw && !(d->kh == 1 || d->kw == 1))) return SMA_ERR_UNSUPPORTED;
+  const bool flat = d->kh == 1 && d->kw == 1 && !d->upsample2 && d->pad_t == 0 && d->pad_l == 0 && d->Ho == d->Hi && d->Wo == d->Wi;
+  if (!flat && (d->Ho < 8 || d->Wo < 4)) return SMA_ERR_UNSUPPORTED;      // tiny feature maps: the gather kernel packs images into one tile
+  Tc2P p;
+  p.x = d->x; p.wtc = d->w_tc; p.bias = d->bias; p.pre_scale = d->pre_scale; p.pre_shift = d->pre_shift; p.res = d->res; p.y = d->y;
+  p.in_bs = d->in_bstride; p.out_bs = d->out_bstride; p.res_bs = d->res_bstride;
+  p.Hi = d->Hi; p.Wi = d->Wi; p.Cin = d->Cin; p.in_ld = d->in_ld; p.Cout = d->Cout; p.kh = d->kh; p.kw = d->kw;
+  p.pad_t = d->pad_t; p.pad_l = d->pad_l; p.up = d->upsample2 ? 1 : 0; p.pre_act = d->pre_act; p.Ho = d->Ho; p.Wo = d->Wo; p.out_ld = d->out_ld;
+  p.act = d->act; p.res_ld = d->res_ld; p.d2s = d->d2s;
+  p.HoWo = d->Ho * d->Wo; p.cpt = d->Cin / KC; p.taps = d->kh * d->kw;
+  p.NT = tc_ntile(d->Cout); p.ntiles_n = (d->Cout + p.NT - 1) / p.NT; p.passes = d->tf32x3 == 2 ? 1 : 3;
+  p.flat = flat ? 1 : 0;
+  if (flat) { p.tiles_x = 1; p.tiles_per_img = (p.HoWo + BM - 1) / BM; p.halo_w = 8; p.HP = BM; }
+  else {
+    p.tiles_x = (d->Wo + 7) / 8; p.tiles_per_img = p.tiles_x * ((d->Ho + 15) / 16);
+    p.halo_w = 8 + d->kw - 1; p.HP = p.halo_w * (16 + d->kh - 1);
+  }
+  const long long total = (long long)d->B * p.tiles_per_img * p.ntiles_n;
+  if (total > 0x7fffffffLL) return SMA_ERR_UNSUPPORTED;
+  p.total_tiles = (int)total;
+  p.a_img_bytes = (p.HP * 128 + 1023) & ~1023;
+  p.a_stage_bytes = 2 * p.a_img_bytes;
+  p.b_img_bytes = p.NT * KC * 4;
+  const int b_stage = 2 * p.b_img_bytes;
+  int SA = 2;
+  int SB = (SMEM_LIMIT - SA * p.a_stage_bytes) / b_stage;
+  if (SB < 2) { SA = 1; SB = (SMEM_LIMIT - p.a_stage_bytes) / b_stage; }
+  if (SB < 2) return SMA_ERR_UNSUPPORTED;
+  if (SB > MAX_SB) SB = MAX_SB;
+  p.SA = SA; p.SB = SB;
+  int cols = 32; while (cols < 2 * p.NT) cols <<= 1;
+  p.tmem_cols = cols;
+  const int smem = SA * p.a_stage_bytes + SB * b_stage + 1024;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(conv_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_DYN_MAX) != cudaSuccess) return SMA_ERR_CUDA;
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return SMA_ERR_CUDA;
+    g_num_sms = sms; configured = true;
+  }
+  const int grid = p.total_tiles < g_num_sms ? p.total_tiles : g_num_sms;
+  conv_tc2_kernel<<<grid, V2_THREADS, smem, st>>>(p);
+  SMA_LAUNCH_CHECK();
+  return SMA_OK;
+}
+
+// returns SMA_ERR_UNSUPPORTED when the shape / layout is not eligible (the caller then uses the CUDA-core kernel)
+int sma_conv2d_tc_try(const sma_conv_desc* d, cudaStream_t st) {
+  if (!d->w_tc || d->out_nchw) return SMA_ERR_UNSUPPORTED;
+  if ((d->Cin % KC) || (d->in_ld & 3) || (d->in_bstride & 3) || (reinterpret_cast<uintptr_t>(d->x) & 15) || (reinterpret_cast<uintptr_t>(d->w_tc) & 15))
+    return SMA_ERR_UNSUPPORTED;
+  if (d->pre_scale && ((reinterpret_cast<uintptr_t>(d->pre_scale) | reinterpret_cast<uintptr_t>(d->pre_shift)) & 15)) return SMA_ERR_UNSUPPORTED;
+  const long long M = (long long)d->B * d->Ho * d->Wo;
+  if (M < 64) return SMA_ERR_UNSUPPORTED;
+  if (!(d->tc_variant & 1)) {
+    int r2 = conv_tc2_try(d, st);
+    if (r2 != SMA_ERR_UNSUPPORTED) return r2;
+  }
+  TcP p;
+  p.x = d->x; p.wtc = d->w_tc; p.bias = d->bias; p.pre_scale = d->pre_scale; p.pre_shift = d->pre_shift; p.res = d->res; p.y = d->y;
+  p.in_bs = d->in_bstride; p.out_bs = d->out_bstride; p.res_bs = d->res_bstride;
+  p.Hi = d->Hi; p.Wi = d->Wi; p.Cin = d->Cin; p.in_ld = d->in_ld; p.Cout = d->Cout; p.kh = d->kh; p.kw = d->kw; p.stride = d->stride;
+  p.pad_t = d->pad_t; p.pad_l = d->pad_l; p.up = d->upsample2 ? 1 : 0; p.pre_act = d->pre_act; p.Ho = d->Ho; p.Wo = d->Wo; p.out_ld = d->out_ld;
+  p.act = d->act; p.res_ld = d->res_ld; p.d2s = d->d2s;
+  p.M = (int)M; p.HoWo = d->Ho * d->Wo; p.cpt = d->Cin / KC; p.nchunks = d->kh * d->kw * p.cpt;
+  p.NT = tc_ntile(d->Cout); p.passes = d->tf32x3 == 2 ? 1 : 3;
+  const int ntiles = (d->Cout + p.NT - 1) / p.NT;
+  const int stage_bytes = 2 * A_BYTES + 2 * p.NT * KC * 4;
+  int stages = SMEM_LIMIT / stage_bytes; if (stages > MAX_STAGES) stages = MAX_STAGES; if (stages > p.nchunks) stages = p.nchunks;
+  if (stages < 1) return SMA_ERR_UNSUPPORTED;
+  p.stages = stages;
+  int cols = 32; while (cols < p.NT) cols <<= 1;
+  p.tmem_cols = cols;
+  const int smem = stages * stage_bytes + 1024;
+  static int configured = 0;   // largest dynamic shared memory size opted in so far (idempotent; benign if raced)
+  if (configured < smem) {
+    if (cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_DYN_MAX) != cudaSuccess) return SMA_ERR_CUDA;
+    configured = SMEM_DYN_MAX;
+  }
+  dim3 grid((unsigned)((M + BM - 1) / BM), (unsigned)ntiles);
+  conv_tc_kernel<<<grid, 192, smem, st>>>(p);
+  SMA_LAUNCH_CHECK();
+  return SMA_OK;
+}

@@ -78,17 +78,33 @@ class ConvW:
     Cin: int
     kh: int
     kw: int
+    w_tc: Optional[torch.Tensor] = None      # tensor-core image (sma_pack_conv_weight_tc); None -> CUDA-core kernel only
 
     def cols(self, start: int, n: int) -> 'ConvW':
-        """Output-column slice (free: the packed weight is row-major [K][ldw])."""
+        """Output-column slice (free for the CUDA-core layout: row-major [K][ldw]; the tensor-core image is re-packed)."""
         assert start % 4 == 0
-        return ConvW(self.w[:, start:], None if self.bias is None else self.bias[start:start + n], n, self.Cin, self.kh, self.kw)
+        cw = ConvW(self.w[:, start:], None if self.bias is None else self.bias[start:start + n], n, self.Cin, self.kh, self.kw)
+        cw.w_tc = _pack_tc(cw)
+        return cw
 
     def as_patch(self, p: int) -> 'ConvW':
         """View a Linear(C*p*p -> N) whose features are ordered (p1 p2 c) as a pxp stride-p conv
         (appmotioncodebook_arch.py:222,229,236)."""
         assert self.kh == 1 and self.kw == 1 and self.Cin % (p * p) == 0
-        return ConvW(self.w, self.bias, self.Cout, self.Cin // (p * p), p, p)
+        cw = ConvW(self.w, self.bias, self.Cout, self.Cin // (p * p), p, p)
+        cw.w_tc = _pack_tc(cw)
+        return cw
+
+
+def _pack_tc(cw: 'ConvW') -> Optional[torch.Tensor]:
+    lib = _lib.load()
+    n = lib.sma_conv_weight_tc_floats(cw.Cout, cw.Cin, cw.kh, cw.kw)
+    if n <= 0:
+        return None
+    out = torch.empty((n,), device=cw.w.device, dtype=torch.float32)
+    check(lib.sma_pack_conv_weight_tc(cw.w.data_ptr(), cw.w.stride(0), cw.Cout, cw.Cin, cw.kh, cw.kw, out.data_ptr(), _stream()),
+          'sma_pack_conv_weight_tc')
+    return out
 
 
 def pack_conv(weight: torch.Tensor, bias: Optional[torch.Tensor], bn: Optional[dict] = None) -> ConvW:
@@ -110,7 +126,9 @@ def pack_conv(weight: torch.Tensor, bias: Optional[torch.Tensor], bn: Optional[d
         eps = float(bn.get('eps', 1e-5))
     check(lib.sma_pack_conv_weight(_ptr(w), _ptr(b), Cout, Cin, kh, kw, _ptr(g), _ptr(be), _ptr(mu), _ptr(var), eps,
                                    _ptr(wp), ldw, _ptr(bo), _stream()), 'sma_pack_conv_weight')
-    return ConvW(wp, None if bo is None else bo[:Cout], Cout, Cin, kh, kw)
+    cw = ConvW(wp, None if bo is None else bo[:Cout], Cout, Cin, kh, kw)
+    cw.w_tc = _pack_tc(cw)
+    return cw
 
 
 def pack_conv_cat(weights, biases) -> ConvW:
@@ -120,13 +138,17 @@ def pack_conv_cat(weights, biases) -> ConvW:
     return pack_conv(w, b)
 
 
-USE_TF32X3 = True   # let sma_conv2d_fwd pick the tcgen05 3xTF32 kernel where the shape allows
+USE_TF32X3 = True        # let sma_conv2d_fwd pick the tcgen05 kernel where the shape allows
+ALLOW_TF32_1PASS = True  # honour `fast=True` requests (single-pass TF32)
+TC_VARIANT = 0           # 0: library picks the tensor-core kernel variant; 1: force the gather kernel (tests)
 
 
 def conv2d(x: torch.Tensor, cw: ConvW, *, stride: int = 1, pad: int = 0, pad_tl: Optional[Tuple[int, int]] = None,
            out: Optional[torch.Tensor] = None, out_hw: Optional[Tuple[int, int]] = None, act: str = 'none',
            pre: Optional[Tuple[torch.Tensor, torch.Tensor, str]] = None, res: Optional[torch.Tensor] = None,
-           upsample2: bool = False, d2s: int = 0, out_nchw: bool = False, exact: bool = False) -> torch.Tensor:
+           upsample2: bool = False, d2s: int = 0, out_nchw: bool = False, exact: bool = False, fast: bool = False) -> torch.Tensor:
+    """`exact`: force the CUDA-core fp32 kernel; `fast`: allow single-pass TF32 on the tensor cores (layers whose
+    contribution to the output error budget was measured to be negligible); default: 3xTF32 (fp32-faithful)."""
     lib = _lib.load()
     B, Hi, Wi, Cin, ibs, ild = _nhwc(x)
     if Cin != cw.Cin:
@@ -168,7 +190,9 @@ def conv2d(x: torch.Tensor, cw: ConvW, *, stride: int = 1, pad: int = 0, pad_tl:
         assert (rB, rH, rW, rC) == (B, Ho, Wo, cw.Cout), (tuple(res.shape), (B, Ho, Wo, cw.Cout))
         d.res, d.res_bstride, d.res_ld = res.data_ptr(), rbs, rld
     d.d2s, d.out_nchw = d2s, 1 if out_nchw else 0
-    d.tf32x3 = 1 if (USE_TF32X3 and not exact) else 0
+    d.tf32x3 = 0 if (exact or not USE_TF32X3 or cw.w_tc is None) else (2 if (fast and ALLOW_TF32_1PASS) else 1)
+    d.w_tc = _ptr(cw.w_tc)
+    d.tc_variant = TC_VARIANT
     K = cw.kh * cw.kw * Cin
     with _Prof('conv', 2.0 * B * Ho * Wo * K * cw.Cout,
                4.0 * (B * Hi * Wi * Cin + B * Ho * Wo * cw.Cout * (2 if res is not None else 1) + K * cw.Cout)):
