@@ -136,6 +136,7 @@ def main():
     ap.add_argument('--ref-frames', type=int, default=12, help='frames per step of the CPU reference / cpu_baseline sample')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-roofline', action='store_true')
+    ap.add_argument('--detail', action='store_true', help='print the per-shape time table of the roofline pass to stderr')
     ap.add_argument('--ncu', action='store_true', help='profiling aid: one warm-up step and one step, nothing else (run under ncu)')
     args = ap.parse_args()
     if args.impl == 'reference':
@@ -246,9 +247,16 @@ def main():
         torch.cuda.synchronize()
         prof, S.ops.PROFILE = S.ops.PROFILE, None
         agg = {}
-        for kind, fl, nb, e0, e1 in prof:
+        detail = {}
+        for kind, fl, nb, e0, e1, label in prof:
+            t = e0.elapsed_time(e1)
             a = agg.setdefault(kind, [0, 0.0, 0.0, 0.0])
-            a[0] += 1; a[1] += fl; a[2] += nb; a[3] += e0.elapsed_time(e1)
+            a[0] += 1; a[1] += fl; a[2] += nb; a[3] += t
+            dd = detail.setdefault(label, [0, 0.0, 0.0])
+            dd[0] += 1; dd[1] += fl; dd[2] += t
+        if args.detail:
+            for label, (n, fl, t) in sorted(detail.items(), key=lambda kv: -kv[1][2])[:45]:
+                print(f'{t:8.2f} ms  {n:4d}x  {fl / max(t, 1e-9) / 1e9:7.1f} TF  {label}', file=sys.stderr)
         pk = peaks()
         stage_table = {k: {'launches': v[0], 'gflop': v[1] / 1e9, 'mbytes': v[2] / 1e6, 'ms': v[3],
                            'tflops': v[1] / (v[3] * 1e-3) / 1e12 if v[3] else None,

@@ -76,6 +76,12 @@ __device__ __forceinline__ float tf32_rna(float v) {
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
   return __uint_as_float(r);
 }
+// prologue activation on the operand load: swish via ex2.approx / rcp.approx (rel. error ~1e-6, far below the tf32 split residual)
+__device__ __forceinline__ float pre_act_fast(float v, int act) {
+  if (act == SMA_ACT_SWISH) return __fdividef(v, 1.f + __expf(-v));
+  if (act == SMA_ACT_NONE) return v;
+  return sma_act(v, act);
+}
 __device__ __forceinline__ void sts128(uint32_t a, float x, float y, float z, float w) {
   asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
 }
@@ -296,7 +302,8 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const TcP p) {
 // =================================================================================================================
 constexpr int V2_PROD_WARPS = 8;                       // halo producers: enough loads in flight to cover HBM latency
 constexpr int V2_THREADS = 192 + 32 * V2_PROD_WARPS;
-constexpr int V2_PROWS = 4 * V2_PROD_WARPS;            // halo rows per producer pass (8 lanes per 128-byte row)
+constexpr int V2_PGROUPS = 2;                          // producer groups working on alternate channel chunks (2x the latency budget each)
+constexpr int V2_PROWS = 4 * V2_PROD_WARPS / V2_PGROUPS;   // halo rows per pass of one group (8 lanes per 128-byte row)
 constexpr int V2_UNROLL = 6;                           // loads in flight per producer thread
 constexpr int MAX_SA = 3, MAX_SB = 8;
 
@@ -310,6 +317,9 @@ struct Tc2P {
   int halo_w, HP, a_img_bytes, a_stage_bytes, b_img_bytes, SA, SB;
 };
 
+// ACT: epilogue activation; PRE: -1 no prologue, else the prologue activation applied after scale/shift (compile-time so that the
+// unrolled epilogue / producer bodies stay small: the three warp roles share one instruction cache)
+template <int ACT, int PRE>
 __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const Tc2P p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[2 * MAX_SA + 2 * MAX_SB + 4];
@@ -328,7 +338,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const Tc2P p) {
   const int b_stage_bytes = 2 * p.b_img_bytes;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < p.SA; s++) { mbar_init(a_full(s), 32 * V2_PROD_WARPS); mbar_init(a_empty(s), 1); }
+    for (int s = 0; s < p.SA; s++) { mbar_init(a_full(s), 32 * V2_PROD_WARPS / V2_PGROUPS); mbar_init(a_empty(s), 1); }
     for (int s = 0; s < p.SB; s++) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
     for (int s = 0; s < 2; s++) { mbar_init(acc_full(s), 1); mbar_init(acc_empty(s), 128); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -392,7 +402,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const Tc2P p) {
             float o[4];
 #pragma unroll
             for (int t = 0; t < 4; t++) {
-              o[t] = sma_act(__uint_as_float(a[q * 4 + t]) + s_bias[n0 + q * 4 + t], p.act);
+              o[t] = sma_act(__uint_as_float(a[q * 4 + t]) + s_bias[n0 + q * 4 + t], ACT);
             }
             if (vec_ok && n + 4 <= p.Cout && (Cq & 3) == 0) {
               float* dst;
@@ -499,7 +509,8 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const Tc2P p) {
     __syncwarp();
   } else {
     // =============================== halo producers ===============================
-    const int ptid = threadIdx.x - 192; const int cq = ptid & 7; const int prow = ptid >> 3;   // V2_PROWS halo rows per pass
+    const int pgroup = (threadIdx.x - 192) / (32 * V2_PROD_WARPS / V2_PGROUPS);
+    const int ptid = (threadIdx.x - 192) % (32 * V2_PROD_WARPS / V2_PGROUPS); const int cq = ptid & 7; const int prow = ptid >> 3;   // V2_PROWS halo rows per pass
     const int Hv = p.Hi << p.up, Wv = p.Wi << p.up;
     const int npass = (p.HP + V2_PROWS - 1) / V2_PROWS;
     int it = 0;
@@ -507,10 +518,11 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const Tc2P p) {
       int b, ty0, tx0, nt; decode(tile, b, ty0, tx0, nt);
       const float* xb = p.x + (long long)b * p.in_bs;
       for (int cc = 0; cc < p.cpt; cc++, it++) {
+        if ((it % V2_PGROUPS) != pgroup) continue;      // the other group's chunk
         const int sa = it % p.SA; const uint32_t pha = (it / p.SA) & 1;
         const int c = cc * KC + cq * 4;
         float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (p.pre_scale) {
+        if (PRE >= 0) {
           sc = __ldg(reinterpret_cast<const float4*>(p.pre_scale + (long long)b * p.Cin + c));
           sh = __ldg(reinterpret_cast<const float4*>(p.pre_shift + (long long)b * p.Cin + c));
         }
@@ -540,9 +552,9 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const Tc2P p) {
             const int hp = (pass0 + u) * V2_PROWS + prow;
             if (hp >= p.HP) continue;
             float4 t = v[u];
-            if (p.pre_scale && ok[u]) {
-              t.x = sma_act(fmaf(t.x, sc.x, sh.x), p.pre_act); t.y = sma_act(fmaf(t.y, sc.y, sh.y), p.pre_act);
-              t.z = sma_act(fmaf(t.z, sc.z, sh.z), p.pre_act); t.w = sma_act(fmaf(t.w, sc.w, sh.w), p.pre_act);
+            if (PRE >= 0 && ok[u]) {
+              t.x = pre_act_fast(fmaf(t.x, sc.x, sh.x), PRE); t.y = pre_act_fast(fmaf(t.y, sc.y, sh.y), PRE);
+              t.z = pre_act_fast(fmaf(t.z, sc.z, sh.z), PRE); t.w = pre_act_fast(fmaf(t.w, sc.w, sh.w), PRE);
             }
             const uint32_t off = (uint32_t)hp * 128u + (uint32_t)((cq ^ (hp & 7)) << 4);
             float hx_ = tf32_rna(t.x), hy_ = tf32_rna(t.y), hz_ = tf32_rna(t.z), hw_ = tf32_rna(t.w);
@@ -606,6 +618,38 @@ extern "C" int sma_pack_conv_weight_tc(const float* w_packed, int ldw, int Cout,
 
 static int g_num_sms = 0;
 
+template <int ACT, int PRE>
+static int launch_tc2_inst(const Tc2P& p, int grid, int smem, cudaStream_t st) {
+  static bool configured = false;     // per instantiation; idempotent, benign if raced
+  if (!configured) {
+    if (cudaFuncSetAttribute(conv_tc2_kernel<ACT, PRE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_DYN_MAX) != cudaSuccess) return SMA_ERR_CUDA;
+    configured = true;
+  }
+  conv_tc2_kernel<ACT, PRE><<<grid, V2_THREADS, smem, st>>>(p);
+  SMA_LAUNCH_CHECK();
+  return SMA_OK;
+}
+template <int ACT>
+static int launch_tc2_pre(int pre, const Tc2P& p, int grid, int smem, cudaStream_t st) {
+  switch (pre) {
+    case -1: return launch_tc2_inst<ACT, -1>(p, grid, smem, st);
+    case SMA_ACT_NONE: return launch_tc2_inst<ACT, SMA_ACT_NONE>(p, grid, smem, st);
+    case SMA_ACT_SWISH: return launch_tc2_inst<ACT, SMA_ACT_SWISH>(p, grid, smem, st);
+    default: return SMA_ERR_UNSUPPORTED;     // other prologue activations: gather / CUDA-core kernels
+  }
+}
+static int launch_tc2(int act, int pre, const Tc2P& p, int grid, int smem, cudaStream_t st) {
+  switch (act) {
+    case SMA_ACT_NONE: return launch_tc2_pre<SMA_ACT_NONE>(pre, p, grid, smem, st);
+    case SMA_ACT_RELU: return launch_tc2_pre<SMA_ACT_RELU>(pre, p, grid, smem, st);
+    case SMA_ACT_LEAKY02: return launch_tc2_pre<SMA_ACT_LEAKY02>(pre, p, grid, smem, st);
+    case SMA_ACT_GELU: return launch_tc2_pre<SMA_ACT_GELU>(pre, p, grid, smem, st);
+    case SMA_ACT_SIGMOID: return launch_tc2_pre<SMA_ACT_SIGMOID>(pre, p, grid, smem, st);
+    case SMA_ACT_SWISH: return launch_tc2_pre<SMA_ACT_SWISH>(pre, p, grid, smem, st);
+    default: return SMA_ERR_BAD_ARG;
+  }
+}
+
 // persistent halo kernel (stride 1); returns SMA_ERR_UNSUPPORTED when not eligible
 static int conv_tc2_try(const sma_conv_desc* d, cudaStream_t st) {
   if (d->stride != 1 || (d->kh != d->kw && !(d->kh == 1 || d->kw == 1))) return SMA_ERR_UNSUPPORTED;
@@ -641,17 +685,14 @@ static int conv_tc2_try(const sma_conv_desc* d, cudaStream_t st) {
   int cols = 32; while (cols < 2 * p.NT) cols <<= 1;
   p.tmem_cols = cols;
   const int smem = SA * p.a_stage_bytes + SB * b_stage + 1024;
-  static bool configured = false;
-  if (!configured) {
-    if (cudaFuncSetAttribute(conv_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_DYN_MAX) != cudaSuccess) return SMA_ERR_CUDA;
+  if (g_num_sms == 0) {
     int dev = 0, sms = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return SMA_ERR_CUDA;
-    g_num_sms = sms; configured = true;
+    g_num_sms = sms;
   }
   const int grid = p.total_tiles < g_num_sms ? p.total_tiles : g_num_sms;
-  conv_tc2_kernel<<<grid, V2_THREADS, smem, st>>>(p);
-  SMA_LAUNCH_CHECK();
-  return SMA_OK;
+  const int pre = d->pre_scale ? d->pre_act : -1;
+  return launch_tc2(d->act, pre, p, grid, smem, st);
 }
 
 // returns SMA_ERR_UNSUPPORTED when the shape / layout is not eligible (the caller then uses the CUDA-core kernel)

@@ -25,10 +25,10 @@ PROFILE = None
 
 
 class _Prof:
-    __slots__ = ('kind', 'flops', 'nbytes', 'e0')
+    __slots__ = ('kind', 'flops', 'nbytes', 'e0', 'label')
 
-    def __init__(self, kind, flops, nbytes):
-        self.kind, self.flops, self.nbytes = kind, flops, nbytes
+    def __init__(self, kind, flops, nbytes, label=''):
+        self.kind, self.flops, self.nbytes, self.label = kind, flops, nbytes, label
 
     def __enter__(self):
         if PROFILE is not None:
@@ -40,7 +40,7 @@ class _Prof:
         if PROFILE is not None:
             e1 = torch.cuda.Event(enable_timing=True)
             e1.record()
-            PROFILE.append((self.kind, self.flops, self.nbytes, self.e0, e1))
+            PROFILE.append((self.kind, self.flops, self.nbytes, self.e0, e1, self.label))
         return False
 
 
@@ -195,7 +195,8 @@ def conv2d(x: torch.Tensor, cw: ConvW, *, stride: int = 1, pad: int = 0, pad_tl:
     d.tc_variant = TC_VARIANT
     K = cw.kh * cw.kw * Cin
     with _Prof('conv', 2.0 * B * Ho * Wo * K * cw.Cout,
-               4.0 * (B * Hi * Wi * Cin + B * Ho * Wo * cw.Cout * (2 if res is not None else 1) + K * cw.Cout)):
+               4.0 * (B * Hi * Wi * Cin + B * Ho * Wo * cw.Cout * (2 if res is not None else 1) + K * cw.Cout),
+               f'conv B{B} {Hi}x{Wi} Cin{Cin} Cout{cw.Cout} k{cw.kh} s{stride}{" up" if upsample2 else ""}{" pre" if pre is not None else ""} tc{d.tf32x3 if d.w_tc else 0}'):
         check(lib.sma_conv2d_fwd(C.byref(d), _stream()), f'sma_conv2d_fwd Cin={Cin} Cout={cw.Cout} k={cw.kh}x{cw.kw}')
     return out
 
@@ -296,7 +297,7 @@ def mha(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, key_mask:
         scale = float(D) ** -0.5
     if key_mask is not None:
         assert key_mask.dtype == torch.uint8 and key_mask.is_contiguous() and key_mask.numel() == B * S
-    with _Prof('mha', 4.0 * B * L * S * E, 4.0 * (2 * B * L * E + 2 * (B if kvbs else 1) * S * E)):
+    with _Prof('mha', 4.0 * B * L * S * E, 4.0 * (2 * B * L * E + 2 * (B if kvbs else 1) * S * E), f'mha B{B} L{L} S{S} h{heads} D{D}'):
         check(lib.sma_mha_fwd(q.data_ptr(), q.stride(1), k.data_ptr(), ldk, v.data_ptr(), ldv, kvbs, B, L, S, heads, D, scale,
                               _ptr(key_mask), out.data_ptr(), out.stride(1), _stream()), f'sma_mha_fwd D={D}')
     return out
