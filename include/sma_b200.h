@@ -121,11 +121,12 @@ int sma_resize_bilinear_ac(const float* x, int B, int Hi, int Wi, int C, int64_t
  * (nn.MultiheadAttention inside TransformerLayer, appmotioncodebook_arch.py:97-116, and the
  * single-head AttnBlock, archs/vqgan_arch.py:233-248).  q:(B,L,*) k,v:(B or shared,S,*) ;
  * head h occupies columns [h*D,(h+1)*D).  key_mask (B,S) uint8, 1 = ignore (may be NULL).
- * D in {4,32,256}.
+ * D in {4,32,256}.  D in {4,32} with L % 128 == 0 and S % 64 == 0 runs on the tensor cores (tcgen05, 3xTF32 for both
+ * contractions); flags bit 0 forces the exact-fp32 CUDA-core kernel.
  * ------------------------------------------------------------------------------------------- */
 int sma_mha_fwd(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv,
                 int64_t kv_bstride, int B, int L, int S, int heads, int D, float scale,
-                const uint8_t* key_mask, float* out, int ldo, sma_stream_t stream);
+                const uint8_t* key_mask, float* out, int ldo, int flags, sma_stream_t stream);
 
 /* VectorQuantizer lookup (archs/vqgan_arch.py:33-73): d = fl(fl(|z|^2+|e|^2) - 2 z.e), argmin with
  * lowest-index ties -> idx (int64), zq = e[idx].  z:(N,E) row-major, codebook (n_codes,E). */

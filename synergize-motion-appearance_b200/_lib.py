@@ -42,7 +42,7 @@ SIGNATURES = {
     'sma_layernorm': ([_V, _I, _I, _V, _V, _F, _V, _I, _V, _V, _V], C.c_int),
     'sma_warp_occlude_fwd': ([_V, _L, _I, _I, _I, _I, _V, _V, _I, _I, _V, _V], C.c_int),
     'sma_resize_bilinear_ac': ([_V, _I, _I, _I, _I, _L, _I, _V, _I, _I, _L, _I, _V], C.c_int),
-    'sma_mha_fwd': ([_V, _I, _V, _I, _V, _I, _L, _I, _I, _I, _I, _I, _F, _V, _V, _I, _V], C.c_int),
+    'sma_mha_fwd': ([_V, _I, _V, _I, _V, _I, _L, _I, _I, _I, _I, _I, _F, _V, _V, _I, _I, _V], C.c_int),
     'sma_vq_lookup_fwd': ([_V, _I, _I, _V, _I, _V, _V, _V, _V], C.c_int),
     'sma_antialias_down4': ([_V, _I, _I, _I, _I, _V, _V, _I, _V], C.c_int),
     'sma_avgpool2': ([_V, _I, _I, _I, _I, _V, _I, _V], C.c_int),

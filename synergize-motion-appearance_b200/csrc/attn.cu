@@ -222,14 +222,21 @@ int launch_mha(const float* q, int ldq, const float* k, int ldk, const float* v,
 
 }  // namespace
 
+int sma_mha_tc_try(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv, long long kv_bs, int B, int L, int S, int heads, int D,
+                   float scale, const uint8_t* mask, float* out, int ldo, cudaStream_t st);   // attn_tc.cu
+
 extern "C" int sma_mha_fwd(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv, int64_t kv_bstride, int B, int L, int S,
-                           int heads, int D, float scale, const uint8_t* key_mask, float* out, int ldo, sma_stream_t stream) {
+                           int heads, int D, float scale, const uint8_t* key_mask, float* out, int ldo, int flags, sma_stream_t stream) {
   if (!q || !k || !v || !out || B <= 0 || L <= 0 || S <= 0 || heads <= 0) return SMA_ERR_BAD_ARG;
   if ((ldq | ldk | ldv | ldo) & 3) return SMA_ERR_UNSUPPORTED;
   if ((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(v) | reinterpret_cast<uintptr_t>(out)) & 15)
     return SMA_ERR_UNSUPPORTED;
   if (kv_bstride & 3) return SMA_ERR_UNSUPPORTED;
   cudaStream_t st = as_stream(stream);
+  if (!(flags & 1)) {
+    int r = sma_mha_tc_try(q, ldq, k, ldk, v, ldv, kv_bstride, B, L, S, heads, D, scale, key_mask, out, ldo, st);
+    if (r != SMA_ERR_UNSUPPORTED) return r;
+  }
   if (D == 4) {
     mha_d4_kernel<<<dim3(cdiv(L, 128), heads, B), 128, 0, st>>>(q, ldq, k, ldk, v, ldv, kv_bstride, L, S, scale, key_mask, out, ldo);
     SMA_LAUNCH_CHECK();

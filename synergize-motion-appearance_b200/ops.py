@@ -278,7 +278,7 @@ def resize_ac(x: torch.Tensor, size: Tuple[int, int], out: Optional[torch.Tensor
 
 
 def mha(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, key_mask: Optional[torch.Tensor] = None,
-        scale: Optional[float] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        scale: Optional[float] = None, out: Optional[torch.Tensor] = None, exact: bool = False) -> torch.Tensor:
     """q (B,L,E-view) ; k,v (B,S,E-view) or (S,E-view) shared by all frames.  Views may be column slices."""
     lib = _lib.load()
     B, L, E = q.shape
@@ -299,7 +299,7 @@ def mha(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, key_mask:
         assert key_mask.dtype == torch.uint8 and key_mask.is_contiguous() and key_mask.numel() == B * S
     with _Prof('mha', 4.0 * B * L * S * E, 4.0 * (2 * B * L * E + 2 * (B if kvbs else 1) * S * E), f'mha B{B} L{L} S{S} h{heads} D{D}'):
         check(lib.sma_mha_fwd(q.data_ptr(), q.stride(1), k.data_ptr(), ldk, v.data_ptr(), ldv, kvbs, B, L, S, heads, D, scale,
-                              _ptr(key_mask), out.data_ptr(), out.stride(1), _stream()), f'sma_mha_fwd D={D}')
+                              _ptr(key_mask), out.data_ptr(), out.stride(1), 1 if (exact or not USE_TF32X3) else 0, _stream()), f'sma_mha_fwd D={D}')
     return out
 
 
