@@ -132,7 +132,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--frames', type=int, default=64, help='driving frames per GPU per step (configs[1]: 64)')
-    ap.add_argument('--batch', type=int, default=16, help='driving frames per micro-batch')
+    ap.add_argument('--batch', type=int, default=64, help='driving frames per micro-batch')
     ap.add_argument('--ref-frames', type=int, default=12, help='frames per step of the CPU reference / cpu_baseline sample')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-roofline', action='store_true')
@@ -203,7 +203,10 @@ def main():
         return float(ms.item())
 
     if args.ncu:
-        step_device(); torch.cuda.synchronize(); step_device(); torch.cuda.synchronize()
+        step_device(); torch.cuda.synchronize()
+        torch.cuda.profiler.start()          # ncu --profile-from-start off: exactly one step is profiled
+        step_device(); torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
         return
     for _ in range(Wm):
         step_device()

@@ -73,9 +73,10 @@ typedef struct sma_conv_desc {
                                     2: tcgen05 single-pass TF32 (only where the 1e-3 parity budget allows it) */
   const float* w_tc;             /* tensor-core weight image from sma_pack_conv_weight_tc (NULL: CUDA-core kernel only) */
   int tc_variant;                /* 0: library picks (persistent halo kernel for stride-1, gather kernel otherwise); 1: force the gather kernel */
+  int kernel_used;               /* OUT: 0 CUDA-core FFMA kernel, 1 tcgen05 gather kernel, 2 tcgen05 persistent halo kernel */
 } sma_conv_desc;
 
-int sma_conv2d_fwd(const sma_conv_desc* d, sma_stream_t stream);
+int sma_conv2d_fwd(sma_conv_desc* d, sma_stream_t stream);
 /* OIHW (or (N,K) Linear) fp32 weight on the device -> packed [kh*kw*Cin][ldw] ; optional BatchNorm(eval)
  * fold: w' = w*g/sqrt(var+eps), b' = (b-mean)*g/sqrt(var+eps)+beta (sync_batchnorm/batchnorm.py:48-53). */
 int sma_pack_conv_weight(const float* w_oihw, const float* bias, int Cout, int Cin, int kh, int kw,

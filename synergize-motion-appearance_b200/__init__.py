@@ -1,7 +1,7 @@
 """B200-native per-driving-frame talking-head generator (drop-in for the hot path of
 ShaelynZ/synergize-motion-appearance).  The directory name contains '-', so import it through
 `importlib.import_module('synergize-motion-appearance_b200')` or the `sma_b200` alias at the repo root."""
-from . import _lib, ops  # noqa: F401
+from . import _lib, ops, dist  # noqa: F401
 from .registry import ARCH_REGISTRY, build_network  # noqa: F401
 from .archs import motion_estimator_arch, appmotioncodebook_arch  # noqa: F401
 from .archs.motion_estimator_arch import Motion_Estimator_keypoint_aware, KPDetector, DenseMotionNetwork  # noqa: F401
@@ -9,4 +9,4 @@ from .archs.appmotioncodebook_arch import AppMotionCompFormer  # noqa: F401
 from .animate import make_animation, make_animation_model, normalize_kp, ClipAnimator  # noqa: F401
 
 __all__ = ['ARCH_REGISTRY', 'build_network', 'Motion_Estimator_keypoint_aware', 'KPDetector', 'DenseMotionNetwork',
-           'AppMotionCompFormer', 'make_animation', 'make_animation_model', 'normalize_kp', 'ClipAnimator', 'ops']
+           'AppMotionCompFormer', 'make_animation', 'make_animation_model', 'normalize_kp', 'ClipAnimator', 'ops', 'dist']

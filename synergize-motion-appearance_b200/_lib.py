@@ -22,7 +22,7 @@ class ConvDesc(C.Structure):
         ('y', C.c_void_p), ('Ho', C.c_int), ('Wo', C.c_int), ('out_bstride', c_i64), ('out_ld', C.c_int),
         ('act', C.c_int),
         ('res', C.c_void_p), ('res_bstride', c_i64), ('res_ld', C.c_int),
-        ('d2s', C.c_int), ('out_nchw', C.c_int), ('tf32x3', C.c_int), ('w_tc', C.c_void_p), ('tc_variant', C.c_int),
+        ('d2s', C.c_int), ('out_nchw', C.c_int), ('tf32x3', C.c_int), ('w_tc', C.c_void_p), ('tc_variant', C.c_int), ('kernel_used', C.c_int),
     ]
 
 

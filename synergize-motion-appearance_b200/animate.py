@@ -95,7 +95,7 @@ class ClipAnimator:
 
 
 def make_animation(source_image, driving_video: Sequence[torch.Tensor], net_g, motion_estimator, relative=True,
-                   adapt_movement_scale=True, cpu=False, batch: int = 16, w: float = 1.0, bgr: bool = False):
+                   adapt_movement_scale=True, cpu=False, batch: int = 64, w: float = 1.0, bgr: bool = False):
     """Same signature/returns as demo.make_animation (demo.py:103-134); `cpu=True` raises (no CPU path)."""
     if cpu:
         raise RuntimeError('the B200 path has no CPU fallback; use the reference for cpu=True')
@@ -120,7 +120,7 @@ def make_animation(source_image, driving_video: Sequence[torch.Tensor], net_g, m
 
 
 def make_animation_model(model_opt: dict, net_g, motion_estimator, source_img, driving: List[torch.Tensor], cpu=False,
-                         batch: int = 16):
+                         batch: int = 64):
     """Twin of AppMotionCompModel.make_animation (appmotioncomp_model.py:607-639): batch-1 NCHW tensors in a list,
     options read from opt['val'] ('relative', 'adapt_scale', 'w'), BGR output."""
     val = model_opt.get('val', {})

@@ -235,11 +235,17 @@ class AppMotionCompFormer(ParamModule):
                 [T[f'fuse_convs_dict.{s}.{b}.0.weight'] for b in ('scale', 'shift')],
                 [T[f'fuse_convs_dict.{s}.{b}.0.bias'] for b in ('scale', 'shift')])
             pc(f'fuse_convs_dict.{s}.scale.2'); pc(f'fuse_convs_dict.{s}.shift.2'); pc(f'fuse_ms_dict.{s}')
-        pc('motion_emb.0'); pc('motion_emb.1.conv'); pres('motion_emb.2', self.Em, self.Em)
-        for n in ('BasicMotionEncoder.convc1', 'BasicMotionEncoder.convc2', 'BasicMotionEncoder.convf1',
-                  'BasicMotionEncoder.convf2', 'BasicMotionEncoder.conv', 'refine.convc1', 'refine.conv2', 'refine.convo2',
+        # the 2-channel pixel-unit flow is kept in a 32-channel zero-padded buffer: both convs reading it run on the tensor cores
+        for n in ('motion_emb.0', 'BasicMotionEncoder.convf1'):
+            W[n] = ops.pack_conv(T[n + '.weight'], T[n + '.bias'], pad_cin=32)
+        pc('motion_emb.1.conv'); pres('motion_emb.2', self.Em, self.Em)
+        for n in ('BasicMotionEncoder.convc1', 'BasicMotionEncoder.convc2',
+                  'BasicMotionEncoder.convf2', 'BasicMotionEncoder.conv', 'refine.convc1',
                   'driving_kp_enc', 'motion_query_enc_1', 'motion_query_enc_2'):
             pc(n)
+        # the two 3x3 output convs of RefineFlow read different halves of one buffer: one block-diagonal launch
+        W['refine.conv2o2'] = ops.pack_conv_blockdiag([T['refine.conv2.weight'], T['refine.convo2.weight']],
+                                                      [T['refine.conv2.bias'], T['refine.convo2.bias']])
         W['refine.conv1o1'] = ops.pack_conv_cat([T['refine.conv1.weight'], T['refine.convo1.weight']],
                                                 [T['refine.conv1.bias'], T['refine.convo1.bias']])
         for i, s in enumerate(self.SCALES):
@@ -360,7 +366,9 @@ class AppMotionCompFormer(ParamModule):
         dev = m_prev.device
         Em = self.Em
         z = torch.empty((B, 64, 64, 256), device=dev, dtype=torch.float32)        # [BME out 126 | flow_px 2 | refine.convc1 128]
-        flow_px = ops.flow_to_px(m_prev, z[..., 126:128])
+        ops.flow_to_px(m_prev, z[..., 126:128])
+        flow_px = torch.zeros((B, 64, 64, 32), device=dev, dtype=torch.float32)      # [flow_px 2 | zero padding]
+        ops.flow_to_px(m_prev, flow_px[..., 0:2])
         mf = ops.conv2d(flow_px, W['motion_emb.0'], pad=1)
         mf = ops.conv2d(mf, W['motion_emb.1.conv'], stride=2, pad_tl=(0, 0), out_hw=(32, 32))
         ops_out = qcat[..., :Em]
@@ -381,8 +389,7 @@ class AppMotionCompFormer(ParamModule):
         ops.conv2d(ctx, W['refine.convc1'], pad=1, act='relu', out=z[..., 128:])
         f = ops.conv2d(z, W['refine.conv1o1'], pad=1, act='relu')                 # [flow branch 128 | occlusion branch 128]
         r = torch.empty((B, 64, 64, 4), device=dev, dtype=torch.float32)
-        ops.conv2d(f[..., :128], W['refine.conv2'], pad=1, out=r[..., 0:2])
-        ops.conv2d(f[..., 128:], W['refine.convo2'], pad=1, out=r[..., 2:3])
+        ops.conv2d(f, W['refine.conv2o2'], pad=1, out=r[..., 0:3])                # [delta-flow 2 | delta-occlusion 1]
         return ops.flow_update(m_prev, occ_prev, r) + (r,)
 
     # ------------------------------------------------------------------------------------------

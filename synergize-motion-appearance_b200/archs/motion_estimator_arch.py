@@ -111,7 +111,9 @@ class KPDetector(ParamModule):
         if self._packed is None:
             T = self.tensors()
             W = self.plan.pack(T, 'predictor')
-            W['heads'] = ops.pack_conv_cat([T['kp.weight'], T['jacobian.weight']], [T['kp.bias'], T['jacobian.bias']])
+            # the 35-channel hourglass output lives in a 64-channel zero-padded buffer so that the 7x7 heads run on the tensor cores
+            self._cpad = (self.plan.out_filters + 31) // 32 * 32
+            W['heads'] = ops.pack_conv_cat([T['kp.weight'], T['jacobian.weight']], [T['kp.bias'], T['jacobian.bias']], pad_cin=self._cpad)
             W['k13'] = T['down.weight'][0, 0].contiguous()
             self._packed = W
         return self._packed
@@ -121,10 +123,11 @@ class KPDetector(ParamModule):
         W = self._weights()
         x = x.contiguous().float()
         B, _, H, Wd = x.shape
-        cat0 = torch.empty((B, H // 4, Wd // 4, self.plan.out_filters), device=x.device, dtype=torch.float32)
+        full = torch.zeros((B, H // 4, Wd // 4, self._cpad), device=x.device, dtype=torch.float32)
+        cat0 = full[..., :self.plan.out_filters]
         ops.antialias_down4(x, W['k13'], out=cat0[..., self.plan.out_filters - self.num_channels:])
-        feat = self.plan.run(W, 'predictor', cat0)
-        pred = ops.conv2d(feat, W['heads'], pad=0)                       # (B,58,58,5K): kp logits | jacobian maps
+        self.plan.run(W, 'predictor', cat0)
+        pred = ops.conv2d(full, W['heads'], pad=0)                       # (B,58,58,5K): kp logits | jacobian maps
         value, jac = ops.kp_head(pred, self.num_kp, float(self.temperature))
         return {'value': value, 'jacobian': jac}
 

@@ -240,9 +240,9 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, const float* __r
 
 }  // namespace
 
-int sma_conv2d_tc_try(const sma_conv_desc* d, cudaStream_t st);   // conv_tc.cu ; returns SMA_ERR_UNSUPPORTED when not applicable
+int sma_conv2d_tc_try(sma_conv_desc* d, cudaStream_t st);   // conv_tc.cu ; returns SMA_ERR_UNSUPPORTED when not applicable
 
-extern "C" int sma_conv2d_fwd(const sma_conv_desc* d, sma_stream_t stream) {
+extern "C" int sma_conv2d_fwd(sma_conv_desc* d, sma_stream_t stream) {
   if (!d || !d->x || !d->w || !d->y) return SMA_ERR_BAD_ARG;
   if (d->B <= 0 || d->Hi <= 0 || d->Wi <= 0 || d->Cin <= 0 || d->Cout <= 0 || d->kh <= 0 || d->kw <= 0 || d->stride <= 0 ||
       d->Ho <= 0 || d->Wo <= 0 || d->ldw < d->Cout || (d->ldw & 3))
@@ -256,6 +256,7 @@ extern "C" int sma_conv2d_fwd(const sma_conv_desc* d, sma_stream_t stream) {
     int r = sma_conv2d_tc_try(d, st);
     if (r != SMA_ERR_UNSUPPORTED) return r;
   }
+  d->kernel_used = 0;
   ConvP p;
   p.x = d->x; p.w = d->w; p.bias = d->bias; p.pre_scale = d->pre_scale; p.pre_shift = d->pre_shift; p.res = d->res; p.y = d->y;
   p.in_bs = d->in_bstride; p.out_bs = d->out_bstride; p.res_bs = d->res_bstride;

@@ -646,7 +646,7 @@ static int conv_tc2_try(const sma_conv_desc* d, cudaStream_t st) {
 }
 
 // returns SMA_ERR_UNSUPPORTED when the shape / layout is not eligible (the caller then uses the CUDA-core kernel)
-int sma_conv2d_tc_try(const sma_conv_desc* d, cudaStream_t st) {
+int sma_conv2d_tc_try(sma_conv_desc* d, cudaStream_t st) {
   if (!d->w_tc || d->out_nchw) return SMA_ERR_UNSUPPORTED;
   if ((d->Cin % KC) || (d->in_ld & 3) || (d->in_bstride & 3) || (reinterpret_cast<uintptr_t>(d->x) & 15) || (reinterpret_cast<uintptr_t>(d->w_tc) & 15))
     return SMA_ERR_UNSUPPORTED;
@@ -655,7 +655,7 @@ int sma_conv2d_tc_try(const sma_conv_desc* d, cudaStream_t st) {
   if (M < 64) return SMA_ERR_UNSUPPORTED;
   if (!(d->tc_variant & 1)) {
     int r2 = conv_tc2_try(d, st);
-    if (r2 != SMA_ERR_UNSUPPORTED) return r2;
+    if (r2 != SMA_ERR_UNSUPPORTED) { d->kernel_used = 2; return r2; }
   }
   TcP p;
   p.x = d->x; p.wtc = d->w_tc; p.bias = d->bias; p.pre_scale = d->pre_scale; p.pre_shift = d->pre_shift; p.res = d->res; p.y = d->y;
@@ -679,6 +679,7 @@ int sma_conv2d_tc_try(const sma_conv_desc* d, cudaStream_t st) {
     configured = SMEM_DYN_MAX;
   }
   dim3 grid((unsigned)((M + BM - 1) / BM), (unsigned)ntiles);
+  d->kernel_used = 1;
   conv_tc_kernel<<<grid, 192, smem, st>>>(p);
   SMA_LAUNCH_CHECK();
   return SMA_OK;

@@ -79,12 +79,18 @@ class ConvW:
     kh: int
     kw: int
     w_tc: Optional[torch.Tensor] = None      # tensor-core image (sma_pack_conv_weight_tc); None -> CUDA-core kernel only
+    _slices: Optional[dict] = None           # cache of cols() results (their tensor-core images are packed once)
 
     def cols(self, start: int, n: int) -> 'ConvW':
-        """Output-column slice (free for the CUDA-core layout: row-major [K][ldw]; the tensor-core image is re-packed)."""
+        """Output-column slice (free for the CUDA-core layout: row-major [K][ldw]; the tensor-core image is re-packed once)."""
         assert start % 4 == 0
-        cw = ConvW(self.w[:, start:], None if self.bias is None else self.bias[start:start + n], n, self.Cin, self.kh, self.kw)
-        cw.w_tc = _pack_tc(cw)
+        if self._slices is None:
+            self._slices = {}
+        cw = self._slices.get((start, n))
+        if cw is None:
+            cw = ConvW(self.w[:, start:], None if self.bias is None else self.bias[start:start + n], n, self.Cin, self.kh, self.kw)
+            cw.w_tc = _pack_tc(cw)
+            self._slices[(start, n)] = cw
         return cw
 
     def as_patch(self, p: int) -> 'ConvW':
@@ -107,12 +113,18 @@ def _pack_tc(cw: 'ConvW') -> Optional[torch.Tensor]:
     return out
 
 
-def pack_conv(weight: torch.Tensor, bias: Optional[torch.Tensor], bn: Optional[dict] = None) -> ConvW:
-    """OIHW conv weight or (N,K) linear weight -> ConvW, optionally folding an eval-mode BatchNorm."""
+def pack_conv(weight: torch.Tensor, bias: Optional[torch.Tensor], bn: Optional[dict] = None, pad_cin: int = 0) -> ConvW:
+    """OIHW conv weight or (N,K) linear weight -> ConvW, optionally folding an eval-mode BatchNorm.
+    `pad_cin`: zero-pad the input channels to this count (the caller feeds a zero-padded activation buffer) so that
+    narrow inputs (2, 35 channels) become eligible for the tensor-core kernels (Cin % 32 == 0)."""
     lib = _lib.load()
     w = weight.detach().float().contiguous()
     if w.dim() == 2:
         w = w.view(w.shape[0], w.shape[1], 1, 1)
+    if pad_cin and pad_cin > w.shape[1]:
+        wp_ = torch.zeros((w.shape[0], pad_cin, w.shape[2], w.shape[3]), device=w.device, dtype=torch.float32)
+        wp_[:, :w.shape[1]] = w
+        w = wp_
     Cout, Cin, kh, kw = w.shape
     ldw = (Cout + 3) // 4 * 4
     wp = torch.empty((kh * kw * Cin, ldw), device=w.device, dtype=torch.float32)
@@ -131,16 +143,30 @@ def pack_conv(weight: torch.Tensor, bias: Optional[torch.Tensor], bn: Optional[d
     return cw
 
 
-def pack_conv_cat(weights, biases) -> ConvW:
+def pack_conv_cat(weights, biases, pad_cin: int = 0) -> ConvW:
     """Several convs over the same input fused along the output dim (q|k|v, scale.0|shift.0, kp|jacobian ...)."""
     w = torch.cat([x.detach().float() for x in weights], dim=0)
     b = torch.cat([x.detach().float() for x in biases], dim=0)
-    return pack_conv(w, b)
+    return pack_conv(w, b, pad_cin=pad_cin)
+
+
+def pack_conv_blockdiag(weights, biases) -> ConvW:
+    """Sibling convs over *different* channel ranges of one concat buffer fused into one launch: conv i reads input
+    channels [sum(Cin_<i), sum(Cin_<=i)) and writes output columns [sum(Cout_<i), ...)."""
+    cin = sum(int(w.shape[1]) for w in weights); cout = sum(int(w.shape[0]) for w in weights)
+    kh, kw = weights[0].shape[2], weights[0].shape[3]
+    big = torch.zeros((cout, cin, kh, kw), device=weights[0].device, dtype=torch.float32)
+    o = c = 0
+    for w in weights:
+        big[o:o + w.shape[0], c:c + w.shape[1]] = w.detach().float()
+        o += w.shape[0]; c += w.shape[1]
+    return pack_conv(big, torch.cat([x.detach().float() for x in biases], dim=0))
 
 
 USE_TF32X3 = True        # let sma_conv2d_fwd pick the tcgen05 kernel where the shape allows
 ALLOW_TF32_1PASS = True  # honour `fast=True` requests (single-pass TF32)
 TC_VARIANT = 0           # 0: library picks the tensor-core kernel variant; 1: force the gather kernel (tests)
+LAST_CONV_KERNEL = -1    # which kernel the last conv2d ran on: 0 CUDA-core, 1 tcgen05 gather, 2 tcgen05 persistent halo
 
 
 def conv2d(x: torch.Tensor, cw: ConvW, *, stride: int = 1, pad: int = 0, pad_tl: Optional[Tuple[int, int]] = None,
@@ -193,11 +219,15 @@ def conv2d(x: torch.Tensor, cw: ConvW, *, stride: int = 1, pad: int = 0, pad_tl:
     d.tf32x3 = 0 if (exact or not USE_TF32X3 or cw.w_tc is None) else (2 if (fast and ALLOW_TF32_1PASS) else 1)
     d.w_tc = _ptr(cw.w_tc)
     d.tc_variant = TC_VARIANT
+    d.kernel_used = -1
     K = cw.kh * cw.kw * Cin
     with _Prof('conv', 2.0 * B * Ho * Wo * K * cw.Cout,
                4.0 * (B * Hi * Wi * Cin + B * Ho * Wo * cw.Cout * (2 if res is not None else 1) + K * cw.Cout),
-               f'conv B{B} {Hi}x{Wi} Cin{Cin} Cout{cw.Cout} k{cw.kh} s{stride}{" up" if upsample2 else ""}{" pre" if pre is not None else ""} tc{d.tf32x3 if d.w_tc else 0}'):
+               f'conv B{B} {Hi}x{Wi} Cin{Cin} Cout{cw.Cout} k{cw.kh} s{stride}{" up" if upsample2 else ""}{" pre" if pre is not None else ""}') as pr:
         check(lib.sma_conv2d_fwd(C.byref(d), _stream()), f'sma_conv2d_fwd Cin={Cin} Cout={cw.Cout} k={cw.kh}x{cw.kw}')
+        pr.label += (' simt', ' tc-gather', ' tc-halo')[d.kernel_used] + ('' if d.tf32x3 != 2 else ' 1pass')
+    global LAST_CONV_KERNEL
+    LAST_CONV_KERNEL = d.kernel_used
     return out
 
 
