@@ -273,13 +273,13 @@ class AppMotionCompFormer(ParamModule):
     def _gn(self, name, x):
         return ops.groupnorm_stats(x, self._T[name + '.weight'], self._T[name + '.bias'], 32, 1e-6)
 
-    def _res(self, name, x, cin, cout, out=None):
+    def _res(self, name, x, cin, cout, out=None, fast=False):
         W = self._packed
         s1, h1 = self._gn(name + '.norm1', x)
-        h = ops.conv2d(x, W[name + '.conv1'], pad=1, pre=(s1, h1, 'swish'))
+        h = ops.conv2d(x, W[name + '.conv1'], pad=1, pre=(s1, h1, 'swish'), fast=fast)
         s2, h2 = self._gn(name + '.norm2', h)
-        skip = x if cin == cout else ops.conv2d(x, W[name + '.conv_out'])
-        return ops.conv2d(h, W[name + '.conv2'], pad=1, pre=(s2, h2, 'swish'), res=skip, out=out)
+        skip = x if cin == cout else ops.conv2d(x, W[name + '.conv_out'], fast=fast)
+        return ops.conv2d(h, W[name + '.conv2'], pad=1, pre=(s2, h2, 'swish'), res=skip, out=out, fast=fast)
 
     def _attn(self, name, x, out=None):
         W = self._packed
@@ -339,23 +339,23 @@ class AppMotionCompFormer(ParamModule):
     # ------------------------------------------------------------------------------------------
     # codebook transformer layer (appmotioncodebook_arch.py:88-126) on (B,1024,E) tokens
     # ------------------------------------------------------------------------------------------
-    def _transformer(self, name, t, E, n_ctx, pos, key_mask=None):
+    def _transformer(self, name, t, E, n_ctx, pos, key_mask=None, fast=False):
         W, T = self._packed, self._T
         B = t.shape[0]
         u, uq = ops.layernorm(t, T[name + '.norm1.weight'], T[name + '.norm1.bias'], pos)
         qkv = torch.empty((B, 1024, 3 * E), device=t.device, dtype=torch.float32)
-        ops.linear(uq, W[name + '.self_in'].cols(0, 2 * E), out=qkv[..., :2 * E])
-        ops.linear(u, W[name + '.self_in'].cols(2 * E, E), out=qkv[..., 2 * E:])
+        ops.linear(uq, W[name + '.self_in'].cols(0, 2 * E), out=qkv[..., :2 * E], fast=fast)
+        ops.linear(u, W[name + '.self_in'].cols(2 * E, E), out=qkv[..., 2 * E:], fast=fast)
         a = ops.mha(qkv[..., :E], qkv[..., E:2 * E], qkv[..., 2 * E:], heads=self.n_head, key_mask=key_mask)
-        t = ops.linear(a, W[name + '.self_out'], res=t)
+        t = ops.linear(a, W[name + '.self_out'], res=t, fast=fast)
         _, uq = ops.layernorm(t, T[name + '.norm2.weight'], T[name + '.norm2.bias'], pos, want_y=False)
-        qc = ops.linear(uq, W[name + '.cross_in'].cols(0, E))
+        qc = ops.linear(uq, W[name + '.cross_in'].cols(0, E), fast=fast)
         kv = W[name + '.ctx_kv']
         a = ops.mha(qc, kv[:n_ctx, :E], kv[:n_ctx, E:], heads=self.n_head)
-        t = ops.linear(a, W[name + '.cross_out'], res=t)
+        t = ops.linear(a, W[name + '.cross_out'], res=t, fast=fast)
         u, _ = ops.layernorm(t, T[name + '.norm3.weight'], T[name + '.norm3.bias'])
-        f = ops.conv2d(u.view(B, 32, 32, E), W[name + '.conv1'], pad=1, act='gelu')
-        return ops.conv2d(f, W[name + '.conv2'], pad=1, res=t.view(B, 32, 32, E)).view(B, 1024, E)
+        f = ops.conv2d(u.view(B, 32, 32, E), W[name + '.conv1'], pad=1, act='gelu', fast=fast)
+        return ops.conv2d(f, W[name + '.conv2'], pad=1, res=t.view(B, 32, 32, E), fast=fast).view(B, 1024, E)
 
     # ------------------------------------------------------------------------------------------
     # stage 3m: motion codebook compensation (appmotioncodebook_arch.py:373-427, 129-168)
@@ -365,31 +365,32 @@ class AppMotionCompFormer(ParamModule):
         B = m_prev.shape[0]
         dev = m_prev.device
         Em = self.Em
+        fs = ops.fast('s3m')
         z = torch.empty((B, 64, 64, 256), device=dev, dtype=torch.float32)        # [BME out 126 | flow_px 2 | refine.convc1 128]
         ops.flow_to_px(m_prev, z[..., 126:128])
         flow_px = torch.zeros((B, 64, 64, 32), device=dev, dtype=torch.float32)      # [flow_px 2 | zero padding]
         ops.flow_to_px(m_prev, flow_px[..., 0:2])
-        mf = ops.conv2d(flow_px, W['motion_emb.0'], pad=1)
-        mf = ops.conv2d(mf, W['motion_emb.1.conv'], stride=2, pad_tl=(0, 0), out_hw=(32, 32))
+        mf = ops.conv2d(flow_px, W['motion_emb.0'], pad=1, fast=fs)
+        mf = ops.conv2d(mf, W['motion_emb.1.conv'], stride=2, pad_tl=(0, 0), out_hw=(32, 32), fast=fs)
         ops_out = qcat[..., :Em]
-        self._res('motion_emb.2', mf, Em, Em, out=ops_out)                        # qcat = [m_feat | query_feat]
-        t = ops.conv2d(qcat, W['motion_query_enc_2']).view(B, 1024, Em)
+        self._res('motion_emb.2', mf, Em, Em, out=ops_out, fast=fs)                        # qcat = [m_feat | query_feat]
+        t = ops.conv2d(qcat, W['motion_query_enc_2'], fast=fs).view(B, 1024, Em)
         for i in range(2):
-            t = self._transformer(f'motion_block.{i}', t, Em, 256 * (int(math.log2(s)) - 4), T['position_emb_motion'])
+            t = self._transformer(f'motion_block.{i}', t, Em, 256 * (int(math.log2(s)) - 4), T['position_emb_motion'], fast=fs)
         mfeat = ops.resize_ac(t.view(B, 32, 32, Em), (64, 64))
         cf = torch.empty((B, 64, 64, 160), device=dev, dtype=torch.float32)       # [cor 96 | flo 64]
-        cor = ops.conv2d(mfeat, W['BasicMotionEncoder.convc1'], act='relu')
-        ops.conv2d(cor, W['BasicMotionEncoder.convc2'], pad=1, act='relu', out=cf[..., :96])
-        flo = ops.conv2d(flow_px, W['BasicMotionEncoder.convf1'], pad=3, act='relu')
-        ops.conv2d(flo, W['BasicMotionEncoder.convf2'], pad=1, act='relu', out=cf[..., 96:])
-        ops.conv2d(cf, W['BasicMotionEncoder.conv'], pad=1, act='relu', out=z[..., :126])
-        ctx = ops.conv2d(warp0, W[f'to_context.{int(math.log2(s)) - 5}'], act='relu')
+        cor = ops.conv2d(mfeat, W['BasicMotionEncoder.convc1'], act='relu', fast=fs)
+        ops.conv2d(cor, W['BasicMotionEncoder.convc2'], pad=1, act='relu', out=cf[..., :96], fast=fs)
+        flo = ops.conv2d(flow_px, W['BasicMotionEncoder.convf1'], pad=3, act='relu', fast=fs)
+        ops.conv2d(flo, W['BasicMotionEncoder.convf2'], pad=1, act='relu', out=cf[..., 96:], fast=fs)
+        ops.conv2d(cf, W['BasicMotionEncoder.conv'], pad=1, act='relu', out=z[..., :126], fast=fs)
+        ctx = ops.conv2d(warp0, W[f'to_context.{int(math.log2(s)) - 5}'], act='relu', fast=fs)
         if s != 64:
             ctx = ops.resize_ac(ctx, (64, 64))
-        ops.conv2d(ctx, W['refine.convc1'], pad=1, act='relu', out=z[..., 128:])
-        f = ops.conv2d(z, W['refine.conv1o1'], pad=1, act='relu')                 # [flow branch 128 | occlusion branch 128]
+        ops.conv2d(ctx, W['refine.convc1'], pad=1, act='relu', out=z[..., 128:], fast=fs)
+        f = ops.conv2d(z, W['refine.conv1o1'], pad=1, act='relu', fast=fs)                 # [flow branch 128 | occlusion branch 128]
         r = torch.empty((B, 64, 64, 4), device=dev, dtype=torch.float32)
-        ops.conv2d(f, W['refine.conv2o2'], pad=1, out=r[..., 0:3])                # [delta-flow 2 | delta-occlusion 1]
+        ops.conv2d(f, W['refine.conv2o2'], pad=1, out=r[..., 0:3], fast=fs)                # [delta-flow 2 | delta-occlusion 1]
         return ops.flow_update(m_prev, occ_prev, r) + (r,)
 
     # ------------------------------------------------------------------------------------------

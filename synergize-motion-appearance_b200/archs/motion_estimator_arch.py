@@ -54,7 +54,7 @@ class _HourglassPlan:
                 out[p] = ops.pack_conv(T[p + '.conv.weight'], T[p + '.conv.bias'], bn)
         return out
 
-    def run(self, W: dict, prefix: str, cat0: torch.Tensor) -> torch.Tensor:
+    def run(self, W: dict, prefix: str, cat0: torch.Tensor, fast: bool = False) -> torch.Tensor:
         """cat0: (B,S,S,e+cin) buffer whose last `cin` channels already hold the hourglass input.
         Returns cat0 with the first `e` channels filled by the last up-block (== the reference's final
         torch.cat([out, skip]))."""
@@ -70,7 +70,7 @@ class _HourglassPlan:
         x = cat0[..., cat0.shape[-1] - self.cin:]
         for i, (ci, co) in enumerate(self.enc):
             s = S >> i
-            y = ops.conv2d(x, W[f'{prefix}.encoder.down_blocks.{i}'], pad=1, act='relu')
+            y = ops.conv2d(x, W[f'{prefix}.encoder.down_blocks.{i}'], pad=1, act='relu', fast=fast)
             if i + 1 < self.nb:
                 dst = cats[i + 1][..., cats[i + 1].shape[-1] - co:]
             else:
@@ -79,7 +79,7 @@ class _HourglassPlan:
         for j, (ci, co) in enumerate(self.dec):
             lvl = self.nb - 1 - j
             dst = cats[lvl][..., :co]
-            ops.conv2d(x, W[f'{prefix}.decoder.up_blocks.{j}'], pad=1, act='relu', upsample2=True, out=dst)
+            ops.conv2d(x, W[f'{prefix}.decoder.up_blocks.{j}'], pad=1, act='relu', upsample2=True, out=dst, fast=fast)
             x = cats[lvl]
         return x
 
@@ -126,8 +126,8 @@ class KPDetector(ParamModule):
         full = torch.zeros((B, H // 4, Wd // 4, self._cpad), device=x.device, dtype=torch.float32)
         cat0 = full[..., :self.plan.out_filters]
         ops.antialias_down4(x, W['k13'], out=cat0[..., self.plan.out_filters - self.num_channels:])
-        self.plan.run(W, 'predictor', cat0)
-        pred = ops.conv2d(full, W['heads'], pad=0)                       # (B,58,58,5K): kp logits | jacobian maps
+        self.plan.run(W, 'predictor', cat0, fast=ops.fast('kp'))
+        pred = ops.conv2d(full, W['heads'], pad=0, fast=ops.fast('kp'))                       # (B,58,58,5K): kp logits | jacobian maps
         value, jac = ops.kp_head(pred, self.num_kp, float(self.temperature))
         return {'value': value, 'jacobian': jac}
 
@@ -190,8 +190,8 @@ class DenseMotionNetwork(ParamModule):
         cin = self.plan.cin
         cat0 = torch.empty((B, h, w, self.plan.out_filters), device=src64.device, dtype=torch.float32)
         heat = ops.dense_motion_prep(src64, sv, sj, dv, dj, cat0[..., self.plan.out_filters - cin:], self.kp_variance)
-        feat = self.plan.run(W, 'hourglass', cat0)
-        logits = ops.conv2d(feat, W['heads'], pad=3)                     # (B,64,64,K+2): mask logits | occlusion logit
+        feat = self.plan.run(W, 'hourglass', cat0, fast=ops.fast('s1'))
+        logits = ops.conv2d(feat, W['heads'], pad=3, fast=ops.fast('s1'))                     # (B,64,64,K+2): mask logits | occlusion logit
         deform, occ, _ = ops.dense_motion_head(logits, sv, sj, dv, dj)
         return {'deformation': deform, 'occlusion_map': occ.view(B, 1, h, w),
                 'driving_kp_heatmap': heat.permute(0, 3, 1, 2), '_driving_kp_heatmap_nhwc': heat,

@@ -16,12 +16,15 @@ dm = {'deformation': golden['deformation1'].cuda(), 'occlusion_map': golden['occ
       'driving_kp_heatmap': O.gaussian_heatmaps(golden['kp_norm1_value'], 64, 64).cuda()}
 for mode in sys.argv[1:] or ['exact', 'tc']:
     S.ops.USE_TF32X3 = mode != 'exact'
+    S.ops.FAST_STAGES = set(mode.split('+')[1:])     # e.g. tc+kp+s1+s3m
     g._src_cache = None
     out = g(src.unsqueeze(0).cuda(), dm, w=1, inference=True)
     d = (out['out'].cpu() - golden['out1']).abs()
     occ = max(float((a.cpu() - b).abs().max()) for a, b in zip(out['out_occ'], golden['out_occ1']))
     mo = max(float((a.cpu() - b).abs().max()) for a, b in zip(out['deformation_list'], golden['deformation_list1']))
+    kp = me.estimate_kp(src.unsqueeze(0).cuda())
+    kperr = float((kp['value'].cpu() - golden['kp_source_value']).abs().max())
     preds, _ = S.make_animation(src, drv, g, me, batch=3)
     u8 = max(int((torch.from_numpy(p).int() - r.int()).abs().max()) for p, r in zip(preds, golden['pred_uint8']))
     nmis = sum(float((torch.from_numpy(p) != r).float().mean()) for p, r in zip(preds, golden['pred_uint8'])) / 3
-    print(f'{mode}: out max {float(d.max()):.3e} mean {float(d.mean()):.3e} | occ {occ:.2e} motion {mo:.2e} | uint8 maxdiff {u8} mismatch frac {nmis:.2e}', flush=True)
+    print(f'{mode}: kp {kperr:.2e} | out max {float(d.max()):.3e} mean {float(d.mean()):.3e} | occ {occ:.2e} motion {mo:.2e} | uint8 maxdiff {u8} mismatch frac {nmis:.2e}', flush=True)
