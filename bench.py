@@ -202,6 +202,10 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
+    if args.detail:           # is the step bound by the host's launch rate?  enqueue time (no sync) vs device time
+        step_device(); torch.cuda.synchronize()
+        t0 = time.perf_counter(); step_device(); t1 = time.perf_counter(); torch.cuda.synchronize(); t2 = time.perf_counter()
+        print(f'host enqueue {1e3 * (t1 - t0):.1f} ms, until device idle {1e3 * (t2 - t0):.1f} ms', file=sys.stderr)
     if args.ncu:
         step_device(); torch.cuda.synchronize()
         torch.cuda.profiler.start()          # ncu --profile-from-start off: exactly one step is profiled

@@ -34,6 +34,14 @@ enum {
   SMA_ERR_NO_DEVICE = -4     /* device is not sm_100                                          */
 };
 
+/* Arithmetic of a dense contraction.  Every mode accumulates in fp32 (TMEM / registers).
+ *   EXACT  fp32 FFMA on the CUDA cores.
+ *   TF32X3 error-compensated split on tcgen05 kind::tf32: x = hi + lo, a*b ~= a_lo*b_hi + a_hi*b_lo + a_hi*b_hi (fp32-faithful).
+ *   F16X3  the same split with fp16 halves on kind::f16 (same 11-bit significands, twice the MACs per tensor cycle); weights are
+ *          pre-scaled per output channel by a power of two, activations saturate at +-65504 and lose their lo half below 2^-25.
+ *   TF32 / F16  single pass (hi*hi only): only for stages whose contribution to the 1e-3 output budget was measured negligible. */
+enum { SMA_PREC_EXACT = 0, SMA_PREC_TF32X3 = 1, SMA_PREC_TF32 = 2, SMA_PREC_F16X3 = 3, SMA_PREC_F16 = 4 };
+
 enum { SMA_ACT_NONE = 0, SMA_ACT_RELU = 1, SMA_ACT_LEAKY02 = 2, SMA_ACT_GELU = 3, SMA_ACT_SIGMOID = 4,
        SMA_ACT_SWISH = 5 };
 
@@ -69,11 +77,13 @@ typedef struct sma_conv_desc {
                                     (oy*p+p1, ox*p+p2) channel c of a (B,Ho*p,Wo*p,C) tensor (un-patchify,
                                     appmotioncodebook_arch.py:223,230,237) */
   int out_nchw;                  /* 1: y is (B,Cout,Ho,Wo) contiguous (API-facing final image) */
-  int tf32x3;                    /* 0: exact fp32 CUDA-core kernel; 1: tcgen05 3xTF32 (fp32-faithful) when the shape allows;
-                                    2: tcgen05 single-pass TF32 (only where the 1e-3 parity budget allows it) */
-  const float* w_tc;             /* tensor-core weight image from sma_pack_conv_weight_tc (NULL: CUDA-core kernel only) */
+  int precision;                 /* SMA_PREC_*: arithmetic of the contraction (the kernels fall back towards tf32 / exact when the
+                                    shape or the available weight images do not allow the requested one) */
+  const float* w_tc;             /* tf32 tensor-core weight image from sma_pack_conv_weight_tc (may be NULL) */
+  const float* w_tc16;           /* fp16 tensor-core weight image from sma_pack_conv_weight_tc16 (may be NULL) */
   int tc_variant;                /* 0: library picks (persistent halo kernel for stride-1, gather kernel otherwise); 1: force the gather kernel */
-  int kernel_used;               /* OUT: 0 CUDA-core FFMA kernel, 1 tcgen05 gather kernel, 2 tcgen05 persistent halo kernel */
+  int kernel_used;               /* OUT: 0 CUDA-core FFMA kernel, 1 tcgen05 tf32 gather kernel, 2 tcgen05 tf32 persistent halo kernel,
+                                    3 tcgen05 fp16 persistent halo kernel */
 } sma_conv_desc;
 
 int sma_conv2d_fwd(sma_conv_desc* d, sma_stream_t stream);
@@ -89,6 +99,10 @@ int sma_pack_conv_weight(const float* w_oihw, const float* bias, int Cout, int C
  * in floats (0 when the shape is not eligible). */
 int64_t sma_conv_weight_tc_floats(int Cout, int Cin, int kh, int kw);
 int sma_pack_conv_weight_tc(const float* w_packed, int ldw, int Cout, int Cin, int kh, int kw, float* w_tc, sma_stream_t stream);
+/* fp16 variant (Cin % 64 == 0): [un-scaling factors per output column][per (N-tile, 64-channel chunk, tap): fp16 hi image | lo image
+ * of w * 2^-e(column)], same SWIZZLE_128B tiles. */
+int64_t sma_conv_weight_tc16_floats(int Cout, int Cin, int kh, int kw);
+int sma_pack_conv_weight_tc16(const float* w_packed, int ldw, int Cout, int Cin, int kh, int kw, float* w_tc16, sma_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * GroupNorm(32, eps) statistics -> per-(b,c) scale/shift consumed by the conv prologue

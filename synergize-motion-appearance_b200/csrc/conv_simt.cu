@@ -252,7 +252,7 @@ extern "C" int sma_conv2d_fwd(sma_conv_desc* d, sma_stream_t stream) {
   if (d->d2s > 1 && (d->res || d->out_nchw || d->Cout % (d->d2s * d->d2s))) return SMA_ERR_UNSUPPORTED;
   if ((long long)d->B * d->Ho * d->Wo > 0x7fffffffLL) return SMA_ERR_UNSUPPORTED;
   cudaStream_t st = as_stream(stream);
-  if (d->tf32x3) {
+  if (d->precision != SMA_PREC_EXACT) {
     int r = sma_conv2d_tc_try(d, st);
     if (r != SMA_ERR_UNSUPPORTED) return r;
   }

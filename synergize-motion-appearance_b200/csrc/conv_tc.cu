@@ -18,6 +18,7 @@
 // empty[s] (tcgen05.commit of the MMAs that read the slot).
 #include "sma_common.cuh"
 #include "tc_common.cuh"
+#include <cuda_fp16.h>
 
 namespace {
 
@@ -25,7 +26,7 @@ constexpr int BM = 128;          // tile rows (UMMA M, cta_group::1)
 constexpr int KC = 32;           // fp32 per K-chunk = one 128-byte swizzle row
 constexpr int A_BYTES = BM * KC * 4;   // 16 KB per A image (hi or lo)
 constexpr int MAX_STAGES = 4;
-constexpr int SMEM_DYN_MAX = 232448 - 2048;  // 227 KB opt-in limit minus room for static shared memory (barriers, bias)
+constexpr int SMEM_DYN_MAX = 232448 - 3072;  // 227 KB opt-in limit minus room for static shared memory (barriers, bias, scales)
 constexpr int SMEM_LIMIT = SMEM_DYN_MAX - 1024;  // minus 1 KB alignment slack
 
 struct TcP {
@@ -262,6 +263,7 @@ struct Tc2P {
   long long in_bs, out_bs, res_bs;
   int Hi, Wi, Cin, in_ld, Cout, kh, kw, pad_t, pad_l, up, pre_act;
   int Ho, Wo, out_ld, act, res_ld, d2s;
+  const float* wscale;        // F16 only: per-output-channel power-of-two factor that undoes the weight pre-scaling
   int HoWo, cpt, taps, NT, ntiles_n, passes, tmem_cols;
   int flat, tiles_x, tiles_per_img, total_tiles;
   int halo_w, HP, a_img_bytes, a_stage_bytes, b_img_bytes, SA, SB;
@@ -269,12 +271,17 @@ struct Tc2P {
 
 // ACT: epilogue activation; PRE: -1 no prologue, else the prologue activation applied after scale/shift (compile-time so that the
 // unrolled epilogue / producer bodies stay small: the three warp roles share one instruction cache)
-template <int ACT, int PRE>
+// F16: operands are split into two fp16 halves (hi = rn(x), lo = rn(x - hi); same 11-bit significand as tf32) and multiplied with
+// kind::f16 (K = 16 per instruction: twice the MACs per tensor-core cycle and per shared-memory byte of kind::tf32); a K-chunk
+// (one 128-byte swizzle row) is then 64 channels.
+template <int ACT, int PRE, int F16>
 __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const Tc2P p) {
+  constexpr int KCH = F16 ? 64 : 32;                       // channels per K-chunk (128 bytes of operand)
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[2 * MAX_SA + 2 * MAX_SB + 4];
   __shared__ uint32_t tmem_slot;
   __shared__ __align__(16) float s_bias[256];              // bias of the current N tile (epilogue warps only)
+  __shared__ __align__(16) float s_scale[F16 ? 256 : 4];   // F16: un-scaling factors of the current N tile
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t bar0 = smem_u32(bars);
@@ -321,7 +328,10 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const Tc2P p) {
       const int ab = tcount & 1; const uint32_t aph = (tcount >> 1) & 1;
       if (nt != cur_nt) {                           // (re)stage the bias slice of this N tile; named barrier 1 = the 4 epilogue warps
         asm volatile("bar.sync 1, 128;" ::: "memory");
-        for (int i = m; i < p.NT; i += 128) { int n = nt * p.NT + i; s_bias[i] = (p.bias && n < p.Cout) ? __ldg(p.bias + n) : 0.f; }
+        for (int i = m; i < p.NT; i += 128) {
+          int n = nt * p.NT + i; s_bias[i] = (p.bias && n < p.Cout) ? __ldg(p.bias + n) : 0.f;
+          if (F16) s_scale[i] = __ldg(p.wscale + n);
+        }
         asm volatile("bar.sync 1, 128;" ::: "memory");
         cur_nt = nt;
       }
@@ -352,7 +362,8 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const Tc2P p) {
             float o[4];
 #pragma unroll
             for (int t = 0; t < 4; t++) {
-              o[t] = sma_act(__uint_as_float(a[q * 4 + t]) + s_bias[n0 + q * 4 + t], ACT);
+              if (F16) o[t] = sma_act(fmaf(__uint_as_float(a[q * 4 + t]), s_scale[n0 + q * 4 + t], s_bias[n0 + q * 4 + t]), ACT);
+              else o[t] = sma_act(__uint_as_float(a[q * 4 + t]) + s_bias[n0 + q * 4 + t], ACT);
             }
             if (vec_ok && n + 4 <= p.Cout && (Cq & 3) == 0) {
               float* dst;
@@ -391,7 +402,8 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const Tc2P p) {
     }
   } else if (warp == 4) {
     // =============================== MMA issuer (whole warp converged, one elected lane issues) ===============================
-    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.NT >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    // fp32 accumulate; A/B format 2 = tf32 (kind::tf32) or 0 = fp16 (kind::f16); K-major A and B
+    const uint32_t idesc = (1u << 4) | (F16 ? 0u : ((2u << 7) | (2u << 10))) | ((uint32_t)(p.NT >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
     // A: 8-row atoms are 8 consecutive halo rows; next atom = next output row = halo row pitch
     const uint64_t a_desc_hi_bits = (1ull << 16) | ((uint64_t)((p.halo_w * 128) >> 4) << 32) | (1ull << 46) | (2ull << 61);
     int it = 0, jt = 0, tcount = 0;
@@ -417,15 +429,15 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const Tc2P p) {
           const bool last_tap = tap == p.taps - 1;
           if (elect_one_sync()) {
 #pragma unroll
-            for (int k4 = 0; k4 < KC / 8; k4++) {
+            for (int k4 = 0; k4 < 4; k4++) {                   // 4 k-steps of 32 bytes (8 tf32 / 16 fp16) per 128-byte row
               const uint64_t ko = (uint64_t)(k4 * 2);
               const uint32_t first = (cc | tap | k4) != 0;
               if (p.passes == 3) {
-                tc_mma_tf32(d_tmem, dal + ko, dbh + ko, idesc, first);
-                tc_mma_tf32(d_tmem, dah + ko, dbl + ko, idesc, 1u);
-                tc_mma_tf32(d_tmem, dah + ko, dbh + ko, idesc, 1u);
+                tc_mma<F16>(d_tmem, dal + ko, dbh + ko, idesc, first);
+                tc_mma<F16>(d_tmem, dah + ko, dbl + ko, idesc, 1u);
+                tc_mma<F16>(d_tmem, dah + ko, dbh + ko, idesc, 1u);
               } else {
-                tc_mma_tf32(d_tmem, dah + ko, dbh + ko, idesc, first);
+                tc_mma<F16>(d_tmem, dah + ko, dbh + ko, idesc, first);
               }
             }
             tc_commit(b_empty(sb));
@@ -467,49 +479,96 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const Tc2P p) {
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       int b, ty0, tx0, nt; decode(tile, b, ty0, tx0, nt);
       const float* xb = p.x + (long long)b * p.in_bs;
+      // halo row hp of this tile -> source pixel index (ok = inside the image; padding rows stay zero)
+      auto halo_pixel = [&](int hp, bool& ok) -> long long {
+        if (p.flat) { int r = ty0 + hp; ok = r < p.HoWo; return r; }
+        int hy = hp / p.halo_w; int hx = hp - hy * p.halo_w;
+        int iy = ty0 + hy - p.pad_t, ix = tx0 + hx - p.pad_l;
+        ok = (unsigned)iy < (unsigned)Hv && (unsigned)ix < (unsigned)Wv;
+        return (long long)(iy >> p.up) * p.Wi + (ix >> p.up);
+      };
       for (int cc = 0; cc < p.cpt; cc++, it++) {
         if ((it % V2_PGROUPS) != pgroup) continue;      // the other group's chunk
         const int sa = it % p.SA; const uint32_t pha = (it / p.SA) & 1;
-        const int c = cc * KC + cq * 4;
-        float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (PRE >= 0) {
-          sc = __ldg(reinterpret_cast<const float4*>(p.pre_scale + (long long)b * p.Cin + c));
-          sh = __ldg(reinterpret_cast<const float4*>(p.pre_shift + (long long)b * p.Cin + c));
-        }
         const uint32_t a_hi = a_ring + (uint32_t)sa * p.a_stage_bytes, a_lo = a_hi + p.a_img_bytes;
         bool waited = false;
-        for (int pass0 = 0; pass0 < npass; pass0 += V2_UNROLL) {
-          float4 v[V2_UNROLL]; bool ok[V2_UNROLL];
+        if (!F16) {
+          const int c = cc * KCH + cq * 4;
+          float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (PRE >= 0) {
+            sc = __ldg(reinterpret_cast<const float4*>(p.pre_scale + (long long)b * p.Cin + c));
+            sh = __ldg(reinterpret_cast<const float4*>(p.pre_shift + (long long)b * p.Cin + c));
+          }
+          for (int pass0 = 0; pass0 < npass; pass0 += V2_UNROLL) {
+            float4 v[V2_UNROLL]; bool ok[V2_UNROLL];
 #pragma unroll
-          for (int u = 0; u < V2_UNROLL; u++) {
-            const int hp = (pass0 + u) * V2_PROWS + prow;
-            ok[u] = false; v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (hp < p.HP) {
-              long long pix;
-              if (p.flat) { int r = ty0 + hp; ok[u] = r < p.HoWo; pix = r; }
-              else {
-                int hy = hp / p.halo_w; int hx = hp - hy * p.halo_w;
-                int iy = ty0 + hy - p.pad_t, ix = tx0 + hx - p.pad_l;
-                ok[u] = (unsigned)iy < (unsigned)Hv && (unsigned)ix < (unsigned)Wv;
-                pix = (long long)(iy >> p.up) * p.Wi + (ix >> p.up);
+            for (int u = 0; u < V2_UNROLL; u++) {
+              const int hp = (pass0 + u) * V2_PROWS + prow;
+              ok[u] = false; v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (hp < p.HP) {
+                const long long pix = halo_pixel(hp, ok[u]);
+                if (ok[u]) v[u] = __ldg(reinterpret_cast<const float4*>(xb + pix * p.in_ld + c));
               }
-              if (ok[u]) v[u] = __ldg(reinterpret_cast<const float4*>(xb + pix * p.in_ld + c));
+            }
+            if (!waited) { mbar_wait(a_empty(sa), pha ^ 1u); waited = true; }     // first loads are in flight while we wait
+#pragma unroll
+            for (int u = 0; u < V2_UNROLL; u++) {
+              const int hp = (pass0 + u) * V2_PROWS + prow;
+              if (hp >= p.HP) continue;
+              float4 t = v[u];
+              if (PRE >= 0 && ok[u]) {
+                t.x = pre_act_fast(fmaf(t.x, sc.x, sh.x), PRE); t.y = pre_act_fast(fmaf(t.y, sc.y, sh.y), PRE);
+                t.z = pre_act_fast(fmaf(t.z, sc.z, sh.z), PRE); t.w = pre_act_fast(fmaf(t.w, sc.w, sh.w), PRE);
+              }
+              const uint32_t off = (uint32_t)hp * 128u + (uint32_t)((cq ^ (hp & 7)) << 4);
+              float hx_ = tf32_rna(t.x), hy_ = tf32_rna(t.y), hz_ = tf32_rna(t.z), hw_ = tf32_rna(t.w);
+              sts128(a_hi + off, hx_, hy_, hz_, hw_);
+              if (p.passes == 3) sts128(a_lo + off, t.x - hx_, t.y - hy_, t.z - hz_, t.w - hw_);
             }
           }
-          if (!waited) { mbar_wait(a_empty(sa), pha ^ 1u); waited = true; }     // first loads are in flight while we wait
+        } else {
+          constexpr int UN = V2_UNROLL / 2;                 // two float4 (8 channels = one 16-byte fp16 unit) per halo row and lane
+          const int c = cc * KCH + cq * 8;
+          float4 sc0 = make_float4(1.f, 1.f, 1.f, 1.f), sh0 = make_float4(0.f, 0.f, 0.f, 0.f), sc1 = sc0, sh1 = sh0;
+          if (PRE >= 0) {
+            sc0 = __ldg(reinterpret_cast<const float4*>(p.pre_scale + (long long)b * p.Cin + c));
+            sc1 = __ldg(reinterpret_cast<const float4*>(p.pre_scale + (long long)b * p.Cin + c + 4));
+            sh0 = __ldg(reinterpret_cast<const float4*>(p.pre_shift + (long long)b * p.Cin + c));
+            sh1 = __ldg(reinterpret_cast<const float4*>(p.pre_shift + (long long)b * p.Cin + c + 4));
+          }
+          for (int pass0 = 0; pass0 < npass; pass0 += UN) {
+            float4 v0[UN], v1[UN]; bool ok[UN];
 #pragma unroll
-          for (int u = 0; u < V2_UNROLL; u++) {
-            const int hp = (pass0 + u) * V2_PROWS + prow;
-            if (hp >= p.HP) continue;
-            float4 t = v[u];
-            if (PRE >= 0 && ok[u]) {
-              t.x = pre_act_fast(fmaf(t.x, sc.x, sh.x), PRE); t.y = pre_act_fast(fmaf(t.y, sc.y, sh.y), PRE);
-              t.z = pre_act_fast(fmaf(t.z, sc.z, sh.z), PRE); t.w = pre_act_fast(fmaf(t.w, sc.w, sh.w), PRE);
+            for (int u = 0; u < UN; u++) {
+              const int hp = (pass0 + u) * V2_PROWS + prow;
+              ok[u] = false; v0[u] = make_float4(0.f, 0.f, 0.f, 0.f); v1[u] = v0[u];
+              if (hp < p.HP) {
+                const long long pix = halo_pixel(hp, ok[u]);
+                if (ok[u]) {
+                  const float4* src = reinterpret_cast<const float4*>(xb + pix * p.in_ld + c);
+                  v0[u] = __ldg(src); v1[u] = __ldg(src + 1);
+                }
+              }
             }
-            const uint32_t off = (uint32_t)hp * 128u + (uint32_t)((cq ^ (hp & 7)) << 4);
-            float hx_ = tf32_rna(t.x), hy_ = tf32_rna(t.y), hz_ = tf32_rna(t.z), hw_ = tf32_rna(t.w);
-            sts128(a_hi + off, hx_, hy_, hz_, hw_);
-            if (p.passes == 3) sts128(a_lo + off, t.x - hx_, t.y - hy_, t.z - hz_, t.w - hw_);
+            if (!waited) { mbar_wait(a_empty(sa), pha ^ 1u); waited = true; }
+#pragma unroll
+            for (int u = 0; u < UN; u++) {
+              const int hp = (pass0 + u) * V2_PROWS + prow;
+              if (hp >= p.HP) continue;
+              float4 t0 = v0[u], t1 = v1[u];
+              if (PRE >= 0 && ok[u]) {
+                t0.x = pre_act_fast(fmaf(t0.x, sc0.x, sh0.x), PRE); t0.y = pre_act_fast(fmaf(t0.y, sc0.y, sh0.y), PRE);
+                t0.z = pre_act_fast(fmaf(t0.z, sc0.z, sh0.z), PRE); t0.w = pre_act_fast(fmaf(t0.w, sc0.w, sh0.w), PRE);
+                t1.x = pre_act_fast(fmaf(t1.x, sc1.x, sh1.x), PRE); t1.y = pre_act_fast(fmaf(t1.y, sc1.y, sh1.y), PRE);
+                t1.z = pre_act_fast(fmaf(t1.z, sc1.z, sh1.z), PRE); t1.w = pre_act_fast(fmaf(t1.w, sc1.w, sh1.w), PRE);
+              }
+              const uint32_t off = (uint32_t)hp * 128u + (uint32_t)((cq ^ (hp & 7)) << 4);
+              uint32_t h0, h1, h2, h3, l0, l1, l2, l3;
+              split_f16x2(t0.x, t0.y, h0, l0); split_f16x2(t0.z, t0.w, h1, l1);
+              split_f16x2(t1.x, t1.y, h2, l2); split_f16x2(t1.z, t1.w, h3, l3);
+              sts128u(a_hi + off, h0, h1, h2, h3);
+              if (p.passes == 3) sts128u(a_lo + off, l0, l1, l2, l3);
+            }
           }
         }
         fence_async_smem();
@@ -543,6 +602,37 @@ __global__ void pack_tc_kernel(const float* __restrict__ wp, int ldw, int Cin, i
   }
 }
 
+// per output column n: factor 2^e with max_k |w[k][n]| * 2^-e in [0.5, 1)  (exact power-of-two pre-scaling keeps the fp16 lo halves
+// of small weights out of the subnormal range); columns >= Cout get 1
+__global__ void f16_colscale_kernel(const float* __restrict__ wp, int ldw, int K, int Cout, int ncols, float* __restrict__ inv_scale) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= ncols) return;
+  float mx = 0.f;
+  if (n < Cout) for (int k = 0; k < K; k++) mx = fmaxf(mx, fabsf(wp[(long long)k * ldw + n]));
+  int e = 0;
+  if (mx > 0.f && mx < 3.0e38f) { frexpf(mx, &e); e = max(-100, min(100, e)); }
+  inv_scale[n] = ldexpf(1.f, e);
+}
+
+// packed [K][ldw] fp32 weight -> per (N-tile, 64-channel chunk, tap) fp16 images [hi: NT rows x 128 B, SWIZZLE_128B][lo: same] of w * 2^-e
+__global__ void pack_tc16_kernel(const float* __restrict__ wp, int ldw, int Cin, int taps, int Cout, int NT, int ntiles,
+                                 const float* __restrict__ inv_scale, uint16_t* __restrict__ out) {
+  constexpr int KH = 64;
+  const int nchunks = taps * Cin / KH;
+  const long long total = (long long)ntiles * nchunks * NT * KH;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int kk = (int)(i % KH); long long t = i / KH; int n = (int)(t % NT); t /= NT; int kc = (int)(t % nchunks); int nt = (int)(t / nchunks);
+    const int cc = kc / taps, tap = kc - cc * taps;
+    int col = nt * NT + n, k = tap * Cin + cc * KH + kk;
+    float w = col < Cout ? wp[(long long)k * ldw + col] / inv_scale[col] : 0.f;      // exact: the divisor is a power of two
+    __half hi = __float2half_rn(w); __half lo = __float2half_rn(w - __half2float(hi));
+    long long blob = ((long long)nt * nchunks + kc) * (2LL * NT * KH);
+    int phys = (n >> 3) * 512 + (n & 7) * 64 + ((((kk >> 3) ^ (n & 7)) << 3) | (kk & 7));    // fp16 index inside the image
+    out[blob + phys] = __half_as_ushort(hi);
+    out[blob + (long long)NT * KH + phys] = __half_as_ushort(lo);
+  }
+}
+
 int tc_ntile(int Cout) { return Cout <= 256 ? ((Cout + 15) & ~15) : 256; }
 
 }  // namespace
@@ -565,54 +655,82 @@ extern "C" int sma_pack_conv_weight_tc(const float* w_packed, int ldw, int Cout,
   return SMA_OK;
 }
 
+// fp16 image: [ntiles*NT floats of un-scaling factors][per (N tile, 64-channel chunk, tap): hi image | lo image]; size in floats
+extern "C" int64_t sma_conv_weight_tc16_floats(int Cout, int Cin, int kh, int kw) {
+  if (Cout <= 0 || Cin <= 0 || kh <= 0 || kw <= 0 || (Cin % 64)) return 0;
+  int NT = tc_ntile(Cout); int ntiles = (Cout + NT - 1) / NT;
+  return (int64_t)ntiles * NT + (int64_t)ntiles * (kh * kw * Cin / 64) * NT * 64;      // 2 images x NT x 64 halfs = NT*64 floats per chunk
+}
 
-static int g_num_sms = 0;
-
-template <int ACT, int PRE>
-static int launch_tc2_inst(const Tc2P& p, int grid, int smem, cudaStream_t st) {
-  static bool configured = false;     // per instantiation; idempotent, benign if raced
-  if (!configured) {
-    if (cudaFuncSetAttribute(conv_tc2_kernel<ACT, PRE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_DYN_MAX) != cudaSuccess) return SMA_ERR_CUDA;
-    configured = true;
-  }
-  conv_tc2_kernel<ACT, PRE><<<grid, V2_THREADS, smem, st>>>(p);
+extern "C" int sma_pack_conv_weight_tc16(const float* w_packed, int ldw, int Cout, int Cin, int kh, int kw, float* w_tc16, sma_stream_t stream) {
+  if (!w_packed || !w_tc16 || Cout <= 0 || Cin <= 0 || kh <= 0 || kw <= 0 || ldw < Cout) return SMA_ERR_BAD_ARG;
+  if (Cin % 64) return SMA_ERR_UNSUPPORTED;
+  if (reinterpret_cast<uintptr_t>(w_tc16) & 15) return SMA_ERR_BAD_ARG;
+  int NT = tc_ntile(Cout); int ntiles = (Cout + NT - 1) / NT; int K = kh * kw * Cin; int ncols = ntiles * NT;
+  f16_colscale_kernel<<<(ncols + 127) / 128, 128, 0, as_stream(stream)>>>(w_packed, ldw, K, Cout, ncols, w_tc16);
+  SMA_LAUNCH_CHECK();
+  long long total = (long long)ntiles * (K / 64) * NT * 64;
+  int blocks = (int)((total + 255) / 256); if (blocks > 8192) blocks = 8192;
+  pack_tc16_kernel<<<blocks, 256, 0, as_stream(stream)>>>(w_packed, ldw, Cin, kh * kw, Cout, NT, ntiles, w_tc16,
+                                                          reinterpret_cast<uint16_t*>(w_tc16 + ncols));
   SMA_LAUNCH_CHECK();
   return SMA_OK;
 }
-template <int ACT>
+
+
+static int g_num_sms = 0;
+
+template <int ACT, int PRE, int F16>
+static int launch_tc2_inst(const Tc2P& p, int grid, int smem, cudaStream_t st) {
+  static bool configured = false;     // per instantiation; idempotent, benign if raced
+  if (!configured) {
+    if (cudaFuncSetAttribute(conv_tc2_kernel<ACT, PRE, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_DYN_MAX) != cudaSuccess) return SMA_ERR_CUDA;
+    configured = true;
+  }
+  conv_tc2_kernel<ACT, PRE, F16><<<grid, V2_THREADS, smem, st>>>(p);
+  SMA_LAUNCH_CHECK();
+  return SMA_OK;
+}
+template <int ACT, int F16>
 static int launch_tc2_pre(int pre, const Tc2P& p, int grid, int smem, cudaStream_t st) {
   switch (pre) {
-    case -1: return launch_tc2_inst<ACT, -1>(p, grid, smem, st);
-    case SMA_ACT_NONE: return launch_tc2_inst<ACT, SMA_ACT_NONE>(p, grid, smem, st);
-    case SMA_ACT_SWISH: return launch_tc2_inst<ACT, SMA_ACT_SWISH>(p, grid, smem, st);
+    case -1: return launch_tc2_inst<ACT, -1, F16>(p, grid, smem, st);
+    case SMA_ACT_NONE: return launch_tc2_inst<ACT, SMA_ACT_NONE, F16>(p, grid, smem, st);
+    case SMA_ACT_SWISH: return launch_tc2_inst<ACT, SMA_ACT_SWISH, F16>(p, grid, smem, st);
     default: return SMA_ERR_UNSUPPORTED;     // other prologue activations: gather / CUDA-core kernels
   }
 }
+template <int F16>
 static int launch_tc2(int act, int pre, const Tc2P& p, int grid, int smem, cudaStream_t st) {
   switch (act) {
-    case SMA_ACT_NONE: return launch_tc2_pre<SMA_ACT_NONE>(pre, p, grid, smem, st);
-    case SMA_ACT_RELU: return launch_tc2_pre<SMA_ACT_RELU>(pre, p, grid, smem, st);
-    case SMA_ACT_LEAKY02: return launch_tc2_pre<SMA_ACT_LEAKY02>(pre, p, grid, smem, st);
-    case SMA_ACT_GELU: return launch_tc2_pre<SMA_ACT_GELU>(pre, p, grid, smem, st);
-    case SMA_ACT_SIGMOID: return launch_tc2_pre<SMA_ACT_SIGMOID>(pre, p, grid, smem, st);
-    case SMA_ACT_SWISH: return launch_tc2_pre<SMA_ACT_SWISH>(pre, p, grid, smem, st);
+    case SMA_ACT_NONE: return launch_tc2_pre<SMA_ACT_NONE, F16>(pre, p, grid, smem, st);
+    case SMA_ACT_RELU: return launch_tc2_pre<SMA_ACT_RELU, F16>(pre, p, grid, smem, st);
+    case SMA_ACT_LEAKY02: return launch_tc2_pre<SMA_ACT_LEAKY02, F16>(pre, p, grid, smem, st);
+    case SMA_ACT_GELU: return launch_tc2_pre<SMA_ACT_GELU, F16>(pre, p, grid, smem, st);
+    case SMA_ACT_SIGMOID: return launch_tc2_pre<SMA_ACT_SIGMOID, F16>(pre, p, grid, smem, st);
+    case SMA_ACT_SWISH: return launch_tc2_pre<SMA_ACT_SWISH, F16>(pre, p, grid, smem, st);
     default: return SMA_ERR_BAD_ARG;
   }
 }
 
 // persistent halo kernel (stride 1); returns SMA_ERR_UNSUPPORTED when not eligible
-static int conv_tc2_try(const sma_conv_desc* d, cudaStream_t st) {
+static int conv_tc2_try(const sma_conv_desc* d, cudaStream_t st, bool f16) {
+  const int kch = f16 ? 64 : KC;
+  if (d->Cin % kch) return SMA_ERR_UNSUPPORTED;
   if (d->stride != 1 || (d->kh != d->kw && !(d->kh == 1 || d->kw == 1))) return SMA_ERR_UNSUPPORTED;
   const bool flat = d->kh == 1 && d->kw == 1 && !d->upsample2 && d->pad_t == 0 && d->pad_l == 0 && d->Ho == d->Hi && d->Wo == d->Wi;
   if (!flat && (d->Ho < 8 || d->Wo < 4)) return SMA_ERR_UNSUPPORTED;      // tiny feature maps: the gather kernel packs images into one tile
   Tc2P p;
-  p.x = d->x; p.wtc = d->w_tc; p.bias = d->bias; p.pre_scale = d->pre_scale; p.pre_shift = d->pre_shift; p.res = d->res; p.y = d->y;
+  p.x = d->x; p.bias = d->bias; p.pre_scale = d->pre_scale; p.pre_shift = d->pre_shift; p.res = d->res; p.y = d->y;
+  p.NT = tc_ntile(d->Cout); p.ntiles_n = (d->Cout + p.NT - 1) / p.NT;
+  p.wscale = f16 ? d->w_tc16 : nullptr;
+  p.wtc = f16 ? d->w_tc16 + p.ntiles_n * p.NT : d->w_tc;
   p.in_bs = d->in_bstride; p.out_bs = d->out_bstride; p.res_bs = d->res_bstride;
   p.Hi = d->Hi; p.Wi = d->Wi; p.Cin = d->Cin; p.in_ld = d->in_ld; p.Cout = d->Cout; p.kh = d->kh; p.kw = d->kw;
   p.pad_t = d->pad_t; p.pad_l = d->pad_l; p.up = d->upsample2 ? 1 : 0; p.pre_act = d->pre_act; p.Ho = d->Ho; p.Wo = d->Wo; p.out_ld = d->out_ld;
   p.act = d->act; p.res_ld = d->res_ld; p.d2s = d->d2s;
-  p.HoWo = d->Ho * d->Wo; p.cpt = d->Cin / KC; p.taps = d->kh * d->kw;
-  p.NT = tc_ntile(d->Cout); p.ntiles_n = (d->Cout + p.NT - 1) / p.NT; p.passes = d->tf32x3 == 2 ? 1 : 3;
+  p.HoWo = d->Ho * d->Wo; p.cpt = d->Cin / kch; p.taps = d->kh * d->kw;
+  p.passes = (d->precision == SMA_PREC_TF32 || d->precision == SMA_PREC_F16) ? 1 : 3;
   p.flat = flat ? 1 : 0;
   if (flat) { p.tiles_x = 1; p.tiles_per_img = (p.HoWo + BM - 1) / BM; p.halo_w = 8; p.HP = BM; }
   else {
@@ -624,7 +742,7 @@ static int conv_tc2_try(const sma_conv_desc* d, cudaStream_t st) {
   p.total_tiles = (int)total;
   p.a_img_bytes = (p.HP * 128 + 1023) & ~1023;
   p.a_stage_bytes = 2 * p.a_img_bytes;
-  p.b_img_bytes = p.NT * KC * 4;
+  p.b_img_bytes = p.NT * 128;                    // NT rows of one 128-byte K-chunk (32 tf32 or 64 fp16)
   const int b_stage = 2 * p.b_img_bytes;
   int SA = 2;
   int SB = (SMEM_LIMIT - SA * p.a_stage_bytes) / b_stage;
@@ -642,19 +760,24 @@ static int conv_tc2_try(const sma_conv_desc* d, cudaStream_t st) {
   }
   const int grid = p.total_tiles < g_num_sms ? p.total_tiles : g_num_sms;
   const int pre = d->pre_scale ? d->pre_act : -1;
-  return launch_tc2(d->act, pre, p, grid, smem, st);
+  return f16 ? launch_tc2<1>(d->act, pre, p, grid, smem, st) : launch_tc2<0>(d->act, pre, p, grid, smem, st);
 }
 
 // returns SMA_ERR_UNSUPPORTED when the shape / layout is not eligible (the caller then uses the CUDA-core kernel)
 int sma_conv2d_tc_try(sma_conv_desc* d, cudaStream_t st) {
-  if (!d->w_tc || d->out_nchw) return SMA_ERR_UNSUPPORTED;
-  if ((d->Cin % KC) || (d->in_ld & 3) || (d->in_bstride & 3) || (reinterpret_cast<uintptr_t>(d->x) & 15) || (reinterpret_cast<uintptr_t>(d->w_tc) & 15))
-    return SMA_ERR_UNSUPPORTED;
+  if ((!d->w_tc && !d->w_tc16) || d->out_nchw) return SMA_ERR_UNSUPPORTED;
+  if ((d->Cin % KC) || (d->in_ld & 3) || (d->in_bstride & 3) || (reinterpret_cast<uintptr_t>(d->x) & 15)) return SMA_ERR_UNSUPPORTED;
   if (d->pre_scale && ((reinterpret_cast<uintptr_t>(d->pre_scale) | reinterpret_cast<uintptr_t>(d->pre_shift)) & 15)) return SMA_ERR_UNSUPPORTED;
   const long long M = (long long)d->B * d->Ho * d->Wo;
   if (M < 64) return SMA_ERR_UNSUPPORTED;
+  const bool want16 = (d->precision == SMA_PREC_F16X3 || d->precision == SMA_PREC_F16) && d->w_tc16 && !(reinterpret_cast<uintptr_t>(d->w_tc16) & 15);
+  if (want16 && !(d->tc_variant & 1)) {
+    int r2 = conv_tc2_try(d, st, true);
+    if (r2 != SMA_ERR_UNSUPPORTED) { d->kernel_used = 3; return r2; }
+  }
+  if (!d->w_tc || (reinterpret_cast<uintptr_t>(d->w_tc) & 15)) return SMA_ERR_UNSUPPORTED;
   if (!(d->tc_variant & 1)) {
-    int r2 = conv_tc2_try(d, st);
+    int r2 = conv_tc2_try(d, st, false);
     if (r2 != SMA_ERR_UNSUPPORTED) { d->kernel_used = 2; return r2; }
   }
   TcP p;
@@ -664,7 +787,7 @@ int sma_conv2d_tc_try(sma_conv_desc* d, cudaStream_t st) {
   p.pad_t = d->pad_t; p.pad_l = d->pad_l; p.up = d->upsample2 ? 1 : 0; p.pre_act = d->pre_act; p.Ho = d->Ho; p.Wo = d->Wo; p.out_ld = d->out_ld;
   p.act = d->act; p.res_ld = d->res_ld; p.d2s = d->d2s;
   p.M = (int)M; p.HoWo = d->Ho * d->Wo; p.cpt = d->Cin / KC; p.nchunks = d->kh * d->kw * p.cpt;
-  p.NT = tc_ntile(d->Cout); p.passes = d->tf32x3 == 2 ? 1 : 3;
+  p.NT = tc_ntile(d->Cout); p.passes = (d->precision == SMA_PREC_TF32 || d->precision == SMA_PREC_F16) ? 1 : 3;
   const int ntiles = (d->Cout + p.NT - 1) / p.NT;
   const int stage_bytes = 2 * A_BYTES + 2 * p.NT * KC * 4;
   int stages = SMEM_LIMIT / stage_bytes; if (stages > MAX_STAGES) stages = MAX_STAGES; if (stages > p.nchunks) stages = p.nchunks;

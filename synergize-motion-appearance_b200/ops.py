@@ -78,7 +78,8 @@ class ConvW:
     Cin: int
     kh: int
     kw: int
-    w_tc: Optional[torch.Tensor] = None      # tensor-core image (sma_pack_conv_weight_tc); None -> CUDA-core kernel only
+    w_tc: Optional[torch.Tensor] = None      # tf32 tensor-core image (sma_pack_conv_weight_tc); None -> not eligible (Cin % 32)
+    w_tc16: Optional[torch.Tensor] = None    # fp16 tensor-core image (sma_pack_conv_weight_tc16); None -> not eligible (Cin % 64)
     _slices: Optional[dict] = None           # cache of cols() results (their tensor-core images are packed once)
 
     def cols(self, start: int, n: int) -> 'ConvW':
@@ -89,7 +90,7 @@ class ConvW:
         cw = self._slices.get((start, n))
         if cw is None:
             cw = ConvW(self.w[:, start:], None if self.bias is None else self.bias[start:start + n], n, self.Cin, self.kh, self.kw)
-            cw.w_tc = _pack_tc(cw)
+            cw.w_tc, cw.w_tc16 = _pack_tc(cw), _pack_tc16(cw)
             self._slices[(start, n)] = cw
         return cw
 
@@ -98,7 +99,7 @@ class ConvW:
         (appmotioncodebook_arch.py:222,229,236)."""
         assert self.kh == 1 and self.kw == 1 and self.Cin % (p * p) == 0
         cw = ConvW(self.w, self.bias, self.Cout, self.Cin // (p * p), p, p)
-        cw.w_tc = _pack_tc(cw)
+        cw.w_tc, cw.w_tc16 = _pack_tc(cw), _pack_tc16(cw)
         return cw
 
 
@@ -110,6 +111,17 @@ def _pack_tc(cw: 'ConvW') -> Optional[torch.Tensor]:
     out = torch.empty((n,), device=cw.w.device, dtype=torch.float32)
     check(lib.sma_pack_conv_weight_tc(cw.w.data_ptr(), cw.w.stride(0), cw.Cout, cw.Cin, cw.kh, cw.kw, out.data_ptr(), _stream()),
           'sma_pack_conv_weight_tc')
+    return out
+
+
+def _pack_tc16(cw: 'ConvW') -> Optional[torch.Tensor]:
+    lib = _lib.load()
+    n = lib.sma_conv_weight_tc16_floats(cw.Cout, cw.Cin, cw.kh, cw.kw)
+    if n <= 0:
+        return None
+    out = torch.empty((n,), device=cw.w.device, dtype=torch.float32)
+    check(lib.sma_pack_conv_weight_tc16(cw.w.data_ptr(), cw.w.stride(0), cw.Cout, cw.Cin, cw.kh, cw.kw, out.data_ptr(), _stream()),
+          'sma_pack_conv_weight_tc16')
     return out
 
 
@@ -139,7 +151,7 @@ def pack_conv(weight: torch.Tensor, bias: Optional[torch.Tensor], bn: Optional[d
     check(lib.sma_pack_conv_weight(_ptr(w), _ptr(b), Cout, Cin, kh, kw, _ptr(g), _ptr(be), _ptr(mu), _ptr(var), eps,
                                    _ptr(wp), ldw, _ptr(bo), _stream()), 'sma_pack_conv_weight')
     cw = ConvW(wp, None if bo is None else bo[:Cout], Cout, Cin, kh, kw)
-    cw.w_tc = _pack_tc(cw)
+    cw.w_tc, cw.w_tc16 = _pack_tc(cw), _pack_tc16(cw)
     return cw
 
 
@@ -163,8 +175,10 @@ def pack_conv_blockdiag(weights, biases) -> ConvW:
     return pack_conv(big, torch.cat([x.detach().float() for x in biases], dim=0))
 
 
-USE_TF32X3 = True        # let sma_conv2d_fwd pick the tcgen05 kernel where the shape allows
-ALLOW_TF32_1PASS = True  # honour `fast=True` requests (single-pass TF32)
+PREC = {'exact': 0, 'tf32x3': 1, 'tf32': 2, 'f16x3': 3, 'f16': 4}     # SMA_PREC_*
+USE_TF32X3 = True        # let sma_conv2d_fwd pick a tcgen05 kernel where the shape allows (False: exact CUDA-core kernels everywhere)
+ALLOW_TF32_1PASS = True  # honour `fast=True` requests (single pass)
+USE_F16 = True           # split operands into fp16 halves (kind::f16, 2x the tensor rate of kind::tf32) where Cin % 64 == 0
 # Per-stage precision policy: stages listed here run their convolutions as single-pass TF32 (3x fewer tensor-core
 # instructions); everything else is fp32-faithful 3xTF32.  See DESIGN.md section 4 for the measured error budget.
 FAST_STAGES = {'kp', 's1', 's3m'}   # measured (tools/e2e_err.py): out max-abs 3.26e-4 -> 3.48e-4, key-points 1.3e-6 -> 4.5e-5
@@ -175,7 +189,7 @@ def fast(stage: str) -> bool:
 
 
 TC_VARIANT = 0           # 0: library picks the tensor-core kernel variant; 1: force the gather kernel (tests)
-LAST_CONV_KERNEL = -1    # which kernel the last conv2d ran on: 0 CUDA-core, 1 tcgen05 gather, 2 tcgen05 persistent halo
+LAST_CONV_KERNEL = -1    # which kernel the last conv2d ran on: 0 CUDA-core, 1 tcgen05 gather, 2 tcgen05 persistent halo (tf32), 3 (fp16)
 
 
 def conv2d(x: torch.Tensor, cw: ConvW, *, stride: int = 1, pad: int = 0, pad_tl: Optional[Tuple[int, int]] = None,
@@ -225,8 +239,12 @@ def conv2d(x: torch.Tensor, cw: ConvW, *, stride: int = 1, pad: int = 0, pad_tl:
         assert (rB, rH, rW, rC) == (B, Ho, Wo, cw.Cout), (tuple(res.shape), (B, Ho, Wo, cw.Cout))
         d.res, d.res_bstride, d.res_ld = res.data_ptr(), rbs, rld
     d.d2s, d.out_nchw = d2s, 1 if out_nchw else 0
-    d.tf32x3 = 0 if (exact or not USE_TF32X3 or cw.w_tc is None) else (2 if (fast and ALLOW_TF32_1PASS) else 1)
-    d.w_tc = _ptr(cw.w_tc)
+    if exact or not USE_TF32X3 or (cw.w_tc is None and cw.w_tc16 is None):
+        d.precision = PREC['exact']
+    else:
+        one = fast and ALLOW_TF32_1PASS
+        d.precision = (PREC['f16'] if one else PREC['f16x3']) if USE_F16 else (PREC['tf32'] if one else PREC['tf32x3'])
+    d.w_tc, d.w_tc16 = _ptr(cw.w_tc), _ptr(cw.w_tc16)
     d.tc_variant = TC_VARIANT
     d.kernel_used = -1
     K = cw.kh * cw.kw * Cin
@@ -234,7 +252,7 @@ def conv2d(x: torch.Tensor, cw: ConvW, *, stride: int = 1, pad: int = 0, pad_tl:
                4.0 * (B * Hi * Wi * Cin + B * Ho * Wo * cw.Cout * (2 if res is not None else 1) + K * cw.Cout),
                f'conv B{B} {Hi}x{Wi} Cin{Cin} Cout{cw.Cout} k{cw.kh} s{stride}{" up" if upsample2 else ""}{" pre" if pre is not None else ""}') as pr:
         check(lib.sma_conv2d_fwd(C.byref(d), _stream()), f'sma_conv2d_fwd Cin={Cin} Cout={cw.Cout} k={cw.kh}x{cw.kw}')
-        pr.label += (' simt', ' tc-gather', ' tc-halo')[d.kernel_used] + ('' if d.tf32x3 != 2 else ' 1pass')
+        pr.label += (' simt', ' tc-gather', ' tc-halo', ' tc-halo-f16')[d.kernel_used] + (' 1pass' if d.precision in (2, 4) else '')
     global LAST_CONV_KERNEL
     LAST_CONV_KERNEL = d.kernel_used
     return out

@@ -64,11 +64,11 @@ def _act_ref(x, act):
             'sigmoid': torch.sigmoid, 'swish': lambda v: v * torch.sigmoid(v)}[act](x)
 
 
-@pytest.mark.parametrize('exact', [True, False, 'gather'])
+@pytest.mark.parametrize('mode', ['exact', 'f16x3', 'tf32x3', 'gather'])
 @pytest.mark.parametrize('case', CONV_CASES)
-def test_conv2d_matches_torch(S, case, exact):
-    S.ops.TC_VARIANT = 1 if exact == 'gather' else 0        # 'gather': force the non-persistent tcgen05 kernel
-    exact = exact is True
+def test_conv2d_matches_torch(S, case, mode):
+    """exact: fp32 FFMA kernel; f16x3 (the default): fp16-split tcgen05 halo kernel where Cin % 64 == 0, else the tf32 kernels;
+    tf32x3: tf32-split tcgen05 kernels; gather: force the non-persistent tcgen05 kernel."""
     B, Cin, H, W, Cout, k, stride, pad, ex = case
     x = rnd(B, Cin, H, W, seed=1)
     w = rnd(Cout, Cin, k, k, seed=2, scale=(Cin * k * k) ** -0.5)
@@ -94,17 +94,39 @@ def test_conv2d_matches_torch(S, case, exact):
         ref = ref + r.double()
         res = nhwc(r)
     cw = S.ops.pack_conv(w.cuda(), b.cuda())
-    y = S.ops.conv2d(nhwc(x), cw, stride=stride, pad=pad, act=ex.get('act', 'none'), pre=pre, res=res,
-                     out_nchw=bool(ex.get('nchw')), exact=exact, **kw)
-    S.ops.TC_VARIANT = 0
+    S.ops.TC_VARIANT = 1 if mode == 'gather' else 0
+    S.ops.USE_F16 = mode == 'f16x3'
+    try:
+        y = S.ops.conv2d(nhwc(x), cw, stride=stride, pad=pad, act=ex.get('act', 'none'), pre=pre, res=res,
+                         out_nchw=bool(ex.get('nchw')), exact=mode == 'exact', **kw)
+    finally:
+        S.ops.TC_VARIANT, S.ops.USE_F16 = 0, True
     got = y.cpu() if ex.get('nchw') else nchw(y)
     err = float((got.double() - ref).abs().max())
     assert got.shape == ref.shape
-    tc_eligible = (not exact) and Cin % 32 == 0 and not ex.get('nchw')
+    tc_eligible = mode != 'exact' and Cin % 32 == 0 and not ex.get('nchw')
     assert (S.ops.LAST_CONV_KERNEL >= 1) == tc_eligible, S.ops.LAST_CONV_KERNEL      # the tensor-core kernels really ran
-    # exact kernel: fp32 FFMA; tcgen05 3xTF32: the TMEM accumulator adds with truncation, error grows ~1e-8 * K
+    if mode == 'f16x3' and tc_eligible and Cin % 64 == 0 and stride == 1:
+        assert S.ops.LAST_CONV_KERNEL == 3, S.ops.LAST_CONV_KERNEL                   # ... and the fp16-split one where eligible
+    # exact kernel: fp32 FFMA; split kernels: the TMEM accumulator adds with truncation, error grows ~1e-8 * K
     tol = (2e-5 + (1e-8 * Cin * k * k if tc_eligible else 0.0)) * max(1.0, float(ref.abs().max()))
     assert err < tol, (err, tol)
+
+
+@pytest.mark.parametrize('scale_w,scale_x,tol', [(1e-3, 1.0, 2e-5), (30.0, 1.0, 2e-5), (0.05, 1e-3, 1e-4), (0.05, 300.0, 2e-5)])
+def test_conv2d_f16_split_dynamic_range(S, scale_w, scale_x, tol):
+    """fp16-split kernel away from unit scale: per-channel power-of-two weight scaling keeps tiny / large weights exact to ~2^-22;
+    small activations lose their lo half below 2^-25 absolute (still ~1e-7 of the output scale), large ones stay finite."""
+    B, Cin, H, W, Cout, k = 1, 128, 24, 24, 64, 3
+    x = rnd(B, Cin, H, W, seed=1) * scale_x
+    w = rnd(Cout, Cin, k, k, seed=2, scale=(Cin * k * k) ** -0.5) * scale_w
+    w[3] *= 1e-4; w[5] *= 50.0                                       # per-channel spread
+    ref = F.conv2d(x.double(), w.double(), None, padding=1)
+    y = S.ops.conv2d(nhwc(x), S.ops.pack_conv(w.cuda(), None), pad=1)
+    assert S.ops.LAST_CONV_KERNEL == 3
+    err = (nchw(y).double() - ref).abs().amax(dim=(0, 2, 3))
+    mag = ref.abs().amax(dim=(0, 2, 3)).clamp_min(1e-30)
+    assert float((err / mag).max()) < tol, (err / mag).max()        # measured: 2.5e-5 for the 1e-3-scale activations, < 1e-5 otherwise
 
 
 def test_conv2d_concat_slices_patchify_and_bn_fold(S):

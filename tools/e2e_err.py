@@ -14,8 +14,9 @@ g, me = g.eval().cuda(), me.eval().cuda()
 src, drv = O.synthetic_frames(3, seed=1234)
 dm = {'deformation': golden['deformation1'].cuda(), 'occlusion_map': golden['occlusion1'].cuda(),
       'driving_kp_heatmap': O.gaussian_heatmaps(golden['kp_norm1_value'], 64, 64).cuda()}
-for mode in sys.argv[1:] or ['exact', 'tc']:
-    S.ops.USE_TF32X3 = mode != 'exact'
+for mode in sys.argv[1:] or ['exact', 'tf32', 'f16', 'f16+kp+s1+s3m']:      # base[+fast stage ...]
+    S.ops.USE_TF32X3 = not mode.startswith('exact')
+    S.ops.USE_F16 = mode.startswith('f16')
     S.ops.FAST_STAGES = set(mode.split('+')[1:])     # e.g. tc+kp+s1+s3m
     g._src_cache = None
     out = g(src.unsqueeze(0).cuda(), dm, w=1, inference=True)
