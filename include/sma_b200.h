@@ -81,9 +81,10 @@ typedef struct sma_conv_desc {
                                     shape or the available weight images do not allow the requested one) */
   const float* w_tc;             /* tf32 tensor-core weight image from sma_pack_conv_weight_tc (may be NULL) */
   const float* w_tc16;           /* fp16 tensor-core weight image from sma_pack_conv_weight_tc16 (may be NULL) */
+  const float* w_ts;             /* fp16 tensor-memory-operand weight image from sma_pack_conv_weight_ts (may be NULL) */
   int tc_variant;                /* 0: library picks (persistent halo kernel for stride-1, gather kernel otherwise); 1: force the gather kernel */
   int kernel_used;               /* OUT: 0 CUDA-core FFMA kernel, 1 tcgen05 tf32 gather kernel, 2 tcgen05 tf32 persistent halo kernel,
-                                    3 tcgen05 fp16 persistent halo kernel */
+                                    3 tcgen05 fp16 persistent halo kernel, 4 tcgen05 fp16 kernel with the weights in tensor memory */
 } sma_conv_desc;
 
 int sma_conv2d_fwd(sma_conv_desc* d, sma_stream_t stream);
@@ -103,6 +104,15 @@ int sma_pack_conv_weight_tc(const float* w_packed, int ldw, int Cout, int Cin, i
  * of w * 2^-e(column)], same SWIZZLE_128B tiles. */
 int64_t sma_conv_weight_tc16_floats(int Cout, int Cin, int kh, int kw);
 int sma_pack_conv_weight_tc16(const float* w_packed, int ldw, int Cout, int Cin, int kh, int kw, float* w_tc16, sma_stream_t stream);
+/* Tensor-memory-operand variant (Cin % 64 == 0; stride-1 convs): the weights are the A operand of the MMA and live in tensor memory,
+ * the pixels are the B operand in shared memory (csrc/conv_ts.cu).  Image: [un-scaling factor per output channel, padded to a multiple
+ * of 128][units of 128 rows x 64 fp16: per (block of 128 channels, 64-channel chunk, tap) the hi and the lo unit; Cout <= 64: one unit
+ * whose rows 0-63 are the hi and rows 64-127 the lo halves]. */
+int64_t sma_conv_weight_ts_floats(int Cout, int Cin, int kh, int kw);
+int sma_pack_conv_weight_ts(const float* w_packed, int ldw, int Cout, int Cin, int kh, int kw, float* w_ts, sma_stream_t stream);
+/* profiling aid: {SM cycles, nanoseconds} the MMA warp of CTA 0 spent in the tile loop of the last tensor-memory-operand conv launch
+ * (synchronises the device) */
+int sma_debug_conv_ts_prof(long long* cycles_ns /* 8 values: cycles, ns, cycles waiting for accumulator / halo / weights, 3 spare */);
 
 /* ---------------------------------------------------------------------------------------------
  * GroupNorm(32, eps) statistics -> per-(b,c) scale/shift consumed by the conv prologue

@@ -22,7 +22,7 @@ class ConvDesc(C.Structure):
         ('y', C.c_void_p), ('Ho', C.c_int), ('Wo', C.c_int), ('out_bstride', c_i64), ('out_ld', C.c_int),
         ('act', C.c_int),
         ('res', C.c_void_p), ('res_bstride', c_i64), ('res_ld', C.c_int),
-        ('d2s', C.c_int), ('out_nchw', C.c_int), ('precision', C.c_int), ('w_tc', C.c_void_p), ('w_tc16', C.c_void_p), ('tc_variant', C.c_int), ('kernel_used', C.c_int),
+        ('d2s', C.c_int), ('out_nchw', C.c_int), ('precision', C.c_int), ('w_tc', C.c_void_p), ('w_tc16', C.c_void_p), ('w_ts', C.c_void_p), ('tc_variant', C.c_int), ('kernel_used', C.c_int),
     ]
 
 
@@ -39,6 +39,9 @@ SIGNATURES = {
     'sma_pack_conv_weight_tc': ([_V, _I, _I, _I, _I, _I, _V, _V], C.c_int),
     'sma_conv_weight_tc16_floats': ([_I, _I, _I, _I], C.c_int64),
     'sma_pack_conv_weight_tc16': ([_V, _I, _I, _I, _I, _I, _V, _V], C.c_int),
+    'sma_conv_weight_ts_floats': ([_I, _I, _I, _I], C.c_int64),
+    'sma_pack_conv_weight_ts': ([_V, _I, _I, _I, _I, _I, _V, _V], C.c_int),
+    'sma_debug_conv_ts_prof': ([_V], C.c_int),
     'sma_groupnorm_stats': ([_V, _I, _I, _I, _L, _I, _I, _F, _V, _V, _V, _V, _V, _V], C.c_int),
     'sma_affine_act': ([_V, _I, _I, _I, _L, _I, _V, _V, _I, _V, _L, _I, _V], C.c_int),
     'sma_layernorm': ([_V, _I, _I, _V, _V, _F, _V, _I, _V, _V, _V], C.c_int),

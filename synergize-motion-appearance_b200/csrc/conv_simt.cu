@@ -241,6 +241,7 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, const float* __r
 }  // namespace
 
 int sma_conv2d_tc_try(sma_conv_desc* d, cudaStream_t st);   // conv_tc.cu ; returns SMA_ERR_UNSUPPORTED when not applicable
+int sma_conv2d_ts_try(sma_conv_desc* d, cudaStream_t st);   // conv_ts.cu ; likewise
 
 extern "C" int sma_conv2d_fwd(sma_conv_desc* d, sma_stream_t stream) {
   if (!d || !d->x || !d->w || !d->y) return SMA_ERR_BAD_ARG;
@@ -253,7 +254,9 @@ extern "C" int sma_conv2d_fwd(sma_conv_desc* d, sma_stream_t stream) {
   if ((long long)d->B * d->Ho * d->Wo > 0x7fffffffLL) return SMA_ERR_UNSUPPORTED;
   cudaStream_t st = as_stream(stream);
   if (d->precision != SMA_PREC_EXACT) {
-    int r = sma_conv2d_tc_try(d, st);
+    int r = sma_conv2d_ts_try(d, st);
+    if (r != SMA_ERR_UNSUPPORTED) { d->kernel_used = 4; return r; }
+    r = sma_conv2d_tc_try(d, st);
     if (r != SMA_ERR_UNSUPPORTED) return r;
   }
   d->kernel_used = 0;

@@ -406,51 +406,56 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const Tc2P p) {
     const uint32_t idesc = (1u << 4) | (F16 ? 0u : ((2u << 7) | (2u << 10))) | ((uint32_t)(p.NT >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
     // A: 8-row atoms are 8 consecutive halo rows; next atom = next output row = halo row pitch
     const uint64_t a_desc_hi_bits = (1ull << 16) | ((uint64_t)((p.halo_w * 128) >> 4) << 32) | (1ull << 46) | (2ull << 61);
-    int it = 0, jt = 0, tcount = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tcount) {
-      const int ab = tcount & 1; const uint32_t aph = (tcount >> 1) & 1;
-      mbar_wait(acc_empty(ab), aph ^ 1u);
-      tc_fence_after();
-      const uint32_t d_tmem = tmem_base + (uint32_t)(ab * p.NT);
-      for (int cc = 0; cc < p.cpt; cc++, it++) {
-        const int sa = it % p.SA; const uint32_t pha = (it / p.SA) & 1;
-        mbar_wait(a_full(sa), pha);
-        const uint32_t a_hi = a_ring + (uint32_t)sa * p.a_stage_bytes, a_lo = a_hi + p.a_img_bytes;
-        int ky = 0, kx = 0;
-        for (int tap = 0; tap < p.taps; tap++, jt++) {
-          const int sb = jt % p.SB; const uint32_t phb = (jt / p.SB) & 1;
-          mbar_wait(b_full(sb), phb);
-          tc_fence_after();
-          const uint32_t aoff = (uint32_t)(ky * p.halo_w + kx) * 128u;
-          const uint64_t dah = a_desc_hi_bits | (uint64_t)(((a_hi + aoff) & 0x3FFFF) >> 4);
-          const uint64_t dal = a_desc_hi_bits | (uint64_t)(((a_lo + aoff) & 0x3FFFF) >> 4);
-          const uint32_t b_hi = b_ring + (uint32_t)sb * b_stage_bytes;
-          const uint64_t dbh = make_desc(b_hi), dbl = make_desc(b_hi + p.b_img_bytes);
-          const bool last_tap = tap == p.taps - 1;
-          if (elect_one_sync()) {
+    // ONE elected lane runs the whole tile loop (the elect region encloses the loops) with wrap-around ring counters instead of
+    // divisions: measured with the tensor-memory-operand kernel, the per-tap scalar overhead of the old form (warp-sync + elect +
+    // reconvergence + `%` and `/` by run-time ring sizes) let the tensor pipe drain between taps.
+    if (elect_one_sync()) {
+      const uint32_t row_step = (uint32_t)(p.halo_w * 128) >> 4;          // one halo row down, in 16-byte units
+      const bool three = p.passes == 3;
+      uint32_t sa = 0, pha = 0, sb = 0, phb = 0, tcount = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tcount) {
+        const uint32_t ab = tcount & 1u;
+        mbar_wait(acc_empty(ab), ((tcount >> 1) & 1u) ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + ab * (uint32_t)p.NT;
+        uint32_t acc = 0u;                                   // the first MMA of a tile overwrites the accumulator
+        for (int cc = 0; cc < p.cpt; cc++) {
+          mbar_wait(a_full(sa), pha);
+          const uint32_t a_hi = a_ring + sa * (uint32_t)p.a_stage_bytes;
+          const uint64_t dah0 = a_desc_hi_bits | (uint64_t)((a_hi & 0x3FFFFu) >> 4);
+          const uint64_t dal0 = a_desc_hi_bits | (uint64_t)(((a_hi + (uint32_t)p.a_img_bytes) & 0x3FFFFu) >> 4);
+          uint32_t roff = 0;
+          for (int ky = 0; ky < p.kh; ky++, roff += row_step) {
+            for (int kx = 0; kx < p.kw; kx++) {
+              mbar_wait(b_full(sb), phb);
+              tc_fence_after();
+              const uint64_t toff = (uint64_t)(roff + (uint32_t)kx * 8u);
+              const uint64_t dah = dah0 + toff, dal = dal0 + toff;
+              const uint32_t b_hi = b_ring + sb * (uint32_t)b_stage_bytes;
+              const uint64_t dbh = make_desc(b_hi), dbl = make_desc(b_hi + p.b_img_bytes);
 #pragma unroll
-            for (int k4 = 0; k4 < 4; k4++) {                   // 4 k-steps of 32 bytes (8 tf32 / 16 fp16) per 128-byte row
-              const uint64_t ko = (uint64_t)(k4 * 2);
-              const uint32_t first = (cc | tap | k4) != 0;
-              if (p.passes == 3) {
-                tc_mma<F16>(d_tmem, dal + ko, dbh + ko, idesc, first);
-                tc_mma<F16>(d_tmem, dah + ko, dbl + ko, idesc, 1u);
-                tc_mma<F16>(d_tmem, dah + ko, dbh + ko, idesc, 1u);
-              } else {
-                tc_mma<F16>(d_tmem, dah + ko, dbh + ko, idesc, first);
+              for (int k4 = 0; k4 < 4; k4++) {                   // 4 k-steps of 32 bytes (8 tf32 / 16 fp16) per 128-byte row
+                const uint64_t ko = (uint64_t)(k4 * 2);
+                if (three) {
+                  tc_mma<F16>(d_tmem, dal + ko, dbh + ko, idesc, acc);
+                  tc_mma<F16>(d_tmem, dah + ko, dbl + ko, idesc, 1u);
+                  tc_mma<F16>(d_tmem, dah + ko, dbh + ko, idesc, 1u);
+                } else {
+                  tc_mma<F16>(d_tmem, dah + ko, dbh + ko, idesc, acc);
+                }
+                acc = 1u;
               }
-            }
-            tc_commit(b_empty(sb));
-            if (last_tap) {
-              tc_commit(a_empty(sa));
-              if (cc == p.cpt - 1) tc_commit(acc_full(ab));
+              tc_commit(b_empty(sb));
+              if (++sb == (uint32_t)p.SB) { sb = 0; phb ^= 1u; }
             }
           }
-          __syncwarp();
-          if (++kx == p.kw) { kx = 0; ++ky; }
+          tc_commit(a_empty(sa));
+          if (++sa == (uint32_t)p.SA) { sa = 0; pha ^= 1u; }
         }
+        tc_commit(acc_full(ab));
       }
     }
+    __syncwarp();
   } else if (warp == 5) {
     // =============================== weight loader ===============================
     if (lane == 0) {

@@ -80,6 +80,7 @@ class ConvW:
     kw: int
     w_tc: Optional[torch.Tensor] = None      # tf32 tensor-core image (sma_pack_conv_weight_tc); None -> not eligible (Cin % 32)
     w_tc16: Optional[torch.Tensor] = None    # fp16 tensor-core image (sma_pack_conv_weight_tc16); None -> not eligible (Cin % 64)
+    w_ts: Optional[torch.Tensor] = None      # fp16 tensor-memory-operand image (sma_pack_conv_weight_ts); None -> not eligible (Cin % 64)
     _slices: Optional[dict] = None           # cache of cols() results (their tensor-core images are packed once)
 
     def cols(self, start: int, n: int) -> 'ConvW':
@@ -90,7 +91,7 @@ class ConvW:
         cw = self._slices.get((start, n))
         if cw is None:
             cw = ConvW(self.w[:, start:], None if self.bias is None else self.bias[start:start + n], n, self.Cin, self.kh, self.kw)
-            cw.w_tc, cw.w_tc16 = _pack_tc(cw), _pack_tc16(cw)
+            cw.w_tc, cw.w_tc16, cw.w_ts = _pack_tc(cw), _pack_tc16(cw), _pack_ts(cw)
             self._slices[(start, n)] = cw
         return cw
 
@@ -99,7 +100,7 @@ class ConvW:
         (appmotioncodebook_arch.py:222,229,236)."""
         assert self.kh == 1 and self.kw == 1 and self.Cin % (p * p) == 0
         cw = ConvW(self.w, self.bias, self.Cout, self.Cin // (p * p), p, p)
-        cw.w_tc, cw.w_tc16 = _pack_tc(cw), _pack_tc16(cw)
+        cw.w_tc, cw.w_tc16, cw.w_ts = _pack_tc(cw), _pack_tc16(cw), _pack_ts(cw)
         return cw
 
 
@@ -122,6 +123,17 @@ def _pack_tc16(cw: 'ConvW') -> Optional[torch.Tensor]:
     out = torch.empty((n,), device=cw.w.device, dtype=torch.float32)
     check(lib.sma_pack_conv_weight_tc16(cw.w.data_ptr(), cw.w.stride(0), cw.Cout, cw.Cin, cw.kh, cw.kw, out.data_ptr(), _stream()),
           'sma_pack_conv_weight_tc16')
+    return out
+
+
+def _pack_ts(cw: 'ConvW') -> Optional[torch.Tensor]:
+    lib = _lib.load()
+    n = lib.sma_conv_weight_ts_floats(cw.Cout, cw.Cin, cw.kh, cw.kw)
+    if n <= 0:
+        return None
+    out = torch.empty((n,), device=cw.w.device, dtype=torch.float32)
+    check(lib.sma_pack_conv_weight_ts(cw.w.data_ptr(), cw.w.stride(0), cw.Cout, cw.Cin, cw.kh, cw.kw, out.data_ptr(), _stream()),
+          'sma_pack_conv_weight_ts')
     return out
 
 
@@ -151,7 +163,7 @@ def pack_conv(weight: torch.Tensor, bias: Optional[torch.Tensor], bn: Optional[d
     check(lib.sma_pack_conv_weight(_ptr(w), _ptr(b), Cout, Cin, kh, kw, _ptr(g), _ptr(be), _ptr(mu), _ptr(var), eps,
                                    _ptr(wp), ldw, _ptr(bo), _stream()), 'sma_pack_conv_weight')
     cw = ConvW(wp, None if bo is None else bo[:Cout], Cout, Cin, kh, kw)
-    cw.w_tc, cw.w_tc16 = _pack_tc(cw), _pack_tc16(cw)
+    cw.w_tc, cw.w_tc16, cw.w_ts = _pack_tc(cw), _pack_tc16(cw), _pack_ts(cw)
     return cw
 
 
@@ -178,6 +190,7 @@ def pack_conv_blockdiag(weights, biases) -> ConvW:
 PREC = {'exact': 0, 'tf32x3': 1, 'tf32': 2, 'f16x3': 3, 'f16': 4}     # SMA_PREC_*
 USE_TF32X3 = True        # let sma_conv2d_fwd pick a tcgen05 kernel where the shape allows (False: exact CUDA-core kernels everywhere)
 ALLOW_TF32_1PASS = True  # honour `fast=True` requests (single pass)
+USE_TS = False           # weights as the tensor-memory A operand (csrc/conv_ts.cu) where eligible; False: shared-memory-operand kernels
 USE_F16 = True           # split operands into fp16 halves (kind::f16, 2x the tensor rate of kind::tf32) where Cin % 64 == 0
 # Per-stage precision policy: stages listed here run their convolutions as single-pass TF32 (3x fewer tensor-core
 # instructions); everything else is fp32-faithful 3xTF32.  See DESIGN.md section 4 for the measured error budget.
@@ -189,7 +202,7 @@ def fast(stage: str) -> bool:
 
 
 TC_VARIANT = 0           # 0: library picks the tensor-core kernel variant; 1: force the gather kernel (tests)
-LAST_CONV_KERNEL = -1    # which kernel the last conv2d ran on: 0 CUDA-core, 1 tcgen05 gather, 2 tcgen05 persistent halo (tf32), 3 (fp16)
+LAST_CONV_KERNEL = -1    # which kernel the last conv2d ran on: 0 CUDA-core, 1 tcgen05 gather, 2 tcgen05 persistent halo (tf32), 3 (fp16), 4 fp16 with weights in tensor memory
 
 
 def conv2d(x: torch.Tensor, cw: ConvW, *, stride: int = 1, pad: int = 0, pad_tl: Optional[Tuple[int, int]] = None,
@@ -239,12 +252,12 @@ def conv2d(x: torch.Tensor, cw: ConvW, *, stride: int = 1, pad: int = 0, pad_tl:
         assert (rB, rH, rW, rC) == (B, Ho, Wo, cw.Cout), (tuple(res.shape), (B, Ho, Wo, cw.Cout))
         d.res, d.res_bstride, d.res_ld = res.data_ptr(), rbs, rld
     d.d2s, d.out_nchw = d2s, 1 if out_nchw else 0
-    if exact or not USE_TF32X3 or (cw.w_tc is None and cw.w_tc16 is None):
+    if exact or not USE_TF32X3 or (cw.w_tc is None and cw.w_tc16 is None and cw.w_ts is None):
         d.precision = PREC['exact']
     else:
         one = fast and ALLOW_TF32_1PASS
         d.precision = (PREC['f16'] if one else PREC['f16x3']) if USE_F16 else (PREC['tf32'] if one else PREC['tf32x3'])
-    d.w_tc, d.w_tc16 = _ptr(cw.w_tc), _ptr(cw.w_tc16)
+    d.w_tc, d.w_tc16, d.w_ts = _ptr(cw.w_tc), _ptr(cw.w_tc16), (_ptr(cw.w_ts) if USE_TS else None)
     d.tc_variant = TC_VARIANT
     d.kernel_used = -1
     K = cw.kh * cw.kw * Cin
@@ -252,7 +265,7 @@ def conv2d(x: torch.Tensor, cw: ConvW, *, stride: int = 1, pad: int = 0, pad_tl:
                4.0 * (B * Hi * Wi * Cin + B * Ho * Wo * cw.Cout * (2 if res is not None else 1) + K * cw.Cout),
                f'conv B{B} {Hi}x{Wi} Cin{Cin} Cout{cw.Cout} k{cw.kh} s{stride}{" up" if upsample2 else ""}{" pre" if pre is not None else ""}') as pr:
         check(lib.sma_conv2d_fwd(C.byref(d), _stream()), f'sma_conv2d_fwd Cin={Cin} Cout={cw.Cout} k={cw.kh}x{cw.kw}')
-        pr.label += (' simt', ' tc-gather', ' tc-halo', ' tc-halo-f16')[d.kernel_used] + (' 1pass' if d.precision in (2, 4) else '')
+        pr.label += (' simt', ' tc-gather', ' tc-halo', ' tc-halo-f16', ' ts-f16')[d.kernel_used] + (' 1pass' if d.precision in (2, 4) else '')
     global LAST_CONV_KERNEL
     LAST_CONV_KERNEL = d.kernel_used
     return out

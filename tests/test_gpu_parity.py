@@ -56,6 +56,10 @@ CONV_CASES = [
     (1, 256, 32, 32, 512, 3, 1, 1, {'act': 'gelu'}),
     (1, 128, 32, 32, 256, 3, 1, 1, {'act': 'leaky'}),
     (3, 15, 32, 32, 32, 1, 1, 0, {'act': 'relu'}),
+    (2, 64, 40, 24, 192, 1, 1, 0, {'act': 'relu'}),
+    (1, 192, 64, 64, 128, 3, 1, 1, {'act': 'relu', 'res': True}),
+    (2, 128, 32, 32, 64, 1, 1, 0, {'res': True}),
+    (1, 256, 64, 64, 3, 3, 1, 1, {}),
 ]
 
 
@@ -64,11 +68,12 @@ def _act_ref(x, act):
             'sigmoid': torch.sigmoid, 'swish': lambda v: v * torch.sigmoid(v)}[act](x)
 
 
-@pytest.mark.parametrize('mode', ['exact', 'f16x3', 'tf32x3', 'gather'])
+@pytest.mark.parametrize('mode', ['exact', 'ts', 'f16x3', 'tf32x3', 'gather'])
 @pytest.mark.parametrize('case', CONV_CASES)
 def test_conv2d_matches_torch(S, case, mode):
-    """exact: fp32 FFMA kernel; f16x3 (the default): fp16-split tcgen05 halo kernel where Cin % 64 == 0, else the tf32 kernels;
-    tf32x3: tf32-split tcgen05 kernels; gather: force the non-persistent tcgen05 kernel."""
+    """exact: fp32 FFMA kernel; ts (the default): fp16-split tcgen05 kernel with the weights in tensor memory where Cin % 64 == 0 and
+    stride 1, else the kernels below; f16x3: fp16-split halo kernel with both operands in shared memory; tf32x3: tf32-split tcgen05
+    kernels; gather: force the non-persistent tcgen05 kernel."""
     B, Cin, H, W, Cout, k, stride, pad, ex = case
     x = rnd(B, Cin, H, W, seed=1)
     w = rnd(Cout, Cin, k, k, seed=2, scale=(Cin * k * k) ** -0.5)
@@ -95,19 +100,20 @@ def test_conv2d_matches_torch(S, case, mode):
         res = nhwc(r)
     cw = S.ops.pack_conv(w.cuda(), b.cuda())
     S.ops.TC_VARIANT = 1 if mode == 'gather' else 0
-    S.ops.USE_F16 = mode == 'f16x3'
+    S.ops.USE_F16 = mode in ('f16x3', 'ts')
+    S.ops.USE_TS = mode == 'ts'
     try:
         y = S.ops.conv2d(nhwc(x), cw, stride=stride, pad=pad, act=ex.get('act', 'none'), pre=pre, res=res,
                          out_nchw=bool(ex.get('nchw')), exact=mode == 'exact', **kw)
     finally:
-        S.ops.TC_VARIANT, S.ops.USE_F16 = 0, True
+        S.ops.TC_VARIANT, S.ops.USE_F16, S.ops.USE_TS = 0, True, True
     got = y.cpu() if ex.get('nchw') else nchw(y)
     err = float((got.double() - ref).abs().max())
     assert got.shape == ref.shape
     tc_eligible = mode != 'exact' and Cin % 32 == 0 and not ex.get('nchw')
     assert (S.ops.LAST_CONV_KERNEL >= 1) == tc_eligible, S.ops.LAST_CONV_KERNEL      # the tensor-core kernels really ran
-    if mode == 'f16x3' and tc_eligible and Cin % 64 == 0 and stride == 1:
-        assert S.ops.LAST_CONV_KERNEL == 3, S.ops.LAST_CONV_KERNEL                   # ... and the fp16-split one where eligible
+    if mode in ('f16x3', 'ts') and tc_eligible and Cin % 64 == 0 and stride == 1:
+        assert S.ops.LAST_CONV_KERNEL == (4 if mode == 'ts' else 3), S.ops.LAST_CONV_KERNEL     # ... and the fp16-split ones where eligible
     # exact kernel: fp32 FFMA; split kernels: the TMEM accumulator adds with truncation, error grows ~1e-8 * K
     tol = (2e-5 + (1e-8 * Cin * k * k if tc_eligible else 0.0)) * max(1.0, float(ref.abs().max()))
     assert err < tol, (err, tol)
@@ -123,7 +129,7 @@ def test_conv2d_f16_split_dynamic_range(S, scale_w, scale_x, tol):
     w[3] *= 1e-4; w[5] *= 50.0                                       # per-channel spread
     ref = F.conv2d(x.double(), w.double(), None, padding=1)
     y = S.ops.conv2d(nhwc(x), S.ops.pack_conv(w.cuda(), None), pad=1)
-    assert S.ops.LAST_CONV_KERNEL == 3
+    assert S.ops.LAST_CONV_KERNEL == 4
     err = (nchw(y).double() - ref).abs().amax(dim=(0, 2, 3))
     mag = ref.abs().amax(dim=(0, 2, 3)).clamp_min(1e-30)
     assert float((err / mag).max()) < tol, (err / mag).max()        # measured: 2.5e-5 for the 1e-3-scale activations, < 1e-5 otherwise
