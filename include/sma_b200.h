@@ -153,6 +153,13 @@ int sma_mha_fwd(const float* q, int ldq, const float* k, int ldk, const float* v
                 int64_t kv_bstride, int B, int L, int S, int heads, int D, float scale,
                 const uint8_t* key_mask, float* out, int ldo, int flags, sma_stream_t stream);
 
+/* Single-head attention with head dim 256 (the AttnBlock, archs/vqgan_arch.py:233-248) on the tensor cores (csrc/attn256.cu): a split
+ * pass writes fp16 hi / lo tile images of q (pre-scaled), k, v into `workspace` (sma_attn256_workspace_bytes), the attention kernel
+ * streams them with bulk copies.  L % 128 == 0, S % 64 == 0; q:(B,L,256) k,v:(B,S,256) views with row strides ld*. */
+int64_t sma_attn256_workspace_bytes(int B, int L, int S);
+int sma_attn256_fwd(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv, int64_t q_bstride, int64_t kv_bstride,
+                    int B, int L, int S, float scale, void* workspace, float* out, int ldo, sma_stream_t stream);
+
 /* VectorQuantizer lookup (archs/vqgan_arch.py:33-73): d = fl(fl(|z|^2+|e|^2) - 2 z.e), argmin with
  * lowest-index ties -> idx (int64), zq = e[idx].  z:(N,E) row-major, codebook (n_codes,E). */
 int sma_vq_lookup_fwd(const float* z, int N, int E, const float* codebook, int n_codes, int64_t* idx,

@@ -367,9 +367,27 @@ def mha(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, key_mask:
         scale = float(D) ** -0.5
     if key_mask is not None:
         assert key_mask.dtype == torch.uint8 and key_mask.is_contiguous() and key_mask.numel() == B * S
+    if D == 256 and heads == 1 and key_mask is None and kvbs and not exact and USE_TF32X3 and L % 128 == 0 and S % 64 == 0:
+        return attn256(q, k, v, scale, out)
     with _Prof('mha', 4.0 * B * L * S * E, 4.0 * (2 * B * L * E + 2 * (B if kvbs else 1) * S * E), f'mha B{B} L{L} S{S} h{heads} D{D}'):
         check(lib.sma_mha_fwd(q.data_ptr(), q.stride(1), k.data_ptr(), ldk, v.data_ptr(), ldv, kvbs, B, L, S, heads, D, scale,
                               _ptr(key_mask), out.data_ptr(), out.stride(1), 1 if (exact or not USE_TF32X3) else 0, _stream()), f'sma_mha_fwd D={D}')
+    return out
+
+
+def attn256(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, scale: float, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Single-head, head-dim-256 attention on the tensor cores (AttnBlock).  q (B,L,256-view), k, v (B,S,256-view): column slices of one
+    qkv buffer are fine."""
+    lib = _lib.load()
+    B, L, D = q.shape
+    S = k.shape[1]
+    assert D == 256 and q.stride(2) == 1 and k.stride(2) == 1 and v.stride(2) == 1 and k.stride(0) == v.stride(0)
+    if out is None:
+        out = torch.empty((B, L, D), device=q.device, dtype=torch.float32)
+    ws = torch.empty((lib.sma_attn256_workspace_bytes(B, L, S),), device=q.device, dtype=torch.uint8)
+    with _Prof('mha', 4.0 * B * L * S * D, 4.0 * (2 * B * L * D + 2 * B * S * D), f'attn256 B{B} L{L} S{S}'):
+        check(lib.sma_attn256_fwd(q.data_ptr(), q.stride(1), k.data_ptr(), k.stride(1), v.data_ptr(), v.stride(1), q.stride(0), k.stride(0),
+                                  B, L, S, scale, ws.data_ptr(), out.data_ptr(), out.stride(1), _stream()), 'sma_attn256_fwd')
     return out
 
 

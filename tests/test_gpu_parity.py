@@ -285,6 +285,24 @@ def test_mha_core(S, E, heads, S_kv, shared, masked, exact):
     assert float((got.cpu().double() - ref).abs().max()) < (2e-5 if exact else 1e-4)
 
 
+@pytest.mark.parametrize('B,L,S_kv,qs', [(3, 1024, 1024, 1.0), (1, 256, 512, 1.0), (2, 1024, 1024, 6.0)])
+def test_attn256_tensor_core_kernel(S, B, L, S_kv, qs):
+    """AttnBlock attention on tcgen05 (csrc/attn256.cu) called directly; qs = 6 makes the scores spread over ~+-100 so that the lazy
+    reference maximum is exceeded and the O rescale in tensor memory runs; q, k, v are column slices of one buffer like the qkv conv output."""
+    qkv = rnd(B, max(L, S_kv), 768, seed=7)
+    qkv[..., :256] *= qs
+    q, k, v = qkv[:, :L, :256], qkv[:, :S_kv, 256:512], qkv[:, :S_kv, 512:]
+    s = (q.double() @ k.double().transpose(-1, -2)) * (256 ** -0.5)
+    ref = torch.softmax(s, -1) @ v.double()
+    dev = qkv.cuda()
+    n0 = S.ops.launch_count()
+    got = S.ops.attn256(dev[:, :L, :256], dev[:, :S_kv, 256:512], dev[:, :S_kv, 512:], 256 ** -0.5)
+    assert S.ops.launch_count() - n0 == 2                            # split + attention kernels
+    assert float((got.cpu().double() - ref).abs().max()) < 1e-4
+    with pytest.raises(RuntimeError):                                # L not a multiple of 128 -> status -2
+        S.ops.attn256(dev[:, :100, :256], dev[:, :S_kv, 256:512], dev[:, :S_kv, 512:], 1.0)
+
+
 def test_mha_all_keys_masked_gives_nan_like_reference(S):
     q, k, v = rnd(1, 1024, 256, seed=1).cuda(), rnd(1, 1024, 256, seed=2).cuda(), rnd(1, 1024, 256, seed=3).cuda()
     mask = torch.ones(1, 1024, dtype=torch.uint8, device='cuda')
