@@ -206,6 +206,63 @@ __global__ void __launch_bounds__(128) mha_d4_kernel(const float* __restrict__ q
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// D = 4, no mask (motion TransformerLayer): CUDA cores beat the tensor cores here - a head is 4 values, so a score costs 4 FFMA and its
+// P.V contribution 4 FFMA, while tcgen05 needs K >= 16 and N >= 16 (>= 75 % padding) plus the softmax round trip through tensor memory.
+// One thread = one query row of one head; the head's K and V (S x 16 B each) sit in shared memory (broadcast LDS.128); scores are
+// computed directly relative to a lazy reference maximum (s - m_ref in the FFMA chain, p = ex2 of it), which only moves when a chunk
+// exceeds it by more than 2^8: ~13 issue slots per (32 queries x 1 key).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float ex2f_(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+__global__ void __launch_bounds__(128) mha_d4_fast_kernel(const float* __restrict__ q, int ldq, const float* __restrict__ k, int ldk,
+                                                          const float* __restrict__ v, int ldv, long long kv_bs, int L, int S, float qscale,
+                                                          float* __restrict__ out, int ldo) {
+  extern __shared__ float4 kv_s[];
+  float4* Ks = kv_s; float4* Vs = kv_s + S;
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int r = blockIdx.x * 128 + threadIdx.x;
+  for (int f = threadIdx.x; f < S; f += 128) {
+    Ks[f] = __ldg(reinterpret_cast<const float4*>(k + (long long)b * kv_bs + (long long)f * ldk + h * 4));
+    Vs[f] = __ldg(reinterpret_cast<const float4*>(v + (long long)b * kv_bs + (long long)f * ldv + h * 4));
+  }
+  float4 qv = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (r < L) qv = __ldg(reinterpret_cast<const float4*>(q + ((long long)b * L + r) * ldq + h * 4));
+  qv.x *= qscale; qv.y *= qscale; qv.z *= qscale; qv.w *= qscale;        // log2 units
+  __syncthreads();
+  constexpr float LAZY = 8.f;
+  float m_ref = -CUDART_INF_F;
+#pragma unroll
+  for (int i = 0; i < 8; i++) { float4 kk = Ks[i]; m_ref = fmaxf(m_ref, fmaf(qv.w, kk.w, fmaf(qv.z, kk.z, fmaf(qv.y, kk.y, qv.x * kk.x)))); }
+  float l = 0.f; float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int c0 = 0; c0 < S; c0 += 8) {
+    float t[8]; float tmax = -CUDART_INF_F;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      const float4 kk = Ks[c0 + i];
+      t[i] = fmaf(qv.w, kk.w, fmaf(qv.z, kk.z, fmaf(qv.y, kk.y, fmaf(qv.x, kk.x, -m_ref))));
+      tmax = fmaxf(tmax, t[i]);
+    }
+    if (__any_sync(0xffffffffu, tmax > LAZY)) {        // rare after the first chunks
+      if (tmax > LAZY) {
+        const float corr = ex2f_(-tmax);
+        l *= corr; o.x *= corr; o.y *= corr; o.z *= corr; o.w *= corr; m_ref += tmax;
+#pragma unroll
+        for (int i = 0; i < 8; i++) t[i] -= tmax;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      const float pr = ex2f_(t[i]); const float4 vv = Vs[c0 + i];
+      l += pr; o.x = fmaf(pr, vv.x, o.x); o.y = fmaf(pr, vv.y, o.y); o.z = fmaf(pr, vv.z, o.z); o.w = fmaf(pr, vv.w, o.w);
+    }
+  }
+  if (r < L) {
+    const float inv = 1.f / l;
+    *reinterpret_cast<float4*>(out + ((long long)b * L + r) * ldo + h * 4) = make_float4(o.x * inv, o.y * inv, o.z * inv, o.w * inv);
+  }
+}
+
 template <int D, int BKV>
 int launch_mha(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv, long long kv_bs, int B, int L, int S, int heads,
                float scale, const uint8_t* mask, float* out, int ldo, cudaStream_t st) {
@@ -233,6 +290,16 @@ extern "C" int sma_mha_fwd(const float* q, int ldq, const float* k, int ldk, con
     return SMA_ERR_UNSUPPORTED;
   if (kv_bstride & 3) return SMA_ERR_UNSUPPORTED;
   cudaStream_t st = as_stream(stream);
+  if (D == 4 && !key_mask && !(flags & 1) && (S % 8) == 0 && S * 32 <= 96 * 1024) {
+    static bool configured = false;   // idempotent attribute set; benign if raced
+    if (!configured) {
+      if (cudaFuncSetAttribute(mha_d4_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024) != cudaSuccess) return SMA_ERR_CUDA;
+      configured = true;
+    }
+    mha_d4_fast_kernel<<<dim3(cdiv(L, 128), heads, B), 128, S * 32, st>>>(q, ldq, k, ldk, v, ldv, kv_bstride, L, S, scale * 1.4426950408889634f, out, ldo);
+    SMA_LAUNCH_CHECK();
+    return SMA_OK;
+  }
   if (!(flags & 1)) {
     int r = sma_mha_tc_try(q, ldq, k, ldk, v, ldv, kv_bstride, B, L, S, heads, D, scale, key_mask, out, ldo, st);
     if (r != SMA_ERR_UNSUPPORTED) return r;
