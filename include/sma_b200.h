@@ -160,6 +160,12 @@ int64_t sma_attn256_workspace_bytes(int B, int L, int S);
 int sma_attn256_fwd(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv, int64_t q_bstride, int64_t kv_bstride,
                     int B, int L, int S, float scale, void* workspace, float* out, int ldo, sma_stream_t stream);
 
+/* 8-head attention with E = 256 (head dim 32: the appearance TransformerLayer) on the tensor cores (csrc/attn_mh.cu), same scheme as
+ * sma_attn256_fwd; kv_bstride == 0: k, v (the codebook projections) are shared by every frame.  key_mask (B,S) uint8 or NULL. */
+int64_t sma_mha_e256_workspace_bytes(int B, int kvB, int L, int S);
+int sma_mha_e256_fwd(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv, int64_t q_bstride, int64_t kv_bstride,
+                     int B, int L, int S, float scale, const uint8_t* key_mask, void* workspace, float* out, int ldo, sma_stream_t stream);
+
 /* VectorQuantizer lookup (archs/vqgan_arch.py:33-73): d = fl(fl(|z|^2+|e|^2) - 2 z.e), argmin with
  * lowest-index ties -> idx (int64), zq = e[idx].  z:(N,E) row-major, codebook (n_codes,E). */
 int sma_vq_lookup_fwd(const float* z, int N, int E, const float* codebook, int n_codes, int64_t* idx,

@@ -43,9 +43,9 @@ __device__ __forceinline__ void a2_mma_ts(uint32_t d, uint32_t a_tmem, uint64_t 
 // 1. split: one thread per (frame, row, group of 8 head-dim values) of q, k and v
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void attn256_split_kernel(const float* __restrict__ q, int ldq, const float* __restrict__ k, int ldk, const float* __restrict__ v, int ldv,
-                                     long long bs_q, long long bs_kv, int B, int L, int S, float qscale, uint16_t* __restrict__ ws) {
-  const long long nq = (long long)B * L * 32, nk = (long long)B * S * 32;
-  const long long img_q = (long long)B * L * A2_D, img_k = (long long)B * S * A2_D;     // halfs per image
+                                     long long bs_q, long long bs_kv, int B, int kvB, int L, int S, float qscale, uint16_t* __restrict__ ws) {
+  const long long nq = (long long)B * L * 32, nk = (long long)kvB * S * 32;
+  const long long img_q = (long long)B * L * A2_D, img_k = (long long)kvB * S * A2_D;     // halfs per image
   uint16_t* qh = ws; uint16_t* ql = qh + img_q; uint16_t* kh = ql + img_q; uint16_t* kl = kh + img_k; uint16_t* vh = kl + img_k; uint16_t* vl = vh + img_k;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nq + 2 * nk; i += (long long)gridDim.x * blockDim.x) {
     const int which = i < nq ? 0 : (i < nq + nk ? 1 : 2);
@@ -282,6 +282,16 @@ __global__ void __launch_bounds__(A2_THREADS, 1) attn256_kernel(const A2P p) {
 
 }  // namespace
 
+// shared with attn_mh.cu: fp16 hi / lo tile images of q (B frames, pre-scaled by qscale), k and v (kvB frames: 1 = shared by all frames)
+int sma_attn_split_launch(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv, long long q_bs, long long kv_bs, int B, int kvB,
+                          int L, int S, float qscale, void* workspace, cudaStream_t st) {
+  const long long items = (long long)B * L * 32 + 2LL * kvB * S * 32;
+  int blocks = (int)((items + 255) / 256); if (blocks > 148 * 16) blocks = 148 * 16;
+  attn256_split_kernel<<<blocks, 256, 0, st>>>(q, ldq, k, ldk, v, ldv, q_bs, kv_bs, B, kvB, L, S, qscale, reinterpret_cast<uint16_t*>(workspace));
+  SMA_LAUNCH_CHECK();
+  return SMA_OK;
+}
+
 extern "C" int64_t sma_attn256_workspace_bytes(int B, int L, int S) {
   if (B <= 0 || L <= 0 || S <= 0) return 0;
   return 2LL * A2_D * 2 * ((long long)B * L + 2LL * B * S);      // fp16 hi + lo images of q, k, v
@@ -296,11 +306,8 @@ extern "C" int sma_attn256_fwd(const float* q, int ldq, const float* k, int ldk,
        reinterpret_cast<uintptr_t>(workspace)) & 15)
     return SMA_ERR_BAD_ARG;
   cudaStream_t st = as_stream(stream);
-  const long long items = (long long)B * L * 32 + 2LL * B * S * 32;
-  int blocks = (int)((items + 255) / 256); if (blocks > 148 * 16) blocks = 148 * 16;
-  attn256_split_kernel<<<blocks, 256, 0, st>>>(q, ldq, k, ldk, v, ldv, q_bstride, kv_bstride, B, L, S, scale * 1.4426950408889634f,
-                                               reinterpret_cast<uint16_t*>(workspace));
-  SMA_LAUNCH_CHECK();
+  int rs = sma_attn_split_launch(q, ldq, k, ldk, v, ldv, q_bstride, kv_bstride, B, B, L, S, scale * 1.4426950408889634f, workspace, st);
+  if (rs != SMA_OK) return rs;
   static bool configured = false;
   if (!configured) {
     if (cudaFuncSetAttribute(attn256_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)A2_SMEM + 1024) != cudaSuccess) return SMA_ERR_CUDA;

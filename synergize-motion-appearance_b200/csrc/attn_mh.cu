@@ -1,0 +1,296 @@
+// 8-head attention of the appearance TransformerLayer (E = 256, head dim 32; appmotioncodebook_arch.py:97-116) on tcgen05 with the
+// fp16 hi/lo split, flash-style.  Same building blocks as attn256.cu: pre-split tile images fetched with bulk copies, q_lo as a
+// tensor-memory operand, V through an MN-major descriptor, lazy reference maximum.
+//
+// A 128-byte row of the tile images holds 64 head-dim values = TWO heads, so a CTA owns one (128-query tile, head PAIR, frame) and runs
+// both heads on every K / V block it loads: head x reads bytes 64x..64x+63 of each row (descriptor start + 64 B; the swizzle is a function
+// of the absolute address, so a shifted start stays consistent).  Per 64-key block and head: S = q k^T (2 k-steps x 3 products, N = 64),
+// O += P V (4 k-steps x 3 products, N = 32).  K / V are double buffered; S, P and O are per head.
+//   warps 0-7  softmax (two threads per query row, 32 keys each; both heads), O rescale, epilogue
+//   warp 8     MMA issue (one elected lane)          warp 9   loader (bulk copies)
+// An all-masked row yields NaN like the reference (l = 0 -> 0 * inf).
+#include "sma_common.cuh"
+#include "tc_common.cuh"
+#include <math_constants.h>
+
+int sma_attn_split_launch(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv, long long q_bs, long long kv_bs, int B, int kvB,
+                          int L, int S, float qscale, void* workspace, cudaStream_t st);   // attn256.cu
+
+namespace {
+
+constexpr int MH_BQ = 128, MH_BKV = 64, MH_E = 256;
+constexpr int MH_THREADS = 320;
+constexpr uint32_t MH_OFF_QH = 0, MH_OFF_K = 16384, MH_OFF_V = 49152, MH_OFF_P = 81920, MH_SMEM = 147456;
+constexpr uint32_t MH_S_COL = 0, MH_O_COL = 128, MH_QL_COL = 192;      // S_A 0 | S_B 64 | O_A 128 | O_B 160 | q_lo 192..223
+constexpr float MH_LAZY = 8.f;
+
+__device__ __forceinline__ uint32_t mh_sw_off(int row, int chunk) { return (uint32_t)row * 128u + (uint32_t)((chunk ^ (row & 7)) << 4); }
+__device__ __forceinline__ float mh_ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ void mh_mma_ts(uint32_t d, uint32_t a_tmem, uint64_t b, uint32_t idesc, uint32_t acc) {
+  asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n}" ::"r"(d), "r"(a_tmem), "l"(b),
+               "r"(idesc), "r"(acc)
+               : "memory");
+}
+
+struct MhP { const uint16_t* ws; const uint8_t* mask; float* out; int ldo, B, kvB, L, S; };
+
+__global__ void __launch_bounds__(MH_THREADS, 1) attn_mh_kernel(const MhP p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[20];
+  __shared__ uint32_t tmem_slot;
+  __shared__ float s_red[2][2][MH_BQ];                  // [head][key half][row]
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qt = blockIdx.x, hp = blockIdx.y, b = blockIdx.z;
+  const int nqt = p.L / MH_BQ, nblk = p.S / MH_BKV;
+  const uint32_t bar0 = smem_u32(bars);
+  const uint32_t q_full = bar0;
+  auto k_full = [&](int s) { return bar0 + 8u * (1 + s); };   auto k_empty = [&](int s) { return bar0 + 8u * (3 + s); };
+  auto v_full = [&](int s) { return bar0 + 8u * (5 + s); };   auto v_empty = [&](int s) { return bar0 + 8u * (7 + s); };
+  auto s_full = [&](int x) { return bar0 + 8u * (9 + x); };   auto s_free = [&](int x) { return bar0 + 8u * (11 + x); };
+  auto p_full = [&](int x) { return bar0 + 8u * (13 + x); };  auto pv_done = [&](int x) { return bar0 + 8u * (15 + x); };
+  const long long img_q = (long long)p.B * p.L * MH_E, img_k = (long long)p.kvB * p.S * MH_E;
+  const uint16_t* qh = p.ws; const uint16_t* ql = qh + img_q; const uint16_t* kh = ql + img_q; const uint16_t* kl = kh + img_k;
+  const uint16_t* vh = kl + img_k; const uint16_t* vl = vh + img_k;
+  const int kvb = p.kvB == 1 ? 0 : b;
+
+  if (threadIdx.x == 0) {
+    mbar_init(q_full, 1 + 4);
+    for (int s = 0; s < 2; s++) {
+      mbar_init(k_full(s), 1); mbar_init(k_empty(s), 1); mbar_init(v_full(s), 1); mbar_init(v_empty(s), 1);
+      mbar_init(s_full(s), 1); mbar_init(s_free(s), 8); mbar_init(p_full(s), 8); mbar_init(pv_done(s), 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 8) tmem_alloc(smem_u32(&tmem_slot), 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+
+  if (warp < 8) {
+    // =============================== softmax / correction / epilogue ===============================
+    const int half = warp >> 2;                          // which 32 keys of every 64-key block; also: which head's O this warp rescales / stores
+    const int r = (warp & 3) * 32 + lane;                // query row = TMEM lane
+    const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+    if (warp < 4) {
+      // q_lo of the head pair -> tensor memory: 64 fp16 = 32 columns
+      const uint4* src = reinterpret_cast<const uint4*>(ql + ((long long)b * nqt + qt) * (4LL * MH_BQ * 64) + (long long)hp * (MH_BQ * 64)) + r;
+      uint32_t t[32];
+#pragma unroll
+      for (int i = 0; i < 8; i++) { uint4 x = __ldg(src + i * MH_BQ); t[4 * i] = x.x; t[4 * i + 1] = x.y; t[4 * i + 2] = x.z; t[4 * i + 3] = x.w; }
+      tmem_st32(lane_addr + MH_QL_COL, t);
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(q_full);
+    }
+    float m_ref[2] = {-CUDART_INF_F, -CUDART_INF_F}, l_run[2] = {0.f, 0.f};
+    for (int j = 0; j < nblk; j++) {
+      const uint32_t par = (uint32_t)j & 1u;
+      uint32_t sv[2][32];
+      uint4 mk0 = make_uint4(0, 0, 0, 0), mk1 = mk0;
+      if (p.mask) {
+        const uint4* mp = reinterpret_cast<const uint4*>(p.mask + (long long)b * p.S + j * MH_BKV + half * 32);
+        mk0 = __ldg(mp); mk1 = __ldg(mp + 1);
+      }
+      float mloc[2];
+#pragma unroll
+      for (int x = 0; x < 2; x++) {
+        mbar_wait(s_full(x), par);
+        tc_fence_after();
+        tmem_ld32(lane_addr + MH_S_COL + (uint32_t)(x * 64 + half * 32), sv[x]);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(s_free(x));             // S_x may be overwritten by the next block's scores
+        if (p.mask) {
+          const uint32_t mw[8] = {mk0.x, mk0.y, mk0.z, mk0.w, mk1.x, mk1.y, mk1.z, mk1.w};
+#pragma unroll
+          for (int i = 0; i < 32; i++)
+            if ((mw[i >> 2] >> ((i & 3) * 8)) & 0xffu) sv[x][i] = __float_as_uint(-CUDART_INF_F);
+        }
+        float m = -CUDART_INF_F;
+#pragma unroll
+        for (int i = 0; i < 32; i++) m = fmaxf(m, __uint_as_float(sv[x][i]));
+        mloc[x] = m;
+        s_red[x][half][r] = m;
+      }
+      asm volatile("bar.sync 2, 256;" ::: "memory");     // the two halves of every row exchange their block maxima (both heads)
+      const float mxo[2] = {s_red[0][half ^ 1][r], s_red[1][half ^ 1][r]};
+      asm volatile("bar.sync 2, 256;" ::: "memory");
+      float alpha[2]; bool need[2];
+#pragma unroll
+      for (int x = 0; x < 2; x++) {
+        const float mx = fmaxf(mloc[x], mxo[x]);
+        need[x] = mx > m_ref[x] + MH_LAZY;               // identical in both halves of the row
+        const float m_new = need[x] ? mx : m_ref[x];
+        alpha[x] = need[x] ? mh_ex2(m_ref[x] - m_new) : 1.f;          // m_ref = -inf (nothing seen yet) -> 0
+        m_ref[x] = m_new;
+        const float base = m_new == -CUDART_INF_F ? 0.f : m_new;      // every key so far masked: p = 2^(-inf) = 0, no inf - inf
+        float psum = 0.f;
+#pragma unroll
+        for (int i = 0; i < 32; i++) { float pv = mh_ex2(__uint_as_float(sv[x][i]) - base); psum += pv; sv[x][i] = __float_as_uint(pv); }
+        l_run[x] = l_run[x] * alpha[x] + psum;
+      }
+#pragma unroll
+      for (int x = 0; x < 2; x++) {
+        if (j > 0) {
+          mbar_wait(pv_done(x), (uint32_t)(j - 1) & 1u);   // P_x V of block j-1 retired: O_x is stable and the P_x buffer is free
+          if (x == half && __any_sync(0xffffffffu, need[x])) {       // this warp rescales O of head `half`
+            tc_fence_after();
+            uint32_t o[32];
+            tmem_ld32(lane_addr + MH_O_COL + (uint32_t)(x * 32), o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; i++) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha[x]);
+            tmem_st32(lane_addr + MH_O_COL + (uint32_t)(x * 32), o);
+            tmem_st_wait();
+          }
+        }
+        const uint32_t p_hi = sbase + MH_OFF_P + (uint32_t)x * 32768u, p_lo = p_hi + 16384u;
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+          uint32_t h0, h1, h2, h3, l0, l1, l2, l3;
+          split_f16x2(__uint_as_float(sv[x][8 * c]), __uint_as_float(sv[x][8 * c + 1]), h0, l0);
+          split_f16x2(__uint_as_float(sv[x][8 * c + 2]), __uint_as_float(sv[x][8 * c + 3]), h1, l1);
+          split_f16x2(__uint_as_float(sv[x][8 * c + 4]), __uint_as_float(sv[x][8 * c + 5]), h2, l2);
+          split_f16x2(__uint_as_float(sv[x][8 * c + 6]), __uint_as_float(sv[x][8 * c + 7]), h3, l3);
+          const uint32_t off = mh_sw_off(r, half * 4 + c);
+          sts128u(p_hi + off, h0, h1, h2, h3);
+          sts128u(p_lo + off, l0, l1, l2, l3);
+        }
+        fence_async_smem();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(p_full(x));
+      }
+    }
+    // final: O / l ; this warp stores head `half` (row sums of the two key halves are exchanged first)
+    s_red[0][half][r] = l_run[0]; s_red[1][half][r] = l_run[1];
+    asm volatile("bar.sync 2, 256;" ::: "memory");
+    const float inv = 1.f / (l_run[half] + s_red[half][half ^ 1][r]);     // l = 0 (all keys masked): 0 * inf = NaN, the reference's behaviour
+    mbar_wait(pv_done(half), (uint32_t)(nblk - 1) & 1u);
+    tc_fence_after();
+    uint32_t o[32];
+    tmem_ld32(lane_addr + MH_O_COL + (uint32_t)(half * 32), o);
+    tmem_ld_wait();
+    float* ob = p.out + ((long long)b * p.L + (long long)qt * MH_BQ + r) * p.ldo + (hp * 2 + half) * 32;
+#pragma unroll
+    for (int i = 0; i < 32; i += 4)
+      *reinterpret_cast<float4*>(ob + i) = make_float4(__uint_as_float(o[i]) * inv, __uint_as_float(o[i + 1]) * inv, __uint_as_float(o[i + 2]) * inv,
+                                                       __uint_as_float(o[i + 3]) * inv);
+    tc_fence_before();
+  } else if (warp == 8) {
+    // =============================== MMA issue (one elected lane runs the whole loop) ===============================
+    if (elect_one_sync()) {
+      const uint32_t idesc_s = (1u << 4) | ((uint32_t)(MH_BKV >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);             // K-major A and B, N = 64
+      const uint32_t idesc_o = (1u << 4) | (1u << 16) | ((uint32_t)(32 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);   // B (= V) MN-major, N = 32
+      // V block, MN-major SWIZZLE_128B: one key per 128-byte row, 8-key groups 1 KB apart (SBO); a single 64-value group (LBO unused)
+      const uint64_t v_desc_bits = ((uint64_t)(8192 >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+      auto issue_scores = [&](int j) {
+        const int st = j & 1;
+        mbar_wait(k_full(st), (uint32_t)(j >> 1) & 1u);
+        const uint32_t k_hi = sbase + MH_OFF_K + (uint32_t)st * 16384u, k_lo = k_hi + 8192u;
+#pragma unroll
+        for (int x = 0; x < 2; x++) {
+          if (j > 0) mbar_wait(s_free(x), (uint32_t)(j - 1) & 1u);
+          tc_fence_after();
+#pragma unroll
+          for (int ks = 0; ks < 2; ks++) {
+            const uint64_t ko = (uint64_t)(x * 4 + ks * 2);                     // head x: bytes 64x.. of the row; 32 bytes per k-step
+            const uint64_t dq = make_desc(sbase + MH_OFF_QH) + ko, dkh = make_desc(k_hi) + ko, dkl = make_desc(k_lo) + ko;
+            mh_mma_ts(tmem_base + MH_S_COL + (uint32_t)(x * 64), tmem_base + MH_QL_COL + (uint32_t)(x * 16 + ks * 8), dkh, idesc_s, ks != 0);   // q_lo * k_hi
+            tc_mma_f16(tmem_base + MH_S_COL + (uint32_t)(x * 64), dq, dkl, idesc_s, 1u);                                                      // q_hi * k_lo
+            tc_mma_f16(tmem_base + MH_S_COL + (uint32_t)(x * 64), dq, dkh, idesc_s, 1u);                                                      // q_hi * k_hi
+          }
+          tc_commit(s_full(x));
+        }
+        tc_commit(k_empty(st));
+      };
+      mbar_wait(q_full, 0);
+      tc_fence_after();
+      issue_scores(0);
+      for (int j = 0; j < nblk; j++) {
+        if (j + 1 < nblk) issue_scores(j + 1);
+        const int st = j & 1;
+        mbar_wait(v_full(st), (uint32_t)(j >> 1) & 1u);
+        const uint32_t v_hi = sbase + MH_OFF_V + (uint32_t)st * 16384u, v_lo = v_hi + 8192u;
+#pragma unroll
+        for (int x = 0; x < 2; x++) {
+          mbar_wait(p_full(x), (uint32_t)j & 1u);
+          tc_fence_after();
+          const uint32_t p_hi = sbase + MH_OFF_P + (uint32_t)x * 32768u;
+#pragma unroll
+          for (int ks = 0; ks < 4; ks++) {               // 16 keys per k-step: 32 bytes of a P row, two 8-key row groups of V
+            const uint64_t dph = make_desc(p_hi) + (uint64_t)(ks * 2), dpl = make_desc(p_hi + 16384u) + (uint64_t)(ks * 2);
+            const uint64_t dvh = v_desc_bits | (uint64_t)(((v_hi + (uint32_t)ks * 2048u + (uint32_t)x * 64u) & 0x3FFFFu) >> 4);
+            const uint64_t dvl = v_desc_bits | (uint64_t)(((v_lo + (uint32_t)ks * 2048u + (uint32_t)x * 64u) & 0x3FFFFu) >> 4);
+            const uint32_t o_tmem = tmem_base + MH_O_COL + (uint32_t)(x * 32);
+            tc_mma_f16(o_tmem, dpl, dvh, idesc_o, (j | ks) != 0);
+            tc_mma_f16(o_tmem, dph, dvl, idesc_o, 1u);
+            tc_mma_f16(o_tmem, dph, dvh, idesc_o, 1u);
+          }
+          tc_commit(pv_done(x));
+        }
+        tc_commit(v_empty(st));
+      }
+    }
+    __syncwarp();
+  } else {
+    // =============================== loader ===============================
+    if (lane == 0) {
+      mbar_expect_tx(q_full, 16384u);
+      bulk_g2s(sbase + MH_OFF_QH, qh + ((long long)b * nqt + qt) * (4LL * MH_BQ * 64) + (long long)hp * (MH_BQ * 64), 16384u, q_full);
+      for (int j = 0; j < nblk; j++) {
+        const int st = j & 1; const uint32_t ph = ((uint32_t)(j >> 1) & 1u) ^ 1u;
+        const long long tile = ((long long)kvb * nblk + j) * (4LL * MH_BKV * 64) + (long long)hp * (MH_BKV * 64);
+        mbar_wait(k_empty(st), ph);
+        mbar_expect_tx(k_full(st), 16384u);
+        bulk_g2s(sbase + MH_OFF_K + (uint32_t)st * 16384u, kh + tile, 8192u, k_full(st));
+        bulk_g2s(sbase + MH_OFF_K + (uint32_t)st * 16384u + 8192u, kl + tile, 8192u, k_full(st));
+        mbar_wait(v_empty(st), ph);
+        mbar_expect_tx(v_full(st), 16384u);
+        bulk_g2s(sbase + MH_OFF_V + (uint32_t)st * 16384u, vh + tile, 8192u, v_full(st));
+        bulk_g2s(sbase + MH_OFF_V + (uint32_t)st * 16384u + 8192u, vl + tile, 8192u, v_full(st));
+      }
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  if (warp == 8) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
+}  // namespace
+
+extern "C" int64_t sma_mha_e256_workspace_bytes(int B, int kvB, int L, int S) {
+  if (B <= 0 || kvB <= 0 || L <= 0 || S <= 0) return 0;
+  return 2LL * MH_E * 2 * ((long long)B * L + 2LL * kvB * S);      // fp16 hi + lo images of q, k, v
+}
+
+extern "C" int sma_mha_e256_fwd(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv, int64_t q_bstride, int64_t kv_bstride,
+                                int B, int L, int S, float scale, const uint8_t* key_mask, void* workspace, float* out, int ldo, sma_stream_t stream) {
+  if (!q || !k || !v || !out || !workspace || B <= 0 || L <= 0 || S <= 0) return SMA_ERR_BAD_ARG;
+  if ((L % MH_BQ) || (S % MH_BKV) || B > 65535) return SMA_ERR_UNSUPPORTED;
+  if (((ldq | ldk | ldv | ldo) & 3) || ((q_bstride | kv_bstride) & 3)) return SMA_ERR_UNSUPPORTED;
+  if ((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(v) | reinterpret_cast<uintptr_t>(out) |
+       reinterpret_cast<uintptr_t>(workspace)) & 15)
+    return SMA_ERR_BAD_ARG;
+  if (key_mask && ((reinterpret_cast<uintptr_t>(key_mask) & 15) || (S & 15))) return SMA_ERR_UNSUPPORTED;
+  cudaStream_t st = as_stream(stream);
+  const int kvB = kv_bstride ? B : 1;
+  int rs = sma_attn_split_launch(q, ldq, k, ldk, v, ldv, q_bstride, kv_bstride, B, kvB, L, S, scale * 1.4426950408889634f, workspace, st);
+  if (rs != SMA_OK) return rs;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(attn_mh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MH_SMEM + 1024) != cudaSuccess) return SMA_ERR_CUDA;
+    configured = true;
+  }
+  MhP p; p.ws = reinterpret_cast<const uint16_t*>(workspace); p.mask = key_mask; p.out = out; p.ldo = ldo; p.B = B; p.kvB = kvB; p.L = L; p.S = S;
+  attn_mh_kernel<<<dim3(L / MH_BQ, 4, B), MH_THREADS, MH_SMEM + 1024, st>>>(p);
+  SMA_LAUNCH_CHECK();
+  return SMA_OK;
+}

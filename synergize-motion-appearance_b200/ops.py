@@ -191,6 +191,7 @@ PREC = {'exact': 0, 'tf32x3': 1, 'tf32': 2, 'f16x3': 3, 'f16': 4}     # SMA_PREC
 USE_TF32X3 = True        # let sma_conv2d_fwd pick a tcgen05 kernel where the shape allows (False: exact CUDA-core kernels everywhere)
 ALLOW_TF32_1PASS = True  # honour `fast=True` requests (single pass)
 USE_TS = False           # weights as the tensor-memory A operand (csrc/conv_ts.cu) where eligible; False: shared-memory-operand kernels
+USE_MH_F16 = True        # 8-head E=256 attention: fp16-split kernel with pre-split tile images (csrc/attn_mh.cu); False: tf32 kernel (attn_tc.cu)
 USE_F16 = True           # split operands into fp16 halves (kind::f16, 2x the tensor rate of kind::tf32) where Cin % 64 == 0
 # Per-stage precision policy: stages listed here run their convolutions as single-pass TF32 (3x fewer tensor-core
 # instructions); everything else is fp32-faithful 3xTF32.  See DESIGN.md section 4 for the measured error budget.
@@ -369,6 +370,12 @@ def mha(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, key_mask:
         assert key_mask.dtype == torch.uint8 and key_mask.is_contiguous() and key_mask.numel() == B * S
     if D == 256 and heads == 1 and key_mask is None and kvbs and not exact and USE_TF32X3 and L % 128 == 0 and S % 64 == 0:
         return attn256(q, k, v, scale, out)
+    if D == 32 and heads == 8 and not exact and USE_TF32X3 and USE_MH_F16 and L % 128 == 0 and S % 64 == 0:
+        ws = torch.empty((lib.sma_mha_e256_workspace_bytes(B, B if kvbs else 1, L, S),), device=q.device, dtype=torch.uint8)
+        with _Prof('mha', 4.0 * B * L * S * E, 4.0 * (2 * B * L * E + 2 * (B if kvbs else 1) * S * E), f'mha-f16 B{B} L{L} S{S} h{heads} D{D}'):
+            check(lib.sma_mha_e256_fwd(q.data_ptr(), q.stride(1), k.data_ptr(), ldk, v.data_ptr(), ldv, q.stride(0), kvbs, B, L, S, scale,
+                                       _ptr(key_mask), ws.data_ptr(), out.data_ptr(), out.stride(1), _stream()), 'sma_mha_e256_fwd')
+        return out
     with _Prof('mha', 4.0 * B * L * S * E, 4.0 * (2 * B * L * E + 2 * (B if kvbs else 1) * S * E), f'mha B{B} L{L} S{S} h{heads} D{D}'):
         check(lib.sma_mha_fwd(q.data_ptr(), q.stride(1), k.data_ptr(), ldk, v.data_ptr(), ldv, kvbs, B, L, S, heads, D, scale,
                               _ptr(key_mask), out.data_ptr(), out.stride(1), 1 if (exact or not USE_TF32X3) else 0, _stream()), f'sma_mha_fwd D={D}')
