@@ -82,7 +82,10 @@ typedef struct sma_conv_desc {
   const float* w_tc;             /* tf32 tensor-core weight image from sma_pack_conv_weight_tc (may be NULL) */
   const float* w_tc16;           /* fp16 tensor-core weight image from sma_pack_conv_weight_tc16 (may be NULL) */
   const float* w_ts;             /* fp16 tensor-memory-operand weight image from sma_pack_conv_weight_ts (may be NULL) */
-  int tc_variant;                /* 0: library picks (persistent halo kernel for stride-1, gather kernel otherwise); 1: force the gather kernel */
+  int tc_variant;                /* 0: library picks (tensor-memory-operand kernel when the weights of a 128-channel block fit in tensor memory, else
+                                    the persistent halo kernel for stride 1, else the gather kernel); bit 0: force the gather kernel; bits 1-3:
+                                    timing experiments (results invalid): no weight loads / no halo loads / no epilogue; bit 4: tensor-memory-
+                                    operand kernel streams its weights through the ring even when they would fit; bit 5: allow the streaming ring */
   int kernel_used;               /* OUT: 0 CUDA-core FFMA kernel, 1 tcgen05 tf32 gather kernel, 2 tcgen05 tf32 persistent halo kernel,
                                     3 tcgen05 fp16 persistent halo kernel, 4 tcgen05 fp16 kernel with the weights in tensor memory */
 } sma_conv_desc;

@@ -751,7 +751,7 @@ static int conv_tc2_try(const sma_conv_desc* d, cudaStream_t st, bool f16) {
   const int b_stage = 2 * p.b_img_bytes;
   int SA = 2;
   int SB = (SMEM_LIMIT - SA * p.a_stage_bytes) / b_stage;
-  if (SB < 2) { SA = 1; SB = (SMEM_LIMIT - p.a_stage_bytes) / b_stage; }
+  // (a single A stage is not an option: the two producer groups could then be two barrier phases apart - parity aliasing)
   if (SB < 2) return SMA_ERR_UNSUPPORTED;
   if (SB > MAX_SB) SB = MAX_SB;
   p.SA = SA; p.SB = SB;

@@ -14,11 +14,11 @@
 // Weights stream L2 -> registers -> tensor memory (tcgen05.st) through 4 writer warps; a ring of 8 x 32 columns holds the units.
 //
 // One CTA per SM, persistent over tiles of 8 x 16 output pixels (1x1 convs: 128 consecutive pixels) x 128 output channels.
-//   warps 0-3   epilogue: accumulator rows are OUTPUT CHANNELS, so a thread holds one channel for 32 pixels; scale/bias/activation are
-//               per-thread scalars; the 32 x 32 block is transposed through a warp-private staging tile so that residual loads and
-//               stores are 128 contiguous bytes (32 channels) per pixel
-//   warps 4-11  weight writers, two groups on alternate units (warp w owns TMEM lanes 32(w%4)..): ld.global 128 B per lane ->
-//               tcgen05.st.32x32b.x32
+//   warps 0-7   epilogue, two groups on alternate 32-pixel blocks (warp w owns TMEM lanes 32(w%4)..): accumulator rows are OUTPUT
+//               CHANNELS, so a thread holds one channel for 32 pixels; scale/bias/activation are per-thread scalars; the 32 x 32 block is
+//               transposed through a warp-private staging tile so that residual loads and stores are 128 contiguous bytes (32 channels)
+//               per pixel
+//   warps 8-11  weight writers (warp w owns TMEM lanes 32(w%4)..): ld.global 128 B per lane -> tcgen05.st.32x32b.x32
 //   warp 12     TMEM allocation + MMA issue (one elected lane)
 //   warps 13-19 halo producers (two groups on alternate channel chunks): load, prologue, fp16 hi/lo split, swizzled store
 #include "sma_common.cuh"
@@ -29,14 +29,14 @@ namespace {
 
 constexpr int TS_PIX = 128;                              // pixels per tile = UMMA N
 constexpr int TS_PROD_WARPS = 7, TS_PGROUPS = 2;     // 20 warps in all = 5 per scheduler: 96 registers per thread
-constexpr int TS_THREADS = 32 * (4 + 8 + 1 + TS_PROD_WARPS);   // 640
+constexpr int TS_THREADS = 32 * (8 + 4 + 1 + TS_PROD_WARPS);   // 640
 constexpr int TS_PROD_T0 = 32 * 13;                     // first producer thread
 constexpr int TS_PROWS = 4 * TS_PROD_WARPS / TS_PGROUPS;      // halo rows per pass of one group (8 lanes per 128-byte row)
 constexpr int TS_UNROLL = 3;                            // halo rows in flight per producer thread (two float4 each)
 constexpr int TS_MAX_SA = 4;
 constexpr int TS_WCOL0 = 256;                           // TMEM: [0,128) accumulator 0 | [128,256) accumulator 1 | [256,512) weight ring
 constexpr int TS_WCOLS = 256;
-constexpr int TS_STG = 4 * 4096;                        // epilogue staging: one 32 x 32 fp32 tile per epilogue warp
+constexpr int TS_STG = 8 * 4096;                        // epilogue staging: one 32 x 32 fp32 tile per epilogue warp
 constexpr int TS_SMEM_DYN_MAX = 232448 - 2048;
 
 struct TsP {
@@ -47,6 +47,9 @@ struct TsP {
   int HoWo, cpt, taps, MB, passes, upt, ustride, nslots;
   int flat, tiles_x, tiles_per_img, total_tiles;
   int halo_w, HP, a_img_bytes, a_stage_bytes, SA, stg_off, dbg;
+  int resident;               // 1: all weight units of a 128-channel block stay in tensor memory (loaded once per block change)
+  int nacc;                   // accumulators in tensor memory: 2 (epilogue of tile t overlaps the MMAs of t+1) or 1 (256-pixel tiles)
+  int npx, tile_h, wcol0, tiles_m;   // pixels per tile (= UMMA N), tile height, first weight column, M tiles (images x tiles per image)
 };
 
 __device__ __forceinline__ void tc_mma_ts_f16(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
@@ -76,8 +79,8 @@ __global__ void __launch_bounds__(TS_THREADS, 1) conv_ts_kernel(const TsP p) {
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.SA; s++) { mbar_init(a_full(s), 32 * TS_PROD_WARPS / TS_PGROUPS); mbar_init(a_empty(s), 1); }
-    for (int s = 0; s < p.nslots; s++) { mbar_init(w_full(s), 4 * p.upt); mbar_init(w_empty(s), 1); }
-    for (int s = 0; s < 2; s++) { mbar_init(acc_full(s), 1); mbar_init(acc_empty(s), 128); }
+    for (int s = 0; s < p.nslots; s++) { mbar_init(w_full(s), p.resident ? 4 * p.cpt * p.taps * p.upt : 4 * p.upt); mbar_init(w_empty(s), 1); }
+    for (int s = 0; s < 2; s++) { mbar_init(acc_full(s), 1); mbar_init(acc_empty(s), 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 12) tmem_alloc(smem_u32(&tmem_slot), 512);
@@ -88,23 +91,27 @@ __global__ void __launch_bounds__(TS_THREADS, 1) conv_ts_kernel(const TsP p) {
 
   // tile -> (image b, first output row / column or first flat pixel, block of 128 output channels)
   auto decode = [&](int tile, int& b, int& ty0, int& tx0, int& mb) {
-    mb = tile % p.MB; int mt = tile / p.MB;
+    int mt;
+    if (p.resident) { mb = tile / p.tiles_m; mt = tile - mb * p.tiles_m; }     // channel-block major: weights change rarely
+    else { mb = tile % p.MB; mt = tile / p.MB; }
     b = mt / p.tiles_per_img; int t = mt - b * p.tiles_per_img;
-    if (p.flat) { ty0 = t * TS_PIX; tx0 = 0; } else { int tyi = t / p.tiles_x; ty0 = tyi * 16; tx0 = (t - tyi * p.tiles_x) * 8; }
+    if (p.flat) { ty0 = t * p.npx; tx0 = 0; } else { int tyi = t / p.tiles_x; ty0 = tyi * p.tile_h; tx0 = (t - tyi * p.tiles_x) * 8; }
   };
   const int my_tiles = blockIdx.x < p.total_tiles ? (p.total_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
 
-  if (warp < 4) {
+  if (warp < 8) {
     // =============================== epilogue ===============================
+    const int eg = warp >> 2, wq = warp & 3;               // group (alternate 32-pixel blocks), TMEM lane quarter
     const bool vec_ok = (p.out_ld & 3) == 0 && (p.out_bs & 3) == 0 && ((reinterpret_cast<uintptr_t>(p.y) & 15) == 0) &&
                         (!p.res || ((p.res_ld & 3) == 0 && (p.res_bs & 3) == 0 && (reinterpret_cast<uintptr_t>(p.res) & 15) == 0));
     const int Cq = p.d2s > 1 ? p.Cout / (p.d2s * p.d2s) : p.Cout;
-    const uint32_t stg0 = sbase + (uint32_t)p.stg_off;
-    const uint32_t stg = stg0 + (uint32_t)warp * 4096u;   // this warp's 32 pixels x 32 rows staging tile (pixel-major)
+    const uint32_t stg0 = sbase + (uint32_t)p.stg_off + (uint32_t)eg * 16384u;      // this group's four staging tiles
+    const uint32_t stg = stg0 + (uint32_t)wq * 4096u;      // this warp's 32 pixels x 32 rows staging tile (pixel-major)
+    const bool simple = vec_ok && p.d2s <= 1 && (p.Cout & 3) == 0;                  // plain NHWC float4 stores
     int tcount = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tcount) {
       int b, ty0, tx0, mb; decode(tile, b, ty0, tx0, mb);
-      const int ab = tcount & 1; const uint32_t aph = (tcount >> 1) & 1;
+      const int ab = p.nacc == 2 ? (tcount & 1) : 0; const uint32_t aph = (uint32_t)(p.nacc == 2 ? (tcount >> 1) : tcount) & 1u;
       const float* resb = p.res ? p.res + (long long)b * p.res_bs : nullptr;
       float* yb = p.y + (long long)b * p.out_bs;
       // four consecutive output channels n.. of tile pixel mm (values already scaled / biased / activated): residual add + store
@@ -112,8 +119,14 @@ __global__ void __launch_bounds__(TS_THREADS, 1) conv_ts_kernel(const TsP p) {
         int oy = 0, ox = 0, r; bool mok;
         if (p.flat) { r = ty0 + mm; mok = r < p.HoWo; if (p.d2s > 1) { oy = r / p.Wo; ox = r - oy * p.Wo; } }
         else { oy = ty0 + (mm >> 3); ox = tx0 + (mm & 7); mok = oy < p.Ho && ox < p.Wo; r = oy * p.Wo + ox; }
-        if (!mok || n >= p.Cout) return;
-        if (vec_ok && n + 4 <= p.Cout && (Cq & 3) == 0) {
+        if (!mok || n >= p.Cout || mm >= p.npx) return;
+        if (simple) {
+          if (resb) {
+            float4 rv = __ldg(reinterpret_cast<const float4*>(resb + (long long)r * p.res_ld + n));
+            o[0] += rv.x; o[1] += rv.y; o[2] += rv.z; o[3] += rv.w;
+          }
+          *reinterpret_cast<float4*>(yb + (long long)r * p.out_ld + n) = make_float4(o[0], o[1], o[2], o[3]);
+        } else if (vec_ok && n + 4 <= p.Cout && (Cq & 3) == 0) {
           float* dst;
           if (p.d2s > 1) {
             int qd = n / Cq; int cval = n - qd * Cq; int p1 = qd / p.d2s, p2 = qd - p1 * p.d2s;
@@ -146,7 +159,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) conv_ts_kernel(const TsP p) {
       // per-thread constants
       float sc = 0.f, bi = 0.f;                            // plain: this lane's accumulator row = one output channel
       float4 sc4 = make_float4(0.f, 0.f, 0.f, 0.f), bi4 = sc4;    // stacked: the four channels this lane stores
-      const int cbase = mb * 128 + warp * 32;
+      const int cbase = mb * 128 + wq * 32;
       if (!STACKED) {
         const int c_lane = cbase + lane;
         sc = c_lane < p.Cout ? __ldg(p.wscale + c_lane) : 0.f;
@@ -160,15 +173,18 @@ __global__ void __launch_bounds__(TS_THREADS, 1) conv_ts_kernel(const TsP p) {
       }
       mbar_wait(acc_full(ab), aph);
       tc_fence_after();
-      if (p.dbg & 4) { tc_fence_before(); mbar_arrive(acc_empty(ab)); continue; }
+      if (p.dbg & 4) { tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(acc_empty(ab)); continue; }
+      bool released = false;
 #pragma unroll 1
-      for (int px0 = 0; px0 < TS_PIX; px0 += 32) {
+      for (int px0 = eg * 32; px0 < p.npx; px0 += 64) {
         uint32_t a[32];
-        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(ab * TS_PIX + px0), a);
+        tmem_ld32(tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(ab * p.npx + px0), a);
         tmem_ld_wait();
-        if (px0 == TS_PIX - 32) {                          // the accumulator can be overwritten now
+        if (px0 + 64 >= p.npx) {                           // this warp's last block: its share of the accumulator has been read
           tc_fence_before();
-          mbar_arrive(acc_empty(ab));
+          __syncwarp();
+          if (lane == 0) mbar_arrive(acc_empty(ab));
+          released = true;
         }
         if (!STACKED) {
           // rows = 32 channels of this warp: scale / bias / activation per thread, transpose through the warp's own tile
@@ -190,15 +206,15 @@ __global__ void __launch_bounds__(TS_THREADS, 1) conv_ts_kernel(const TsP p) {
           }
           __syncwarp();
         } else {
-          // rows 0-63 (warps 0,1) = w_hi * x, rows 64-127 (warps 2,3) = w_lo * x of channels 0..63: every warp parks its raw block,
-          // then each warp finishes 8 of the 32 pixels for all 64 channels (hi + lo, scale, bias, activation, residual, store)
+          // rows 0-63 (quarters 0,1) = w_hi * x, rows 64-127 (quarters 2,3) = w_lo * x of channels 0..63: every warp of the group parks its
+          // raw block, then each warp finishes 8 of the 32 pixels for all 64 channels (hi + lo, scale, bias, activation, residual, store)
 #pragma unroll
           for (int j = 0; j < 32; j++) asm volatile("st.shared.b32 [%0], %1;" ::"r"(stg + (uint32_t)(j * 32 + lane) * 4u), "r"(a[j]) : "memory");
-          asm volatile("bar.sync 1, 128;" ::: "memory");
+          asm volatile("bar.sync %0, 128;" ::"r"(1 + eg) : "memory");
           const int q = lane & 15, half = q >> 3;          // channels 4q..4q+3 live in tile `half` (hi) and `half + 2` (lo)
 #pragma unroll
           for (int t = 0; t < 4; t++) {
-            const int pl = warp * 8 + t * 2 + (lane >> 4);
+            const int pl = wq * 8 + t * 2 + (lane >> 4);
             const uint32_t off = (uint32_t)(pl * 32 + (q & 7) * 4) * 4u;
             float4 vh, vl;
             asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(vh.x), "=f"(vh.y), "=f"(vh.z), "=f"(vh.w) : "r"(stg0 + (uint32_t)half * 4096u + off));
@@ -207,15 +223,16 @@ __global__ void __launch_bounds__(TS_THREADS, 1) conv_ts_kernel(const TsP p) {
                           sma_act(fmaf(vh.z + vl.z, sc4.z, bi4.z), ACT), sma_act(fmaf(vh.w + vl.w, sc4.w, bi4.w), ACT)};
             emit(px0 + pl, q * 4, o);
           }
-          asm volatile("bar.sync 1, 128;" ::: "memory");     // staging tiles are rewritten by the next pixel block
+          asm volatile("bar.sync %0, 128;" ::"r"(1 + eg) : "memory");     // staging tiles are rewritten by the next pixel block
         }
       }
+      if (!released) { tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(acc_empty(ab)); }   // group without a block in this tile
     }
   } else if (warp < 12) {
     // =============================== weight writers: L2 -> registers -> tensor memory ===============================
-    // two groups of 4 warps on alternate units, two units in registers each: four units (64 KB) of L2 latency cover
+    // two units in registers: the next unit's loads are in flight while the current one is written
     const int qd = warp & 3;                               // TMEM lane quarter of this warp (= warp % 4)
-    const int wgroup = (warp - 4) >> 2;
+    constexpr int wgroup = 0, WG = 1;
     const int m = qd * 32 + lane;                          // accumulator row / A row fed by this thread
     const int upt_tile = p.cpt * p.taps * p.upt;           // units per tile
     const long long total = (long long)my_tiles * upt_tile;
@@ -239,7 +256,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) conv_ts_kernel(const TsP p) {
       const int slot = (int)(blob % p.nslots); const uint32_t ph = (uint32_t)(blob / p.nslots) & 1u;
       mbar_wait(w_empty(slot), ph ^ 1u);                   // the MMAs that read this slot have retired
       tc_fence_after();
-      tmem_st32(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(TS_WCOL0 + slot * 32 * p.upt + within * 32), r);
+      tmem_st32(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(p.wcol0 + slot * 32 * p.upt + within * 32), r);
       tmem_st_wait();                                      // warp-collective: every lane's rows have landed
       tc_fence_before();
       __syncwarp();
@@ -248,14 +265,39 @@ __global__ void __launch_bounds__(TS_THREADS, 1) conv_ts_kernel(const TsP p) {
     uint32_t r0[32], r1[32];
 #pragma unroll
     for (int i = 0; i < 32; i++) { r0[i] = 0u; r1[i] = 0u; }
-    long long g = wgroup;
+    if (p.resident) {
+      // one epoch per run of tiles with the same channel block: (re)load all its units; the two groups take alternate units
+      int cur_mb = -1, epoch = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const int mb = tile / p.tiles_m;
+        if (mb == cur_mb) continue;
+        cur_mb = mb;
+        if (epoch > 0) { mbar_wait(w_empty(0), (uint32_t)(epoch - 1) & 1u); tc_fence_after(); }    // every MMA on the old weights has retired
+        for (int u = wgroup; u < upt_tile; u += WG) {
+          if (!(p.dbg & 1)) {
+            const int blob = u / p.upt, within = u - blob * p.upt;
+            const long long unit = ((long long)mb * p.cpt * p.taps + blob) * p.ustride + within;
+            const uint4* src = reinterpret_cast<const uint4*>(p.wts + unit * 4096) + m;
+#pragma unroll
+            for (int i = 0; i < 8; i++) { uint4 v = __ldg(src + i * 128); r0[4 * i] = v.x; r0[4 * i + 1] = v.y; r0[4 * i + 2] = v.z; r0[4 * i + 3] = v.w; }
+          }
+          tmem_st32(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(p.wcol0 + u * 32), r0);
+          tmem_st_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(w_full(0));
+        }
+        ++epoch;
+      }
+    }
+    long long g = p.resident ? total : wgroup;
     if (g < total) load(g, r0);
-    for (; g < total; g += 4) {
-      if (g + 2 < total) load(g + 2, r1);                  // the next unit's loads are in flight while this one is written
+    for (; g < total; g += 2 * WG) {
+      if (g + WG < total) load(g + WG, r1);                // the next unit's loads are in flight while this one is written
       put(g, r0);
-      if (g + 2 < total) {
-        if (g + 4 < total) load(g + 4, r0);
-        put(g + 2, r1);
+      if (g + WG < total) {
+        if (g + 2 * WG < total) load(g + 2 * WG, r0);
+        put(g + WG, r1);
       }
     }
   } else if (warp == 12) {
@@ -264,21 +306,33 @@ __global__ void __launch_bounds__(TS_THREADS, 1) conv_ts_kernel(const TsP p) {
     // with wrap-around counters instead of divisions: this scalar instruction stream has to stay well below the 768 tensor cycles of
     // a tap, or the tensor pipe drains while the thread computes descriptors (measured: 103 instead of 64 cycles per MMA).
     if (elect_one_sync()) {
-      const uint32_t idesc = (1u << 4) | ((uint32_t)(TS_PIX >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);     // f16 x f16 -> f32, M = 128, N = 128
+      const uint32_t idesc = (1u << 4) | ((uint32_t)(p.npx >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);     // f16 x f16 -> f32, M = 128, N = npx
       // pixel operand descriptor (K-major, SWIZZLE_128B): 8-row atoms are 8 consecutive halo rows; next atom = next output row
       const uint64_t x_desc_hi = ((uint64_t)((uint32_t)((p.halo_w * 128) >> 4) | (1u << 14) | (2u << 29))) << 32;
       const uint32_t row_step = (uint32_t)(p.halo_w * 128) >> 4;          // one halo row down, in 16-byte units
       const uint32_t slot_cols = (uint32_t)(32 * p.upt);
       const bool three = p.passes == 3;
       uint32_t slot = 0, wph = 0, sa = 0, apha = 0, tcount = 0;
+      int cur_mb = -1; uint32_t epoch = 0;
       long long prof_c0 = 0, prof_g0 = 0;
       if (blockIdx.x == 0) { prof_c0 = clock64(); asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(prof_g0)); }
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tcount) {
-        const uint32_t ab = tcount & 1u;
-        mbar_wait(acc_empty(ab), ((tcount >> 1) & 1u) ^ 1u);
+        const uint32_t ab = p.nacc == 2 ? (tcount & 1u) : 0u;
+        mbar_wait(acc_empty(ab), ((p.nacc == 2 ? (tcount >> 1) : tcount) & 1u) ^ 1u);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + ab * TS_PIX;
+        const uint32_t d_tmem = tmem_base + ab * (uint32_t)p.npx;
         uint32_t acc = 0u;                                   // first MMA of the tile overwrites the accumulator
+        if (p.resident) {
+          const int mb = tile / p.tiles_m;
+          if (mb != cur_mb) {                                // new channel block: hand the weight columns back, wait for the new set
+            if (cur_mb >= 0) tc_commit(w_empty(0));
+            cur_mb = mb;
+            mbar_wait(w_full(0), epoch & 1u);
+            tc_fence_after();
+            ++epoch;
+          }
+          slot = 0;                                          // unit index within the resident set
+        }
         for (int cc = 0; cc < p.cpt; cc++) {
           mbar_wait(a_full(sa), apha);
           const uint32_t x_hi = a_ring + sa * (uint32_t)p.a_stage_bytes;
@@ -286,11 +340,10 @@ __global__ void __launch_bounds__(TS_THREADS, 1) conv_ts_kernel(const TsP p) {
           uint32_t roff = 0;
           for (int ky = 0; ky < p.kh; ky++, roff += row_step) {
             for (int kx = 0; kx < p.kw; kx++) {
-              mbar_wait(w_full(slot), wph);
-              tc_fence_after();
+              if (!p.resident) { mbar_wait(w_full(slot), wph); tc_fence_after(); }
               const uint64_t dxh = x_desc_hi | (uint64_t)(lo_h + roff + (uint32_t)kx * 8u);
               const uint64_t dxl = x_desc_hi | (uint64_t)(lo_l + roff + (uint32_t)kx * 8u);
-              const uint32_t wcol = tmem_base + (uint32_t)TS_WCOL0 + slot * slot_cols;
+              const uint32_t wcol = tmem_base + (uint32_t)p.wcol0 + slot * slot_cols;
 #pragma unroll
               for (int k4 = 0; k4 < 4; k4++) {               // 4 k-steps of 16 fp16 = 8 TMEM columns = 32 bytes of a halo row
                 const uint64_t ko = (uint64_t)(k4 * 2);
@@ -307,8 +360,8 @@ __global__ void __launch_bounds__(TS_THREADS, 1) conv_ts_kernel(const TsP p) {
                 }
                 acc = 1u;
               }
-              tc_commit(w_empty(slot));
-              if (++slot == (uint32_t)p.nslots) { slot = 0; wph ^= 1u; }
+              if (p.resident) ++slot;
+              else { tc_commit(w_empty(slot)); if (++slot == (uint32_t)p.nslots) { slot = 0; wph ^= 1u; } }
             }
           }
           tc_commit(a_empty(sa));
@@ -518,13 +571,28 @@ int sma_conv2d_ts_try(sma_conv_desc* d, cudaStream_t st) {
   p.passes = d->precision == SMA_PREC_F16 ? 1 : 3;
   p.ustride = stacked ? 1 : 2;                          // units stored per (chunk, tap)
   p.upt = (!stacked && p.passes == 3) ? 2 : 1;          // units used per (chunk, tap)
-  p.nslots = TS_WCOLS / (32 * p.upt);
-  p.flat = flat ? 1 : 0;
-  if (flat) { p.tiles_x = 1; p.tiles_per_img = (p.HoWo + TS_PIX - 1) / TS_PIX; p.halo_w = 8; p.HP = TS_PIX; }
-  else {
-    p.tiles_x = (d->Wo + 7) / 8; p.tiles_per_img = p.tiles_x * ((d->Ho + 15) / 16);
-    p.halo_w = 8 + d->kw - 1; p.HP = p.halo_w * (16 + d->kh - 1);
+  // resident weights: all units of a 128-channel block fit beside two accumulators of 128 (or, for 3x3, 112) pixels
+  const int units_mb = p.cpt * p.taps * p.upt;
+  p.resident = 0; p.npx = TS_PIX; p.tile_h = 16;
+  if (units_mb * 32 <= 512 - 2 * TS_PIX) p.resident = 1;
+  else if (!flat && units_mb * 32 <= 512 - 2 * 112) { p.resident = 1; p.npx = 112; p.tile_h = 14; }
+  if (d->tc_variant & 16) { p.resident = 0; p.npx = TS_PIX; p.tile_h = 16; }      // experiments: force the streaming ring
+  p.nacc = 2;
+  if (!p.resident && !flat && !(d->tc_variant & 64)) {
+    // streamed weights: 8 x 32 = 256-pixel tiles (one N = 256 MMA per weight k-step) halve the L2 -> SM weight traffic per MAC, which is what
+    // bounds the 128-pixel variant (32 KB per tap and SM); the single accumulator exposes the epilogue drain (~10 % of a tile)
+    p.npx = 256; p.tile_h = 32; p.nacc = 1;
   }
+  if (!p.resident && p.nacc == 2 && !(d->tc_variant & 32)) return SMA_ERR_UNSUPPORTED;   // 128-pixel streaming ring (flat 1x1 with many channels): on request
+  p.wcol0 = p.nacc * p.npx;
+  p.nslots = p.resident ? 1 : TS_WCOLS / (32 * p.upt);
+  p.flat = flat ? 1 : 0;
+  if (flat) { p.tiles_x = 1; p.tiles_per_img = (p.HoWo + p.npx - 1) / p.npx; p.halo_w = 8; p.HP = p.npx; }
+  else {
+    p.tiles_x = (d->Wo + 7) / 8; p.tiles_per_img = p.tiles_x * ((d->Ho + p.tile_h - 1) / p.tile_h);
+    p.halo_w = 8 + d->kw - 1; p.HP = p.halo_w * (p.tile_h + d->kh - 1);
+  }
+  p.tiles_m = d->B * p.tiles_per_img;
   const long long total = (long long)d->B * p.tiles_per_img * p.MB;
   if (total > 0x7fffffffLL) return SMA_ERR_UNSUPPORTED;
   p.total_tiles = (int)total;
@@ -532,7 +600,8 @@ int sma_conv2d_ts_try(sma_conv_desc* d, cudaStream_t st) {
   p.a_stage_bytes = 2 * p.a_img_bytes;
   const int avail = TS_SMEM_DYN_MAX - 1024 - TS_STG;
   int SA = avail / p.a_stage_bytes;
-  if (SA < 1) return SMA_ERR_UNSUPPORTED;
+  // two producer groups work on alternate chunks: with a single stage a group could be two barrier phases ahead (parity aliasing)
+  if (SA < 2) return SMA_ERR_UNSUPPORTED;
   if (SA > TS_MAX_SA) SA = TS_MAX_SA;
   p.SA = SA; p.stg_off = SA * p.a_stage_bytes; p.dbg = (d->tc_variant >> 1) & 7;
   const int smem = p.stg_off + TS_STG + 1024;

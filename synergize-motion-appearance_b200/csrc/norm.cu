@@ -1,5 +1,6 @@
 // GroupNorm statistics (-> per-(b,c) scale/shift for the conv prologue), affine+activation, LayerNorm.
 #include "sma_common.cuh"
+#include <cstdlib>
 
 namespace {
 
@@ -28,6 +29,51 @@ __global__ void gn_partial_kernel(const float* __restrict__ x, int HW, int C, lo
       for (int r = 0; r < rows; r++) { ss += sm[r * cpt + tid]; qq += sm[256 + r * cpt + tid]; }
       float* o = partial + (((long long)b * nchunk + chunk) * C + cb + tid) * 2;
       o[0] = ss; o[1] = qq;
+    }
+    __syncthreads();
+  }
+}
+
+// same partial sums with 128-bit loads: a thread owns 4 consecutive channels and every `rows`-th pixel of the chunk, 4 loads in flight
+__global__ void gn_partial4_kernel(const float* __restrict__ x, int HW, int C, long long bstride, int ld, float* __restrict__ partial, int nchunk) {
+  const int chunk = blockIdx.x, b = blockIdx.y;
+  const int p0 = chunk * GN_CHUNK, p1 = min(HW, p0 + GN_CHUNK);
+  __shared__ float sm[8][256];
+  const int tid = threadIdx.x;
+  const int nq = C >> 2;                 // channel quads per pixel
+  const int cpt = min(nq, 256);          // quads covered per pass
+  const int rows = 256 / cpt;            // pixels processed concurrently
+  const int c_in = tid % cpt, r_in = tid / cpt;
+  const int ld4 = ld >> 2;
+  for (int cb = 0; cb < nq; cb += cpt) {
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f), q = s;
+    const int cq = cb + c_in;
+    if (r_in < rows && cq < nq) {
+      const float4* px = reinterpret_cast<const float4*>(x + (long long)b * bstride) + cq;
+      int p = p0 + r_in;
+      for (; p + 3 * rows < p1; p += 4 * rows) {
+        const float4 v0 = __ldg(px + (long long)p * ld4), v1 = __ldg(px + (long long)(p + rows) * ld4), v2 = __ldg(px + (long long)(p + 2 * rows) * ld4),
+                     v3 = __ldg(px + (long long)(p + 3 * rows) * ld4);
+        s.x += (v0.x + v1.x) + (v2.x + v3.x); s.y += (v0.y + v1.y) + (v2.y + v3.y); s.z += (v0.z + v1.z) + (v2.z + v3.z); s.w += (v0.w + v1.w) + (v2.w + v3.w);
+        q.x = fmaf(v0.x, v0.x, fmaf(v1.x, v1.x, fmaf(v2.x, v2.x, fmaf(v3.x, v3.x, q.x)))); q.y = fmaf(v0.y, v0.y, fmaf(v1.y, v1.y, fmaf(v2.y, v2.y, fmaf(v3.y, v3.y, q.y))));
+        q.z = fmaf(v0.z, v0.z, fmaf(v1.z, v1.z, fmaf(v2.z, v2.z, fmaf(v3.z, v3.z, q.z)))); q.w = fmaf(v0.w, v0.w, fmaf(v1.w, v1.w, fmaf(v2.w, v2.w, fmaf(v3.w, v3.w, q.w))));
+      }
+      for (; p < p1; p += rows) {
+        const float4 v = __ldg(px + (long long)p * ld4);
+        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+        q.x = fmaf(v.x, v.x, q.x); q.y = fmaf(v.y, v.y, q.y); q.z = fmaf(v.z, v.z, q.z); q.w = fmaf(v.w, v.w, q.w);
+      }
+    }
+    sm[0][tid] = s.x; sm[1][tid] = q.x; sm[2][tid] = s.y; sm[3][tid] = q.y; sm[4][tid] = s.z; sm[5][tid] = q.z; sm[6][tid] = s.w; sm[7][tid] = q.w;
+    __syncthreads();
+    if (tid < cpt && cb + tid < nq) {
+      float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      for (int r = 0; r < rows; r++) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) acc[i] += sm[i][r * cpt + tid];
+      }
+      float4* o = reinterpret_cast<float4*>(partial + (((long long)b * nchunk + chunk) * C + (cb + tid) * 4) * 2);     // [c][{sum, sumsq}] x 4 channels
+      o[0] = make_float4(acc[0], acc[1], acc[2], acc[3]); o[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
     }
     __syncthreads();
   }
@@ -108,7 +154,10 @@ extern "C" int sma_groupnorm_stats(const float* x, int B, int HW, int C, int64_t
                                    const float* beta, float* partial, float* scale, float* shift, sma_stream_t stream) {
   if (!x || !partial || !scale || !shift || B <= 0 || HW <= 0 || C <= 0 || groups <= 0 || C % groups) return SMA_ERR_BAD_ARG;
   int nchunk = cdiv(HW, GN_CHUNK);
-  gn_partial_kernel<<<dim3(nchunk, B), 256, 512 * sizeof(float), as_stream(stream)>>>(x, HW, C, bstride, ld, partial, nchunk);
+  static const bool force_scalar = getenv("SMA_GN_SCALAR") != nullptr;     // debugging aid
+  const bool vec = !force_scalar && (C & 3) == 0 && (ld & 3) == 0 && (bstride & 3) == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(partial)) & 15) == 0;
+  if (vec) gn_partial4_kernel<<<dim3(nchunk, B), 256, 0, as_stream(stream)>>>(x, HW, C, bstride, ld, partial, nchunk);
+  else gn_partial_kernel<<<dim3(nchunk, B), 256, 512 * sizeof(float), as_stream(stream)>>>(x, HW, C, bstride, ld, partial, nchunk);
   SMA_LAUNCH_CHECK();
   gn_finalize_kernel<<<dim3(groups, B), 128, 0, as_stream(stream)>>>(partial, nchunk, C, groups, HW, eps, gamma, beta, scale, shift);
   SMA_LAUNCH_CHECK();

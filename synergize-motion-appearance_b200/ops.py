@@ -190,7 +190,7 @@ def pack_conv_blockdiag(weights, biases) -> ConvW:
 PREC = {'exact': 0, 'tf32x3': 1, 'tf32': 2, 'f16x3': 3, 'f16': 4}     # SMA_PREC_*
 USE_TF32X3 = True        # let sma_conv2d_fwd pick a tcgen05 kernel where the shape allows (False: exact CUDA-core kernels everywhere)
 ALLOW_TF32_1PASS = True  # honour `fast=True` requests (single pass)
-USE_TS = False           # weights as the tensor-memory A operand (csrc/conv_ts.cu) where eligible; False: shared-memory-operand kernels
+USE_TS = False           # weights as the tensor-memory A operand (csrc/conv_ts.cu) where they fit in tensor memory; False: shared-memory-operand kernels
 USE_MH_F16 = True        # 8-head E=256 attention: fp16-split kernel with pre-split tile images (csrc/attn_mh.cu); False: tf32 kernel (attn_tc.cu)
 USE_F16 = True           # split operands into fp16 halves (kind::f16, 2x the tensor rate of kind::tf32) where Cin % 64 == 0
 # Per-stage precision policy: stages listed here run their convolutions as single-pass TF32 (3x fewer tensor-core

@@ -24,11 +24,11 @@ def run(B, Cin, H, Cout, k, pad):
                     import ctypes
                     buf = (ctypes.c_longlong * 8)()
                     S._lib.load().sma_debug_conv_ts_prof(ctypes.cast(buf, ctypes.c_void_p))
-                    mmas = (B * ((H + 15) // 16) * ((H + 7) // 8) * (1 if Cout <= 64 else (Cout + 127) // 128) / 148.0) * (Cin // 64) * k * k * 4 * ((2 if Cout <= 64 else 3) if not fast else 1)
+                    mmas = (B * ((H + 15) // 16) * ((H + 7) // 8) * (1 if Cout <= 64 else (Cout + 127) // 128) / 148.0) * (Cin // 64) * k * k * 4 * ((2 if Cout <= 64 else 3) if not fast else 1) * (0.5 if (k > 1 and Cin * k * k // 64 * (1 if Cout <= 64 else 2) * 32 > 288) else 1.0)
                     prof = f' | CTA0 {buf[0]/1e3:.0f} kcyc {buf[1]/1e3:.0f} us -> {buf[0]/max(buf[1],1)*1e3:.0f} MHz, {buf[0]/mmas:.0f} cyc/MMA'
                 res.append(f"{'ts' if ts else 'ss'}{'x1' if fast else 'x3'} dbg{dbg}: {ms:.3f} ms {2.0*B*H*H*Cin*k*k*Cout/ms/1e9:.0f} TF" + prof)
     S.ops.USE_TS, S.ops.USE_F16, S.ops.TC_VARIANT = True, True, 0
     print(f'B{B} Cin{Cin} H{H} Cout{Cout} k{k}\n   ' + '\n   '.join(res), flush=True)
 
-for a in [(64, 64, 256, 64, 3, 1), (64, 128, 128, 128, 3, 1), (64, 256, 64, 256, 3, 1), (64, 256, 32, 256, 1, 0)]:
+for a in [(64, 64, 256, 64, 3, 1), (64, 128, 128, 128, 3, 1), (64, 256, 64, 256, 3, 1), (64, 128, 256, 64, 3, 1), (64, 256, 32, 512, 3, 1)]:
     run(*a)
