@@ -13,7 +13,8 @@ reassembles the clip on every rank.
 Printed JSON line (rank 0): `value` = frames/s with inputs resident in HBM; `e2e` = the same clip through the public
 `make_animation` call with HOST tensors (pinned H2D of every driving frame, D2H of the uint8 frames inside the timed
 region); `roofline` = the dominant kernel (implicit-GEMM convolution) timed per launch with CUDA events on the
-launching stream in a separate pass; `cpu_baseline` = the CPU oracle port (oracle/sma_oracle.py, the reference's
+launching stream in a separate pass (algorithmic fp32 flops / time against the measured bf16 dense peak; the kernels spend three
+fp16 tensor-core MACs per fp32 MAC, so the ceiling of this fraction is 1/3); `cpu_baseline` = the CPU oracle port (oracle/sma_oracle.py, the reference's
 algorithm in plain fp32 torch ops) on the host cores over a bounded sample of the same clip.
 
 `--impl reference` times the reference's own algorithm on the host CPU (the oracle port: the Python reference cannot
@@ -271,11 +272,17 @@ def main():
         c = agg.get('conv')
         if c:
             ach = c[1] / (c[3] * 1e-3) / 1e12
-            roof = {'kernel': 'implicit-GEMM conv (sma_conv2d_fwd)', 'bound': 'tensor', 'achieved': ach, 'peak': pk['tflops_sustained'],
-                    'unit': 'TFLOP/s', 'frac': ach / pk['tflops_sustained'], 'traffic': None, 'peak_source': pk['source'] + ' bf16 dense, sustained',
+            traffic = None                      # dram bytes (read + write) per conv launch from the committed ncu pass of this command
+            tp = os.path.join(ROOT, 'profiles', 'r1_conv_traffic.json')
+            if os.path.exists(tp):
+                traffic = json.load(open(tp)).get('dram_bytes_per_conv_launch')
+            roof = {'kernel': 'implicit-GEMM conv (sma_conv2d_fwd: conv_tc2_kernel and friends)', 'bound': 'tensor', 'achieved': ach,
+                    'peak': pk['tflops_sustained'], 'unit': 'TFLOP/s', 'frac': ach / pk['tflops_sustained'], 'traffic': traffic,
+                    'peak_source': pk['source'] + ' bf16 dense, sustained',
                     'launches_per_step': c[0], 'avg_launch_ms': c[3] / c[0], 'gflop_per_launch': c[1] / c[0] / 1e9,
                     'share_of_step_ms': c[3] / (ms / K),
-                    'note': 'fp32-faithful arithmetic (3xTF32 on tcgen05 where shapes allow, else FFMA); algorithmic flops = 2*M*N*K fp32'}
+                    'note': 'algorithmic flops = 2*M*N*K of the fp32 convolution; the kernels spend 3 fp16 tensor-core MACs per fp32 MAC '
+                            '(fp16 hi/lo split, fp32 accumulate) to stay within 1e-3 of the fp32 reference, so frac <= 1/3 by construction'}
         w_ = agg.get('warp')
         if w_:
             stage_table['warp']['hbm_frac'] = w_[2] / (w_[3] * 1e-3) / 1e9 / pk['hbm_gbs']
