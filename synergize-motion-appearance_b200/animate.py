@@ -94,6 +94,20 @@ class ClipAnimator:
         return (u8, r['out']) if want_fp32 else u8
 
 
+_PINNED = {}
+
+
+def _pinned(tag: str, shape, dtype) -> torch.Tensor:
+    """Page-locked staging buffers are kept across calls (cudaHostAlloc costs milliseconds; a clip needs three of them)."""
+    key = (tag, tuple(shape), dtype)
+    t = _PINNED.get(key)
+    if t is None:
+        if len(_PINNED) > 16:
+            _PINNED.clear()
+        t = _PINNED[key] = torch.empty(tuple(shape), dtype=dtype).pin_memory()
+    return t
+
+
 def make_animation(source_image, driving_video: Sequence[torch.Tensor], net_g, motion_estimator, relative=True,
                    adapt_movement_scale=True, cpu=False, batch: int = 64, w: float = 1.0, bgr: bool = False):
     """Same signature/returns as demo.make_animation (demo.py:103-134); `cpu=True` raises (no CPU path)."""
@@ -105,17 +119,21 @@ def make_animation(source_image, driving_video: Sequence[torch.Tensor], net_g, m
         first = driving_video[0].unsqueeze(0).to(dev, non_blocking=True)
         anim = ClipAnimator(net_g, motion_estimator, src, first, relative, adapt_movement_scale, w)
         n = len(driving_video)
-        pred_host = torch.empty((n, src.shape[2], src.shape[3], 3), dtype=torch.uint8).pin_memory()
-        drv_host = torch.empty_like(pred_host).pin_memory()
+        pred_host = _pinned('pred', (n, src.shape[2], src.shape[3], 3), torch.uint8)
+        drv_host = _pinned('drv', (n, src.shape[2], src.shape[3], 3), torch.uint8)
         for i0 in range(0, n, batch):
             chunk = driving_video[i0:i0 + batch]
-            host = torch.stack([f.float() for f in chunk]).pin_memory() if not chunk[0].is_cuda else torch.stack(list(chunk))
+            if chunk[0].is_cuda:
+                host = torch.stack(list(chunk)).float()
+            else:                       # gather the frames straight into page-locked memory (one pass over the data)
+                host = _pinned('in%d' % ((i0 // batch) & 1), (len(chunk),) + tuple(chunk[0].shape), torch.float32)
+                torch.stack([f.float() for f in chunk], out=host)
             frames = host.to(dev, non_blocking=True)
             u8 = anim.step(frames, bgr)
             pred_host[i0:i0 + len(chunk)].copy_(u8, non_blocking=True)
             drv_host[i0:i0 + len(chunk)].copy_(ops.to_uint8(ops.nchw_to_nhwc(frames), bgr), non_blocking=True)
         torch.cuda.current_stream().synchronize()
-    p, d = pred_host.numpy(), drv_host.numpy()
+    p, d = pred_host.numpy().copy(), drv_host.numpy().copy()        # the staging buffers are reused by the next call
     return [p[i] for i in range(n)], [d[i] for i in range(n)]
 
 
