@@ -265,6 +265,10 @@ struct Tc2P {
   int Ho, Wo, out_ld, act, res_ld, d2s;
   const float* wscale;        // F16 only: per-output-channel power-of-two factor that undoes the weight pre-scaling
   int HoWo, cpt, taps, NT, ntiles_n, passes, tmem_cols;
+  int fuse;                   // 3-pass, NT <= 128: the hi and lo weight images (adjacent in the ring) are read as ONE B tile of 2*NT rows, so
+                              // a_hi*[b_hi | b_lo] is one MMA; its lo half lands in accumulator columns [NT, 2NT) and is added in the epilogue
+  int acc_cols;               // TMEM columns per accumulator (NT or 2*NT)
+  int dbg;                    // timing experiments (results invalid): bit 2 = epilogue skips its residual loads and stores
   int flat, tiles_x, tiles_per_img, total_tiles;
   int halo_w, HP, a_img_bytes, a_stage_bytes, b_img_bytes, SA, SB;
 };
@@ -322,6 +326,8 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const Tc2P p) {
     const bool vec_ok = (p.out_ld & 3) == 0 && (p.out_bs & 3) == 0 && ((reinterpret_cast<uintptr_t>(p.y) & 15) == 0) &&
                         (!p.res || ((p.res_ld & 3) == 0 && (p.res_bs & 3) == 0 && (reinterpret_cast<uintptr_t>(p.res) & 15) == 0));
     const int Cq = p.d2s > 1 ? p.Cout / (p.d2s * p.d2s) : p.Cout;
+    const bool v8_ok = p.d2s <= 1 && (p.Cout & 7) == 0 && (p.out_ld & 7) == 0 && (p.out_bs & 7) == 0 && ((reinterpret_cast<uintptr_t>(p.y) & 31) == 0) &&
+                       (!p.res || ((p.res_ld & 7) == 0 && (p.res_bs & 7) == 0 && (reinterpret_cast<uintptr_t>(p.res) & 31) == 0));
     int tcount = 0, cur_nt = -1;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tcount) {
       int b, ty0, tx0, nt; decode(tile, b, ty0, tx0, nt);
@@ -343,18 +349,43 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const Tc2P p) {
       tc_fence_after();
       for (int n0 = 0; n0 < p.NT && nbase + n0 < p.Cout; n0 += 32) {
         uint32_t a[32];
-        const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(ab * p.NT + n0);
-        asm volatile(
-            "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, "
-            "%20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-            : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]), "=r"(a[4]), "=r"(a[5]), "=r"(a[6]), "=r"(a[7]), "=r"(a[8]), "=r"(a[9]), "=r"(a[10]),
-              "=r"(a[11]), "=r"(a[12]), "=r"(a[13]), "=r"(a[14]), "=r"(a[15]), "=r"(a[16]), "=r"(a[17]), "=r"(a[18]), "=r"(a[19]), "=r"(a[20]),
-              "=r"(a[21]), "=r"(a[22]), "=r"(a[23]), "=r"(a[24]), "=r"(a[25]), "=r"(a[26]), "=r"(a[27]), "=r"(a[28]), "=r"(a[29]), "=r"(a[30]),
-              "=r"(a[31])
-            : "r"(taddr)
-            : "memory");
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (mok) {
+        const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(ab * p.acc_cols + n0);
+        tmem_ld32(taddr, a);
+        if (p.fuse) {                                  // a_hi * b_lo was accumulated NT columns further right
+          uint32_t a2[32];
+          tmem_ld32(taddr + (uint32_t)p.NT, a2);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; i++) a[i] = __float_as_uint(__uint_as_float(a[i]) + __uint_as_float(a2[i]));
+        } else {
+          tmem_ld_wait();
+        }
+        if (mok && !(p.dbg & 4) && v8_ok) {
+          // 256-bit residual loads / stores: every lane moves whole 32-byte sectors (with 128-bit accesses a warp-level instruction touches
+          // half of 32 different sectors, and the epilogue - not the MMAs - bounds the low-K layers)
+          float* yrow = p.y + (long long)b * p.out_bs + (long long)r * p.out_ld;
+          const float* rrow = p.res ? p.res + (long long)b * p.res_bs + (long long)r * p.res_ld : nullptr;
+#pragma unroll
+          for (int q8 = 0; q8 < 4; q8++) {
+            const int n = nbase + n0 + q8 * 8;
+            if (n >= p.Cout) break;
+            float o[8];
+#pragma unroll
+            for (int t = 0; t < 8; t++) {
+              if (F16) o[t] = sma_act(fmaf(__uint_as_float(a[q8 * 8 + t]), s_scale[n0 + q8 * 8 + t], s_bias[n0 + q8 * 8 + t]), ACT);
+              else o[t] = sma_act(__uint_as_float(a[q8 * 8 + t]) + s_bias[n0 + q8 * 8 + t], ACT);
+            }
+            if (rrow) {
+              float r0, r1, r2, r3, r4, r5, r6, r7;
+              asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];" : "=f"(r0), "=f"(r1), "=f"(r2), "=f"(r3), "=f"(r4), "=f"(r5), "=f"(r6), "=f"(r7)
+                           : "l"(rrow + n));
+              o[0] += r0; o[1] += r1; o[2] += r2; o[3] += r3; o[4] += r4; o[5] += r5; o[6] += r6; o[7] += r7;
+            }
+            asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(yrow + n), "f"(o[0]), "f"(o[1]), "f"(o[2]), "f"(o[3]), "f"(o[4]), "f"(o[5]),
+                         "f"(o[6]), "f"(o[7])
+                         : "memory");
+          }
+        } else if (mok && !(p.dbg & 4)) {
 #pragma unroll
           for (int q = 0; q < 8; q++) {
             const int n = nbase + n0 + q * 4;
@@ -404,6 +435,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const Tc2P p) {
     // =============================== MMA issuer (whole warp converged, one elected lane issues) ===============================
     // fp32 accumulate; A/B format 2 = tf32 (kind::tf32) or 0 = fp16 (kind::f16); K-major A and B
     const uint32_t idesc = (1u << 4) | (F16 ? 0u : ((2u << 7) | (2u << 10))) | ((uint32_t)(p.NT >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    const uint32_t idesc2 = (idesc & ~(0x3Fu << 17)) | ((uint32_t)((2 * p.NT) >> 3) << 17);      // same, N = 2 NT
     // A: 8-row atoms are 8 consecutive halo rows; next atom = next output row = halo row pitch
     const uint64_t a_desc_hi_bits = (1ull << 16) | ((uint64_t)((p.halo_w * 128) >> 4) << 32) | (1ull << 46) | (2ull << 61);
     // ONE elected lane runs the whole tile loop (the elect region encloses the loops) with wrap-around ring counters instead of
@@ -417,7 +449,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const Tc2P p) {
         const uint32_t ab = tcount & 1u;
         mbar_wait(acc_empty(ab), ((tcount >> 1) & 1u) ^ 1u);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + ab * (uint32_t)p.NT;
+        const uint32_t d_tmem = tmem_base + ab * (uint32_t)p.acc_cols;
         uint32_t acc = 0u;                                   // the first MMA of a tile overwrites the accumulator
         for (int cc = 0; cc < p.cpt; cc++) {
           mbar_wait(a_full(sa), pha);
@@ -436,7 +468,10 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const Tc2P p) {
 #pragma unroll
               for (int k4 = 0; k4 < 4; k4++) {                   // 4 k-steps of 32 bytes (8 tf32 / 16 fp16) per 128-byte row
                 const uint64_t ko = (uint64_t)(k4 * 2);
-                if (three) {
+                if (p.fuse) {
+                  tc_mma<F16>(d_tmem, dah + ko, dbh + ko, idesc2, acc);          // a_hi * [b_hi | b_lo]  (N = 2 NT)
+                  tc_mma<F16>(d_tmem, dal + ko, dbh + ko, idesc, 1u);            // a_lo * b_hi
+                } else if (three) {
                   tc_mma<F16>(d_tmem, dal + ko, dbh + ko, idesc, acc);
                   tc_mma<F16>(d_tmem, dah + ko, dbl + ko, idesc, 1u);
                   tc_mma<F16>(d_tmem, dah + ko, dbh + ko, idesc, 1u);
@@ -755,7 +790,11 @@ static int conv_tc2_try(const sma_conv_desc* d, cudaStream_t st, bool f16) {
   if (SB < 2) return SMA_ERR_UNSUPPORTED;
   if (SB > MAX_SB) SB = MAX_SB;
   p.SA = SA; p.SB = SB;
-  int cols = 32; while (cols < 2 * p.NT) cols <<= 1;
+  p.fuse = (p.passes == 3 && p.NT <= 128 && !(d->tc_variant & 128)) ? 1 : 0;       // tc_variant bit 7: keep the three separate MMAs (tests)
+  p.acc_cols = p.fuse ? 2 * p.NT : p.NT;
+  p.dbg = (d->tc_variant >> 1) & 7;
+  int cols = 32; while (cols < 2 * p.acc_cols + ((p.NT & 31) ? 32 : 0)) cols <<= 1;      // the epilogue reads 32 columns at a time
+  if (cols > 512) return SMA_ERR_UNSUPPORTED;
   p.tmem_cols = cols;
   const int smem = SA * p.a_stage_bytes + SB * b_stage + 1024;
   if (g_num_sms == 0) {

@@ -71,12 +71,13 @@ def _act_ref(x, act):
             'sigmoid': torch.sigmoid, 'swish': lambda v: v * torch.sigmoid(v)}[act](x)
 
 
-@pytest.mark.parametrize('mode', ['exact', 'default', 'ts', 'ts-stream', 'ts-stream128', 'f16x3', 'tf32x3', 'gather'])
+@pytest.mark.parametrize('mode', ['exact', 'default', 'ts', 'ts-stream', 'ts-stream128', 'f16x3', 'f16x3-3mma', 'tf32x3', 'gather'])
 @pytest.mark.parametrize('case', CONV_CASES)
 def test_conv2d_matches_torch(S, case, mode):
     """exact: fp32 FFMA kernel; default: the library's choice; ts: fp16-split tcgen05 kernel with the weights as the tensor-memory operand
     wherever Cin % 64 == 0 and stride 1 (resident where they fit, streamed over 256-pixel tiles otherwise); ts-stream: the same, always streamed; ts-stream128: streamed over
-    128-pixel tiles with two accumulators; f16x3:
+    128-pixel tiles with two accumulators; f16x3-3mma: the halo kernel with three separate MMAs per k-step instead of the fused
+    [hi | lo] weight tile; f16x3:
     fp16-split halo kernel with both operands in shared memory; tf32x3: tf32-split tcgen05 kernels; gather: force the non-persistent
     tcgen05 kernel."""
     B, Cin, H, W, Cout, k, stride, pad, ex = case
@@ -105,8 +106,8 @@ def test_conv2d_matches_torch(S, case, mode):
         res = nhwc(r)
     cw = S.ops.pack_conv(w.cuda(), b.cuda())
     saved = (S.ops.TC_VARIANT, S.ops.USE_F16, S.ops.USE_TS)
-    S.ops.TC_VARIANT = {'gather': 1, 'ts': 32, 'ts-stream': 48, 'ts-stream128': 112}.get(mode, 0)
-    S.ops.USE_F16 = mode in ('f16x3', 'ts', 'ts-stream', 'ts-stream128', 'default')
+    S.ops.TC_VARIANT = {'gather': 1, 'ts': 32, 'ts-stream': 48, 'ts-stream128': 112, 'f16x3-3mma': 128}.get(mode, 0)
+    S.ops.USE_F16 = mode in ('f16x3', 'f16x3-3mma', 'ts', 'ts-stream', 'ts-stream128', 'default')
     S.ops.USE_TS = mode in ('ts', 'ts-stream', 'ts-stream128', 'default')
     try:
         y = S.ops.conv2d(nhwc(x), cw, stride=stride, pad=pad, act=ex.get('act', 'none'), pre=pre, res=res,
@@ -118,9 +119,9 @@ def test_conv2d_matches_torch(S, case, mode):
     assert got.shape == ref.shape
     tc_eligible = mode != 'exact' and Cin % 32 == 0 and not ex.get('nchw')
     assert (S.ops.LAST_CONV_KERNEL >= 1) == tc_eligible, S.ops.LAST_CONV_KERNEL      # the tensor-core kernels really ran
-    if mode in ('f16x3', 'ts', 'ts-stream', 'ts-stream128') and tc_eligible and Cin % 64 == 0 and stride == 1:
+    if mode in ('f16x3', 'f16x3-3mma', 'ts', 'ts-stream', 'ts-stream128') and tc_eligible and Cin % 64 == 0 and stride == 1:
         # ... and the fp16-split ones where eligible (7x7 halos leave the tensor-memory-operand kernel fewer than two stages: it declines)
-        assert S.ops.LAST_CONV_KERNEL in ((3,) if mode == 'f16x3' else ((3, 4) if k == 7 else (4,))), S.ops.LAST_CONV_KERNEL
+        assert S.ops.LAST_CONV_KERNEL in ((3,) if mode.startswith('f16x3') else ((3, 4) if k == 7 else (4,))), S.ops.LAST_CONV_KERNEL
     # exact kernel: fp32 FFMA; split kernels: the TMEM accumulator adds with truncation, error grows ~1e-8 * K
     tol = (2e-5 + (1e-8 * Cin * k * k if tc_eligible else 0.0)) * max(1.0, float(ref.abs().max()))
     assert err < tol, (err, tol)
