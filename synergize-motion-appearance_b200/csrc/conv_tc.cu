@@ -360,6 +360,10 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const Tc2P p) {
         } else {
           tmem_ld_wait();
         }
+        if (n0 + 32 >= p.NT || nbase + n0 + 32 >= p.Cout) {     // last column block: the accumulator may be overwritten while we store
+          tc_fence_before();
+          mbar_arrive(acc_empty(ab));
+        }
         if (mok && !(p.dbg & 4) && v8_ok) {
           // 256-bit residual loads / stores: every lane moves whole 32-byte sectors (with 128-bit accesses a warp-level instruction touches
           // half of 32 different sectors, and the epilogue - not the MMAs - bounds the low-K layers)
@@ -428,8 +432,6 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const Tc2P p) {
           }
         }
       }
-      tc_fence_before();
-      mbar_arrive(acc_empty(ab));                 // this thread's TMEM reads of accumulator `ab` are complete
     }
   } else if (warp == 4) {
     // =============================== MMA issuer (whole warp converged, one elected lane issues) ===============================
@@ -515,6 +517,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const Tc2P p) {
     const int ptid = (threadIdx.x - 192) % (32 * V2_PROD_WARPS / V2_PGROUPS); const int cq = ptid & 7; const int prow = ptid >> 3;   // V2_PROWS halo rows per pass
     const int Hv = p.Hi << p.up, Wv = p.Wi << p.up;
     const int npass = (p.HP + V2_PROWS - 1) / V2_PROWS;
+    const bool in32 = (p.in_ld & 7) == 0 && (p.in_bs & 7) == 0 && (reinterpret_cast<uintptr_t>(p.x) & 31) == 0;
     int it = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       int b, ty0, tx0, nt; decode(tile, b, ty0, tx0, nt);
@@ -585,8 +588,13 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const Tc2P p) {
               if (hp < p.HP) {
                 const long long pix = halo_pixel(hp, ok[u]);
                 if (ok[u]) {
-                  const float4* src = reinterpret_cast<const float4*>(xb + pix * p.in_ld + c);
-                  v0[u] = __ldg(src); v1[u] = __ldg(src + 1);
+                  const float* src = xb + pix * p.in_ld + c;
+                  if (in32) {                     // one 256-bit load = one whole 32-byte sector per lane
+                    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];" : "=f"(v0[u].x), "=f"(v0[u].y), "=f"(v0[u].z), "=f"(v0[u].w),
+                                 "=f"(v1[u].x), "=f"(v1[u].y), "=f"(v1[u].z), "=f"(v1[u].w) : "l"(src));
+                  } else {
+                    v0[u] = __ldg(reinterpret_cast<const float4*>(src)); v1[u] = __ldg(reinterpret_cast<const float4*>(src) + 1);
+                  }
                 }
               }
             }
