@@ -24,11 +24,21 @@ __device__ __forceinline__ float4 f4_fma(float w, float4 a, float4 acc) {
   return acc;
 }
 
-// one thread per (pixel, channel-quad)
+struct F8 { float4 a, b; };
+__device__ __forceinline__ F8 ldg256(const float* p) {
+  F8 r;
+  asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];" : "=f"(r.a.x), "=f"(r.a.y), "=f"(r.a.z), "=f"(r.a.w), "=f"(r.b.x), "=f"(r.b.y),
+               "=f"(r.b.z), "=f"(r.b.w) : "l"(p));
+  return r;
+}
+
+// one thread per (pixel, VEC channels); VEC = 8 uses 256-bit loads / stores (whole 32-byte sectors per lane) and halves the per-pixel
+// flow / occlusion resize work that every thread of a pixel repeats
+template <int VEC>
 __global__ void warp_occlude_kernel(const float* __restrict__ feat, long long fbs, int B, int H, int W, int C,
                                     const float* __restrict__ flow, const float* __restrict__ occ, int hf, int wf,
                                     float* __restrict__ out, long long total4) {
-  const int C4 = C >> 2;
+  const int C4 = C / VEC;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
     int c4 = (int)(i % C4); long long pp = i / C4; int x = (int)(pp % W); long long t = pp / W; int y = (int)(t % H); int b = (int)(t / H);
     // resized flow / occlusion at (y,x)
@@ -58,16 +68,28 @@ __global__ void warp_occlude_kernel(const float* __restrict__ feat, long long fb
     float fx = floorf(ix), fy = floorf(iy);
     int x0 = (int)fx, y0 = (int)fy, x1 = x0 + 1, y1 = y0 + 1;
     float wx1 = ix - fx, wy1 = iy - fy, wx0 = 1.f - wx1, wy0 = 1.f - wy1;
-    const float* fb = feat + (long long)b * fbs + c4 * 4;
+    const float* fb = feat + (long long)b * fbs + c4 * VEC;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     bool vx0 = (unsigned)x0 < (unsigned)W, vx1 = (unsigned)x1 < (unsigned)W, vy0 = (unsigned)y0 < (unsigned)H, vy1 = (unsigned)y1 < (unsigned)H;
     // same accumulation order as ATen's grid_sampler_2d (nw, ne, sw, se)
-    if (vy0 && vx0) acc = f4_fma(wy0 * wx0, __ldg(reinterpret_cast<const float4*>(fb + ((long long)y0 * W + x0) * C)), acc);
-    if (vy0 && vx1) acc = f4_fma(wy0 * wx1, __ldg(reinterpret_cast<const float4*>(fb + ((long long)y0 * W + x1) * C)), acc);
-    if (vy1 && vx0) acc = f4_fma(wy1 * wx0, __ldg(reinterpret_cast<const float4*>(fb + ((long long)y1 * W + x0) * C)), acc);
-    if (vy1 && vx1) acc = f4_fma(wy1 * wx1, __ldg(reinterpret_cast<const float4*>(fb + ((long long)y1 * W + x1) * C)), acc);
-    if (occ) { acc.x *= oc; acc.y *= oc; acc.z *= oc; acc.w *= oc; }
-    *reinterpret_cast<float4*>(out + (pp * C) + c4 * 4) = acc;
+    if (VEC == 8) {
+      float4 acc2 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (vy0 && vx0) { F8 v = ldg256(fb + ((long long)y0 * W + x0) * C); acc = f4_fma(wy0 * wx0, v.a, acc); acc2 = f4_fma(wy0 * wx0, v.b, acc2); }
+      if (vy0 && vx1) { F8 v = ldg256(fb + ((long long)y0 * W + x1) * C); acc = f4_fma(wy0 * wx1, v.a, acc); acc2 = f4_fma(wy0 * wx1, v.b, acc2); }
+      if (vy1 && vx0) { F8 v = ldg256(fb + ((long long)y1 * W + x0) * C); acc = f4_fma(wy1 * wx0, v.a, acc); acc2 = f4_fma(wy1 * wx0, v.b, acc2); }
+      if (vy1 && vx1) { F8 v = ldg256(fb + ((long long)y1 * W + x1) * C); acc = f4_fma(wy1 * wx1, v.a, acc); acc2 = f4_fma(wy1 * wx1, v.b, acc2); }
+      if (occ) { acc.x *= oc; acc.y *= oc; acc.z *= oc; acc.w *= oc; acc2.x *= oc; acc2.y *= oc; acc2.z *= oc; acc2.w *= oc; }
+      asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(out + (pp * C) + c4 * 8), "f"(acc.x), "f"(acc.y), "f"(acc.z), "f"(acc.w),
+                   "f"(acc2.x), "f"(acc2.y), "f"(acc2.z), "f"(acc2.w)
+                   : "memory");
+    } else {
+      if (vy0 && vx0) acc = f4_fma(wy0 * wx0, __ldg(reinterpret_cast<const float4*>(fb + ((long long)y0 * W + x0) * C)), acc);
+      if (vy0 && vx1) acc = f4_fma(wy0 * wx1, __ldg(reinterpret_cast<const float4*>(fb + ((long long)y0 * W + x1) * C)), acc);
+      if (vy1 && vx0) acc = f4_fma(wy1 * wx0, __ldg(reinterpret_cast<const float4*>(fb + ((long long)y1 * W + x0) * C)), acc);
+      if (vy1 && vx1) acc = f4_fma(wy1 * wx1, __ldg(reinterpret_cast<const float4*>(fb + ((long long)y1 * W + x1) * C)), acc);
+      if (occ) { acc.x *= oc; acc.y *= oc; acc.z *= oc; acc.w *= oc; }
+      *reinterpret_cast<float4*>(out + (pp * C) + c4 * 4) = acc;
+    }
   }
 }
 
@@ -84,6 +106,25 @@ __global__ void resize_ac_kernel(const float* __restrict__ x, int Hi, int Wi, in
   }
 }
 
+// 4 channels per thread (128-bit accesses)
+__global__ void resize_ac4_kernel(const float* __restrict__ x, int Hi, int Wi, int C4, long long ibs, int ild,
+                                  float* __restrict__ y, int Ho, int Wo, long long obs, int old_, long long total) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % C4) * 4; long long pp = i / C4; int ox = (int)(pp % Wo); long long t = pp / Wo; int oy = (int)(t % Ho); int b = (int)(t / Ho);
+    Bil by = bil_ac(oy, Hi, Ho), bx = bil_ac(ox, Wi, Wo);
+    const float* xb = x + (long long)b * ibs + c;
+    const float4 v00 = __ldg(reinterpret_cast<const float4*>(xb + ((long long)by.i0 * Wi + bx.i0) * ild)), v01 = __ldg(reinterpret_cast<const float4*>(xb + ((long long)by.i0 * Wi + bx.i1) * ild));
+    const float4 v10 = __ldg(reinterpret_cast<const float4*>(xb + ((long long)by.i1 * Wi + bx.i0) * ild)), v11 = __ldg(reinterpret_cast<const float4*>(xb + ((long long)by.i1 * Wi + bx.i1) * ild));
+    const float w0y = 1.f - by.w1, w0x = 1.f - bx.w1;
+    float4 o;
+    o.x = w0y * (w0x * v00.x + bx.w1 * v01.x) + by.w1 * (w0x * v10.x + bx.w1 * v11.x);
+    o.y = w0y * (w0x * v00.y + bx.w1 * v01.y) + by.w1 * (w0x * v10.y + bx.w1 * v11.y);
+    o.z = w0y * (w0x * v00.z + bx.w1 * v01.z) + by.w1 * (w0x * v10.z + bx.w1 * v11.z);
+    o.w = w0y * (w0x * v00.w + bx.w1 * v01.w) + by.w1 * (w0x * v10.w + bx.w1 * v11.w);
+    *reinterpret_cast<float4*>(y + (long long)b * obs + ((long long)oy * Wo + ox) * old_ + c) = o;
+  }
+}
+
 }  // namespace
 
 extern "C" int sma_warp_occlude_fwd(const float* feat, int64_t fbs, int B, int H, int W, int C, const float* flow, const float* occ,
@@ -92,9 +133,11 @@ extern "C" int sma_warp_occlude_fwd(const float* feat, int64_t fbs, int B, int H
   if ((C & 3) || (fbs & 3) || ((reinterpret_cast<uintptr_t>(feat) | reinterpret_cast<uintptr_t>(out)) & 15) ||
       (reinterpret_cast<uintptr_t>(flow) & 7))
     return SMA_ERR_UNSUPPORTED;
-  long long total4 = (long long)B * H * W * (C >> 2);
+  const bool v8 = (C & 7) == 0 && (fbs & 7) == 0 && ((reinterpret_cast<uintptr_t>(feat) | reinterpret_cast<uintptr_t>(out)) & 31) == 0;
+  long long total4 = (long long)B * H * W * (C / (v8 ? 8 : 4));
   long long blocks = (total4 + 255) / 256; if (blocks > kNumSMs * 32) blocks = kNumSMs * 32;
-  warp_occlude_kernel<<<(int)blocks, 256, 0, as_stream(stream)>>>(feat, fbs, B, H, W, C, flow, occ, hf, wf, out, total4);
+  if (v8) warp_occlude_kernel<8><<<(int)blocks, 256, 0, as_stream(stream)>>>(feat, fbs, B, H, W, C, flow, occ, hf, wf, out, total4);
+  else warp_occlude_kernel<4><<<(int)blocks, 256, 0, as_stream(stream)>>>(feat, fbs, B, H, W, C, flow, occ, hf, wf, out, total4);
   SMA_LAUNCH_CHECK();
   return SMA_OK;
 }
@@ -102,9 +145,12 @@ extern "C" int sma_warp_occlude_fwd(const float* feat, int64_t fbs, int B, int H
 extern "C" int sma_resize_bilinear_ac(const float* x, int B, int Hi, int Wi, int C, int64_t ibs, int ild, float* y, int Ho, int Wo,
                                       int64_t obs, int old_, sma_stream_t stream) {
   if (!x || !y || B <= 0 || Hi <= 0 || Wi <= 0 || C <= 0 || Ho <= 0 || Wo <= 0) return SMA_ERR_BAD_ARG;
-  long long total = (long long)B * Ho * Wo * C;
+  const bool v4 = (C & 3) == 0 && (ild & 3) == 0 && (old_ & 3) == 0 && (ibs & 3) == 0 && (obs & 3) == 0 &&
+                  ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0;
+  long long total = (long long)B * Ho * Wo * (v4 ? C / 4 : C);
   long long blocks = (total + 255) / 256; if (blocks > kNumSMs * 32) blocks = kNumSMs * 32;
-  resize_ac_kernel<<<(int)blocks, 256, 0, as_stream(stream)>>>(x, Hi, Wi, C, ibs, ild, y, Ho, Wo, obs, old_, total);
+  if (v4) resize_ac4_kernel<<<(int)blocks, 256, 0, as_stream(stream)>>>(x, Hi, Wi, C / 4, ibs, ild, y, Ho, Wo, obs, old_, total);
+  else resize_ac_kernel<<<(int)blocks, 256, 0, as_stream(stream)>>>(x, Hi, Wi, C, ibs, ild, y, Ho, Wo, obs, old_, total);
   SMA_LAUNCH_CHECK();
   return SMA_OK;
 }
