@@ -74,8 +74,11 @@ class ClipAnimator:
         self.relative, self.w = relative, float(w)
         self.source = source.contiguous().float()
         with torch.no_grad():
-            self.kp_source = self.me.estimate_kp(self.source)
-            self.kp_initial = self.me.estimate_kp(driving_initial.contiguous().float())
+            # one key-point detector pass for the source and the first driving frame (the tiny hourglass bottleneck layers are
+            # weight-streaming bound at batch 1: batching the two per-clip calls halves that cost)
+            kp2 = self.me.estimate_kp(torch.cat([self.source, driving_initial.contiguous().float()], dim=0))
+            self.kp_source = {k: v[0:1].contiguous() for k, v in kp2.items()}
+            self.kp_initial = {k: v[1:2].contiguous() for k, v in kp2.items()}
             self.scale = movement_scale(self.kp_source, self.kp_initial) if (adapt_movement_scale and relative) else 1.0
             self.feats = self.net_g.encode_source(self.source)
             self.me.dense_motion_network.source_down(self.source)
