@@ -374,10 +374,16 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const Tc2P p) {
             const int n = nbase + n0 + q8 * 8;
             if (n >= p.Cout) break;
             float o[8];
+            const float4 b0 = *reinterpret_cast<const float4*>(&s_bias[n0 + q8 * 8]), b1 = *reinterpret_cast<const float4*>(&s_bias[n0 + q8 * 8 + 4]);
+            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+            if (F16) {
+              const float4 s0 = *reinterpret_cast<const float4*>(&s_scale[n0 + q8 * 8]), s1 = *reinterpret_cast<const float4*>(&s_scale[n0 + q8 * 8 + 4]);
+              const float ss[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
 #pragma unroll
-            for (int t = 0; t < 8; t++) {
-              if (F16) o[t] = sma_act(fmaf(__uint_as_float(a[q8 * 8 + t]), s_scale[n0 + q8 * 8 + t], s_bias[n0 + q8 * 8 + t]), ACT);
-              else o[t] = sma_act(__uint_as_float(a[q8 * 8 + t]) + s_bias[n0 + q8 * 8 + t], ACT);
+              for (int t = 0; t < 8; t++) o[t] = sma_act(fmaf(__uint_as_float(a[q8 * 8 + t]), ss[t], bb[t]), ACT);
+            } else {
+#pragma unroll
+              for (int t = 0; t < 8; t++) o[t] = sma_act(__uint_as_float(a[q8 * 8 + t]) + bb[t], ACT);
             }
             if (rrow) {
               float r0, r1, r2, r3, r4, r5, r6, r7;
