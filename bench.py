@@ -158,6 +158,8 @@ def main():
     dev = torch.device('cuda', local)
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
+    # host-side frame gathering of the e2e arm (torch.stack into pinned memory): torchrun pins OMP_NUM_THREADS to 1, give every rank its share of the cores
+    torch.set_num_threads(max(1, (os.cpu_count() or 1) // world))
     T, Bm, K, Wm = args.frames, args.batch, args.steps, max(3, args.warmup)
 
     CFG = net_cfg()
