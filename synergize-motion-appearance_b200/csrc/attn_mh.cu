@@ -3,9 +3,10 @@
 // tensor-memory operand, V through an MN-major descriptor, lazy reference maximum.
 //
 // A 128-byte row of the tile images holds 64 head-dim values = TWO heads, so a CTA owns one (128-query tile, head PAIR, frame) and runs
-// both heads on every K / V block it loads: head x reads bytes 64x..64x+63 of each row (descriptor start + 64 B; the swizzle is a function
-// of the absolute address, so a shifted start stays consistent).  Per 64-key block and head: S = q k^T (2 k-steps x 3 products, N = 64),
-// O += P V (4 k-steps x 3 products, N = 32, P read from TENSOR MEMORY).  K / V are double buffered; S, P and O are per head.
+// the two heads one after the other over the K / V tile stream: head x reads bytes 64x..64x+63 of each row (descriptor start + 64 B; the
+// swizzle is a function of the absolute address, so a shifted start stays consistent).  Per 64-key block: S = q k^T (2 k-steps x 3
+// products, N = 64), O += P V (4 k-steps x 3 products, N = 32, P read from TENSOR MEMORY).  K / V are double buffered.  80 KB of shared
+// memory and 256 tensor-memory columns per CTA: two CTAs per SM.
 //   warps 0-7  softmax (two threads per query row, 32 keys each; both heads), O rescale, epilogue
 //   warp 8     MMA issue (one elected lane)          warp 9   loader (bulk copies)
 // An all-masked row yields NaN like the reference (l = 0 -> 0 * inf).
@@ -21,10 +22,9 @@ namespace {
 constexpr int MH_BQ = 128, MH_BKV = 64, MH_E = 256;
 constexpr int MH_THREADS = 320;
 constexpr uint32_t MH_OFF_QH = 0, MH_OFF_K = 16384, MH_OFF_V = 49152, MH_SMEM = 81920;
-constexpr uint32_t MH_S_COL = 0, MH_O_COL = 128, MH_QL_COL = 192, MH_P_COL = 224;      // S_A 0 | S_B 64 | O_A 128 | O_B 160 | q_lo 192 | P_A hi,lo 224 | P_B 288..351
+constexpr uint32_t MH_S_COL = 0, MH_O_COL = 64, MH_QL_COL = 96, MH_P_COL = 128;      // S 0 | O 64 | q_lo 96 (two heads) | P hi 128, lo 160 ; 192 of 256 columns
 constexpr float MH_LAZY = 8.f;
 
-__device__ __forceinline__ uint32_t mh_sw_off(int row, int chunk) { return (uint32_t)row * 128u + (uint32_t)((chunk ^ (row & 7)) << 4); }
 __device__ __forceinline__ float mh_ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ void mh_mma_ts(uint32_t d, uint32_t a_tmem, uint64_t b, uint32_t idesc, uint32_t acc) {
   asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n}" ::"r"(d), "r"(a_tmem), "l"(b),
@@ -34,35 +34,32 @@ __device__ __forceinline__ void mh_mma_ts(uint32_t d, uint32_t a_tmem, uint64_t 
 
 struct MhP { const uint16_t* ws; const uint8_t* mask; float* out; int ldo, B, kvB, L, S; };
 
-__global__ void __launch_bounds__(MH_THREADS, 1) attn_mh_kernel(const MhP p) {
+// Two CTAs per SM (80 KB of shared memory, 256 tensor-memory columns each): the softmax of one CTA overlaps the MMA waits of the other.  The two
+// heads of the pair run one after the other over the same K / V tile stream (block index g = head * nblk + j drives every barrier phase).
+__global__ void __launch_bounds__(MH_THREADS, 2) attn_mh_kernel(const MhP p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bars[20];
+  __shared__ __align__(8) uint64_t bars[16];
   __shared__ uint32_t tmem_slot;
-  __shared__ float s_red[2][2][MH_BQ];                  // [head][key half][row]
+  __shared__ float s_red[2][MH_BQ];                     // [key half][row]
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qt = blockIdx.x, hp = blockIdx.y, b = blockIdx.z;
-  const int nqt = p.L / MH_BQ, nblk = p.S / MH_BKV;
+  const int nqt = p.L / MH_BQ, nblk = p.S / MH_BKV, ntot = 2 * nblk;
   const uint32_t bar0 = smem_u32(bars);
-  const uint32_t q_full = bar0;
-  auto k_full = [&](int s) { return bar0 + 8u * (1 + s); };   auto k_empty = [&](int s) { return bar0 + 8u * (3 + s); };
-  auto v_full = [&](int s) { return bar0 + 8u * (5 + s); };   auto v_empty = [&](int s) { return bar0 + 8u * (7 + s); };
-  auto s_full = [&](int x) { return bar0 + 8u * (9 + x); };   auto s_free = [&](int x) { return bar0 + 8u * (11 + x); };
-  auto p_full = [&](int x) { return bar0 + 8u * (13 + x); };  auto pv_done = [&](int x) { return bar0 + 8u * (15 + x); };
+  const uint32_t q_full = bar0, s_full = bar0 + 8, s_free = bar0 + 16, p_full = bar0 + 24, pv_done = bar0 + 32;
+  auto k_full = [&](int s) { return bar0 + 8u * (5 + s); };   auto k_empty = [&](int s) { return bar0 + 8u * (7 + s); };
+  auto v_full = [&](int s) { return bar0 + 8u * (9 + s); };   auto v_empty = [&](int s) { return bar0 + 8u * (11 + s); };
   const long long img_q = (long long)p.B * p.L * MH_E, img_k = (long long)p.kvB * p.S * MH_E;
   const uint16_t* qh = p.ws; const uint16_t* ql = qh + img_q; const uint16_t* kh = ql + img_q; const uint16_t* kl = kh + img_k;
   const uint16_t* vh = kl + img_k; const uint16_t* vl = vh + img_k;
   const int kvb = p.kvB == 1 ? 0 : b;
 
   if (threadIdx.x == 0) {
-    mbar_init(q_full, 1 + 4);
-    for (int s = 0; s < 2; s++) {
-      mbar_init(k_full(s), 1); mbar_init(k_empty(s), 1); mbar_init(v_full(s), 1); mbar_init(v_empty(s), 1);
-      mbar_init(s_full(s), 1); mbar_init(s_free(s), 8); mbar_init(p_full(s), 8); mbar_init(pv_done(s), 1);
-    }
+    mbar_init(q_full, 1 + 4); mbar_init(s_full, 1); mbar_init(s_free, 8); mbar_init(p_full, 8); mbar_init(pv_done, 1);
+    for (int s = 0; s < 2; s++) { mbar_init(k_full(s), 1); mbar_init(k_empty(s), 1); mbar_init(v_full(s), 1); mbar_init(v_empty(s), 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 8) tmem_alloc(smem_u32(&tmem_slot), 512);
+  if (warp == 8) tmem_alloc(smem_u32(&tmem_slot), 256);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -70,7 +67,7 @@ __global__ void __launch_bounds__(MH_THREADS, 1) attn_mh_kernel(const MhP p) {
 
   if (warp < 8) {
     // =============================== softmax / correction / epilogue ===============================
-    const int half = warp >> 2;                          // which 32 keys of every 64-key block; also: which head's O this warp rescales / stores
+    const int half = warp >> 2;                          // which 32 keys of every 64-key block; also which 16 columns of O this warp rescales / stores
     const int r = (warp & 3) * 32 + lane;                // query row = TMEM lane
     const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
     if (warp < 4) {
@@ -85,97 +82,87 @@ __global__ void __launch_bounds__(MH_THREADS, 1) attn_mh_kernel(const MhP p) {
       __syncwarp();
       if (lane == 0) mbar_arrive(q_full);
     }
-    float m_ref[2] = {-CUDART_INF_F, -CUDART_INF_F}, l_run[2] = {0.f, 0.f};
-    for (int j = 0; j < nblk; j++) {
-      const uint32_t par = (uint32_t)j & 1u;
-      uint32_t sv[2][32];
+    float m_ref = -CUDART_INF_F, l_run = 0.f;
+    for (int g = 0; g < ntot; g++) {
+      const int x = g >= nblk ? 1 : 0, j = g - x * nblk;
+      const uint32_t par = (uint32_t)g & 1u;
+      uint32_t sv[32];
       uint4 mk0 = make_uint4(0, 0, 0, 0), mk1 = mk0;
       if (p.mask) {
         const uint4* mp = reinterpret_cast<const uint4*>(p.mask + (long long)b * p.S + j * MH_BKV + half * 32);
         mk0 = __ldg(mp); mk1 = __ldg(mp + 1);
       }
-      float mloc[2];
+      mbar_wait(s_full, par);
+      tc_fence_after();
+      tmem_ld32(lane_addr + MH_S_COL + (uint32_t)(half * 32), sv);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(s_free);                  // S may be overwritten by the next block's scores
+      if (p.mask) {
+        const uint32_t mw[8] = {mk0.x, mk0.y, mk0.z, mk0.w, mk1.x, mk1.y, mk1.z, mk1.w};
 #pragma unroll
-      for (int x = 0; x < 2; x++) {
-        mbar_wait(s_full(x), par);
+        for (int i = 0; i < 32; i++)
+          if ((mw[i >> 2] >> ((i & 3) * 8)) & 0xffu) sv[i] = __float_as_uint(-CUDART_INF_F);
+      }
+      float mloc = -CUDART_INF_F;
+#pragma unroll
+      for (int i = 0; i < 32; i++) mloc = fmaxf(mloc, __uint_as_float(sv[i]));
+      s_red[half][r] = mloc;
+      asm volatile("bar.sync 2, 256;" ::: "memory");     // the two halves of every row exchange their block maxima
+      const float mx = fmaxf(mloc, s_red[half ^ 1][r]);
+      asm volatile("bar.sync 2, 256;" ::: "memory");
+      const bool need = mx > m_ref + MH_LAZY;            // identical in both halves of the row
+      const float m_new = need ? mx : m_ref;
+      const float alpha = need ? mh_ex2(m_ref - m_new) : 1.f;          // m_ref = -inf (nothing seen yet) -> 0
+      m_ref = m_new;
+      const float base = m_new == -CUDART_INF_F ? 0.f : m_new;         // every key so far masked: p = 2^(-inf) = 0, no inf - inf
+      float psum = 0.f;
+#pragma unroll
+      for (int i = 0; i < 32; i++) { float pv = mh_ex2(__uint_as_float(sv[i]) - base); psum += pv; sv[i] = __float_as_uint(pv); }
+      l_run = l_run * alpha + psum;
+      if (g > 0) {
+        mbar_wait(pv_done, (uint32_t)(g - 1) & 1u);      // P V of the previous block retired: O is stable and the P columns are free
+        if (j > 0 && __any_sync(0xffffffffu, need)) {    // rescale this warp's 16 columns of O (warp-uniform: tcgen05.ld / st are collectives)
+          tc_fence_after();
+          uint32_t o[16];
+          tmem_ld16(lane_addr + MH_O_COL + (uint32_t)(half * 16), o);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; i++) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+          tmem_st16(lane_addr + MH_O_COL + (uint32_t)(half * 16), o);
+        }
+      }
+      // P as the TENSOR-MEMORY operand of P.V: this thread's 32 keys are 16 columns of fp16 pairs in the hi image and 16 in the lo image
+      uint32_t ph[16], pl[16];
+#pragma unroll
+      for (int c = 0; c < 16; c++) split_f16x2(__uint_as_float(sv[2 * c]), __uint_as_float(sv[2 * c + 1]), ph[c], pl[c]);
+      tmem_st16(lane_addr + MH_P_COL + (uint32_t)(half * 16), ph);
+      tmem_st16(lane_addr + MH_P_COL + 32u + (uint32_t)(half * 16), pl);
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full);
+      if (j == nblk - 1) {
+        // head finished: O / l (row sums of the two key halves are exchanged first); this warp stores 16 of the head's 32 columns
+        s_red[half][r] = l_run;
+        asm volatile("bar.sync 2, 256;" ::: "memory");
+        const float inv = 1.f / (l_run + s_red[half ^ 1][r]);        // l = 0 (all keys masked): 0 * inf = NaN, the reference's behaviour
+        asm volatile("bar.sync 2, 256;" ::: "memory");
+        mbar_wait(pv_done, (uint32_t)g & 1u);
         tc_fence_after();
-        tmem_ld32(lane_addr + MH_S_COL + (uint32_t)(x * 64 + half * 32), sv[x]);
+        uint32_t o[16];
+        tmem_ld16(lane_addr + MH_O_COL + (uint32_t)(half * 16), o);
         tmem_ld_wait();
         tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(s_free(x));             // S_x may be overwritten by the next block's scores
-        if (p.mask) {
-          const uint32_t mw[8] = {mk0.x, mk0.y, mk0.z, mk0.w, mk1.x, mk1.y, mk1.z, mk1.w};
+        float* ob = p.out + ((long long)b * p.L + (long long)qt * MH_BQ + r) * p.ldo + (hp * 2 + x) * 32 + half * 16;
 #pragma unroll
-          for (int i = 0; i < 32; i++)
-            if ((mw[i >> 2] >> ((i & 3) * 8)) & 0xffu) sv[x][i] = __float_as_uint(-CUDART_INF_F);
-        }
-        float m = -CUDART_INF_F;
-#pragma unroll
-        for (int i = 0; i < 32; i++) m = fmaxf(m, __uint_as_float(sv[x][i]));
-        mloc[x] = m;
-        s_red[x][half][r] = m;
-      }
-      asm volatile("bar.sync 2, 256;" ::: "memory");     // the two halves of every row exchange their block maxima (both heads)
-      const float mxo[2] = {s_red[0][half ^ 1][r], s_red[1][half ^ 1][r]};
-      asm volatile("bar.sync 2, 256;" ::: "memory");
-      float alpha[2]; bool need[2];
-#pragma unroll
-      for (int x = 0; x < 2; x++) {
-        const float mx = fmaxf(mloc[x], mxo[x]);
-        need[x] = mx > m_ref[x] + MH_LAZY;               // identical in both halves of the row
-        const float m_new = need[x] ? mx : m_ref[x];
-        alpha[x] = need[x] ? mh_ex2(m_ref[x] - m_new) : 1.f;          // m_ref = -inf (nothing seen yet) -> 0
-        m_ref[x] = m_new;
-        const float base = m_new == -CUDART_INF_F ? 0.f : m_new;      // every key so far masked: p = 2^(-inf) = 0, no inf - inf
-        float psum = 0.f;
-#pragma unroll
-        for (int i = 0; i < 32; i++) { float pv = mh_ex2(__uint_as_float(sv[x][i]) - base); psum += pv; sv[x][i] = __float_as_uint(pv); }
-        l_run[x] = l_run[x] * alpha[x] + psum;
-      }
-#pragma unroll
-      for (int x = 0; x < 2; x++) {
-        if (j > 0) {
-          mbar_wait(pv_done(x), (uint32_t)(j - 1) & 1u);   // P_x V of block j-1 retired: O_x is stable and the P_x buffer is free
-          if (x == half && __any_sync(0xffffffffu, need[x])) {       // this warp rescales O of head `half`
-            tc_fence_after();
-            uint32_t o[32];
-            tmem_ld32(lane_addr + MH_O_COL + (uint32_t)(x * 32), o);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; i++) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha[x]);
-            tmem_st32(lane_addr + MH_O_COL + (uint32_t)(x * 32), o);
-            tmem_st_wait();
-          }
-        }
-        // P_x as the TENSOR-MEMORY operand of P.V (N = 32: 25 instead of 56 cycles per MMA, and no shared-memory round trip): this thread's 32 keys
-        // are 16 columns of fp16 pairs in the hi image and 16 in the lo image
-        uint32_t ph[16], pl[16];
-#pragma unroll
-        for (int c = 0; c < 16; c++) split_f16x2(__uint_as_float(sv[x][2 * c]), __uint_as_float(sv[x][2 * c + 1]), ph[c], pl[c]);
-        tmem_st16(lane_addr + MH_P_COL + (uint32_t)(x * 64 + half * 16), ph);
-        tmem_st16(lane_addr + MH_P_COL + (uint32_t)(x * 64 + 32 + half * 16), pl);
-        tmem_st_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(p_full(x));
+        for (int i = 0; i < 16; i += 4)
+          *reinterpret_cast<float4*>(ob + i) = make_float4(__uint_as_float(o[i]) * inv, __uint_as_float(o[i + 1]) * inv, __uint_as_float(o[i + 2]) * inv,
+                                                           __uint_as_float(o[i + 3]) * inv);
+        m_ref = -CUDART_INF_F; l_run = 0.f;
       }
     }
-    // final: O / l ; this warp stores head `half` (row sums of the two key halves are exchanged first)
-    s_red[0][half][r] = l_run[0]; s_red[1][half][r] = l_run[1];
-    asm volatile("bar.sync 2, 256;" ::: "memory");
-    const float inv = 1.f / (l_run[half] + s_red[half][half ^ 1][r]);     // l = 0 (all keys masked): 0 * inf = NaN, the reference's behaviour
-    mbar_wait(pv_done(half), (uint32_t)(nblk - 1) & 1u);
-    tc_fence_after();
-    uint32_t o[32];
-    tmem_ld32(lane_addr + MH_O_COL + (uint32_t)(half * 32), o);
-    tmem_ld_wait();
-    float* ob = p.out + ((long long)b * p.L + (long long)qt * MH_BQ + r) * p.ldo + (hp * 2 + half) * 32;
-#pragma unroll
-    for (int i = 0; i < 32; i += 4)
-      *reinterpret_cast<float4*>(ob + i) = make_float4(__uint_as_float(o[i]) * inv, __uint_as_float(o[i + 1]) * inv, __uint_as_float(o[i + 2]) * inv,
-                                                       __uint_as_float(o[i + 3]) * inv);
-    tc_fence_before();
   } else if (warp == 8) {
     // =============================== MMA issue (one elected lane runs the whole loop) ===============================
     if (elect_one_sync()) {
@@ -183,50 +170,44 @@ __global__ void __launch_bounds__(MH_THREADS, 1) attn_mh_kernel(const MhP p) {
       const uint32_t idesc_o = (1u << 4) | (1u << 16) | ((uint32_t)(32 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);   // B (= V) MN-major, N = 32
       // V block, MN-major SWIZZLE_128B: one key per 128-byte row, 8-key groups 1 KB apart (SBO); a single 64-value group (LBO unused)
       const uint64_t v_desc_bits = ((uint64_t)(8192 >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
-      auto issue_scores = [&](int j) {
-        const int st = j & 1;
-        mbar_wait(k_full(st), (uint32_t)(j >> 1) & 1u);
+      const uint32_t s_tmem = tmem_base + MH_S_COL, o_tmem = tmem_base + MH_O_COL;
+      auto issue_scores = [&](int g) {
+        const int st = g & 1, x = g >= nblk ? 1 : 0;
+        mbar_wait(k_full(st), (uint32_t)(g >> 1) & 1u);
+        if (g > 0) mbar_wait(s_free, (uint32_t)(g - 1) & 1u);
+        tc_fence_after();
         const uint32_t k_hi = sbase + MH_OFF_K + (uint32_t)st * 16384u, k_lo = k_hi + 8192u;
 #pragma unroll
-        for (int x = 0; x < 2; x++) {
-          if (j > 0) mbar_wait(s_free(x), (uint32_t)(j - 1) & 1u);
-          tc_fence_after();
-#pragma unroll
-          for (int ks = 0; ks < 2; ks++) {
-            const uint64_t ko = (uint64_t)(x * 4 + ks * 2);                     // head x: bytes 64x.. of the row; 32 bytes per k-step
-            const uint64_t dq = make_desc(sbase + MH_OFF_QH) + ko, dkh = make_desc(k_hi) + ko, dkl = make_desc(k_lo) + ko;
-            mh_mma_ts(tmem_base + MH_S_COL + (uint32_t)(x * 64), tmem_base + MH_QL_COL + (uint32_t)(x * 16 + ks * 8), dkh, idesc_s, ks != 0);   // q_lo * k_hi
-            tc_mma_f16(tmem_base + MH_S_COL + (uint32_t)(x * 64), dq, dkl, idesc_s, 1u);                                                      // q_hi * k_lo
-            tc_mma_f16(tmem_base + MH_S_COL + (uint32_t)(x * 64), dq, dkh, idesc_s, 1u);                                                      // q_hi * k_hi
-          }
-          tc_commit(s_full(x));
+        for (int ks = 0; ks < 2; ks++) {
+          const uint64_t ko = (uint64_t)(x * 4 + ks * 2);                     // head x: bytes 64x.. of the row; 32 bytes per k-step
+          const uint64_t dq = make_desc(sbase + MH_OFF_QH) + ko, dkh = make_desc(k_hi) + ko, dkl = make_desc(k_lo) + ko;
+          mh_mma_ts(s_tmem, tmem_base + MH_QL_COL + (uint32_t)(x * 16 + ks * 8), dkh, idesc_s, ks != 0);   // q_lo * k_hi
+          tc_mma_f16(s_tmem, dq, dkl, idesc_s, 1u);                                                      // q_hi * k_lo
+          tc_mma_f16(s_tmem, dq, dkh, idesc_s, 1u);                                                      // q_hi * k_hi
         }
+        tc_commit(s_full);
         tc_commit(k_empty(st));
       };
       mbar_wait(q_full, 0);
       tc_fence_after();
       issue_scores(0);
-      for (int j = 0; j < nblk; j++) {
-        if (j + 1 < nblk) issue_scores(j + 1);
-        const int st = j & 1;
-        mbar_wait(v_full(st), (uint32_t)(j >> 1) & 1u);
+      for (int g = 0; g < ntot; g++) {
+        if (g + 1 < ntot) issue_scores(g + 1);
+        const int st = g & 1, x = g >= nblk ? 1 : 0, j = g - x * nblk;
+        mbar_wait(v_full(st), (uint32_t)(g >> 1) & 1u);
+        mbar_wait(p_full, (uint32_t)g & 1u);
+        tc_fence_after();
         const uint32_t v_hi = sbase + MH_OFF_V + (uint32_t)st * 16384u, v_lo = v_hi + 8192u;
+        const uint32_t p_hi = tmem_base + MH_P_COL, p_lo = p_hi + 32u;
 #pragma unroll
-        for (int x = 0; x < 2; x++) {
-          mbar_wait(p_full(x), (uint32_t)j & 1u);
-          tc_fence_after();
-          const uint32_t p_hi = tmem_base + MH_P_COL + (uint32_t)(x * 64), p_lo = p_hi + 32u;
-#pragma unroll
-          for (int ks = 0; ks < 4; ks++) {               // 16 keys per k-step: 8 TMEM columns of P, two 8-key row groups of V
-            const uint64_t dvh = v_desc_bits | (uint64_t)(((v_hi + (uint32_t)ks * 2048u + (uint32_t)x * 64u) & 0x3FFFFu) >> 4);
-            const uint64_t dvl = v_desc_bits | (uint64_t)(((v_lo + (uint32_t)ks * 2048u + (uint32_t)x * 64u) & 0x3FFFFu) >> 4);
-            const uint32_t o_tmem = tmem_base + MH_O_COL + (uint32_t)(x * 32);
-            mh_mma_ts(o_tmem, p_lo + (uint32_t)(ks * 8), dvh, idesc_o, (j | ks) != 0);
-            mh_mma_ts(o_tmem, p_hi + (uint32_t)(ks * 8), dvl, idesc_o, 1u);
-            mh_mma_ts(o_tmem, p_hi + (uint32_t)(ks * 8), dvh, idesc_o, 1u);
-          }
-          tc_commit(pv_done(x));
+        for (int ks = 0; ks < 4; ks++) {               // 16 keys per k-step: 8 TMEM columns of P, two 8-key row groups of V
+          const uint64_t dvh = v_desc_bits | (uint64_t)(((v_hi + (uint32_t)ks * 2048u + (uint32_t)x * 64u) & 0x3FFFFu) >> 4);
+          const uint64_t dvl = v_desc_bits | (uint64_t)(((v_lo + (uint32_t)ks * 2048u + (uint32_t)x * 64u) & 0x3FFFFu) >> 4);
+          mh_mma_ts(o_tmem, p_lo + (uint32_t)(ks * 8), dvh, idesc_o, (j | ks) != 0);
+          mh_mma_ts(o_tmem, p_hi + (uint32_t)(ks * 8), dvl, idesc_o, 1u);
+          mh_mma_ts(o_tmem, p_hi + (uint32_t)(ks * 8), dvh, idesc_o, 1u);
         }
+        tc_commit(pv_done);
         tc_commit(v_empty(st));
       }
     }
@@ -236,8 +217,8 @@ __global__ void __launch_bounds__(MH_THREADS, 1) attn_mh_kernel(const MhP p) {
     if (lane == 0) {
       mbar_expect_tx(q_full, 16384u);
       bulk_g2s(sbase + MH_OFF_QH, qh + ((long long)b * nqt + qt) * (4LL * MH_BQ * 64) + (long long)hp * (MH_BQ * 64), 16384u, q_full);
-      for (int j = 0; j < nblk; j++) {
-        const int st = j & 1; const uint32_t ph = ((uint32_t)(j >> 1) & 1u) ^ 1u;
+      for (int g = 0; g < ntot; g++) {
+        const int st = g & 1, j = g >= nblk ? g - nblk : g; const uint32_t ph = ((uint32_t)(g >> 1) & 1u) ^ 1u;
         const long long tile = ((long long)kvb * nblk + j) * (4LL * MH_BKV * 64) + (long long)hp * (MH_BKV * 64);
         mbar_wait(k_empty(st), ph);
         mbar_expect_tx(k_full(st), 16384u);
@@ -251,10 +232,11 @@ __global__ void __launch_bounds__(MH_THREADS, 1) attn_mh_kernel(const MhP p) {
     }
     __syncwarp();
   }
+  tc_fence_before();
   __syncthreads();
   if (warp == 8) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    tmem_dealloc(tmem_base, 256);
   }
 }
 
