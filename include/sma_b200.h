@@ -92,6 +92,7 @@ typedef struct sma_conv_desc {
 } sma_conv_desc;
 
 int sma_conv2d_fwd(sma_conv_desc* d, sma_stream_t stream);
+int sma_sizeof_conv_desc(void);            /* sizeof(sma_conv_desc) as compiled: bindings assert their mirror of the struct against it */
 /* OIHW (or (N,K) Linear) fp32 weight on the device -> packed [kh*kw*Cin][ldw] ; optional BatchNorm(eval)
  * fold: w' = w*g/sqrt(var+eps), b' = (b-mean)*g/sqrt(var+eps)+beta (sync_batchnorm/batchnorm.py:48-53). */
 int sma_pack_conv_weight(const float* w_oihw, const float* bias, int Cout, int Cin, int kh, int kw,

@@ -34,6 +34,7 @@ SIGNATURES = {
     'sma_device_check': ([_I], C.c_int),
     'sma_kernel_launch_count': ([], C.c_int),
     'sma_conv2d_fwd': ([C.POINTER(ConvDesc), _V], C.c_int),
+    'sma_sizeof_conv_desc': ([], C.c_int),
     'sma_pack_conv_weight': ([_V, _V, _I, _I, _I, _I, _V, _V, _V, _V, _F, _V, _I, _V, _V], C.c_int),
     'sma_conv_weight_tc_floats': ([_I, _I, _I, _I], C.c_int64),
     'sma_pack_conv_weight_tc': ([_V, _I, _I, _I, _I, _I, _V, _V], C.c_int),
@@ -88,6 +89,9 @@ def load():
         fn = getattr(lib, name)          # AttributeError if the symbol is not exported
         fn.argtypes = args
         fn.restype = res
+    if lib.sma_sizeof_conv_desc() != C.sizeof(ConvDesc):
+        raise SmaError(f'struct sma_conv_desc is {lib.sma_sizeof_conv_desc()} bytes in {LIB_PATH} but {C.sizeof(ConvDesc)} in _lib.ConvDesc: '
+                       f'rebuild the library (python __graft_entry__.py)')
     _lib = lib
     return lib
 

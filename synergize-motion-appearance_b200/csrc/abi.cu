@@ -22,4 +22,6 @@ extern "C" int sma_device_check(int device) {
   return p.major == 10 ? SMA_OK : SMA_ERR_NO_DEVICE;
 }
 
+extern "C" int sma_sizeof_conv_desc(void) { return (int)sizeof(sma_conv_desc); }
+
 extern "C" int sma_kernel_launch_count(void) { return g_sma_launches.load(std::memory_order_relaxed); }

@@ -74,7 +74,8 @@ def test_c_abi_exports_every_declared_symbol():
     from importlib import import_module
     _lib = import_module('synergize-motion-appearance_b200._lib')
     assert sorted(_lib.SIGNATURES) == names       # the ctypes table binds exactly the declared ABI
-    _lib.load()
+    bound = _lib.load()
+    assert bound.sma_sizeof_conv_desc() == ctypes.sizeof(_lib.ConvDesc)      # the struct mirror matches the compiled layout
 
 
 def test_cpu_tensors_fail_loudly(weights):
