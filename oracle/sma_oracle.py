@@ -399,6 +399,14 @@ def sft_fuse(P: SD, name: str, enc: T, dec: T, w: float) -> T:
     return dec + w * (dec * scale + shift)
 
 
+def decode_plain(P: SD, x: T) -> T:
+    """Generator.forward (vqgan_arch.py:347-350): the decoder blocks alone, no fusion - what
+    `net_g.generator(lq_feat)` computes in AppMotionCompModel.test (models/appmotioncomp_model.py:453-454)."""
+    for i, kind in enumerate(GENERATOR_BLOCKS):
+        x = run_block(P, kind, f'generator.blocks.{i}', x)
+    return x
+
+
 def generator_forward(P: SD, src_feats: Dict[str, T], dm: Dict[str, T], w: float = 1.0,
                       collect: Optional[dict] = None) -> Dict[str, T]:
     """Everything in AppMotionCompFormer.forward after the (source-only) encoder loop,

@@ -17,9 +17,11 @@ Design (B200-first, not a module-for-module port):
   * the third (duplicate) warp per scale that only feeds `deform_feat_list` is not computed.
 """
 import math
+import weakref
 from typing import Dict, List, Optional, Tuple
 
 import torch
+from torch import nn
 
 from .. import ops
 from ..registry import ARCH_REGISTRY
@@ -65,6 +67,14 @@ def _generator_layout(nf, ch_mult, res_blocks, resolution, attn_res, emb_dim):
     return blocks
 
 
+class _PlainDecoder(nn.Module):
+    """`net_g.generator(feat)`: the reference's Generator.forward (vqgan_arch.py:347-350), which AppMotionCompModel.test calls on `lq_feat`
+    (models/appmotioncomp_model.py:453-454).  The parameter container named `generator` is given this class so that the attribute is callable."""
+
+    def forward(self, x):
+        return self._owner().decode_plain(x)
+
+
 @ARCH_REGISTRY.register()
 class AppMotionCompFormer(ParamModule):
     SCALES = (32, 64, 128, 256)
@@ -98,6 +108,9 @@ class AppMotionCompFormer(ParamModule):
         self.enc_layout.append(('conv', latent_c, 256))
         self.gen_layout = _generator_layout(nf, ch_mult, res_blocks, img_size, attn_resolutions, 256)
         self._declare_all()
+        gen = self._modules['generator']
+        gen.__class__ = _PlainDecoder
+        object.__setattr__(gen, '_owner', weakref.ref(self))      # not a registered sub-module: no cycle in the module tree
         self._src_cache = None
         if ae_path is not None:
             self.load_state_dict(torch.load(ae_path, map_location='cpu')['params_ema'])
@@ -330,6 +343,15 @@ class AppMotionCompFormer(ParamModule):
         feats[32] = h
         self._src_cache = (key, feats)
         return feats
+
+    @torch.no_grad()
+    def decode_plain(self, x: torch.Tensor) -> torch.Tensor:
+        """(B,256,32,32) NCHW latent -> (B,3,256,256): the 19 decoder blocks without the multi-scale fusion."""
+        self._weights()
+        h = ops.nchw_to_nhwc(x.contiguous().float())
+        for i in range(len(self.gen_layout)):
+            h = self._block('generator', i, self.gen_layout, h)
+        return ops.nhwc_to_nchw(h)
 
     def encode_driving(self, x):
         """Reference API (appmotioncodebook_arch.py:364-371): NCHW feature dict keyed by resolution string."""

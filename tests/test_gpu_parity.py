@@ -456,6 +456,26 @@ def test_full_batch_is_frame_independent(S, nets):
     assert all(np.isfinite(p.astype(np.float32)).all() for p in p64)
 
 
+def test_caller_surface_plain_decoder_and_estimator_forward(S, nets, clip):
+    """what AppMotionCompModel.test calls besides the forward (models/appmotioncomp_model.py:437-456):
+    `motion_estimator(driving, source)` and `net_g.generator(lq_feat)`, against the fixtures of the live reference."""
+    import os
+    from conftest import GOLD
+    fx = torch.load(os.path.join(GOLD, 'reference_callers.pt'))
+    g, me = nets
+    src, drv = clip
+    lq = torch.randn(1, 256, 32, 32, generator=torch.Generator().manual_seed(fx['lq_seed'])) * 0.5
+    recon = g.generator(lq.cuda()).cpu()
+    assert recon.shape == (1, 3, 256, 256)
+    assert float((recon[:, :, ::2, ::2] - fx['recon_s2']).abs().max()) < 1e-3
+    dm = me(drv[1].unsqueeze(0).cuda(), src.unsqueeze(0).cuda())
+    assert float((dm['deformation'].cpu() - fx['fwd_deformation']).abs().max()) < 1e-4
+    assert float((dm['occlusion_map'].cpu() - fx['fwd_occlusion']).abs().max()) < 1e-4
+    assert float((dm['kp_driving']['value'].cpu() - fx['fwd_kp_driving_value']).abs().max()) < 1e-4
+    sd = g.state_dict()                                   # the callable container does not disturb the key inventory
+    assert 'generator.blocks.0.weight' in sd and not any(k.startswith('generator._') for k in sd)
+
+
 def test_to_uint8_round_half_even_bit_exact(S):
     x = torch.linspace(-1.2, 1.2, 256 * 256 * 3).view(1, 256, 256, 3)
     x[0, 0, 0, 0] = 1.0 / 255.0 * 2 * 0.5 - 1      # (v+1)/2*255 = 0.5 -> rounds to 0 (half to even)

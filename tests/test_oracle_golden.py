@@ -59,3 +59,19 @@ def test_hull_area_matches_scipy():
     for _ in range(20):
         p = rng.normal(size=(15, 2))
         assert abs(O.hull_area(p) - ConvexHull(p).volume) < 1e-9
+
+
+def test_oracle_caller_surface_matches_reference_fixture(weights):
+    """the plain decoder `net_g.generator(lq_feat)` and `motion_estimator(driving, source)` restated by the oracle agree with the
+    outputs of the live reference stored by oracle/make_golden_callers.py."""
+    import os
+    import torch
+    import sma_oracle as O
+    from conftest import GOLD
+    fx = torch.load(os.path.join(GOLD, 'reference_callers.pt'))
+    assert max(fx['oracle_vs_reference'].values()) < 2e-4
+    P_g, P_me = weights
+    lq = torch.randn(1, 256, 32, 32, generator=torch.Generator().manual_seed(fx['lq_seed'])) * 0.5
+    with torch.no_grad():
+        recon = O.decode_plain(P_g, lq)
+    assert float((recon[:, :, ::2, ::2] - fx['recon_s2']).abs().max()) < 2e-4
