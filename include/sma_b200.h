@@ -7,7 +7,10 @@
  * basicsr/ops/dcn/src/deform_conv_ext.cpp:150-164, basicsr/ops/dcn/deform_conv.py:51-64).  This
  * library occupies that slot: every entry point takes raw device pointers, explicit
  * dims/strides, a cudaStream_t and caller-provided workspaces, and returns an int status.
- * It never allocates, never synchronises, never aborts, and keeps no global mutable state.
+ * It never allocates, never synchronises and never aborts.  The only process-wide state is a launch
+ * counter and per-device one-time attributes (shared-memory opt-in, SM count), kept per device
+ * ordinal so that one process may drive several GPUs; entry points act on the CURRENT device, which
+ * must be the device that owns the pointers and the stream.
  *
  * All activations are fp32, channels-last (NHWC): element (b,y,x,c) of a tensor with pixel
  * stride `ld` floats and batch stride `bstride` floats lives at  p[b*bstride + (y*W+x)*ld + c].
@@ -89,6 +92,14 @@ typedef struct sma_conv_desc {
                                     force that ring; bit 7: halo kernel issues three separate MMAs per k-step instead of the fused [hi | lo] weight tile */
   int kernel_used;               /* OUT: 0 CUDA-core FFMA kernel, 1 tcgen05 tf32 gather kernel, 2 tcgen05 tf32 persistent halo kernel,
                                     3 tcgen05 fp16 persistent halo kernel, 4 tcgen05 fp16 kernel with the weights in tensor memory */
+  int w_tc_nt;                   /* IN: output-channel tile the tf32 image `w_tc` was packed with (0 = the default, min(256, Cout rounded up to 16));
+                                    OUT in plan mode: the tile the planned kernel wants (the gather kernel narrows it when there are few rows) */
+  int plan_only;                 /* 1: launch nothing; set kernel_used / w_tc_nt to what this call would use if every weight image were present
+                                    (lets the binding pack only the image a layer needs) */
+  /* SFT epilogue (Fuse_sft_block tail, appmotioncodebook_arch.py:50-51), aux != NULL: y = res + sft_w * (res * aux + v) with v = act(conv + bias):
+   * this conv is `shift.2`, aux the output of `scale.2`, res the decoder feature.  Persistent tensor-core kernel only (SMA_ERR_UNSUPPORTED
+   * otherwise: use sma_sft_combine). */
+  const float* aux;  int64_t aux_bstride;  int aux_ld;  float sft_w;
 } sma_conv_desc;
 
 int sma_conv2d_fwd(sma_conv_desc* d, sma_stream_t stream);
@@ -103,8 +114,8 @@ int sma_pack_conv_weight(const float* w_oihw, const float* bias, int Cout, int C
  * packed weight, each laid out as the K-major SWIZZLE_128B shared-memory tile tcgen05.mma reads, so that the kernel
  * fetches it with one bulk copy per chunk.  Needs Cin % 32 == 0.  sma_conv_weight_tc_floats gives the buffer size
  * in floats (0 when the shape is not eligible). */
-int64_t sma_conv_weight_tc_floats(int Cout, int Cin, int kh, int kw);
-int sma_pack_conv_weight_tc(const float* w_packed, int ldw, int Cout, int Cin, int kh, int kw, float* w_tc, sma_stream_t stream);
+int64_t sma_conv_weight_tc_floats(int Cout, int Cin, int kh, int kw, int nt /* N tile, 0 = default */);
+int sma_pack_conv_weight_tc(const float* w_packed, int ldw, int Cout, int Cin, int kh, int kw, int nt, float* w_tc, sma_stream_t stream);
 /* fp16 variant (Cin % 64 == 0): [un-scaling factors per output column][per (N-tile, 64-channel chunk, tap): fp16 hi image | lo image
  * of w * 2^-e(column)], same SWIZZLE_128B tiles. */
 int64_t sma_conv_weight_tc16_floats(int Cout, int Cin, int kh, int kw);
@@ -187,10 +198,15 @@ int sma_avgpool2(const float* x, int B, int H, int W, int C, float* y, int y_ld,
  * [K,5K) = jacobian maps -> value (B,K,2), jacobian (B,K,2,2) */
 int sma_kp_head_fwd(const float* pred, int B, int h, int w, int ld, int K, float temperature, float* value,
                     float* jacobian, sma_stream_t stream);
-/* normalize_kp relative mode (demo.py:24-44): value = kp_src + s*(kp_drv-kp_drv0); jac = J_drv J_drv0^-1 J_src */
+/* normalize_kp relative mode (demo.py:24-44): value = kp_src + s*(kp_drv-kp_drv0); jac = J_drv J_drv0^-1 J_src.
+ * The movement scale s is `scale`, or *scale_dev when scale_dev != NULL (a device scalar written by sma_hull_scale: no host round trip). */
 int sma_normalize_kp(const float* src_v, const float* src_j, const float* drv_v, const float* drv_j,
-                     const float* drv0_v, const float* drv0_j, int B, int K, float scale, int relative,
+                     const float* drv0_v, const float* drv0_j, int B, int K, float scale, const float* scale_dev, int relative,
                      float* out_v, float* out_j, sma_stream_t stream);
+/* adapt_movement_scale of normalize_kp (demo.py:26-29): sqrt(area of the convex hull of the K source key-points) /
+ * sqrt(area of the hull of the K initial driving key-points), fp64 on the device, written to scale_out[0].  Replaces
+ * scipy.spatial.ConvexHull(...).volume and the two .cpu() syncs per frame.  3 <= K <= 64. */
+int sma_hull_scale(const float* src_v, const float* drv0_v, int K, float* scale_out, sma_stream_t stream);
 /* DenseMotionNetwork input (archs/dense_motion_arch.py:65-130): heat-map differences, sparse motions and the
  * 16 warped copies of the down-sampled source (grid_sample align_corners=False) interleaved k-major into
  * hg_in (B,h,w,4*(K+1)); also the driving heat-maps drv_heat (B,h,w,K). src64 is (h,w,3) NHWC shared. */
@@ -214,6 +230,10 @@ int sma_sft_combine(const float* dec, const float* scale, const float* shift, fl
                     sma_stream_t stream);
 /* tensor2img (utils/img_util.py:42-98): NHWC fp32 in [-1,1] -> HWC uint8 (round half even), optional BGR */
 int sma_to_uint8(const float* x_nhwc, int B, int H, int W, int C, int ld, int bgr, uint8_t* out, sma_stream_t stream);
+/* the reference's host-side frame preparation on the device (demo.py:177-185, utils/img_util.py:13-39): uint8 HWC frames ->
+ * fp32 NCHW, v = (float(u8)/255 - 0.5)/0.5, optional BGR->RGB; bit-exact with astype(float32)/255. + normalize(0.5, 0.5).
+ * A quarter of the PCIe bytes of uploading fp32 frames. */
+int sma_u8hwc_to_f32nchw(const uint8_t* x_hwc, int B, int H, int W, int C, int swap_rb, float* y_nchw, sma_stream_t stream);
 /* (B,C,H,W) <-> (B,H,W,C) */
 int sma_nchw_to_nhwc(const float* x, int B, int C, int H, int W, float* y, int y_ld, sma_stream_t stream);
 int sma_nhwc_to_nchw(const float* x, int B, int C, int H, int W, int x_ld, float* y, sma_stream_t stream);

@@ -23,6 +23,7 @@ class ConvDesc(C.Structure):
         ('act', C.c_int),
         ('res', C.c_void_p), ('res_bstride', c_i64), ('res_ld', C.c_int),
         ('d2s', C.c_int), ('out_nchw', C.c_int), ('precision', C.c_int), ('w_tc', C.c_void_p), ('w_tc16', C.c_void_p), ('w_ts', C.c_void_p), ('tc_variant', C.c_int), ('kernel_used', C.c_int),
+        ('w_tc_nt', C.c_int), ('plan_only', C.c_int), ('aux', C.c_void_p), ('aux_bstride', c_i64), ('aux_ld', C.c_int), ('sft_w', C.c_float),
     ]
 
 
@@ -36,8 +37,8 @@ SIGNATURES = {
     'sma_conv2d_fwd': ([C.POINTER(ConvDesc), _V], C.c_int),
     'sma_sizeof_conv_desc': ([], C.c_int),
     'sma_pack_conv_weight': ([_V, _V, _I, _I, _I, _I, _V, _V, _V, _V, _F, _V, _I, _V, _V], C.c_int),
-    'sma_conv_weight_tc_floats': ([_I, _I, _I, _I], C.c_int64),
-    'sma_pack_conv_weight_tc': ([_V, _I, _I, _I, _I, _I, _V, _V], C.c_int),
+    'sma_conv_weight_tc_floats': ([_I, _I, _I, _I, _I], C.c_int64),
+    'sma_pack_conv_weight_tc': ([_V, _I, _I, _I, _I, _I, _I, _V, _V], C.c_int),
     'sma_conv_weight_tc16_floats': ([_I, _I, _I, _I], C.c_int64),
     'sma_pack_conv_weight_tc16': ([_V, _I, _I, _I, _I, _I, _V, _V], C.c_int),
     'sma_conv_weight_ts_floats': ([_I, _I, _I, _I], C.c_int64),
@@ -57,7 +58,9 @@ SIGNATURES = {
     'sma_antialias_down4': ([_V, _I, _I, _I, _I, _V, _V, _I, _V], C.c_int),
     'sma_avgpool2': ([_V, _I, _I, _I, _I, _V, _I, _V], C.c_int),
     'sma_kp_head_fwd': ([_V, _I, _I, _I, _I, _I, _F, _V, _V, _V], C.c_int),
-    'sma_normalize_kp': ([_V, _V, _V, _V, _V, _V, _I, _I, _F, _I, _V, _V, _V], C.c_int),
+    'sma_normalize_kp': ([_V, _V, _V, _V, _V, _V, _I, _I, _F, _V, _I, _V, _V, _V], C.c_int),
+    'sma_hull_scale': ([_V, _V, _I, _V, _V], C.c_int),
+    'sma_u8hwc_to_f32nchw': ([_V, _I, _I, _I, _I, _I, _V, _V], C.c_int),
     'sma_dense_motion_prep': ([_V, _I, _I, _V, _V, _V, _V, _I, _I, _F, _V, _I, _V, _V], C.c_int),
     'sma_dense_motion_head': ([_V, _I, _I, _I, _V, _V, _V, _V, _I, _I, _V, _V, _V, _V], C.c_int),
     'sma_flow_to_px': ([_V, _I, _I, _I, _V, _I, _V], C.c_int),

@@ -2,8 +2,10 @@
 
 Drop-in for basicsr/archs/appmotioncodebook_arch.py:170-764 (generator of options/test.yml:8-45, built
 on the VQGAN blocks of basicsr/archs/vqgan_arch.py): same constructor kwargs, same 472 state_dict keys,
-same call `net_g(source, dense_motion, w=1, inference=True) -> dict` with the keys callers read
-(`out`, `lq_feat`, `out_occ`, `deformation_list`, `res_deform_list`), plus `encode_driving`.  Inference only.
+same call `net_g(source, dense_motion, w=1, inference=True) -> dict` with the reference's full inference key set
+(`out`, `lq_feat`, `out_occ`, `deformation_list`, `res_deform_list`, `deform_feat_list`, `app_comp_list`,
+`app_before_comp_list`; `app_query_feat_list` / `app_comp_feat_list` with visualize_app_feat, `x_before_app_32` with
+vis_app_before_comp: appmotioncodebook_arch.py:745-764), plus `encode_driving` and the callable `generator`.  Inference only.
 
 Design (B200-first, not a module-for-module port):
   * everything NHWC fp32; torch only allocates buffers; every op is a kernel from csrc/;
@@ -94,7 +96,9 @@ class AppMotionCompFormer(ParamModule):
                      multiscale_sft and app_codebook_split and not wo_motion_cdbk_share and not wo_app_cdbk_share and
                      list(connect_list) == ['64', '128', '256'] and list(connect_app_list) == ['32', '64', '128', '256'] and
                      embed_dim_motion == dim_embd_motion and embed_dim_app == dim_embd_app and n_layers_motion == 2 and
-                     n_layers_app == 2 and dim_embd_app == 256 and dim_embd_motion == 32 and n_head == 8)
+                     n_layers_app == 2 and dim_embd_app == 256 and dim_embd_motion == 32 and n_head == 8 and
+                     codebook_size_app % 4 == 0 and codebook_size_motion % 4 == 0 and
+                     codebook_size_app // 4 % 64 == 0 and codebook_size_motion // 4 % 8 == 0)
         if not supported:
             raise NotImplementedError('B200 AppMotionCompFormer implements the options/test.yml configuration only')
         self.beta, self.n_head, self.num_kp = beta, n_head, num_kp
@@ -216,6 +220,10 @@ class AppMotionCompFormer(ParamModule):
         if self._packed is not None:
             return self._packed
         T = self.tensors()
+        W = self._restore_packed()
+        if W is not None:                 # pre-packed blob of these exact weights: no pack kernel is launched
+            self._packed, self._T, self._src_cache, self._pack_saved = W, T, None, True
+            return W
         W: Dict[str, object] = {}
 
         def pc(name):
@@ -327,13 +335,17 @@ class AppMotionCompFormer(ParamModule):
     # ------------------------------------------------------------------------------------------
     # per-source work: encoder features (cached)
     # ------------------------------------------------------------------------------------------
+    def clear_source_cache(self):
+        self._src_cache = None
+
     @torch.no_grad()
     def encode_source(self, x: torch.Tensor) -> Dict[int, torch.Tensor]:
-        """x (N,3,256,256) NCHW -> {256,128,64,32: NHWC features}.  Cached on the tensor identity."""
+        """x (N,3,256,256) NCHW -> {256,128,64,32: NHWC features}.  Cached on the tensor OBJECT (which the cache entry keeps
+        alive, so that its address cannot be recycled for another clip's source) and its in-place version counter."""
         self._weights()
-        key = (x.data_ptr(), x._version, tuple(x.shape))
-        if self._src_cache is not None and self._src_cache[0] == key:
-            return self._src_cache[1]
+        c = self._src_cache
+        if c is not None and c[0] is x and c[1] == x._version:
+            return c[2]
         h = ops.nchw_to_nhwc(x.contiguous().float())
         feats = {}
         for i in range(len(self.enc_layout)):
@@ -341,7 +353,7 @@ class AppMotionCompFormer(ParamModule):
             if i in (2, 5, 8):
                 feats[h.shape[2]] = h
         feats[32] = h
-        self._src_cache = (key, feats)
+        self._src_cache = (x, x._version, feats)
         return feats
 
     @torch.no_grad()
@@ -361,6 +373,11 @@ class AppMotionCompFormer(ParamModule):
     # ------------------------------------------------------------------------------------------
     # codebook transformer layer (appmotioncodebook_arch.py:88-126) on (B,1024,E) tokens
     # ------------------------------------------------------------------------------------------
+    @staticmethod
+    def _n_ctx(codebook_size: int, s: int) -> int:
+        """Codebook split = shared prefix of codebook_size//4 * k rows, k = 1..4 for scales 32..256 (appmotioncodebook_arch.py:374,405,473,514)."""
+        return codebook_size // 4 * (int(math.log2(s)) - 4)
+
     def _transformer(self, name, t, E, n_ctx, pos, key_mask=None, fast=False):
         W, T = self._packed, self._T
         B = t.shape[0]
@@ -398,7 +415,7 @@ class AppMotionCompFormer(ParamModule):
         self._res('motion_emb.2', mf, Em, Em, out=ops_out, fast=fs)                        # qcat = [m_feat | query_feat]
         t = ops.conv2d(qcat, W['motion_query_enc_2'], fast=fs).view(B, 1024, Em)
         for i in range(2):
-            t = self._transformer(f'motion_block.{i}', t, Em, 256 * (int(math.log2(s)) - 4), T['position_emb_motion'], fast=fs)
+            t = self._transformer(f'motion_block.{i}', t, Em, self._n_ctx(self.n_codes_motion, s), T['position_emb_motion'], fast=fs)
         mfeat = ops.resize_ac(t.view(B, 32, 32, Em), (64, 64))
         cf = torch.empty((B, 64, 64, 160), device=dev, dtype=torch.float32)       # [cor 96 | flo 64]
         cor = ops.conv2d(mfeat, W['BasicMotionEncoder.convc1'], act='relu', fast=fs)
@@ -428,7 +445,7 @@ class AppMotionCompFormer(ParamModule):
             p = s // 32
             tok = ops.conv2d(feat, W[f'app_feat_emb_{s}.1'], stride=p)
         tok = tok.view(B, 1024, self.Ea)
-        n_ctx = 256 * (int(math.log2(s)) - 4)
+        n_ctx = self._n_ctx(self.n_codes_app, s)
         tok = self._transformer('app_block.0', tok, self.Ea, n_ctx, T['position_emb_app'], key_mask=mask)
         tok = self._transformer('app_block.1', tok, self.Ea, n_ctx, T['position_emb_app'])
         tok = tok.view(B, 32, 32, self.Ea)
@@ -491,9 +508,8 @@ class AppMotionCompFormer(ParamModule):
                 e = self._res(n + '.encode_enc', cat, 2 * c, c)
                 ss = ops.conv2d(e, W[n + '.ss0'], pad=1, act='leaky')                  # [scale.0 | shift.0]
                 scale = ops.conv2d(ss[..., :c], W[n + '.scale.2'], pad=1)
-                shift = ops.conv2d(ss[..., c:], W[n + '.shift.2'], pad=1)
-                xd = ops.affine_act(x, None, None)                                     # dense copy of the decoder half
-                xf = ops.sft_combine(xd, scale, shift, float(w))
+                # dec + w * (dec * scale + shift) in the epilogue of the `shift.2` conv; the decoder half is read in place (channel slice of `cat`)
+                xf = ops.conv2d(ss[..., c:], W[n + '.shift.2'], pad=1, res=x, sft=(scale, float(w)))
                 x = ops.conv2d(enc, W[f'fuse_ms_dict.{s}'], pad=1, res=xf, out=xf)
             else:
                 x = self._block('generator', i, self.gen_layout, x)
@@ -515,13 +531,26 @@ class AppMotionCompFormer(ParamModule):
         if heat is None:
             heat = ops.nchw_to_nhwc(dense_motion['driving_kp_heatmap'].contiguous().float())
         occ = dense_motion['occlusion_map'].contiguous().float().view(B, 64, 64)
-        r = self.generate(feats, deformation, occ, heat, float(w))
+        collect = {}
+        r = self.generate(feats, deformation, occ, heat, float(w), collect=collect)
         half = (deformation.shape[1] - 1.0) / 2.0
-        return {
+        scales = [s for s in self.SCALES if f'warped_{s}' in collect]
+        before = [ops.nhwc_to_nchw(collect[f'warped_{s}']) for s in scales]
+        after = [ops.nhwc_to_nchw(collect[f'app_{s}']) for s in scales]
+        out = {
             'out': ops.nhwc_to_nchw(r['out']),
             '_out_nhwc': r['out'],
             'lq_feat': ops.nhwc_to_nchw(r['lq_feat']),
             'out_occ': [o.view(B, 1, 64, 64) for o in r['out_occ']],
             'deformation_list': r['deformation_list'],
             'res_deform_list': [q[..., 0:2] / half for q in r['residuals']],
+            # the reference computes the occluded final warp a third time for this list (:604,609-615,700,705-719): same values
+            'deform_feat_list': before,
+            'app_comp_list': after,
+            'app_before_comp_list': before,
         }
+        if visualize_app_feat:      # vis_original_size=True: the query is the warped feature, the result the compensated one (:497-500,534-536)
+            out['app_query_feat_list'], out['app_comp_feat_list'] = before, after
+        if vis_app_before_comp:     # the plain decoder run on the un-compensated 32x32 feature (:654-655,661-662)
+            out['x_before_app_32'] = self.decode_plain(before[0])
+        return out

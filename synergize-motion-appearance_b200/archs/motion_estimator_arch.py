@@ -110,9 +110,13 @@ class KPDetector(ParamModule):
     def _weights(self):
         if self._packed is None:
             T = self.tensors()
+            self._cpad = (self.plan.out_filters + 31) // 32 * 32
+            W = self._restore_packed()
+            if W is not None:
+                self._packed, self._pack_saved = W, True
+                return W
             W = self.plan.pack(T, 'predictor')
             # the 35-channel hourglass output lives in a 64-channel zero-padded buffer so that the 7x7 heads run on the tensor cores
-            self._cpad = (self.plan.out_filters + 31) // 32 * 32
             W['heads'] = ops.pack_conv_cat([T['kp.weight'], T['jacobian.weight']], [T['kp.bias'], T['jacobian.bias']], pad_cin=self._cpad)
             W['k13'] = T['down.weight'][0, 0].contiguous()
             self._packed = W
@@ -156,6 +160,10 @@ class DenseMotionNetwork(ParamModule):
     def _weights(self):
         if self._packed is None:
             T = self.tensors()
+            W = self._restore_packed()
+            if W is not None:
+                self._packed, self._src_cache, self._pack_saved = W, None, True
+                return W
             W = self.plan.pack(T, 'hourglass')
             W['heads'] = ops.pack_conv_cat([T['mask.weight'], T['occlusion.weight']], [T['mask.bias'], T['occlusion.bias']])
             W['k13'] = T['down.weight'][0, 0].contiguous()
@@ -167,10 +175,13 @@ class DenseMotionNetwork(ParamModule):
         """Anti-aliased 64x64 source (1,64,64,3) NHWC; cached per source tensor (the reference recomputes
         it for every frame, dense_motion_arch.py:119-120)."""
         W = self._weights()
-        key = (source_image.data_ptr(), source_image._version, tuple(source_image.shape))
-        if self._src_cache is None or self._src_cache[0] != key:
-            self._src_cache = (key, ops.antialias_down4(source_image[:1].contiguous().float(), W['k13']))
-        return self._src_cache[1]
+        c = self._src_cache           # keyed on the tensor object (kept alive by the entry: its address cannot be recycled) + version
+        if c is None or c[0] is not source_image or c[1] != source_image._version:
+            c = self._src_cache = (source_image, source_image._version, ops.antialias_down4(source_image[:1].contiguous().float(), W['k13']))
+        return c[2]
+
+    def clear_source_cache(self):
+        self._src_cache = None
 
     @torch.no_grad()
     def forward(self, source_image, kp_driving, kp_source):

@@ -13,6 +13,8 @@ class ParamModule(nn.Module):
     def __init__(self):
         super().__init__()
         self._packed: Optional[dict] = None
+        self._pack_cache_dir: Optional[str] = None
+        self._pack_saved = False
 
     # ---- declaration -------------------------------------------------------------------------
     def _leaf_parent(self, dotted: str):
@@ -65,11 +67,34 @@ class ParamModule(nn.Module):
     # ---- packed-weight cache invalidation ----------------------------------------------------
     def invalidate_cache(self):
         self._packed = None
+        self._state_hash = None
 
     def _apply(self, fn, *a, **k):
-        self._packed = None
+        self.invalidate_cache()
         return super()._apply(fn, *a, **k)
 
     def load_state_dict(self, *a, **k):
-        self._packed = None
+        self.invalidate_cache()
         return super().load_state_dict(*a, **k)
+
+    # ---- persisted pre-packed blob (packcache.py) --------------------------------
+    def _restore_packed(self):
+        """The packed dictionary of these exact weights from the pack cache, or None (cache disabled / miss)."""
+        from .. import packcache
+        d = packcache.cache_dir_of(self)
+        if d is None:
+            return None
+        return packcache.load(self, d, next(self.parameters()).device)
+
+    def save_pack_cache(self, force: bool = False):
+        """Persist the packed dictionary (base layouts + every tensor-core image packed so far) if a cache directory is configured and
+        something was packed since the last save.  Returns the file path or None."""
+        from .. import packcache
+        d = packcache.cache_dir_of(self)
+        if d is None or self._packed is None:
+            return None
+        if not force and not packcache.is_dirty(self._packed) and getattr(self, '_pack_saved', False):
+            return None
+        path = packcache.save(self, self._packed, d)
+        self._pack_saved = True
+        return path

@@ -267,11 +267,8 @@ template <int D, int BKV>
 int launch_mha(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv, long long kv_bs, int B, int L, int S, int heads,
                float scale, const uint8_t* mask, float* out, int ldo, cudaStream_t st) {
   constexpr int smem = (64 * (D + 4) + BKV * (D + 4) + BKV * D + 64 * (BKV + 4)) * (int)sizeof(float);
-  static bool configured = false;   // idempotent attribute set; benign if raced
-  if (!configured) {
-    if (cudaFuncSetAttribute(mha_kernel<D, BKV>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return SMA_ERR_CUDA;
-    configured = true;
-  }
+  static SmaDevOnce once;           // per device: the opt-in is a (kernel, device) attribute
+  if (int rc = sma_opt_in_smem(once, mha_kernel<D, BKV>, smem)) return rc;
   mha_kernel<D, BKV><<<dim3(cdiv(L, 64), heads, B), 256, smem, st>>>(q, ldq, k, ldk, v, ldv, kv_bs, L, S, scale, mask, out, ldo);
   SMA_LAUNCH_CHECK();
   return SMA_OK;
@@ -291,11 +288,8 @@ extern "C" int sma_mha_fwd(const float* q, int ldq, const float* k, int ldk, con
   if (kv_bstride & 3) return SMA_ERR_UNSUPPORTED;
   cudaStream_t st = as_stream(stream);
   if (D == 4 && !key_mask && !(flags & 1) && (S % 8) == 0 && S * 32 <= 96 * 1024) {
-    static bool configured = false;   // idempotent attribute set; benign if raced
-    if (!configured) {
-      if (cudaFuncSetAttribute(mha_d4_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024) != cudaSuccess) return SMA_ERR_CUDA;
-      configured = true;
-    }
+    static SmaDevOnce once;
+    if (int rc = sma_opt_in_smem(once, mha_d4_fast_kernel, 96 * 1024)) return rc;
     mha_d4_fast_kernel<<<dim3(cdiv(L, 128), heads, B), 128, S * 32, st>>>(q, ldq, k, ldk, v, ldv, kv_bstride, L, S, scale * 1.4426950408889634f, out, ldo);
     SMA_LAUNCH_CHECK();
     return SMA_OK;

@@ -308,11 +308,8 @@ extern "C" int sma_attn256_fwd(const float* q, int ldq, const float* k, int ldk,
   cudaStream_t st = as_stream(stream);
   int rs = sma_attn_split_launch(q, ldq, k, ldk, v, ldv, q_bstride, kv_bstride, B, B, L, S, scale * 1.4426950408889634f, workspace, st);
   if (rs != SMA_OK) return rs;
-  static bool configured = false;
-  if (!configured) {
-    if (cudaFuncSetAttribute(attn256_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)A2_SMEM + 1024) != cudaSuccess) return SMA_ERR_CUDA;
-    configured = true;
-  }
+  static SmaDevOnce once;
+  if (int rc = sma_opt_in_smem(once, attn256_kernel, (int)A2_SMEM + 1024)) return rc;
   A2P p; p.ws = reinterpret_cast<const uint16_t*>(workspace); p.out = out; p.ldo = ldo; p.B = B; p.L = L; p.S = S;
   attn256_kernel<<<dim3(L / A2_BQ, B), A2_THREADS, A2_SMEM + 1024, st>>>(p);
   SMA_LAUNCH_CHECK();

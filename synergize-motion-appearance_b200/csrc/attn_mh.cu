@@ -260,11 +260,8 @@ extern "C" int sma_mha_e256_fwd(const float* q, int ldq, const float* k, int ldk
   const int kvB = kv_bstride ? B : 1;
   int rs = sma_attn_split_launch(q, ldq, k, ldk, v, ldv, q_bstride, kv_bstride, B, kvB, L, S, scale * 1.4426950408889634f, workspace, st);
   if (rs != SMA_OK) return rs;
-  static bool configured = false;
-  if (!configured) {
-    if (cudaFuncSetAttribute(attn_mh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MH_SMEM + 1024) != cudaSuccess) return SMA_ERR_CUDA;
-    configured = true;
-  }
+  static SmaDevOnce once;
+  if (int rc = sma_opt_in_smem(once, attn_mh_kernel, (int)MH_SMEM + 1024)) return rc;
   MhP p; p.ws = reinterpret_cast<const uint16_t*>(workspace); p.mask = key_mask; p.out = out; p.ldo = ldo; p.B = B; p.kvB = kvB; p.L = L; p.S = S;
   attn_mh_kernel<<<dim3(L / MH_BQ, 4, B), MH_THREADS, MH_SMEM + 1024, st>>>(p);
   SMA_LAUNCH_CHECK();

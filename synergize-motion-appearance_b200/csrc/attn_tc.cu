@@ -337,11 +337,8 @@ int launch_att(const AttP& p, int B, int heads, cudaStream_t st) {
   constexpr int DO = D < 16 ? 16 : D;
   constexpr int VT_PAD = (DO * 128 + 1023) & ~1023;
   constexpr int smem = 2 * BQ * 128 + 4 * BKV * 128 + 8 * VT_PAD + 8 * BQ * 128;
-  static bool configured = false;
-  if (!configured) {
-    if (cudaFuncSetAttribute(mha_tc_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return SMA_ERR_CUDA;
-    configured = true;
-  }
+  static SmaDevOnce once;
+  if (int rc = sma_opt_in_smem(once, mha_tc_kernel<D>, smem)) return rc;
   mha_tc_kernel<D><<<dim3(p.L / BQ, heads, B), ATT_THREADS, smem, st>>>(p);
   SMA_LAUNCH_CHECK();
   return SMA_OK;

@@ -263,6 +263,7 @@ struct Tc2P {
   long long in_bs, out_bs, res_bs;
   int Hi, Wi, Cin, in_ld, Cout, kh, kw, pad_t, pad_l, up, pre_act;
   int Ho, Wo, out_ld, act, res_ld, d2s;
+  const float* aux; long long aux_bs; int aux_ld; float sft_w;   // SFT epilogue (aux != nullptr): y = res + sft_w * (res * aux + v), v = act(acc + bias)
   const float* wscale;        // F16 only: per-output-channel power-of-two factor that undoes the weight pre-scaling
   int HoWo, cpt, taps, NT, ntiles_n, passes, tmem_cols;
   int fuse;                   // 3-pass, NT <= 128: the hi and lo weight images (adjacent in the ring) are read as ONE B tile of 2*NT rows, so
@@ -327,7 +328,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const Tc2P p) {
                         (!p.res || ((p.res_ld & 3) == 0 && (p.res_bs & 3) == 0 && (reinterpret_cast<uintptr_t>(p.res) & 15) == 0));
     const int Cq = p.d2s > 1 ? p.Cout / (p.d2s * p.d2s) : p.Cout;
     const bool v8_ok = p.d2s <= 1 && (p.Cout & 7) == 0 && (p.out_ld & 7) == 0 && (p.out_bs & 7) == 0 && ((reinterpret_cast<uintptr_t>(p.y) & 31) == 0) &&
-                       (!p.res || ((p.res_ld & 7) == 0 && (p.res_bs & 7) == 0 && (reinterpret_cast<uintptr_t>(p.res) & 31) == 0));
+                       (!p.res || ((p.res_ld & 7) == 0 && (p.res_bs & 7) == 0 && (reinterpret_cast<uintptr_t>(p.res) & 31) == 0));   // (the SFT epilogue is only dispatched here when this holds)
     int tcount = 0, cur_nt = -1;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tcount) {
       int b, ty0, tx0, nt; decode(tile, b, ty0, tx0, nt);
@@ -369,6 +370,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const Tc2P p) {
           // half of 32 different sectors, and the epilogue - not the MMAs - bounds the low-K layers)
           float* yrow = p.y + (long long)b * p.out_bs + (long long)r * p.out_ld;
           const float* rrow = p.res ? p.res + (long long)b * p.res_bs + (long long)r * p.res_ld : nullptr;
+          const float* arow = p.aux ? p.aux + (long long)b * p.aux_bs + (long long)r * p.aux_ld : nullptr;
 #pragma unroll
           for (int q8 = 0; q8 < 4; q8++) {
             const int n = nbase + n0 + q8 * 8;
@@ -389,7 +391,16 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const Tc2P p) {
               float r0, r1, r2, r3, r4, r5, r6, r7;
               asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];" : "=f"(r0), "=f"(r1), "=f"(r2), "=f"(r3), "=f"(r4), "=f"(r5), "=f"(r6), "=f"(r7)
                            : "l"(rrow + n));
-              o[0] += r0; o[1] += r1; o[2] += r2; o[3] += r3; o[4] += r4; o[5] += r5; o[6] += r6; o[7] += r7;
+              if (arow) {       // Fuse_sft_block tail (appmotioncodebook_arch.py:50-51): dec + w * (dec * scale + shift), this conv = shift
+                float a0, a1, a2, a3, a4, a5, a6, a7;
+                asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];" : "=f"(a0), "=f"(a1), "=f"(a2), "=f"(a3), "=f"(a4), "=f"(a5), "=f"(a6), "=f"(a7)
+                             : "l"(arow + n));
+                o[0] = r0 + p.sft_w * (r0 * a0 + o[0]); o[1] = r1 + p.sft_w * (r1 * a1 + o[1]); o[2] = r2 + p.sft_w * (r2 * a2 + o[2]);
+                o[3] = r3 + p.sft_w * (r3 * a3 + o[3]); o[4] = r4 + p.sft_w * (r4 * a4 + o[4]); o[5] = r5 + p.sft_w * (r5 * a5 + o[5]);
+                o[6] = r6 + p.sft_w * (r6 * a6 + o[6]); o[7] = r7 + p.sft_w * (r7 * a7 + o[7]);
+              } else {
+                o[0] += r0; o[1] += r1; o[2] += r2; o[3] += r3; o[4] += r4; o[5] += r5; o[6] += r6; o[7] += r7;
+              }
             }
             asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(yrow + n), "f"(o[0]), "f"(o[1]), "f"(o[2]), "f"(o[3]), "f"(o[4]), "f"(o[5]),
                          "f"(o[6]), "f"(o[7])
@@ -691,17 +702,17 @@ int tc_ntile(int Cout) { return Cout <= 256 ? ((Cout + 15) & ~15) : 256; }
 
 }  // namespace
 
-extern "C" int64_t sma_conv_weight_tc_floats(int Cout, int Cin, int kh, int kw) {
-  if (Cout <= 0 || Cin <= 0 || kh <= 0 || kw <= 0 || (Cin % KC)) return 0;
-  int NT = tc_ntile(Cout); int ntiles = (Cout + NT - 1) / NT;
+extern "C" int64_t sma_conv_weight_tc_floats(int Cout, int Cin, int kh, int kw, int nt) {
+  if (Cout <= 0 || Cin <= 0 || kh <= 0 || kw <= 0 || (Cin % KC) || nt < 0 || nt > 256 || (nt & 15)) return 0;
+  int NT = nt ? nt : tc_ntile(Cout); int ntiles = (Cout + NT - 1) / NT;
   return (int64_t)ntiles * (kh * kw * Cin / KC) * 2 * NT * KC;
 }
 
-extern "C" int sma_pack_conv_weight_tc(const float* w_packed, int ldw, int Cout, int Cin, int kh, int kw, float* w_tc, sma_stream_t stream) {
-  if (!w_packed || !w_tc || Cout <= 0 || Cin <= 0 || kh <= 0 || kw <= 0 || ldw < Cout) return SMA_ERR_BAD_ARG;
+extern "C" int sma_pack_conv_weight_tc(const float* w_packed, int ldw, int Cout, int Cin, int kh, int kw, int nt, float* w_tc, sma_stream_t stream) {
+  if (!w_packed || !w_tc || Cout <= 0 || Cin <= 0 || kh <= 0 || kw <= 0 || ldw < Cout || nt < 0 || nt > 256 || (nt & 15)) return SMA_ERR_BAD_ARG;
   if (Cin % KC) return SMA_ERR_UNSUPPORTED;
   if (reinterpret_cast<uintptr_t>(w_tc) & 15) return SMA_ERR_BAD_ARG;
-  int NT = tc_ntile(Cout); int ntiles = (Cout + NT - 1) / NT; int K = kh * kw * Cin;
+  int NT = nt ? nt : tc_ntile(Cout); int ntiles = (Cout + NT - 1) / NT; int K = kh * kw * Cin;
   long long total = (long long)ntiles * (K / KC) * NT * KC;
   int blocks = (int)((total + 255) / 256); if (blocks > 8192) blocks = 8192;
   pack_tc_kernel<<<blocks, 256, 0, as_stream(stream)>>>(w_packed, ldw, Cin, kh * kw, Cout, NT, ntiles, w_tc);
@@ -732,15 +743,11 @@ extern "C" int sma_pack_conv_weight_tc16(const float* w_packed, int ldw, int Cou
 }
 
 
-static int g_num_sms = 0;
 
 template <int ACT, int PRE, int F16>
 static int launch_tc2_inst(const Tc2P& p, int grid, int smem, cudaStream_t st) {
-  static bool configured = false;     // per instantiation; idempotent, benign if raced
-  if (!configured) {
-    if (cudaFuncSetAttribute(conv_tc2_kernel<ACT, PRE, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_DYN_MAX) != cudaSuccess) return SMA_ERR_CUDA;
-    configured = true;
-  }
+  static SmaDevOnce once;             // per instantiation and per device
+  if (int rc = sma_opt_in_smem(once, conv_tc2_kernel<ACT, PRE, F16>, SMEM_DYN_MAX)) return rc;
   conv_tc2_kernel<ACT, PRE, F16><<<grid, V2_THREADS, smem, st>>>(p);
   SMA_LAUNCH_CHECK();
   return SMA_OK;
@@ -771,11 +778,18 @@ static int launch_tc2(int act, int pre, const Tc2P& p, int grid, int smem, cudaS
 static int conv_tc2_try(const sma_conv_desc* d, cudaStream_t st, bool f16) {
   const int kch = f16 ? 64 : KC;
   if (d->Cin % kch) return SMA_ERR_UNSUPPORTED;
+  if (d->aux) {      // SFT epilogue: only on the 256-bit epilogue path, with a residual (the decoder feature) of the same geometry
+    const bool ok = d->res && d->d2s <= 1 && (d->Cout & 7) == 0 && (d->out_ld & 7) == 0 && (d->out_bstride & 7) == 0 && (reinterpret_cast<uintptr_t>(d->y) & 31) == 0 &&
+                    (d->res_ld & 7) == 0 && (d->res_bstride & 7) == 0 && (reinterpret_cast<uintptr_t>(d->res) & 31) == 0 &&
+                    (d->aux_ld & 7) == 0 && (d->aux_bstride & 7) == 0 && (reinterpret_cast<uintptr_t>(d->aux) & 31) == 0;
+    if (!ok) return SMA_ERR_UNSUPPORTED;
+  }
   if (d->stride != 1 || (d->kh != d->kw && !(d->kh == 1 || d->kw == 1))) return SMA_ERR_UNSUPPORTED;
   const bool flat = d->kh == 1 && d->kw == 1 && !d->upsample2 && d->pad_t == 0 && d->pad_l == 0 && d->Ho == d->Hi && d->Wo == d->Wi;
   if (!flat && (d->Ho < 8 || d->Wo < 4)) return SMA_ERR_UNSUPPORTED;      // tiny feature maps: the gather kernel packs images into one tile
   Tc2P p;
   p.x = d->x; p.bias = d->bias; p.pre_scale = d->pre_scale; p.pre_shift = d->pre_shift; p.res = d->res; p.y = d->y;
+  p.aux = d->aux; p.aux_bs = d->aux_bstride; p.aux_ld = d->aux_ld; p.sft_w = d->sft_w;
   p.NT = tc_ntile(d->Cout); p.ntiles_n = (d->Cout + p.NT - 1) / p.NT;
   p.wscale = f16 ? d->w_tc16 : nullptr;
   p.wtc = f16 ? d->w_tc16 + p.ntiles_n * p.NT : d->w_tc;
@@ -811,11 +825,9 @@ static int conv_tc2_try(const sma_conv_desc* d, cudaStream_t st, bool f16) {
   if (cols > 512) return SMA_ERR_UNSUPPORTED;
   p.tmem_cols = cols;
   const int smem = SA * p.a_stage_bytes + SB * b_stage + 1024;
-  if (g_num_sms == 0) {
-    int dev = 0, sms = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return SMA_ERR_CUDA;
-    g_num_sms = sms;
-  }
+  if (d->plan_only) return SMA_OK;
+  const int g_num_sms = sma_num_sms();
+  if (g_num_sms <= 0) return SMA_ERR_CUDA;
   const int grid = p.total_tiles < g_num_sms ? p.total_tiles : g_num_sms;
   const int pre = d->pre_scale ? d->pre_act : -1;
   return f16 ? launch_tc2<1>(d->act, pre, p, grid, smem, st) : launch_tc2<0>(d->act, pre, p, grid, smem, st);
@@ -823,21 +835,35 @@ static int conv_tc2_try(const sma_conv_desc* d, cudaStream_t st, bool f16) {
 
 // returns SMA_ERR_UNSUPPORTED when the shape / layout is not eligible (the caller then uses the CUDA-core kernel)
 int sma_conv2d_tc_try(sma_conv_desc* d, cudaStream_t st) {
-  if ((!d->w_tc && !d->w_tc16) || d->out_nchw) return SMA_ERR_UNSUPPORTED;
+  if ((!d->w_tc && !d->w_tc16 && !d->plan_only) || d->out_nchw) return SMA_ERR_UNSUPPORTED;
   if ((d->Cin % KC) || (d->in_ld & 3) || (d->in_bstride & 3) || (reinterpret_cast<uintptr_t>(d->x) & 15)) return SMA_ERR_UNSUPPORTED;
   if (d->pre_scale && ((reinterpret_cast<uintptr_t>(d->pre_scale) | reinterpret_cast<uintptr_t>(d->pre_shift)) & 15)) return SMA_ERR_UNSUPPORTED;
   const long long M = (long long)d->B * d->Ho * d->Wo;
   if (M < 64) return SMA_ERR_UNSUPPORTED;
-  const bool want16 = (d->precision == SMA_PREC_F16X3 || d->precision == SMA_PREC_F16) && d->w_tc16 && !(reinterpret_cast<uintptr_t>(d->w_tc16) & 15);
+  // plan_only: report the kernel (and the tf32 image tile) this launch would use if every weight image were available; nothing is launched
+  const bool want16 = (d->precision == SMA_PREC_F16X3 || d->precision == SMA_PREC_F16) && (d->plan_only || (d->w_tc16 && !(reinterpret_cast<uintptr_t>(d->w_tc16) & 15)));
   if (want16 && !(d->tc_variant & 1)) {
     int r2 = conv_tc2_try(d, st, true);
     if (r2 != SMA_ERR_UNSUPPORTED) { d->kernel_used = 3; return r2; }
   }
-  if (!d->w_tc || (reinterpret_cast<uintptr_t>(d->w_tc) & 15)) return SMA_ERR_UNSUPPORTED;
-  if (!(d->tc_variant & 1)) {
+  if (!d->plan_only && (!d->w_tc || (reinterpret_cast<uintptr_t>(d->w_tc) & 15))) return SMA_ERR_UNSUPPORTED;
+  const int nt_default = tc_ntile(d->Cout);
+  if (!(d->tc_variant & 1) && (d->plan_only || d->w_tc_nt == 0 || d->w_tc_nt == nt_default)) {
     int r2 = conv_tc2_try(d, st, false);
-    if (r2 != SMA_ERR_UNSUPPORTED) { d->kernel_used = 2; return r2; }
+    if (r2 != SMA_ERR_UNSUPPORTED) { d->kernel_used = 2; if (d->plan_only) d->w_tc_nt = nt_default; return r2; }
   }
+  if (d->aux) return SMA_ERR_UNSUPPORTED;
+  // gather kernel: one CTA per (128 rows, NT columns).  Few rows (tiny feature maps: the hourglass bottlenecks) would leave most SMs idle
+  // with the widest tile, so the image may be packed with a narrower NT (more CTAs, each streaming a quarter of the weights).
+  int NTg = d->w_tc_nt ? d->w_tc_nt : nt_default;
+  if (d->plan_only) {
+    NTg = nt_default;
+    const long long mt = (M + BM - 1) / BM;
+    while (NTg > 64 && (NTg % 32) == 0 && mt * ((d->Cout + NTg - 1) / NTg) < 128) NTg >>= 1;
+    d->w_tc_nt = NTg; d->kernel_used = 1;
+    return SMA_OK;
+  }
+  if (NTg < 16 || NTg > 256 || (NTg & 15)) return SMA_ERR_BAD_ARG;
   TcP p;
   p.x = d->x; p.wtc = d->w_tc; p.bias = d->bias; p.pre_scale = d->pre_scale; p.pre_shift = d->pre_shift; p.res = d->res; p.y = d->y;
   p.in_bs = d->in_bstride; p.out_bs = d->out_bstride; p.res_bs = d->res_bstride;
@@ -845,7 +871,7 @@ int sma_conv2d_tc_try(sma_conv_desc* d, cudaStream_t st) {
   p.pad_t = d->pad_t; p.pad_l = d->pad_l; p.up = d->upsample2 ? 1 : 0; p.pre_act = d->pre_act; p.Ho = d->Ho; p.Wo = d->Wo; p.out_ld = d->out_ld;
   p.act = d->act; p.res_ld = d->res_ld; p.d2s = d->d2s;
   p.M = (int)M; p.HoWo = d->Ho * d->Wo; p.cpt = d->Cin / KC; p.nchunks = d->kh * d->kw * p.cpt;
-  p.NT = tc_ntile(d->Cout); p.passes = (d->precision == SMA_PREC_TF32 || d->precision == SMA_PREC_F16) ? 1 : 3;
+  p.NT = NTg; p.passes = (d->precision == SMA_PREC_TF32 || d->precision == SMA_PREC_F16) ? 1 : 3;
   const int ntiles = (d->Cout + p.NT - 1) / p.NT;
   const int stage_bytes = 2 * A_BYTES + 2 * p.NT * KC * 4;
   int stages = SMEM_LIMIT / stage_bytes; if (stages > MAX_STAGES) stages = MAX_STAGES; if (stages > p.nchunks) stages = p.nchunks;
@@ -854,11 +880,8 @@ int sma_conv2d_tc_try(sma_conv_desc* d, cudaStream_t st) {
   int cols = 32; while (cols < p.NT) cols <<= 1;
   p.tmem_cols = cols;
   const int smem = stages * stage_bytes + 1024;
-  static int configured = 0;   // largest dynamic shared memory size opted in so far (idempotent; benign if raced)
-  if (configured < smem) {
-    if (cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_DYN_MAX) != cudaSuccess) return SMA_ERR_CUDA;
-    configured = SMEM_DYN_MAX;
-  }
+  static SmaDevOnce once;
+  if (int rc = sma_opt_in_smem(once, conv_tc_kernel, SMEM_DYN_MAX)) return rc;
   dim3 grid((unsigned)((M + BM - 1) / BM), (unsigned)ntiles);
   d->kernel_used = 1;
   conv_tc_kernel<<<grid, 192, smem, st>>>(p);

@@ -489,11 +489,8 @@ __global__ void pack_ts_kernel(const float* __restrict__ wp, int ldw, int Cin, i
 
 template <int ACT, int PRE, int STACKED>
 int launch_ts_inst(const TsP& p, int grid, int smem, cudaStream_t st) {
-  static bool configured = false;     // per instantiation; idempotent, benign if raced
-  if (!configured) {
-    if (cudaFuncSetAttribute(conv_ts_kernel<ACT, PRE, STACKED>, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM_DYN_MAX) != cudaSuccess) return SMA_ERR_CUDA;
-    configured = true;
-  }
+  static SmaDevOnce once;             // per instantiation and per device
+  if (int rc = sma_opt_in_smem(once, conv_ts_kernel<ACT, PRE, STACKED>, TS_SMEM_DYN_MAX)) return rc;
   conv_ts_kernel<ACT, PRE, STACKED><<<grid, TS_THREADS, smem, st>>>(p);
   SMA_LAUNCH_CHECK();
   return SMA_OK;
@@ -520,7 +517,6 @@ int launch_ts(int act, int pre, const TsP& p, int grid, int smem, cudaStream_t s
   }
 }
 
-int ts_num_sms = 0;
 
 }  // namespace
 
@@ -550,6 +546,7 @@ extern "C" int sma_pack_conv_weight_ts(const float* w_packed, int ldw, int Cout,
 
 // returns SMA_ERR_UNSUPPORTED when the shape / layout is not eligible (the caller then tries the shared-memory-operand kernels)
 int sma_conv2d_ts_try(sma_conv_desc* d, cudaStream_t st) {
+  if (d->aux || d->plan_only) return SMA_ERR_UNSUPPORTED;      // (the tensor-memory-operand kernel is an opt-in experiment: never planned)
   if (!d->w_ts || d->out_nchw || (d->precision != SMA_PREC_F16X3 && d->precision != SMA_PREC_F16) || (d->tc_variant & 1)) return SMA_ERR_UNSUPPORTED;
   if ((d->Cin % 64) || (d->in_ld & 3) || (d->in_bstride & 3) || (reinterpret_cast<uintptr_t>(d->x) & 15) || (reinterpret_cast<uintptr_t>(d->w_ts) & 15))
     return SMA_ERR_UNSUPPORTED;
@@ -605,11 +602,8 @@ int sma_conv2d_ts_try(sma_conv_desc* d, cudaStream_t st) {
   if (SA > TS_MAX_SA) SA = TS_MAX_SA;
   p.SA = SA; p.stg_off = SA * p.a_stage_bytes; p.dbg = (d->tc_variant >> 1) & 7;
   const int smem = p.stg_off + TS_STG + 1024;
-  if (ts_num_sms == 0) {
-    int dev = 0, sms = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return SMA_ERR_CUDA;
-    ts_num_sms = sms;
-  }
+  const int ts_num_sms = sma_num_sms();
+  if (ts_num_sms <= 0) return SMA_ERR_CUDA;
   const int grid = p.total_tiles < ts_num_sms ? p.total_tiles : ts_num_sms;
   const int pre = d->pre_scale ? d->pre_act : -1;
   return stacked ? launch_ts<1>(d->act, pre, p, grid, smem, st) : launch_ts<0>(d->act, pre, p, grid, smem, st);

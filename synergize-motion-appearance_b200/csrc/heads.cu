@@ -90,11 +90,41 @@ __device__ __forceinline__ void mm2(const float* a, const float* b, float* o) {
   o[2] = a[2] * b[0] + a[3] * b[2]; o[3] = a[2] * b[1] + a[3] * b[3];
 }
 
+// area of the convex hull of n <= 64 points (monotone chain + shoelace, fp64): what scipy's ConvexHull(points).volume returns for 2-D input
+__device__ double hull_area_dev(const float* pts, int n) {
+  double x[64], y[64]; int h[130];
+  for (int i = 0; i < n; i++) { x[i] = pts[2 * i]; y[i] = pts[2 * i + 1]; }
+  for (int i = 1; i < n; i++) {            // insertion sort, lexicographic
+    double xi = x[i], yi = y[i]; int j = i - 1;
+    while (j >= 0 && (x[j] > xi || (x[j] == xi && y[j] > yi))) { x[j + 1] = x[j]; y[j + 1] = y[j]; j--; }
+    x[j + 1] = xi; y[j + 1] = yi;
+  }
+  if (n < 3) return 0.0;
+  int m = 0;
+  for (int i = 0; i < n; i++) {            // lower hull
+    while (m >= 2 && (x[h[m - 1]] - x[h[m - 2]]) * (y[i] - y[h[m - 2]]) - (y[h[m - 1]] - y[h[m - 2]]) * (x[i] - x[h[m - 2]]) <= 0.0) m--;
+    h[m++] = i;
+  }
+  for (int i = n - 2, t = m + 1; i >= 0; i--) {   // upper hull
+    while (m >= t && (x[h[m - 1]] - x[h[m - 2]]) * (y[i] - y[h[m - 2]]) - (y[h[m - 1]] - y[h[m - 2]]) * (x[i] - x[h[m - 2]]) <= 0.0) m--;
+    h[m++] = i;
+  }
+  m--;                                     // the last point repeats the first
+  double a = 0.0;
+  for (int i = 0; i < m; i++) { int j = (i + 1) % m; a += x[h[i]] * y[h[j]] - x[h[j]] * y[h[i]]; }
+  return 0.5 * fabs(a);
+}
+// movement scale of normalize_kp: sqrt(hull area of the source key-points) / sqrt(hull area of the initial driving key-points), demo.py:26-29
+__global__ void hull_scale_kernel(const float* src_v, const float* drv0_v, int K, float* scale_out) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) scale_out[0] = (float)(sqrt(hull_area_dev(src_v, K)) / sqrt(hull_area_dev(drv0_v, K)));
+}
+
 __global__ void normalize_kp_kernel(const float* src_v, const float* src_j, const float* drv_v, const float* drv_j, const float* drv0_v,
-                                    const float* drv0_j, int B, int K, float scale, int relative, float* out_v, float* out_j) {
+                                    const float* drv0_j, int B, int K, float scale, const float* scale_dev, int relative, float* out_v, float* out_j) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * K) return;
   int k = i % K;
+  if (scale_dev) scale = scale_dev[0];
   if (!relative) {
     out_v[i * 2] = drv_v[i * 2]; out_v[i * 2 + 1] = drv_v[i * 2 + 1];
     for (int j = 0; j < 4; j++) out_j[i * 4 + j] = drv_j[i * 4 + j];
@@ -247,6 +277,17 @@ __global__ void to_uint8_kernel(const float* __restrict__ x, long long npix, int
   }
 }
 
+// uint8 HWC frames -> normalised fp32 NCHW, bit-exact with the reference's host-side preparation:
+// img.astype(float32) / 255. (demo.py:180-181), HWC -> CHW with optional BGR -> RGB (img_util.py:13-39), normalize(mean 0.5, std 0.5) (demo.py:183-185)
+__global__ void u8hwc_to_f32nchw_kernel(const uint8_t* __restrict__ x, int B, int C, int HW, int swap_rb, float* __restrict__ y) {
+  long long total = (long long)B * C * HW;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int p = (int)(i % HW); long long t = i / HW; int c = (int)(t % C); int b = (int)(t / C);
+    float v = (float)x[((long long)b * HW + p) * C + (swap_rb ? C - 1 - c : c)] / 255.f;
+    y[i] = (v - 0.5f) / 0.5f;
+  }
+}
+
 __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, int B, int C, int HW, float* __restrict__ y, int yld) {
   long long total = (long long)B * HW * C;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -283,9 +324,19 @@ extern "C" int sma_kp_head_fwd(const float* pred, int B, int h, int w, int ld, i
   SMA_LAUNCH_CHECK(); return SMA_OK;
 }
 extern "C" int sma_normalize_kp(const float* sv, const float* sj, const float* dv, const float* dj, const float* d0v, const float* d0j, int B,
-                                int K, float scale, int relative, float* ov, float* oj, sma_stream_t s) {
+                                int K, float scale, const float* scale_dev, int relative, float* ov, float* oj, sma_stream_t s) {
   if (!sv || !sj || !dv || !dj || !d0v || !d0j || !ov || !oj || B <= 0 || K <= 0) return SMA_ERR_BAD_ARG;
-  normalize_kp_kernel<<<cdiv(B * K, 128), 128, 0, as_stream(s)>>>(sv, sj, dv, dj, d0v, d0j, B, K, scale, relative, ov, oj);
+  normalize_kp_kernel<<<cdiv(B * K, 128), 128, 0, as_stream(s)>>>(sv, sj, dv, dj, d0v, d0j, B, K, scale, scale_dev, relative, ov, oj);
+  SMA_LAUNCH_CHECK(); return SMA_OK;
+}
+extern "C" int sma_hull_scale(const float* src_v, const float* drv0_v, int K, float* scale_out, sma_stream_t s) {
+  if (!src_v || !drv0_v || !scale_out || K < 3 || K > 64) return SMA_ERR_BAD_ARG;
+  hull_scale_kernel<<<1, 32, 0, as_stream(s)>>>(src_v, drv0_v, K, scale_out);
+  SMA_LAUNCH_CHECK(); return SMA_OK;
+}
+extern "C" int sma_u8hwc_to_f32nchw(const uint8_t* x, int B, int H, int W, int C, int swap_rb, float* y, sma_stream_t s) {
+  if (!x || !y || B <= 0 || H <= 0 || W <= 0 || C <= 0) return SMA_ERR_BAD_ARG;
+  u8hwc_to_f32nchw_kernel<<<nblocks((long long)B * C * H * W), 256, 0, as_stream(s)>>>(x, B, C, H * W, swap_rb, y);
   SMA_LAUNCH_CHECK(); return SMA_OK;
 }
 extern "C" int sma_dense_motion_prep(const float* src64, int h, int w, const float* sv, const float* sj, const float* dv, const float* dj, int B,

@@ -69,29 +69,60 @@ def _nhwc(t: torch.Tensor) -> Tuple[int, int, int, int, int, int]:
     return B, H, W, Cc, sb, sw
 
 
+PACK_EVENTS = 0          # number of weight-image packs since import (tests: a pre-packed cache load must not add any)
+
+
 @dataclass
 class ConvW:
-    """Packed conv / linear weight: w[(ky*kw+kx)*Cin+c][ldw], bias[Cout]."""
+    """Packed conv / linear weight: w[(ky*kw+kx)*Cin+c][ldw], bias[Cout], plus the tensor-core weight images, which are packed LAZILY - the
+    first time a launch plan (sma_conv2d_fwd with plan_only) says a kernel needs them - so that only the image a layer really uses is ever
+    built (and persisted by packcache.py)."""
     w: torch.Tensor
     bias: Optional[torch.Tensor]
     Cout: int
     Cin: int
     kh: int
     kw: int
-    w_tc: Optional[torch.Tensor] = None      # tf32 tensor-core image (sma_pack_conv_weight_tc); None -> not eligible (Cin % 32)
-    w_tc16: Optional[torch.Tensor] = None    # fp16 tensor-core image (sma_pack_conv_weight_tc16); None -> not eligible (Cin % 64)
-    w_ts: Optional[torch.Tensor] = None      # fp16 tensor-memory-operand image (sma_pack_conv_weight_ts); None -> not eligible (Cin % 64)
-    _slices: Optional[dict] = None           # cache of cols() results (their tensor-core images are packed once)
+    images: Optional[dict] = None            # ('tc', nt) tf32 image packed with N tile nt | ('tc16',) fp16 image | ('ts',) tensor-memory-operand image
+    plans: Optional[dict] = None             # launch signature -> (kernel, nt) as reported by the library's plan mode
+    _slices: Optional[dict] = None           # cache of cols() results
+    dirty: bool = False                      # an image was packed since the last packcache save
+
+    def image(self, kind: str, nt: int = 0) -> Optional[torch.Tensor]:
+        global PACK_EVENTS
+        if self.images is None:
+            self.images = {}
+        key = (kind, nt) if kind == 'tc' else (kind,)
+        t = self.images.get(key, False)
+        if t is False:
+            with torch.cuda.device(self.w.device):
+                t = {'tc': lambda: _pack_tc(self, nt), 'tc16': lambda: _pack_tc16(self), 'ts': lambda: _pack_ts(self)}[kind]()
+            self.images[key] = t
+            self.dirty = True
+            PACK_EVENTS += 1
+        return t
+
+    # eager accessors (tests / the tensor-memory-operand experiment)
+    @property
+    def w_tc(self):
+        return self.image('tc', 0)
+
+    @property
+    def w_tc16(self):
+        return self.image('tc16')
+
+    @property
+    def w_ts(self):
+        return self.image('ts')
 
     def cols(self, start: int, n: int) -> 'ConvW':
-        """Output-column slice (free for the CUDA-core layout: row-major [K][ldw]; the tensor-core image is re-packed once)."""
+        """Output-column slice (free for the CUDA-core layout: row-major [K][ldw]; tensor-core images are packed on first use)."""
         assert start % 4 == 0
         if self._slices is None:
             self._slices = {}
         cw = self._slices.get((start, n))
         if cw is None:
             cw = ConvW(self.w[:, start:], None if self.bias is None else self.bias[start:start + n], n, self.Cin, self.kh, self.kw)
-            cw.w_tc, cw.w_tc16, cw.w_ts = _pack_tc(cw), _pack_tc16(cw), _pack_ts(cw)
             self._slices[(start, n)] = cw
         return cw
 
@@ -99,18 +130,16 @@ class ConvW:
         """View a Linear(C*p*p -> N) whose features are ordered (p1 p2 c) as a pxp stride-p conv
         (appmotioncodebook_arch.py:222,229,236)."""
         assert self.kh == 1 and self.kw == 1 and self.Cin % (p * p) == 0
-        cw = ConvW(self.w, self.bias, self.Cout, self.Cin // (p * p), p, p)
-        cw.w_tc, cw.w_tc16, cw.w_ts = _pack_tc(cw), _pack_tc16(cw), _pack_ts(cw)
-        return cw
+        return ConvW(self.w, self.bias, self.Cout, self.Cin // (p * p), p, p)
 
 
-def _pack_tc(cw: 'ConvW') -> Optional[torch.Tensor]:
+def _pack_tc(cw: 'ConvW', nt: int = 0) -> Optional[torch.Tensor]:
     lib = _lib.load()
-    n = lib.sma_conv_weight_tc_floats(cw.Cout, cw.Cin, cw.kh, cw.kw)
+    n = lib.sma_conv_weight_tc_floats(cw.Cout, cw.Cin, cw.kh, cw.kw, nt)
     if n <= 0:
         return None
     out = torch.empty((n,), device=cw.w.device, dtype=torch.float32)
-    check(lib.sma_pack_conv_weight_tc(cw.w.data_ptr(), cw.w.stride(0), cw.Cout, cw.Cin, cw.kh, cw.kw, out.data_ptr(), _stream()),
+    check(lib.sma_pack_conv_weight_tc(cw.w.data_ptr(), cw.w.stride(0), cw.Cout, cw.Cin, cw.kh, cw.kw, nt, out.data_ptr(), _stream()),
           'sma_pack_conv_weight_tc')
     return out
 
@@ -162,9 +191,7 @@ def pack_conv(weight: torch.Tensor, bias: Optional[torch.Tensor], bn: Optional[d
         eps = float(bn.get('eps', 1e-5))
     check(lib.sma_pack_conv_weight(_ptr(w), _ptr(b), Cout, Cin, kh, kw, _ptr(g), _ptr(be), _ptr(mu), _ptr(var), eps,
                                    _ptr(wp), ldw, _ptr(bo), _stream()), 'sma_pack_conv_weight')
-    cw = ConvW(wp, None if bo is None else bo[:Cout], Cout, Cin, kh, kw)
-    cw.w_tc, cw.w_tc16, cw.w_ts = _pack_tc(cw), _pack_tc16(cw), _pack_ts(cw)
-    return cw
+    return ConvW(wp, None if bo is None else bo[:Cout], Cout, Cin, kh, kw)
 
 
 def pack_conv_cat(weights, biases, pad_cin: int = 0) -> ConvW:
@@ -209,9 +236,12 @@ LAST_CONV_KERNEL = -1    # which kernel the last conv2d ran on: 0 CUDA-core, 1 t
 def conv2d(x: torch.Tensor, cw: ConvW, *, stride: int = 1, pad: int = 0, pad_tl: Optional[Tuple[int, int]] = None,
            out: Optional[torch.Tensor] = None, out_hw: Optional[Tuple[int, int]] = None, act: str = 'none',
            pre: Optional[Tuple[torch.Tensor, torch.Tensor, str]] = None, res: Optional[torch.Tensor] = None,
-           upsample2: bool = False, d2s: int = 0, out_nchw: bool = False, exact: bool = False, fast: bool = False) -> torch.Tensor:
+           upsample2: bool = False, d2s: int = 0, out_nchw: bool = False, exact: bool = False, fast: bool = False,
+           sft: Optional[Tuple[torch.Tensor, float]] = None) -> torch.Tensor:
     """`exact`: force the CUDA-core fp32 kernel; `fast`: allow single-pass TF32 on the tensor cores (layers whose
-    contribution to the output error budget was measured to be negligible); default: 3xTF32 (fp32-faithful)."""
+    contribution to the output error budget was measured to be negligible); default: 3xTF32 (fp32-faithful).
+    `sft=(scale, w)`: Fuse_sft_block tail fused into the epilogue, y = res + w*(res*scale + conv(x)) (needs `res`; raises SmaError with
+    status -2 when the launch cannot run on the persistent tensor-core kernel: callers then use sft_combine)."""
     lib = _lib.load()
     B, Hi, Wi, Cin, ibs, ild = _nhwc(x)
     if Cin != cw.Cin:
@@ -253,20 +283,45 @@ def conv2d(x: torch.Tensor, cw: ConvW, *, stride: int = 1, pad: int = 0, pad_tl:
         assert (rB, rH, rW, rC) == (B, Ho, Wo, cw.Cout), (tuple(res.shape), (B, Ho, Wo, cw.Cout))
         d.res, d.res_bstride, d.res_ld = res.data_ptr(), rbs, rld
     d.d2s, d.out_nchw = d2s, 1 if out_nchw else 0
-    if exact or not USE_TF32X3 or (cw.w_tc is None and cw.w_tc16 is None and cw.w_ts is None):
+    if sft is not None:
+        assert res is not None
+        aB, aH, aW, aC, abs_, ald = _nhwc(sft[0])
+        assert (aB, aH, aW, aC) == (B, Ho, Wo, cw.Cout)
+        d.aux, d.aux_bstride, d.aux_ld, d.sft_w = sft[0].data_ptr(), abs_, ald, float(sft[1])
+    d.tc_variant = TC_VARIANT
+    d.kernel_used = -1
+    planned = None
+    if exact or not USE_TF32X3 or Cin % 32:
         d.precision = PREC['exact']
     else:
         one = fast and ALLOW_TF32_1PASS
         d.precision = (PREC['f16'] if one else PREC['f16x3']) if USE_F16 else (PREC['tf32'] if one else PREC['tf32x3'])
-    d.w_tc, d.w_tc16, d.w_ts = _ptr(cw.w_tc), _ptr(cw.w_tc16), (_ptr(cw.w_ts) if USE_TS else None)
-    d.tc_variant = TC_VARIANT
-    d.kernel_used = -1
+        if USE_TS:       # the tensor-memory-operand experiment: every image up front, the library picks
+            d.w_tc, d.w_tc16, d.w_ts = _ptr(cw.image('tc', 0)), _ptr(cw.image('tc16')), _ptr(cw.image('ts'))
+        else:
+            # ask the library which kernel this launch will run on (nothing is launched), then pack / fetch exactly the image it reads
+            key = (B, Hi, Wi, stride, pt, pl, upsample2, Ho, Wo, out_nchw, d2s, d.precision, TC_VARIANT, x.data_ptr() & 15, ild & 3, ibs & 3,
+                   pre is not None, sft is not None, 0 if res is None else (d.res_ld & 7, d.res_bstride & 7), d.out_ld & 7, d.out_bstride & 7)
+            if cw.plans is None:
+                cw.plans = {}
+            planned = cw.plans.get(key)
+            if planned is None:
+                d.plan_only = 1
+                check(lib.sma_conv2d_fwd(C.byref(d), _stream()), 'sma_conv2d_fwd(plan)')
+                planned = cw.plans[key] = (d.kernel_used, d.w_tc_nt)
+                d.plan_only, d.kernel_used, d.w_tc_nt = 0, -1, 0
+            if planned[0] in (1, 2):
+                d.w_tc, d.w_tc_nt = _ptr(cw.image('tc', planned[1])), planned[1]
+            elif planned[0] == 3:
+                d.w_tc16 = _ptr(cw.image('tc16'))
     K = cw.kh * cw.kw * Cin
     with _Prof('conv', 2.0 * B * Ho * Wo * K * cw.Cout,
                4.0 * (B * Hi * Wi * Cin + B * Ho * Wo * cw.Cout * (2 if res is not None else 1) + K * cw.Cout),
                f'conv B{B} {Hi}x{Wi} Cin{Cin} Cout{cw.Cout} k{cw.kh} s{stride}{" up" if upsample2 else ""}{" pre" if pre is not None else ""}') as pr:
         check(lib.sma_conv2d_fwd(C.byref(d), _stream()), f'sma_conv2d_fwd Cin={Cin} Cout={cw.Cout} k={cw.kh}x{cw.kw}')
         pr.label += (' simt', ' tc-gather', ' tc-halo', ' tc-halo-f16', ' ts-f16')[d.kernel_used] + (' 1pass' if d.precision in (2, 4) else '')
+    if planned is not None and d.kernel_used != planned[0]:
+        raise _lib.SmaError(f'conv2d ran on kernel {d.kernel_used} but was planned on {planned[0]} (Cin={Cin} Cout={cw.Cout} k={cw.kh}): binding bug')
     global LAST_CONV_KERNEL
     LAST_CONV_KERNEL = d.kernel_used
     return out
@@ -446,14 +501,43 @@ def kp_head(pred: torch.Tensor, K: int, temperature: float):
     return value, jac
 
 
-def normalize_kp(src_v, src_j, drv_v, drv_j, drv0_v, drv0_j, scale: float, relative: bool):
+def normalize_kp(src_v, src_j, drv_v, drv_j, drv0_v, drv0_j, scale, relative: bool):
+    """`scale`: python float, or a 1-element device tensor (written by hull_scale: no host round trip).  Source / initial key-points are
+    per-clip constants: batch 1."""
     lib = _lib.load()
     B, K, _ = drv_v.shape
+    if src_v.shape[0] != 1 or drv0_v.shape[0] != 1 or src_j.shape[0] != 1 or drv0_j.shape[0] != 1:
+        raise _lib.SmaError('normalize_kp: kp_source and kp_driving_initial must have batch 1 (per-clip constants)')
     ov, oj = torch.empty_like(drv_v), torch.empty_like(drv_j)
+    dev_scale = scale if isinstance(scale, torch.Tensor) else None
     check(lib.sma_normalize_kp(src_v.data_ptr(), src_j.data_ptr(), drv_v.data_ptr(), drv_j.data_ptr(), drv0_v.data_ptr(),
-                               drv0_j.data_ptr(), B, K, scale, 1 if relative else 0, ov.data_ptr(), oj.data_ptr(), _stream()),
-          'sma_normalize_kp')
+                               drv0_j.data_ptr(), B, K, 1.0 if dev_scale is not None else float(scale), _ptr(dev_scale), 1 if relative else 0,
+                               ov.data_ptr(), oj.data_ptr(), _stream()), 'sma_normalize_kp')
     return ov, oj
+
+
+def hull_scale(src_v: torch.Tensor, drv0_v: torch.Tensor) -> torch.Tensor:
+    """sqrt(hull area of the source key-points) / sqrt(hull area of the initial driving key-points) as a device scalar (demo.py:26-29)."""
+    lib = _lib.load()
+    assert src_v.is_cuda and src_v.is_contiguous() and drv0_v.is_contiguous() and src_v.dtype == torch.float32
+    K = src_v.shape[-2]
+    out = torch.empty((1,), device=src_v.device, dtype=torch.float32)
+    check(lib.sma_hull_scale(src_v.data_ptr(), drv0_v.data_ptr(), K, out.data_ptr(), _stream()), 'sma_hull_scale')
+    return out
+
+
+def u8hwc_to_f32nchw(frames: torch.Tensor, swap_rb: bool = False, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """(B,H,W,C) uint8 device frames -> (B,C,H,W) fp32 in [-1,1]: the reference's astype(float32)/255 + img2tensor + normalize(0.5,0.5)
+    (demo.py:177-185) on the device, bit-exact."""
+    lib = _lib.load()
+    if not frames.is_cuda or frames.dtype != torch.uint8 or frames.dim() != 4 or not frames.is_contiguous():
+        raise _lib.SmaError('u8hwc_to_f32nchw needs a contiguous (B,H,W,C) uint8 CUDA tensor')
+    B, H, W, Cc = frames.shape
+    if out is None:
+        out = torch.empty((B, Cc, H, W), device=frames.device, dtype=torch.float32)
+    assert out.is_contiguous() and tuple(out.shape) == (B, Cc, H, W)
+    check(lib.sma_u8hwc_to_f32nchw(frames.data_ptr(), B, H, W, Cc, 1 if swap_rb else 0, out.data_ptr(), _stream()), 'sma_u8hwc_to_f32nchw')
+    return out
 
 
 def dense_motion_prep(src64: torch.Tensor, kp_src_v, kp_src_j, kp_drv_v, kp_drv_j, hg_in: torch.Tensor, var: float = 0.01):
@@ -546,3 +630,28 @@ def nhwc_to_nchw(x: torch.Tensor) -> torch.Tensor:
 
 def launch_count() -> int:
     return _lib.load().sma_kernel_launch_count()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The library acts on the CURRENT device (include/sma_b200.h); run every op on the device that owns its first tensor argument, so that a
+# process driving several GPUs never launches on the wrong one.
+# ---------------------------------------------------------------------------------------------------------------------
+import functools as _functools
+
+
+def _on_device(fn):
+    @_functools.wraps(fn)
+    def wrap(x, *a, **k):
+        t = x.w if isinstance(x, ConvW) else (x[0] if isinstance(x, (list, tuple)) and x else x)
+        if isinstance(t, torch.Tensor) and t.is_cuda and t.device.index != torch.cuda.current_device():
+            with torch.cuda.device(t.device):
+                return fn(x, *a, **k)
+        return fn(x, *a, **k)
+    return wrap
+
+
+for _name in ('pack_conv', 'pack_conv_cat', 'pack_conv_blockdiag', 'conv2d', 'linear', 'groupnorm_stats', 'affine_act', 'layernorm', 'warp_occlude',
+              'resize_ac', 'mha', 'attn256', 'vq_lookup', 'antialias_down4', 'avgpool2', 'kp_head', 'normalize_kp', 'hull_scale', 'u8hwc_to_f32nchw',
+              'dense_motion_prep', 'dense_motion_head', 'flow_to_px', 'flow_update', 'motion_ignore_mask', 'sft_combine', 'to_uint8', 'nchw_to_nhwc',
+              'nhwc_to_nchw'):
+    globals()[_name] = _on_device(globals()[_name])
