@@ -27,10 +27,10 @@ SD = Dict[str, T]
 # ----------------------------------------------------------------------------------------------
 
 
-def coord_grid(h: int, w: int, dtype=torch.float32) -> T:
+def coord_grid(h: int, w: int, dtype=torch.float32, device=None) -> T:
     """(h,w,2) grid, x then y, 2*i/(n-1)-1.  utils/motion_estimator_util.py:56-72."""
-    xs = 2 * (torch.arange(w, dtype=dtype) / (w - 1)) - 1
-    ys = 2 * (torch.arange(h, dtype=dtype) / (h - 1)) - 1
+    xs = 2 * (torch.arange(w, dtype=dtype, device=device) / (w - 1)) - 1
+    ys = 2 * (torch.arange(h, dtype=dtype, device=device) / (h - 1)) - 1
     return torch.stack([xs.view(1, w).expand(h, w), ys.view(h, 1).expand(h, w)], dim=-1)
 
 
@@ -99,7 +99,7 @@ def kp_detector(P: SD, x: T, temperature: float = 0.1, prefix: str = 'kp_detecto
     pred = conv(P, prefix + '.kp', feat)                         # 7x7, pad 0 -> (B,15,58,58)
     b, k, h, w = pred.shape
     heat = F.softmax(pred.view(b, k, -1) / temperature, dim=2).view(b, k, h, w)
-    grid = coord_grid(h, w, x.dtype)
+    grid = coord_grid(h, w, x.dtype, x.device)
     value = (heat.unsqueeze(-1) * grid.view(1, 1, h, w, 2)).sum(dim=(2, 3))
     jm = conv(P, prefix + '.jacobian', feat).reshape(b, k, 4, h, w)
     jac = (heat.unsqueeze(2) * jm).view(b, k, 4, -1).sum(-1).view(b, k, 2, 2)
@@ -108,7 +108,7 @@ def kp_detector(P: SD, x: T, temperature: float = 0.1, prefix: str = 'kp_detecto
 
 def gaussian_heatmaps(kp_value: T, h: int, w: int, var: float = 0.01) -> T:
     """utils/motion_estimator_util.py:11-32 -> (B,K,h,w)."""
-    g = coord_grid(h, w, kp_value.dtype).view(1, 1, h, w, 2)
+    g = coord_grid(h, w, kp_value.dtype, kp_value.device).view(1, 1, h, w, 2)
     d = g - kp_value.view(*kp_value.shape[:2], 1, 1, 2)
     return torch.exp(-0.5 * (d ** 2).sum(-1) / var)
 
@@ -121,9 +121,9 @@ def dense_motion(P: SD, source: T, kp_driving: Dict[str, T], kp_source: Dict[str
     K = kp_driving['value'].shape[1]
     g_drv = gaussian_heatmaps(kp_driving['value'], h, w)
     g_src = gaussian_heatmaps(kp_source['value'], h, w)
-    heat = torch.cat([torch.zeros(b, 1, h, w, dtype=src.dtype), g_drv - g_src], dim=1)      # (B,K+1,h,w)
+    heat = torch.cat([torch.zeros(b, 1, h, w, dtype=src.dtype, device=src.device), g_drv - g_src], dim=1)      # (B,K+1,h,w)
     # sparse motions  T_{s<-d}(z) = J_s J_d^-1 (z - kp_d) + kp_s ; background = identity
-    ident = coord_grid(h, w, src.dtype).view(1, 1, h, w, 2)
+    ident = coord_grid(h, w, src.dtype, src.device).view(1, 1, h, w, 2)
     z = ident - kp_driving['value'].view(b, K, 1, 1, 2)
     jac = torch.matmul(kp_source['jacobian'], torch.inverse(kp_driving['jacobian']))          # (B,K,2,2)
     z = torch.matmul(jac.view(b, K, 1, 1, 2, 2), z.unsqueeze(-1)).squeeze(-1)
@@ -176,8 +176,8 @@ def normalize_kp(kp_source, kp_driving, kp_driving_initial, adapt_movement_scale
     """demo.py:24-44."""
     s = 1.0
     if adapt_movement_scale:
-        s = math.sqrt(hull_area(kp_source['value'][0].numpy())) / \
-            math.sqrt(hull_area(kp_driving_initial['value'][0].numpy()))
+        s = math.sqrt(hull_area(kp_source['value'][0].cpu().numpy())) / \
+            math.sqrt(hull_area(kp_driving_initial['value'][0].cpu().numpy()))
     out = dict(kp_driving)
     if use_relative_movement:
         out['value'] = (kp_driving['value'] - kp_driving_initial['value']) * s + kp_source['value']
@@ -414,8 +414,8 @@ def generator_forward(P: SD, src_feats: Dict[str, T], dm: Dict[str, T], w: float
     deformation = dm['deformation']
     b, hs, ws, _ = deformation.shape
     # the residual grid uses linspace (appmotioncodebook_arch.py:562-565), not the arithmetic grid
-    xx = torch.linspace(-1., 1., hs)
-    yy = torch.linspace(-1., 1., ws)
+    xx = torch.linspace(-1., 1., hs, device=deformation.device)
+    yy = torch.linspace(-1., 1., ws, device=deformation.device)
     gx, gy = torch.meshgrid(xx, yy, indexing='xy')
     grid = torch.stack([gx, gy], dim=-1).unsqueeze(0)
     half = (hs - 1.) / 2.
@@ -450,7 +450,11 @@ def generator_forward(P: SD, src_feats: Dict[str, T], dm: Dict[str, T], w: float
             s = x.shape[-1]
             enc = compensate(src_feats[str(s)], s, occs[-1])
             x = sft_fuse(P, f'fuse_convs_dict.{s}', enc, x, w)
+            if collect is not None:
+                collect[f'sft_{s}'] = x
             x = x + conv(P, f'fuse_ms_dict.{s}', enc, padding=1)
+            if collect is not None:
+                collect[f'fused_{s}'] = x
     return {'out': x, 'lq_feat': lq_feat, 'out_occ': occs, 'deformation_list': motions}
 
 
@@ -459,7 +463,7 @@ def to_uint8(x: T, bgr: bool = False) -> np.ndarray:
     HWC, optional channel flip, x255, round half to even, uint8."""
     t = x.detach().float().clamp(-1, 1)
     t = (t - (-1)) / (1 - (-1))
-    a = t.numpy().transpose(1, 2, 0)
+    a = t.cpu().numpy().transpose(1, 2, 0)
     if bgr:
         a = a[:, :, ::-1]
     return (a * 255.0).round().astype(np.uint8)

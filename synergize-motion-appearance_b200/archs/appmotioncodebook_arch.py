@@ -510,7 +510,11 @@ class AppMotionCompFormer(ParamModule):
                 scale = ops.conv2d(ss[..., :c], W[n + '.scale.2'], pad=1)
                 # dec + w * (dec * scale + shift) in the epilogue of the `shift.2` conv; the decoder half is read in place (channel slice of `cat`)
                 xf = ops.conv2d(ss[..., c:], W[n + '.shift.2'], pad=1, res=x, sft=(scale, float(w)))
+                if collect is not None:
+                    collect[f'sft_{s}'] = xf.clone()                                   # (the next conv accumulates in place)
                 x = ops.conv2d(enc, W[f'fuse_ms_dict.{s}'], pad=1, res=xf, out=xf)
+                if collect is not None:
+                    collect[f'fused_{s}'] = x
             else:
                 x = self._block('generator', i, self.gen_layout, x)
         return {'out': x, 'lq_feat': lq_feat, 'out_occ': occs, 'deformation_list': motions, 'residuals': residuals}

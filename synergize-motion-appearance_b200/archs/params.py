@@ -15,6 +15,7 @@ class ParamModule(nn.Module):
         self._packed: Optional[dict] = None
         self._pack_cache_dir: Optional[str] = None
         self._pack_saved = False
+        self._state_hash: Optional[str] = None
 
     # ---- declaration -------------------------------------------------------------------------
     def _leaf_parent(self, dotted: str):

@@ -66,7 +66,7 @@ def state_hash(module) -> str:
     for k, v in sorted(module.state_dict().items()):
         t = v.detach().cpu().contiguous()
         h.update(k.encode()); h.update(repr((tuple(t.shape), str(t.dtype))).encode())
-        h.update(t.view(torch.uint8).numpy() if t.numel() else b'')
+        h.update(t.reshape(-1).view(torch.uint8).numpy() if t.numel() else b'')
     return h.hexdigest()
 
 
@@ -81,10 +81,9 @@ def _convw_to_blob(cw: ops.ConvW) -> dict:
 
 def _convw_from_blob(b: dict, dev) -> ops.ConvW:
     w = b['w'].to(dev)
-    ldw = w.shape[1]
     Cout, Cin, kh, kw = b['dims']
     bias = None if b['bias'] is None else b['bias'].to(dev)
-    cw = ops.ConvW(w if ldw == w.stride(0) else w.contiguous(), bias, Cout, Cin, kh, kw)
+    cw = ops.ConvW(w, bias, Cout, Cin, kh, kw)
     cw.images = {k: (None if t is None else t.to(dev)) for k, t in b['images'].items()}
     cw.plans = dict(b['plans'])
     for (start, n), sb in b['slices'].items():
@@ -111,7 +110,10 @@ def _clear_dirty(W):
 
 
 def path_for(module, directory: str) -> str:
-    return os.path.join(directory, f'{module.__class__.__name__}-{state_hash(module)}.smapack')
+    h = getattr(module, '_state_hash', None)            # cleared by ParamModule.invalidate_cache (load_state_dict / .to())
+    if h is None:
+        h = module._state_hash = state_hash(module)
+    return os.path.join(directory, f'{module.__class__.__name__}-{h}.smapack')
 
 
 def save(module, W: Dict[str, object], directory: str) -> str:

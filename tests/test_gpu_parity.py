@@ -4,6 +4,7 @@ produced by the live reference (tests/golden/, written by oracle/make_golden.py)
 tighter per stage; bit-exact for indices, masks and uint8 conversion.
 """
 import ctypes
+import os
 
 import numpy as np
 import pytest
@@ -13,6 +14,10 @@ import torch.nn.functional as F
 import sma_oracle as O
 
 pytestmark = pytest.mark.gpu
+
+# normalize_kp's jacobian J_drv J_drv0^-1 J_src amplifies the single-pass (fp16) error of the key-point detector's jacobian head through the
+# inverse of J_drv0 (condition number ~5 on the synthetic weights); measured on B200: see the printed value
+KP_NORM_JAC_TOL = 1e-3
 
 
 @pytest.fixture(scope='module')
@@ -330,12 +335,7 @@ def test_vq_lookup_indices_bit_exact(S, E, init):
         idx, zq, md = S.ops.vq_lookup(zf.cuda(), cb.cuda(), n)
         idx = idx.cpu()
         mism = int((idx != idx_r[:, 0]).sum())
-        if mism:
-            # a different summation order may move a row across an exact fp32 tie; the distances must still be
-            # equal to the last bit of the reference's own formula for the index we picked
-            d = (zf ** 2).sum(1, keepdim=True) + (cb[:n] ** 2).sum(1) - 2 * zf @ cb[:n].t()
-            bad = (idx != idx_r[:, 0]).nonzero()[:, 0]
-            assert mism <= 2 and bool((d[bad, idx[bad]] - d[bad, idx_r[bad, 0]]).abs().max() <= 4e-6 * d[bad].abs().max()), mism
+        assert mism == 0, f'{mism} of {idx.numel()} indices differ from the reference (E={E}, init={init}, prefix={n})'      # bit-exact, no tolerance
         assert torch.equal(zq.cpu(), cb[idx])
         # idempotence: quantising code vectors returns the same codes
         idx2, _, _ = S.ops.vq_lookup(zq, cb.cuda(), n)
@@ -370,8 +370,15 @@ def test_kp_detector_and_dense_motion(S, nets, weights, clip, golden):
     kp_b = me.estimate_kp(torch.cat([d0, d1]))
     assert float((kp_b['value'][1] - kp_d['value'][0]).abs().max()) < 1e-5
     kpn = S.normalize_kp(kp_s, kp_d, kp_0, adapt_movement_scale=True, use_relative_movement=True, use_relative_jacobian=True)
-    assert float((kpn['value'].cpu() - golden['kp_norm1_value']).abs().max()) < 2e-4
-    assert float((kpn['jacobian'].cpu() - golden['kp_norm1_jacobian']).abs().max()) < 2e-3
+    ev = float((kpn['value'].cpu() - golden['kp_norm1_value']).abs().max())
+    ej = float((kpn['jacobian'].cpu() - golden['kp_norm1_jacobian']).abs().max())
+    print(f'normalize_kp vs reference fixture: value {ev:.3e}, jacobian {ej:.3e}')
+    assert ev < 2e-4 and ej < KP_NORM_JAC_TOL, (ev, ej)
+    # the device-side hull scale equals the host one (scipy ConvexHull.volume semantics) to fp32 rounding
+    from importlib import import_module
+    an = import_module('synergize-motion-appearance_b200.animate')
+    s_dev = float(S.ops.hull_scale(kp_s['value'].contiguous(), kp_0['value'].contiguous()).cpu())
+    assert abs(s_dev - an.movement_scale(kp_s, kp_0)) <= 1e-6 * abs(s_dev)
     # dense motion from the reference's own normalised keypoints (isolates this stage)
     kpn_ref = {'value': golden['kp_norm1_value'].cuda(), 'jacobian': golden['kp_norm1_jacobian'].cuda()}
     kps_ref = {'value': golden['kp_source_value'].cuda(), 'jacobian': golden['kp_source_jacobian'].cuda()}
@@ -491,3 +498,234 @@ def test_launch_counter_counts_kernels(S):
     n0 = S.ops.launch_count()
     S.ops.to_uint8(torch.zeros(1, 4, 4, 3, device='cuda'))
     assert S.ops.launch_count() == n0 + 1
+
+
+# ---------------------------------------------------------------------------------------------------
+# round 2: the benchmarked configuration against the oracle, stage gates, frame I/O, caches, multi-source
+# ---------------------------------------------------------------------------------------------------
+def _stage_err(got_nhwc, ref_nchw):
+    ref = ref_nchw.float()
+    return float((nchw(got_nhwc) - ref).abs().max()) / max(1.0, float(ref.abs().max()))
+
+
+def test_batch64_clip_matches_oracle_on_sampled_frames(S, nets, weights):
+    """The benchmarked configuration itself (BASELINE configs[1]: 64 driving frames in ONE micro-batch of 64) against the oracle on sampled
+    frames: fp32 `out` <= 1e-3 max-abs (north star) and uint8 frames <= 1 level.  Tile scheduling, batch-stride-0 sharing of the source
+    features and workspace sizes all depend on the batch, so the small-batch fixtures do not cover this."""
+    g, me = nets
+    src, drv = O.synthetic_frames(64, seed=77)
+    idx = [0, 17, 38, 63]
+    anim = S.ClipAnimator(g, me, src.unsqueeze(0).cuda(), None, True, True, 1.0)
+    u8, out = anim.step(torch.stack(drv).cuda(), want_fp32=True)                        # one 64-frame micro-batch
+    assert tuple(u8.shape) == (64, 256, 256, 3)
+    ref_p, _, ref_o = O.make_animation(weights[0], weights[1], src, [drv[0]] + [drv[i] for i in idx[1:]], True, True)
+    errs = []
+    for j, i in enumerate(idx):
+        errs.append(float((out[i].permute(2, 0, 1).cpu() - ref_o[j]).abs().max()))
+        d = np.abs(u8[i].cpu().numpy().astype(int) - ref_p[j].astype(int))
+        assert d.max() <= 1 and (d > 0).mean() < 0.01, (i, d.max(), (d > 0).mean())
+    print('batch-64 out max-abs vs oracle on frames', idx, ['%.2e' % e for e in errs])
+    assert max(errs) < 1e-3, errs
+    # the public API on host uint8 frames, same micro-batch: identical to the device path fed with the converted frames
+    src8, drv8 = O.to_uint8(src), [O.to_uint8(f) for f in drv]
+    p_u8, d_u8 = S.make_animation(src8, drv8, g, me, relative=True, adapt_movement_scale=True, batch=64)
+    assert all(np.array_equal(a, b) for a, b in zip(d_u8, drv8))                         # driving frames are echoed bit-exactly
+    f32 = [(torch.from_numpy(f.astype(np.float32) / 255.).permute(2, 0, 1) - 0.5) / 0.5 for f in drv8]
+    s32 = (torch.from_numpy(src8.astype(np.float32) / 255.).permute(2, 0, 1) - 0.5) / 0.5
+    p_f32, _ = S.make_animation(s32, f32, g, me, relative=True, adapt_movement_scale=True, batch=64)
+    assert all(np.array_equal(a, b) for a, b in zip(p_u8, p_f32))
+
+
+def test_stage_gates_against_oracle(S, nets, weights, clip, golden):
+    """Per-stage gates (S2 warp, S3m delta-flow, S3a compensation, SFT fusion) at <= 2e-4 of the stage's scale, so that a regression in one
+    stage cannot hide inside the 1e-3 budget of the final image; plus the reference's own `app_comp_list` fixture."""
+    g, me = nets
+    src, drv = clip
+    dm = {'deformation': golden['deformation1'], 'occlusion_map': golden['occlusion1'],
+          'driving_kp_heatmap': O.gaussian_heatmaps(golden['kp_norm1_value'], 64, 64)}
+    ref_c = {}
+    O.generator_forward(weights[0], O.encode_source(weights[0], src.unsqueeze(0)), dm, 1.0, ref_c)
+    got_c = {}
+    feats = g.encode_source(src.unsqueeze(0).cuda())
+    r = g.generate(feats, dm['deformation'].cuda(), dm['occlusion_map'].cuda().view(1, 64, 64), nhwc(dm['driving_kp_heatmap']), 1.0, collect=got_c)
+    worst = {}
+    for s in (32, 64, 128, 256):
+        for key in ('warp0', 'warped', 'app') + (('sft', 'fused') if s > 32 else ()):
+            worst[f'{key}_{s}'] = _stage_err(got_c[f'{key}_{s}'], ref_c[f'{key}_{s}'])
+    for i, s in enumerate((32, 64, 128, 256)):
+        worst[f'res_{s}'] = float((r['residuals'][i][..., :3].cpu() - ref_c[f'res_{s}']).abs().max())      # delta-flow in pixels + delta-occlusion logits
+    print('stage errors (max-abs / max(1, stage max)):', {k: '%.1e' % v for k, v in worst.items()})
+    assert max(worst.values()) < 2e-4, worst
+    # the reference's own tensors for the compensated features (fixture written by the live reference)
+    out = g(src.unsqueeze(0).cuda(), {k: v.cuda() for k, v in dm.items()}, w=1, inference=True, visualize_app_feat=True, vis_app_before_comp=True)
+    for a, b in zip(out['app_comp_list'], golden['app_comp1_s']):
+        a = a.cpu()
+        sub = a[:, ::8, ::max(1, a.shape[-1] // 16), ::max(1, a.shape[-1] // 16)]
+        assert float((sub - b).abs().max()) < 2e-4 * max(1.0, float(b.abs().max()))
+    # the reference's full inference key set (appmotioncodebook_arch.py:745-764)
+    assert set(out) >= {'out', 'lq_feat', 'out_occ', 'deformation_list', 'res_deform_list', 'deform_feat_list', 'app_comp_list',
+                        'app_before_comp_list', 'app_query_feat_list', 'app_comp_feat_list', 'x_before_app_32'}
+    assert [tuple(t.shape) for t in out['app_before_comp_list']] == [(1, 256, 32, 32), (1, 128, 64, 64), (1, 128, 128, 128), (1, 64, 256, 256)]
+    assert tuple(out['x_before_app_32'].shape) == (1, 3, 256, 256) and len(out['deform_feat_list']) == 4
+    assert float((out['app_before_comp_list'][1].cpu() - ref_c['warped_64']).abs().max()) < 2e-4 * max(1.0, float(ref_c['warped_64'].abs().max()))
+
+
+def test_two_sources_back_to_back_do_not_share_cached_features(S, nets, weights):
+    """The per-source caches are keyed on the tensor object (kept alive by the entry): a second clip with another identity, whose device
+    tensor may land at the recycled address of the first, must not reuse the first identity's encoder features / 64x64 source."""
+    g, me = nets
+    srcA, drv = O.synthetic_frames(2, seed=5)
+    srcB, _ = O.synthetic_frames(0, seed=6)
+    pA, _ = S.make_animation(srcA, drv, g, me, batch=2)
+    pB, _ = S.make_animation(srcB, drv, g, me, batch=2)           # same nets, same shapes, fresh .to(device) tensor
+    pA2, _ = S.make_animation(srcA, drv, g, me, batch=2)
+    rB, _, _ = O.make_animation(weights[0], weights[1], srcB, drv, True, True)
+    assert all(np.array_equal(a, b) for a, b in zip(pA, pA2))
+    assert any(not np.array_equal(a, b) for a, b in zip(pA, pB))
+    for p, r in zip(pB, rB):
+        assert np.abs(p.astype(int) - r.astype(int)).max() <= 1
+
+
+def test_u8hwc_to_f32nchw_bit_exact(S):
+    """sma_u8hwc_to_f32nchw against the reference's host preparation (demo.py:177-185, utils/img_util.py:13-39), incl. BGR->RGB."""
+    g = torch.Generator().manual_seed(3)
+    u = torch.randint(0, 256, (3, 40, 24, 3), generator=g, dtype=torch.uint8)
+    u[0, 0, :, 0] = torch.arange(24, dtype=torch.uint8) * 10
+    ref = (torch.from_numpy(u.numpy().astype(np.float32) / 255.).permute(0, 3, 1, 2) - 0.5) / 0.5
+    got = S.ops.u8hwc_to_f32nchw(u.cuda()).cpu()
+    assert torch.equal(got, ref)
+    got = S.ops.u8hwc_to_f32nchw(u.cuda(), swap_rb=True).cpu()
+    assert torch.equal(got, ref.flip(1))
+    with pytest.raises(RuntimeError):
+        S.ops.u8hwc_to_f32nchw(u.float().cuda())
+
+
+def test_sft_epilogue_matches_unfused(S):
+    """Fuse_sft_block tail fused into the `shift.2` conv epilogue == conv -> sma_sft_combine (appmotioncodebook_arch.py:50-51), with the
+    decoder feature read in place from a channel slice."""
+    B, C, s = 2, 128, 64
+    x = rnd(B, C, s, s, seed=1); dec = rnd(B, C, s, s, seed=2); scale = rnd(B, C, s, s, seed=3)
+    w = rnd(C, C, 3, 3, seed=4, scale=(C * 9) ** -0.5); b = rnd(C, seed=5, scale=0.1)
+    cw = S.ops.pack_conv(w.cuda(), b.cuda())
+    cat = torch.zeros(B, s, s, 2 * C, device='cuda'); cat[..., C:] = nhwc(dec)
+    fused = S.ops.conv2d(nhwc(x), cw, pad=1, res=cat[..., C:], sft=(nhwc(scale), 0.7))
+    assert S.ops.LAST_CONV_KERNEL == 3
+    shift = S.ops.conv2d(nhwc(x), cw, pad=1)
+    unfused = S.ops.sft_combine(nhwc(dec), nhwc(scale), shift, 0.7)
+    assert float((fused - unfused).abs().max()) < 1e-5
+    ref = dec.double() + 0.7 * (dec.double() * scale.double() + F.conv2d(x.double(), w.double(), b.double(), padding=1))
+    assert float((nchw(fused).double() - ref).abs().max()) < 5e-5
+    with pytest.raises(RuntimeError):                                # shapes the persistent kernel cannot take: loud, not silent
+        S.ops.conv2d(nhwc(rnd(1, 3, 16, 16, seed=1)), S.ops.pack_conv(rnd(8, 3, 3, 3, seed=2).cuda(), None), pad=1,
+                     res=torch.zeros(1, 16, 16, 8, device='cuda'), sft=(torch.zeros(1, 16, 16, 8, device='cuda'), 1.0))
+
+
+def test_lazy_packing_builds_only_the_image_a_layer_uses(S):
+    w = rnd(128, 128, 3, 3, seed=1, scale=0.03)
+    cw = S.ops.pack_conv(w.cuda(), None)
+    assert not cw.images
+    S.ops.conv2d(nhwc(rnd(1, 128, 32, 32, seed=2)), cw, pad=1)
+    assert set(cw.images) == {('tc16',)} and S.ops.LAST_CONV_KERNEL == 3          # fp16 halo kernel: only its image exists
+    S.ops.conv2d(nhwc(rnd(64, 128, 4, 4, seed=3)), cw, pad=1)                      # tiny maps: gather kernel, narrowed N tile
+    assert S.ops.LAST_CONV_KERNEL == 1 and any(k[0] == 'tc' for k in cw.images)
+    ref = F.conv2d(rnd(64, 128, 4, 4, seed=3).double(), w.double(), None, padding=1)
+    got = nchw(S.ops.conv2d(nhwc(rnd(64, 128, 4, 4, seed=3)), cw, pad=1))
+    assert float((got.double() - ref).abs().max()) < 5e-5
+
+
+def test_gather_kernel_narrow_tiles_match_torch(S):
+    """Hourglass bottleneck shape (few rows, many channels): the gather kernel runs on an image packed with a narrower N tile."""
+    x = rnd(64, 512, 4, 4, seed=1); w = rnd(1024, 512, 3, 3, seed=2, scale=(512 * 9) ** -0.5); b = rnd(1024, seed=3, scale=0.1)
+    cw = S.ops.pack_conv(w.cuda(), b.cuda())
+    for fast in (False, True):
+        y = S.ops.conv2d(nhwc(x), cw, pad=1, act='relu', fast=fast)
+        assert S.ops.LAST_CONV_KERNEL == 1
+        ref = F.relu(F.conv2d(x.double(), w.double(), b.double(), padding=1))
+        err = float((nchw(y).double() - ref).abs().max())
+        assert err < (5e-3 if fast else 1e-4), (fast, err)
+    assert ('tc', 64) in cw.images, list(cw.images)
+
+
+def test_pack_cache_second_load_launches_no_pack_kernels(S, weights, tmp_path):
+    """the packed blob is persisted keyed by the state-dict hash; loading the same weights again restores it without a
+    single pack launch and gives bit-identical frames."""
+    from conftest import CFG
+    src, drv = O.synthetic_frames(2, seed=11)
+
+    def fresh():
+        g = S.build_network(CFG['network_g']); me = S.build_network(CFG['network_motion_estimator'])
+        g.load_state_dict(weights[0]); me.load_state_dict(weights[1])
+        S.enable_pack_cache(g, str(tmp_path)); S.enable_pack_cache(me, str(tmp_path))
+        return g.eval().cuda(), me.eval().cuda()
+    g1, me1 = fresh()
+    n0 = S.ops.PACK_EVENTS
+    p1, _ = S.make_animation(src, drv, g1, me1, batch=2)
+    assert S.ops.PACK_EVENTS > n0                                           # first load packs (lazily) ...
+    files = sorted(os.listdir(tmp_path))
+    assert len(files) == 3 and all(f.endswith('.smapack') for f in files)   # ... and persists: generator, key-point detector, dense motion
+    steady0 = S.ops.launch_count()
+    S.make_animation(src, drv, g1, me1, batch=2)
+    steady = S.ops.launch_count() - steady0                                 # launches of a clip with everything packed
+    g2, me2 = fresh()
+    n1, l1 = S.ops.PACK_EVENTS, S.ops.launch_count()
+    p2, _ = S.make_animation(src, drv, g2, me2, batch=2)
+    assert S.ops.PACK_EVENTS == n1                                          # no image packed
+    assert S.ops.launch_count() - l1 == steady                              # and no pack_conv_weight / codebook K,V projection launch either
+    assert all(np.array_equal(a, b) for a, b in zip(p1, p2))
+
+
+def test_make_animation_multi_matches_oracle(S, nets, weights):
+    """BASELINE configs[4] in small: 2 identities x 3 shared driving frames == demo.make_animation per identity (oracle), uint8 <= 1 level;
+    driving key-points are detected once and shared."""
+    g, me = nets
+    srcA, drv = O.synthetic_frames(3, seed=21)
+    srcB, _ = O.synthetic_frames(0, seed=22)
+    preds, drvs = S.make_animation_multi([srcA, srcB], drv, g, me, relative=True, adapt_movement_scale=True, batch=2)
+    assert len(preds) == 2 and len(preds[0]) == 3 and len(drvs) == 3
+    for s_, p in zip((srcA, srcB), preds):
+        r, _, _ = O.make_animation(weights[0], weights[1], s_, drv, True, True)
+        for a, b in zip(p, r):
+            d = np.abs(a.astype(int) - b.astype(int))
+            assert d.max() <= 1 and (d > 0).mean() < 0.01
+    single, _ = S.make_animation(srcB, drv, g, me, batch=2)
+    assert all(np.abs(a.astype(int) - b.astype(int)).max() <= 1 for a, b in zip(single, preds[1]))
+
+
+def test_result_buffers_are_not_recycled_while_referenced(S, nets):
+    g, me = nets
+    src, drv = O.synthetic_frames(2, seed=31)
+    p1, _ = S.make_animation(src, drv, g, me, batch=2)
+    keep = [a.copy() for a in p1]
+    src2, _ = O.synthetic_frames(0, seed=32)
+    p2, _ = S.make_animation(src2, drv, g, me, batch=2)                    # while p1 is alive its page-locked buffer must not be reused
+    assert all(np.array_equal(a, b) for a, b in zip(p1, keep))
+    assert any(not np.array_equal(a, b) for a, b in zip(p1, p2))
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs 2 GPUs')
+def test_second_device_in_the_same_process(S):
+    """The shared-memory opt-in and SM count are per device: a conv on cuda:1 while cuda:0 is current must work (and give the same bits)."""
+    x = rnd(2, 64, 32, 32, seed=1); w = rnd(64, 64, 3, 3, seed=2, scale=0.04)
+    y0 = S.ops.conv2d(nhwc(x), S.ops.pack_conv(w.cuda(), None), pad=1)
+    assert torch.cuda.current_device() == 0
+    x1 = x.permute(0, 2, 3, 1).contiguous().to('cuda:1')
+    y1 = S.ops.conv2d(x1, S.ops.pack_conv(w.to('cuda:1'), None), pad=1)
+    assert y1.device.index == 1 and torch.equal(y0.cpu(), y1.cpu())
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs 2 GPUs')
+def test_sharded_clip_over_two_gpus_is_bit_identical_to_one_gpu(S, nets, tmp_path):
+    """2 ranks (NCCL), each rendering its block of the clip, one all-gather: the gathered clip equals the
+    world-size-1 result bit for bit (same micro-batch)."""
+    import subprocess
+    import sys
+    from conftest import ROOT
+    g, me = nets
+    src, drv = O.synthetic_frames(8, seed=41)
+    one = S.make_animation_sharded(src, drv, g, me, batch=4).cpu()
+    out = str(tmp_path / 'clip.pt')
+    r = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2', '--master-addr', '127.0.0.1',
+                        '--master-port', '29713', os.path.join(ROOT, 'tests', 'sharded_worker.py'), out], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-3000:]
+    two = torch.load(out)
+    assert two['world'] == 2 and torch.equal(two['rank0'], one) and torch.equal(two['rank1'], one)
