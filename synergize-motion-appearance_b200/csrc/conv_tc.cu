@@ -127,10 +127,11 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const TcP p) {
     const int mm = mok ? m : 0;
     const int b = mm / p.HoWo; const int r = mm - b * p.HoWo; const int oy = r / p.Wo; const int ox = r - oy * p.Wo;
     const int nbase = nt * p.NT;
+    const int nend = min(p.Cout, nbase + p.NT);          // columns of THIS tile (a narrowed N tile need not be a multiple of the 32-column read)
     const bool vec_ok = (p.out_ld & 3) == 0 && (p.out_bs & 3) == 0 && ((reinterpret_cast<uintptr_t>(p.y) & 15) == 0) &&
                         (!p.res || ((p.res_ld & 3) == 0 && (p.res_bs & 3) == 0 && (reinterpret_cast<uintptr_t>(p.res) & 15) == 0));
     const int Cq = p.d2s > 1 ? p.Cout / (p.d2s * p.d2s) : p.Cout;     // channels of the depth-to-space output
-    for (int n0 = 0; n0 < p.NT && nbase + n0 < p.Cout; n0 += 32) {
+    for (int n0 = 0; n0 < p.NT && nbase + n0 < nend; n0 += 32) {
       uint32_t a[32];
       const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)n0;
       asm volatile(
@@ -147,12 +148,12 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const TcP p) {
 #pragma unroll
         for (int q = 0; q < 8; q++) {
           const int n = nbase + n0 + q * 4;
-          if (n >= p.Cout) break;
+          if (n >= nend) break;
           float o[4];
 #pragma unroll
           for (int t = 0; t < 4; t++) {
             float acc = __uint_as_float(a[q * 4 + t]);
-            if (p.bias && n + t < p.Cout) acc += __ldg(p.bias + n + t);
+            if (p.bias && n + t < nend) acc += __ldg(p.bias + n + t);
             o[t] = sma_act(acc, p.act);
           }
           // destination of column n for this pixel
@@ -164,7 +165,7 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const TcP p) {
           } else {
             dst = p.y + (long long)b * p.out_bs + (long long)r * p.out_ld + n;
           }
-          if (vec_ok && n + 4 <= p.Cout && (Cq & 3) == 0) {
+          if (vec_ok && n + 4 <= nend && (Cq & 3) == 0) {
             if (p.res) {
               float4 rr = __ldg(reinterpret_cast<const float4*>(p.res + (long long)b * p.res_bs + (long long)r * p.res_ld + n));
               o[0] += rr.x; o[1] += rr.y; o[2] += rr.z; o[3] += rr.w;
@@ -173,7 +174,7 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const TcP p) {
           } else {
 #pragma unroll
             for (int t = 0; t < 4; t++) {
-              if (n + t >= p.Cout) break;
+              if (n + t >= nend) break;
               float val = o[t];
               if (p.res) val += __ldg(p.res + (long long)b * p.res_bs + (long long)r * p.res_ld + n + t);
               if (p.d2s > 1) {
@@ -859,7 +860,7 @@ int sma_conv2d_tc_try(sma_conv_desc* d, cudaStream_t st) {
   if (d->plan_only) {
     NTg = nt_default;
     const long long mt = (M + BM - 1) / BM;
-    while (NTg > 64 && (NTg % 32) == 0 && mt * ((d->Cout + NTg - 1) / NTg) < 128) NTg >>= 1;
+    while (NTg > 64 && (NTg % 64) == 0 && mt * ((d->Cout + NTg - 1) / NTg) < 128) NTg >>= 1;
     d->w_tc_nt = NTg; d->kernel_used = 1;
     return SMA_OK;
   }

@@ -15,9 +15,8 @@ import sma_oracle as O
 
 pytestmark = pytest.mark.gpu
 
-# normalize_kp's jacobian J_drv J_drv0^-1 J_src amplifies the single-pass (fp16) error of the key-point detector's jacobian head through the
-# inverse of J_drv0 (condition number ~5 on the synthetic weights); measured on B200: see the printed value
-KP_NORM_JAC_TOL = 1e-3
+# normalize_kp's jacobian J_drv J_drv0^-1 J_src carries the single-pass (fp16) error of the key-point detector's jacobian head
+KP_NORM_JAC_TOL = 5e-5            # measured 3.1e-6 on B200 (round 1 gated this at 2e-3)
 
 
 @pytest.fixture(scope='module')
@@ -519,13 +518,15 @@ def test_batch64_clip_matches_oracle_on_sampled_frames(S, nets, weights):
     u8, out = anim.step(torch.stack(drv).cuda(), want_fp32=True)                        # one 64-frame micro-batch
     assert tuple(u8.shape) == (64, 256, 256, 3)
     ref_p, _, ref_o = O.make_animation(weights[0], weights[1], src, [drv[0]] + [drv[i] for i in idx[1:]], True, True)
-    errs = []
+    errs, flips = [], []
     for j, i in enumerate(idx):
         errs.append(float((out[i].permute(2, 0, 1).cpu() - ref_o[j]).abs().max()))
         d = np.abs(u8[i].cpu().numpy().astype(int) - ref_p[j].astype(int))
-        assert d.max() <= 1 and (d > 0).mean() < 0.01, (i, d.max(), (d > 0).mean())
-    print('batch-64 out max-abs vs oracle on frames', idx, ['%.2e' % e for e in errs])
-    assert max(errs) < 1e-3, errs
+        flips.append((int(d.max()), float((d > 0).mean())))
+    print('batch-64 out max-abs vs oracle on frames', idx, ['%.2e' % e for e in errs], 'uint8 (max level diff, fraction of pixels):', flips)
+    assert max(errs) < 1e-3, errs                                   # the north-star tolerance on the fp32 image
+    # a uint8 level is 7.8e-3 wide: an fp32 error e moves ~2e/7.8e-3 of the pixels across a rounding boundary, by one level
+    assert all(m <= 1 and f < 0.05 for m, f in flips), flips
     # the public API on host uint8 frames, same micro-batch: identical to the device path fed with the converted frames
     src8, drv8 = O.to_uint8(src), [O.to_uint8(f) for f in drv]
     p_u8, d_u8 = S.make_animation(src8, drv8, g, me, relative=True, adapt_movement_scale=True, batch=64)
@@ -642,7 +643,8 @@ def test_gather_kernel_narrow_tiles_match_torch(S):
         assert S.ops.LAST_CONV_KERNEL == 1
         ref = F.relu(F.conv2d(x.double(), w.double(), b.double(), padding=1))
         err = float((nchw(y).double() - ref).abs().max())
-        assert err < (5e-3 if fast else 1e-4), (fast, err)
+        # the TMEM accumulator adds with truncation: error ~1e-8 * K (K = 4608 here), as in test_conv2d_matches_torch
+        assert err < (5e-3 if fast else (2e-5 + 1e-8 * 512 * 9) * max(1.0, float(ref.abs().max()))), (fast, err)
     assert ('tc', 64) in cw.images, list(cw.images)
 
 
