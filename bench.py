@@ -249,7 +249,8 @@ def main():
         """Inputs resident in HBM.  `gather=False`: the collective-free variant used by the rank-0-only roofline pass."""
         clear_caches()
         for si, s_d in enumerate(srcs_d):
-            anim = S.ClipAnimator(g, me, s_d, first_d, True, True, 1.0)
+            # the clip's first driving frame fixes kp_driving_initial: on rank 0 of a single-identity clip it is frame 0 of the first micro-batch
+            anim = S.ClipAnimator(g, me, s_d, first_d if (rank > 0 or nsrc_total) else None, True, True, 1.0)
             for i0 in range(0, T, Bm):
                 clip_u8[si * T + i0:si * T + i0 + Bm] = anim.step(drv_d[i0:i0 + Bm])
         if world > 1 and gather:

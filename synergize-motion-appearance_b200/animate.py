@@ -80,8 +80,9 @@ class ClipAnimator:
     batched per-frame step.  `make_animation` is a thin loop over `step`.
 
     `driving_initial=None`: the first frame of the first `step` is the initial driving frame (what demo.make_animation does:
-    kp_driving_initial = kp_detector(driving_video[0])); the source then rides in that step's key-point pass too (one batch of
-    B+1 frames instead of a separate batch-2 pass through the weight-streaming-bound hourglass bottleneck)."""
+    kp_driving_initial = kp_detector(driving_video[0])).  Either way the source (and an explicit initial frame) ride in the key-point
+    pass of the first `step` (one batch of B+1 / B+2 frames instead of a separate batch-2 pass through the weight-streaming-bound
+    hourglass bottleneck)."""
 
     def __init__(self, net_g, motion_estimator, source: torch.Tensor, driving_initial: Optional[torch.Tensor] = None, relative=True,
                  adapt_movement_scale=True, w: float = 1.0):
@@ -92,16 +93,25 @@ class ClipAnimator:
         self.adapt = adapt_movement_scale
         self.source = source.contiguous().float()
         self.kp_source = self.kp_initial = self.scale = None
+        self._initial = None if driving_initial is None else driving_initial.contiguous().float()
         with torch.no_grad():
             self.feats = self.net_g.encode_source(self.source)
             self.me.dense_motion_network.source_down(self.source)
-            if driving_initial is not None:
-                kp2 = self.me.estimate_kp(torch.cat([self.source, driving_initial.contiguous().float()], dim=0))
-                self._set_clip_kp({k: v[0:1].contiguous() for k, v in kp2.items()}, {k: v[1:2].contiguous() for k, v in kp2.items()})
 
     def _set_clip_kp(self, kp_source, kp_initial):
         self.kp_source, self.kp_initial = kp_source, kp_initial
         self.scale = (ops.hull_scale(kp_source['value'], kp_initial['value']) if (self.adapt and self.relative) else 1.0)
+
+    @torch.no_grad()
+    def clip_keypoints(self):
+        """(kp_source, kp_initial, movement scale), computing them now if no `step` has run yet (needs an explicit initial frame)."""
+        if self.kp_source is None:
+            if self._initial is None:
+                raise RuntimeError('clip_keypoints() before the first step needs driving_initial')
+            kp = self.me.estimate_kp(torch.cat([self.source, self._initial], dim=0))
+            self._set_clip_kp({k: v[0:1].contiguous() for k, v in kp.items()}, {k: v[1:2].contiguous() for k, v in kp.items()})
+            self._initial = None
+        return self.kp_source, self.kp_initial, self.scale
 
     @torch.no_grad()
     def detect(self, frames: torch.Tensor) -> Dict[str, torch.Tensor]:
@@ -114,13 +124,17 @@ class ClipAnimator:
         `kp_driving`: precomputed `detect(frames)`."""
         B = frames.shape[0]
         if self.kp_source is None:
+            extra = [self.source] + ([self._initial] if self._initial is not None else [])
+            ne = len(extra)
             if kp_driving is None:
-                kp = self.me.estimate_kp(torch.cat([self.source, frames], dim=0))
-                kp_driving = {k: v[1:] for k, v in kp.items()}
+                kp = self.me.estimate_kp(torch.cat(extra + [frames], dim=0))
+                kp_driving = {k: v[ne:] for k, v in kp.items()}
                 self._set_clip_kp({k: v[0:1].contiguous() for k, v in kp.items()}, {k: v[1:2].contiguous() for k, v in kp.items()})
             else:
-                kp_s = self.me.estimate_kp(self.source)
-                self._set_clip_kp(kp_s, {k: v[0:1].contiguous() for k, v in kp_driving.items()})
+                kp = self.me.estimate_kp(torch.cat(extra, dim=0))
+                self._set_clip_kp({k: v[0:1].contiguous() for k, v in kp.items()},
+                                  {k: (v[1:2] if ne == 2 else kp_driving[k][0:1]).contiguous() for k, v in kp.items()})
+            self._initial = None
         kp_d = self.me.estimate_kp(frames) if kp_driving is None else kp_driving
         kp_n = normalize_kp(self.kp_source, kp_d, self.kp_initial, adapt_movement_scale=self.adapt,
                             use_relative_movement=self.relative, use_relative_jacobian=self.relative, _scale=self.scale)
