@@ -97,6 +97,9 @@ class ClockSampler:
 
 
 def workload_text(args, world):
+    if args.size == 512:
+        return (f'512x512 variant (token grid 64x64; no reference behaviour at 512: parity unpinned by the reference), {args.frames} synthetic driving '
+                f'frames per GPU on {world} GPU(s) (BASELINE configs[3])')
     if args.sources:
         return (f'{args.sources} source identities x {args.frames} shared synthetic driving frames, cross-reenactment batch (BASELINE configs[4]), '
                 f'identities partitioned over {world} GPU(s)')
@@ -178,7 +181,8 @@ def main():
     ap.add_argument('--frames', type=int, default=64, help='driving frames per GPU per step (configs[1]: 64)')
     ap.add_argument('--clip-frames', type=int, default=0, help='TOTAL driving frames of the clip, sharded over the ranks (configs[2]: 1024); overrides --frames')
     ap.add_argument('--sources', type=int, default=0, help='configs[4]: this many source identities share the --frames driving frames; identities are partitioned over the ranks')
-    ap.add_argument('--batch', type=int, default=64, help='driving frames per micro-batch')
+    ap.add_argument('--batch', type=int, default=0, help='driving frames per micro-batch (default 64; 32 at --size 512)')
+    ap.add_argument('--size', type=int, default=256, choices=[256, 512], help='image size: 512 = the 512x512 variant of BASELINE configs[3] (use with --frames 256)')
     ap.add_argument('--ref-frames', type=int, default=12, help='frames per step of the CPU reference / cpu_baseline sample')
     ap.add_argument('--device', default='cpu', choices=['cpu', 'cuda'], help='--impl reference: where the oracle port runs')
     ap.add_argument('--tf32', action='store_true', help='--impl reference --device cuda: leave cudnn.allow_tf32 at the PyTorch default (True)')
@@ -212,6 +216,10 @@ def main():
         if args.clip_frames % world:
             raise SystemExit('--clip-frames must be a multiple of the number of ranks')
         args.frames = args.clip_frames // world
+    global H, W
+    H = W = args.size
+    if not args.batch:
+        args.batch = 64 if args.size == 256 else 32
     T, Bm, K, Wm = args.frames, args.batch, args.steps, max(3, args.warmup)
     nsrc_total = args.sources
     if nsrc_total and nsrc_total % world:
@@ -219,19 +227,20 @@ def main():
     nsrc = nsrc_total // world if nsrc_total else 1
 
     CFG = net_cfg()
+    CFG['network_g']['img_size'] = args.size
     g = S.build_network(CFG['network_g']); me = S.build_network(CFG['network_motion_estimator'])
-    g.load_state_dict(O.synthetic_state_dict(CFG_KEYS['net_g'], 0)); me.load_state_dict(O.synthetic_state_dict(CFG_KEYS['motion_estimator'], 1))
+    g.load_state_dict(O.synthetic_state_dict(O.variant_shapes(CFG_KEYS['net_g'], args.size), 0)); me.load_state_dict(O.synthetic_state_dict(CFG_KEYS['motion_estimator'], 1))
     g, me = g.eval().to(dev), me.eval().to(dev)
     if nsrc_total:
         # configs[4]: every rank animates its own identities over the SAME T driving frames
-        src0, drv_all = O.synthetic_frames(T, seed=1234)
+        src0, drv_all = O.synthetic_frames(T, seed=1234, size=args.size)
         my_ids = S.dist.shard_sources(nsrc_total, rank, world)
-        srcs = [src0 if i == 0 else O.synthetic_frames(0, seed=1234 + i)[0] for i in my_ids]
+        srcs = [src0 if i == 0 else O.synthetic_frames(0, seed=1234 + i, size=args.size)[0] for i in my_ids]
         drv, first = drv_all, drv_all[0]
         n_clip = T
     else:
         # rank r owns frames [r*T, (r+1)*T) of the N*T-frame clip (same source on every rank)
-        src0, drv_all = O.synthetic_frames(world * T, seed=1234)
+        src0, drv_all = O.synthetic_frames(world * T, seed=1234, size=args.size)
         srcs = [src0]
         drv, first = drv_all[rank * T:(rank + 1) * T], drv_all[0]
         n_clip = world * T
@@ -393,9 +402,9 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
         torch.set_num_threads(threads)
-        n = max(2, min(T, args.ref_frames))
-        P_g, P_me = O.synthetic_state_dict(CFG_KEYS['net_g'], 0), O.synthetic_state_dict(CFG_KEYS['motion_estimator'], 1)
-        s_, d_ = O.synthetic_frames(n + 1, seed=1234)
+        n = max(2, min(T, args.ref_frames if args.size == 256 else 3))
+        P_g, P_me = O.synthetic_state_dict(O.variant_shapes(CFG_KEYS['net_g'], args.size), 0), O.synthetic_state_dict(CFG_KEYS['motion_estimator'], 1)
+        s_, d_ = O.synthetic_frames(n + 1, seed=1234, size=args.size)
         oracle_clip(O, P_g, P_me, s_, d_[:1], 'cpu')            # warm-up frame
         dt = oracle_clip(O, P_g, P_me, s_, d_[1:], 'cpu')
         cpu = {'value': n / dt, 'unit': 'frames/s', 'cores': threads, 'kind': 'port',
@@ -403,7 +412,7 @@ def main():
                          f'{threads} threads, {dt:.1f} s'}
 
     if rank == 0:
-        line = {'metric': '256x256 frames/sec', 'value': fps, 'unit': 'frames/s', 'n_gpus': world, 'steps': K, 'warmup': Wm,
+        line = {'metric': f'{args.size}x{args.size} frames/sec', 'value': fps, 'unit': 'frames/s', 'n_gpus': world, 'steps': K, 'warmup': Wm,
                 'ms_per_step': ms / K, 'higher_is_better': True, 'scaling': 'strong' if args.clip_frames or nsrc_total else 'weak', 'vs_baseline': None,
                 'dtype': DTYPE, 'data': 'synthetic',
                 'config': {'workload': workload_text(args, world),

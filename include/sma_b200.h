@@ -89,7 +89,8 @@ typedef struct sma_conv_desc {
                                     the persistent halo kernel for stride 1, else the gather kernel); bit 0: force the gather kernel; bits 1-3:
                                     timing experiments (results invalid): no weight loads / no halo loads / no epilogue; bit 4: tensor-memory-
                                     operand kernel streams its weights through the ring even when they would fit; bit 5: allow its 128-pixel streaming ring; bit 6:
-                                    force that ring; bit 7: halo kernel issues three separate MMAs per k-step instead of the fused [hi | lo] weight tile */
+                                    force that ring; bit 7: halo kernel issues three separate MMAs per k-step instead of the fused [hi | lo] weight tile;
+                                    bit 8: no accumulation-bias correction in the fp16 halo kernel's epilogue */
   int kernel_used;               /* OUT: 0 CUDA-core FFMA kernel, 1 tcgen05 tf32 gather kernel, 2 tcgen05 tf32 persistent halo kernel,
                                     3 tcgen05 fp16 persistent halo kernel, 4 tcgen05 fp16 kernel with the weights in tensor memory */
   int w_tc_nt;                   /* IN: output-channel tile the tf32 image `w_tc` was packed with (0 = the default, min(256, Cout rounded up to 16));

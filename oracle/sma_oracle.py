@@ -255,7 +255,7 @@ def encode_source(P: SD, x: T) -> Dict[str, T]:
         x = run_block(P, kind, f'encoder.blocks.{i}', x)
         if i in (2, 5, 8):
             feats[str(x.shape[-1])] = x
-    feats['32'] = x
+    feats[str(x.shape[-1])] = x          # the latent: '32' at 256x256, '64' for the 512x512 variant
     return feats
 
 
@@ -285,14 +285,16 @@ def mha(P: SD, name: str, q: T, k: T, v: T, n_head: int, key_padding_mask: Optio
 
 def transformer_layer(P: SD, name: str, t: T, ctx: T, pos: T, n_head: int = 8,
                       key_padding_mask: Optional[T] = None) -> T:
-    """archs/appmotioncodebook_arch.py:88-126.  t,pos:(1024,B,E)  ctx:(K,B,E)."""
+    """archs/appmotioncodebook_arch.py:88-126.  t,pos:(L,B,E) with L = 1024 tokens on a 32x32 grid (4096 on 64x64 for the 512x512
+    variant)  ctx:(K,B,E)."""
     L, B, E = t.shape
+    tg = int(round(math.sqrt(L)))
     u = F.layer_norm(t, (E,), P[name + '.norm1.weight'], P[name + '.norm1.bias'])
     t = t + mha(P, name + '.self_attn', u + pos, u + pos, u, n_head, key_padding_mask)
     u = F.layer_norm(t, (E,), P[name + '.norm2.weight'], P[name + '.norm2.bias'])
     t = t + mha(P, name + '.cross_attn', u + pos, ctx, ctx, n_head)
     u = F.layer_norm(t, (E,), P[name + '.norm3.weight'], P[name + '.norm3.bias'])
-    u = u.permute(1, 2, 0).reshape(B, E, 32, 32)
+    u = u.permute(1, 2, 0).reshape(B, E, tg, tg)
     u = conv(P, name + '.conv2', F.gelu(conv(P, name + '.conv1', u, padding=1)), padding=1)
     return t + u.reshape(B, E, L).permute(2, 0, 1)
 
@@ -318,6 +320,13 @@ def vq_lookup(codebook: T, z: T, scale: Optional[float] = None):
 # ----------------------------------------------------------------------------------------------
 
 SCALE_K = {32: 1, 64: 2, 128: 3, 256: 4}
+
+# The 512x512 variant (BASELINE configs[3]; SURVEY.md 8d "Config 4").  The reference itself cannot run it: its 32x32 token grid,
+# position_emb (1024,E) and resolution-keyed module names are hard-coded.  The variant defined there is the direct generalisation: the same
+# layer graph and weight shapes except position_emb_* (4096,E); every spatial size doubles (token grid 64x64, flow / occlusion grid 128x128,
+# feature scales 64..512) while module names and codebook prefixes keep their 256x256 ("nominal") scale s0 = s / R, R = image size / 256.
+# Everything below infers R from the tensors it is given (flow grid = 64 R), so the 256x256 path is untouched.  PARITY UNPINNED BY THE
+# REFERENCE at 512: this restatement is proven equal to the reference at 256 (oracle/make_golden.py) and is then run at 512.
 
 
 def warp_ac(feat: T, deformation: T) -> T:
@@ -346,12 +355,14 @@ def motion_compensation(P: SD, flow_px: T, qfeat: T, warp0: T, s: int) -> T:
     mf = res_block(P, 'motion_emb.2', mf)                                          # (B,32,32,32)
     q = conv(P, 'motion_query_enc_2', torch.cat([mf, resize_ac(qfeat, mf.shape[-2:])], dim=1))
     E = q.shape[1]
-    t = q.reshape(b, E, 1024).permute(2, 0, 1)
+    R = h // 64                                                                    # 1 at 256x256, 2 for the 512x512 variant
+    s0, tg = s // R, mf.shape[-1]                                                  # nominal scale (names, codebook prefix), token grid
+    t = q.reshape(b, E, tg * tg).permute(2, 0, 1)
     pos = P['position_emb_motion'].unsqueeze(1).expand(-1, b, -1)
-    ctx = P['quantize_motion.embedding.weight'][:256 * SCALE_K[s]].unsqueeze(1).expand(-1, b, -1)
+    ctx = P['quantize_motion.embedding.weight'][:256 * SCALE_K[s0]].unsqueeze(1).expand(-1, b, -1)
     for i in range(2):
         t = transformer_layer(P, f'motion_block.{i}', t, ctx, pos)
-    mfeat = resize_ac(t.permute(1, 2, 0).reshape(b, E, 32, 32), (h, w))
+    mfeat = resize_ac(t.permute(1, 2, 0).reshape(b, E, tg, tg), (h, w))
     # BasicMotionEncoder
     cor = F.relu(conv(P, 'BasicMotionEncoder.convc1', mfeat))
     cor = F.relu(conv(P, 'BasicMotionEncoder.convc2', cor, padding=1))
@@ -359,7 +370,7 @@ def motion_compensation(P: SD, flow_px: T, qfeat: T, warp0: T, s: int) -> T:
     flo = F.relu(conv(P, 'BasicMotionEncoder.convf2', flo, padding=1))
     mo = F.relu(conv(P, 'BasicMotionEncoder.conv', torch.cat([cor, flo], dim=1), padding=1))
     m_f = torch.cat([mo, m], dim=1)                                                # 128 ch
-    ctxf = F.relu(conv(P, f'to_context.{int(math.log2(s)) - 5}', warp0))
+    ctxf = F.relu(conv(P, f'to_context.{int(math.log2(s0)) - 5}', warp0))
     ctxf = resize_ac(ctxf, (h, w))
     # RefineFlow
     c = F.relu(conv(P, 'refine.convc1', ctxf, padding=1))
@@ -372,23 +383,26 @@ def motion_compensation(P: SD, flow_px: T, qfeat: T, warp0: T, s: int) -> T:
 def app_compensation(P: SD, feat: T, m_com: T) -> T:
     """app_codebook_compensation (appmotioncodebook_arch.py:472-544), split=1, shared prefixes."""
     b, c, s, _ = feat.shape
-    m32 = resize_ac(m_com.permute(0, 3, 1, 2), (32, 32)).reshape(b, 2, 1024)
-    ignore = ((m32 > 1) | (m32 < -1)).any(dim=1)                                   # (B,1024) bool
-    if s == 32:
-        tok = conv(P, 'app_feat_emb_32', feat).reshape(b, 256, 1024).permute(2, 0, 1)
+    R = m_com.shape[1] // 64
+    s0, tg = s // R, 32 * R                                                        # nominal scale, token grid (32x32; 64x64 at 512x512)
+    L = tg * tg
+    m32 = resize_ac(m_com.permute(0, 3, 1, 2), (tg, tg)).reshape(b, 2, L)
+    ignore = ((m32 > 1) | (m32 < -1)).any(dim=1)                                   # (B,L) bool
+    if s0 == 32:
+        tok = conv(P, 'app_feat_emb_32', feat).reshape(b, 256, L).permute(2, 0, 1)
     else:
-        p = s // 32
-        x = feat.view(b, c, 32, p, 32, p).permute(0, 2, 4, 3, 5, 1).reshape(b, 1024, p * p * c)
-        tok = F.linear(x, P[f'app_feat_emb_{s}.1.weight'], P[f'app_feat_emb_{s}.1.bias']).permute(1, 0, 2)
+        p = s0 // 32
+        x = feat.view(b, c, tg, p, tg, p).permute(0, 2, 4, 3, 5, 1).reshape(b, L, p * p * c)
+        tok = F.linear(x, P[f'app_feat_emb_{s0}.1.weight'], P[f'app_feat_emb_{s0}.1.bias']).permute(1, 0, 2)
     pos = P['position_emb_app'].unsqueeze(1).expand(-1, b, -1)
-    ctx = P['quantize_app.embedding.weight'][:256 * SCALE_K[s]].unsqueeze(1).expand(-1, b, -1)
+    ctx = P['quantize_app.embedding.weight'][:256 * SCALE_K[s0]].unsqueeze(1).expand(-1, b, -1)
     tok = transformer_layer(P, 'app_block.0', tok, ctx, pos, key_padding_mask=ignore)
     tok = transformer_layer(P, 'app_block.1', tok, ctx, pos)
-    if s == 32:
-        return conv(P, 'to_app_feat_32', tok.permute(1, 2, 0).reshape(b, 256, 32, 32))
-    y = F.linear(tok.permute(1, 0, 2), P[f'to_app_feat_{s}.0.weight'], P[f'to_app_feat_{s}.0.bias'])
-    p = s // 32
-    return y.view(b, 32, 32, p, p, c).permute(0, 5, 1, 3, 2, 4).reshape(b, c, s, s)
+    if s0 == 32:
+        return conv(P, 'to_app_feat_32', tok.permute(1, 2, 0).reshape(b, 256, tg, tg))
+    y = F.linear(tok.permute(1, 0, 2), P[f'to_app_feat_{s0}.0.weight'], P[f'to_app_feat_{s0}.0.bias'])
+    p = s0 // 32
+    return y.view(b, tg, tg, p, p, c).permute(0, 5, 1, 3, 2, 4).reshape(b, c, s, s)
 
 
 def sft_fuse(P: SD, name: str, enc: T, dec: T, w: float) -> T:
@@ -421,12 +435,14 @@ def generator_forward(P: SD, src_feats: Dict[str, T], dm: Dict[str, T], w: float
     half = (hs - 1.) / 2.
     motions = [deformation]
     occs: List[T] = []
-    kp_feat = F.relu(conv(P, 'driving_kp_enc', resize_ac(dm['driving_kp_heatmap'], (32, 32))))
+    R = hs // 64
+    tg = 32 * R
+    kp_feat = F.relu(conv(P, 'driving_kp_enc', resize_ac(dm['driving_kp_heatmap'], (tg, tg))))
 
     def compensate(feat_s: T, s: int, occ_prev: T):
         m_prev = motions[-1]
         warp0 = warp_ac(feat_s, m_prev)
-        ws_ = F.relu(conv(P, f'warped_source_enc_{s}', resize_ac(warp0, (32, 32))))
+        ws_ = F.relu(conv(P, f'warped_source_enc_{s // R}', resize_ac(warp0, (tg, tg))))
         qf = conv(P, 'motion_query_enc_1', torch.cat([ws_, kp_feat], dim=1))
         res = motion_compensation(P, (m_prev - grid) * half, qf, warp0, s)
         m_com = m_prev + res[..., 0:2] / half
@@ -442,17 +458,17 @@ def generator_forward(P: SD, src_feats: Dict[str, T], dm: Dict[str, T], w: float
             collect[f'app_{s}'] = out
         return out
 
-    x = compensate(src_feats['32'], 32, dm['occlusion_map'])
+    x = compensate(src_feats[str(tg)], tg, dm['occlusion_map'])
     lq_feat = x
     for i, kind in enumerate(GENERATOR_BLOCKS):
         x = run_block(P, kind, f'generator.blocks.{i}', x)
         if i in (9, 12, 15) and w > 0:
             s = x.shape[-1]
             enc = compensate(src_feats[str(s)], s, occs[-1])
-            x = sft_fuse(P, f'fuse_convs_dict.{s}', enc, x, w)
+            x = sft_fuse(P, f'fuse_convs_dict.{s // R}', enc, x, w)
             if collect is not None:
                 collect[f'sft_{s}'] = x
-            x = x + conv(P, f'fuse_ms_dict.{s}', enc, padding=1)
+            x = x + conv(P, f'fuse_ms_dict.{s // R}', enc, padding=1)
             if collect is not None:
                 collect[f'fused_{s}'] = x
     return {'out': x, 'lq_feat': lq_feat, 'out_occ': occs, 'deformation_list': motions}
@@ -567,3 +583,14 @@ def synthetic_frames(n_driving: int, seed: int = 1234, size: int = 256, smooth: 
     src = frame()
     drv = [frame() for _ in range(n_driving)]
     return src, drv
+
+
+def variant_shapes(shapes: Dict[str, List[int]], img_size: int = 256) -> Dict[str, List[int]]:
+    """State-dict inventory of the `img_size` variant: identical to the reference's (tests/golden/state_keys.json) except the position
+    embeddings, which have one row per token of the (img_size/8)^2 grid (Config 4)."""
+    tg = img_size // 8
+    out = {k: list(v) for k, v in shapes.items()}
+    for k in ('position_emb_app', 'position_emb_motion'):
+        if k in out:
+            out[k] = [tg * tg, out[k][1]]
+    return out

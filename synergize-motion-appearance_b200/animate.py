@@ -139,7 +139,7 @@ class ClipAnimator:
         kp_n = normalize_kp(self.kp_source, kp_d, self.kp_initial, adapt_movement_scale=self.adapt,
                             use_relative_movement=self.relative, use_relative_jacobian=self.relative, _scale=self.scale)
         dm = self.me.estimate_motion_w_kp(kp_source=self.kp_source, kp_driving=kp_n, source_image=self.source)
-        r = self.net_g.generate(self.feats, dm['deformation'], dm['occlusion_map'].view(B, 64, 64),
+        r = self.net_g.generate(self.feats, dm['deformation'], dm['occlusion_map'].view(B, *dm['deformation'].shape[1:3]),
                                 dm['_driving_kp_heatmap_nhwc'], self.w)
         u8 = ops.to_uint8(r['out'], bgr)
         return (u8, r['out']) if want_fp32 else u8

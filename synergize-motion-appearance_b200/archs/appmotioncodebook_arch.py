@@ -90,7 +90,7 @@ class AppMotionCompFormer(ParamModule):
                  wo_motion_cdbk_share=False, wo_app_cdbk_share=False, connect_list=['64', '128', '256'],
                  connect_app_list=['32', '64', '128', '256'], fix_modules=[], ae_path=None):
         super().__init__()
-        supported = (img_size == 256 and nf == 64 and list(ch_mult) == [1, 2, 2, 4] and res_blocks == 2 and
+        supported = (img_size in (256, 512) and nf == 64 and list(ch_mult) == [1, 2, 2, 4] and res_blocks == 2 and
                      list(attn_resolutions) == [32] and quantizer_type == 'nearest' and split == 1 and with_position_emb and
                      warp_s_d_kp_query and MRFA_motion_enc and motion_codebook_split and multiscale_feature_fusion and
                      multiscale_sft and app_codebook_split and not wo_motion_cdbk_share and not wo_app_cdbk_share and
@@ -100,17 +100,23 @@ class AppMotionCompFormer(ParamModule):
                      codebook_size_app % 4 == 0 and codebook_size_motion % 4 == 0 and
                      codebook_size_app // 4 % 64 == 0 and codebook_size_motion // 4 % 8 == 0)
         if not supported:
-            raise NotImplementedError('B200 AppMotionCompFormer implements the options/test.yml configuration only')
+            raise NotImplementedError('B200 AppMotionCompFormer implements the options/test.yml configuration (and its 512x512 variant) only')
         self.beta, self.n_head, self.num_kp = beta, n_head, num_kp
         self.Ea, self.Em = dim_embd_app, dim_embd_motion
         self.n_codes_app, self.n_codes_motion = codebook_size_app, codebook_size_motion
-        self.channels = {32: 256, 64: 128, 128: 128, 256: 64}
+        # 512x512 variant (BASELINE configs[3]; SURVEY.md 8d "Config 4"; the reference itself crashes at 512): the same layer graph and weight
+        # shapes except position_emb_* (one row per token), every spatial size scaled by R = img_size / 256 (token grid 32R, flow / occlusion
+        # grid 64R, feature scales 32R..256R); module names and codebook prefixes keep their NOMINAL 256x256 scale s0 = s / R.
+        self.img_size, self.R = img_size, img_size // 256
+        self.tg, self.fg = 32 * self.R, 64 * self.R               # token grid, flow / occlusion grid
+        self.L = self.tg * self.tg
+        self.channels = {32: 256, 64: 128, 128: 128, 256: 64}      # keyed by nominal scale
         self.connect_list, self.connect_app_list = list(connect_list), list(connect_app_list)
         self.fuse_encoder_block = {'256': 2, '128': 5, '64': 8, '32': 11}
         self.fuse_generator_block = {'32': 6, '64': 9, '128': 12, '256': 15}
-        self.enc_layout, latent_c = _encoder_layout(nf, ch_mult, res_blocks, img_size, attn_resolutions)
+        self.enc_layout, latent_c = _encoder_layout(nf, ch_mult, res_blocks, 256, attn_resolutions)      # (attention blocks sit at the latent scale)
         self.enc_layout.append(('conv', latent_c, 256))
-        self.gen_layout = _generator_layout(nf, ch_mult, res_blocks, img_size, attn_resolutions, 256)
+        self.gen_layout = _generator_layout(nf, ch_mult, res_blocks, 256, attn_resolutions, 256)
         self._declare_all()
         gen = self._modules['generator']
         gen.__class__ = _PlainDecoder
@@ -180,8 +186,8 @@ class AppMotionCompFormer(ParamModule):
                 self.declare_conv(f'fuse_convs_dict.{s}.{br}.0', c, c, 3)
                 self.declare_conv(f'fuse_convs_dict.{s}.{br}.2', c, c, 3)
             self.declare_conv(f'fuse_ms_dict.{s}', c, c, 3)
-        self.declare('position_emb_app', (1024, Ea), lambda t: t.zero_())                      # :266-267
-        self.declare('position_emb_motion', (1024, Em), lambda t: t.zero_())
+        self.declare('position_emb_app', (self.L, Ea), lambda t: t.zero_())                      # :266-267 (1024 rows at 256x256)
+        self.declare('position_emb_motion', (self.L, Em), lambda t: t.zero_())
         self.declare('quantize_motion.embedding.weight', (self.n_codes_motion, Em),
                      lambda t: t.uniform_(-1.0 / self.n_codes_motion, 1.0 / self.n_codes_motion))
         self.declare_conv('motion_emb.0', Em, 2, 3)
@@ -340,7 +346,7 @@ class AppMotionCompFormer(ParamModule):
 
     @torch.no_grad()
     def encode_source(self, x: torch.Tensor) -> Dict[int, torch.Tensor]:
-        """x (N,3,256,256) NCHW -> {256,128,64,32: NHWC features}.  Cached on the tensor OBJECT (which the cache entry keeps
+        """x (N,3,H,W) NCHW -> {H, H/2, H/4, H/8: NHWC features} (256, 128, 64, 32 at 256x256).  Cached on the tensor OBJECT (which the cache entry keeps
         alive, so that its address cannot be recycled for another clip's source) and its in-place version counter."""
         self._weights()
         c = self._src_cache
@@ -352,7 +358,7 @@ class AppMotionCompFormer(ParamModule):
             h = self._block('encoder', i, self.enc_layout, h)
             if i in (2, 5, 8):
                 feats[h.shape[2]] = h
-        feats[32] = h
+        feats[h.shape[2]] = h
         self._src_cache = (x, x._version, feats)
         return feats
 
@@ -382,7 +388,8 @@ class AppMotionCompFormer(ParamModule):
         W, T = self._packed, self._T
         B = t.shape[0]
         u, uq = ops.layernorm(t, T[name + '.norm1.weight'], T[name + '.norm1.bias'], pos)
-        qkv = torch.empty((B, 1024, 3 * E), device=t.device, dtype=torch.float32)
+        L, tg = self.L, self.tg
+        qkv = torch.empty((B, L, 3 * E), device=t.device, dtype=torch.float32)
         ops.linear(uq, W[name + '.self_in'].cols(0, 2 * E), out=qkv[..., :2 * E], fast=fast)
         ops.linear(u, W[name + '.self_in'].cols(2 * E, E), out=qkv[..., 2 * E:], fast=fast)
         a = ops.mha(qkv[..., :E], qkv[..., E:2 * E], qkv[..., 2 * E:], heads=self.n_head, key_mask=key_mask)
@@ -393,8 +400,8 @@ class AppMotionCompFormer(ParamModule):
         a = ops.mha(qc, kv[:n_ctx, :E], kv[:n_ctx, E:], heads=self.n_head)
         t = ops.linear(a, W[name + '.cross_out'], res=t, fast=fast)
         u, _ = ops.layernorm(t, T[name + '.norm3.weight'], T[name + '.norm3.bias'])
-        f = ops.conv2d(u.view(B, 32, 32, E), W[name + '.conv1'], pad=1, act='gelu', fast=fast)
-        return ops.conv2d(f, W[name + '.conv2'], pad=1, res=t.view(B, 32, 32, E), fast=fast).view(B, 1024, E)
+        f = ops.conv2d(u.view(B, tg, tg, E), W[name + '.conv1'], pad=1, act='gelu', fast=fast)
+        return ops.conv2d(f, W[name + '.conv2'], pad=1, res=t.view(B, tg, tg, E), fast=fast).view(B, L, E)
 
     # ------------------------------------------------------------------------------------------
     # stage 3m: motion codebook compensation (appmotioncodebook_arch.py:373-427, 129-168)
@@ -404,31 +411,32 @@ class AppMotionCompFormer(ParamModule):
         B = m_prev.shape[0]
         dev = m_prev.device
         Em = self.Em
+        fg, tg, s0 = self.fg, self.tg, s // self.R             # flow grid, token grid, nominal scale (module names, codebook prefix)
         fs = ops.fast('s3m')
-        z = torch.empty((B, 64, 64, 256), device=dev, dtype=torch.float32)        # [BME out 126 | flow_px 2 | refine.convc1 128]
+        z = torch.empty((B, fg, fg, 256), device=dev, dtype=torch.float32)        # [BME out 126 | flow_px 2 | refine.convc1 128]
         ops.flow_to_px(m_prev, z[..., 126:128])
-        flow_px = torch.zeros((B, 64, 64, 32), device=dev, dtype=torch.float32)      # [flow_px 2 | zero padding]
+        flow_px = torch.zeros((B, fg, fg, 32), device=dev, dtype=torch.float32)      # [flow_px 2 | zero padding]
         ops.flow_to_px(m_prev, flow_px[..., 0:2])
         mf = ops.conv2d(flow_px, W['motion_emb.0'], pad=1, fast=fs)
-        mf = ops.conv2d(mf, W['motion_emb.1.conv'], stride=2, pad_tl=(0, 0), out_hw=(32, 32), fast=fs)
+        mf = ops.conv2d(mf, W['motion_emb.1.conv'], stride=2, pad_tl=(0, 0), out_hw=(tg, tg), fast=fs)
         ops_out = qcat[..., :Em]
         self._res('motion_emb.2', mf, Em, Em, out=ops_out, fast=fs)                        # qcat = [m_feat | query_feat]
-        t = ops.conv2d(qcat, W['motion_query_enc_2'], fast=fs).view(B, 1024, Em)
+        t = ops.conv2d(qcat, W['motion_query_enc_2'], fast=fs).view(B, self.L, Em)
         for i in range(2):
-            t = self._transformer(f'motion_block.{i}', t, Em, self._n_ctx(self.n_codes_motion, s), T['position_emb_motion'], fast=fs)
-        mfeat = ops.resize_ac(t.view(B, 32, 32, Em), (64, 64))
-        cf = torch.empty((B, 64, 64, 160), device=dev, dtype=torch.float32)       # [cor 96 | flo 64]
+            t = self._transformer(f'motion_block.{i}', t, Em, self._n_ctx(self.n_codes_motion, s0), T['position_emb_motion'], fast=fs)
+        mfeat = ops.resize_ac(t.view(B, tg, tg, Em), (fg, fg))
+        cf = torch.empty((B, fg, fg, 160), device=dev, dtype=torch.float32)       # [cor 96 | flo 64]
         cor = ops.conv2d(mfeat, W['BasicMotionEncoder.convc1'], act='relu', fast=fs)
         ops.conv2d(cor, W['BasicMotionEncoder.convc2'], pad=1, act='relu', out=cf[..., :96], fast=fs)
         flo = ops.conv2d(flow_px, W['BasicMotionEncoder.convf1'], pad=3, act='relu', fast=fs)
         ops.conv2d(flo, W['BasicMotionEncoder.convf2'], pad=1, act='relu', out=cf[..., 96:], fast=fs)
         ops.conv2d(cf, W['BasicMotionEncoder.conv'], pad=1, act='relu', out=z[..., :126], fast=fs)
-        ctx = ops.conv2d(warp0, W[f'to_context.{int(math.log2(s)) - 5}'], act='relu', fast=fs)
-        if s != 64:
-            ctx = ops.resize_ac(ctx, (64, 64))
+        ctx = ops.conv2d(warp0, W[f'to_context.{int(math.log2(s0)) - 5}'], act='relu', fast=fs)
+        if s != fg:
+            ctx = ops.resize_ac(ctx, (fg, fg))
         ops.conv2d(ctx, W['refine.convc1'], pad=1, act='relu', out=z[..., 128:], fast=fs)
         f = ops.conv2d(z, W['refine.conv1o1'], pad=1, act='relu', fast=fs)                 # [flow branch 128 | occlusion branch 128]
-        r = torch.empty((B, 64, 64, 4), device=dev, dtype=torch.float32)
+        r = torch.empty((B, fg, fg, 4), device=dev, dtype=torch.float32)
         ops.conv2d(f, W['refine.conv2o2'], pad=1, out=r[..., 0:3], fast=fs)                # [delta-flow 2 | delta-occlusion 1]
         return ops.flow_update(m_prev, occ_prev, r) + (r,)
 
@@ -438,20 +446,21 @@ class AppMotionCompFormer(ParamModule):
     def _app_comp(self, feat, m_com, s, out=None):
         W, T = self._packed, self._T
         B = feat.shape[0]
-        mask = ops.motion_ignore_mask(m_com, (32, 32))
-        if s == 32:
+        tg, s0 = self.tg, s // self.R
+        mask = ops.motion_ignore_mask(m_com, (tg, tg))
+        if s0 == 32:
             tok = ops.conv2d(feat, W['app_feat_emb_32'])
         else:
-            p = s // 32
-            tok = ops.conv2d(feat, W[f'app_feat_emb_{s}.1'], stride=p)
-        tok = tok.view(B, 1024, self.Ea)
-        n_ctx = self._n_ctx(self.n_codes_app, s)
+            p = s0 // 32
+            tok = ops.conv2d(feat, W[f'app_feat_emb_{s0}.1'], stride=p)
+        tok = tok.view(B, self.L, self.Ea)
+        n_ctx = self._n_ctx(self.n_codes_app, s0)
         tok = self._transformer('app_block.0', tok, self.Ea, n_ctx, T['position_emb_app'], key_mask=mask)
         tok = self._transformer('app_block.1', tok, self.Ea, n_ctx, T['position_emb_app'])
-        tok = tok.view(B, 32, 32, self.Ea)
-        if s == 32:
+        tok = tok.view(B, tg, tg, self.Ea)
+        if s0 == 32:
             return ops.conv2d(tok, W['to_app_feat_32'], out=out)
-        return ops.conv2d(tok, W[f'to_app_feat_{s}.0'], d2s=s // 32, out=out)
+        return ops.conv2d(tok, W[f'to_app_feat_{s0}.0'], d2s=s0 // 32, out=out)
 
     # ------------------------------------------------------------------------------------------
     # the per-driving-frame body (appmotioncodebook_arch.py:556-764, inference=True)
@@ -460,8 +469,8 @@ class AppMotionCompFormer(ParamModule):
     def generate(self, feats: Dict[int, torch.Tensor], deformation: torch.Tensor, occlusion: torch.Tensor,
                  kp_heat_nhwc: torch.Tensor, w: float = 1.0, collect: Optional[dict] = None) -> dict:
         """feats: encode_source() output (batch 1 = shared by all frames, or batch B).
-        deformation (B,64,64,2), occlusion (B,64,64) post-sigmoid, kp_heat_nhwc (B,64,64,15).
-        Returns NHWC tensors: out (B,256,256,3), lq_feat (B,32,32,256), lists of motions / occlusions."""
+        deformation (B,64,64,2), occlusion (B,64,64) post-sigmoid, kp_heat_nhwc (B,64,64,15)   [128x128 grids for the 512x512 variant].
+        Returns NHWC tensors: out (B,H,W,3), lq_feat (B,H/8,W/8,256), lists of motions / occlusions."""
         W = self._weights()
         B = deformation.shape[0]
         dev = deformation.device
@@ -472,17 +481,18 @@ class AppMotionCompFormer(ParamModule):
             return f if f.shape[0] == B else f.expand(B, -1, -1, -1)
 
         motions, occs, residuals = [deformation.contiguous()], [], []
-        occ_prev = occlusion.contiguous().view(B, 64, 64)
-        qk = torch.empty((B, 32, 32, 2 * Em), device=dev, dtype=torch.float32)     # [warped-source query | driving kp feat]
-        qcat = torch.empty((B, 32, 32, 2 * Em), device=dev, dtype=torch.float32)   # [motion feat | query feat]
-        ops.conv2d(ops.resize_ac(kp_heat_nhwc, (32, 32)), W['driving_kp_enc'], act='relu', out=qk[..., Em:])
+        fg, tg, R = self.fg, self.tg, self.R
+        occ_prev = occlusion.contiguous().view(B, fg, fg)
+        qk = torch.empty((B, tg, tg, 2 * Em), device=dev, dtype=torch.float32)     # [warped-source query | driving kp feat]
+        qcat = torch.empty((B, tg, tg, 2 * Em), device=dev, dtype=torch.float32)   # [motion feat | query feat]
+        ops.conv2d(ops.resize_ac(kp_heat_nhwc, (tg, tg)), W['driving_kp_enc'], act='relu', out=qk[..., Em:])
 
         def compensate(s, out=None):
             nonlocal occ_prev
             f = src(s)
             warp0 = ops.warp_occlude(f, motions[-1], None)
-            w32 = warp0 if s == 32 else ops.resize_ac(warp0, (32, 32))
-            ops.conv2d(w32, W[f'warped_source_enc_{s}'], act='relu', out=qk[..., :Em])
+            w32 = warp0 if s == tg else ops.resize_ac(warp0, (tg, tg))
+            ops.conv2d(w32, W[f'warped_source_enc_{s // R}'], act='relu', out=qk[..., :Em])
             ops.conv2d(qk, W['motion_query_enc_1'], out=qcat[..., Em:])
             m_com, occ, r = self._motion_comp(motions[-1], occ_prev, warp0, qcat, s)
             motions.append(m_com); occs.append(occ); residuals.append(r)
@@ -493,18 +503,19 @@ class AppMotionCompFormer(ParamModule):
                 collect[f'warp0_{s}'], collect[f'warped_{s}'], collect[f'app_{s}'] = warp0, warped, enc
             return enc
 
-        x = compensate(32)
+        x = compensate(tg)
         lq_feat = x
         fuse_at = {9: 64, 12: 128, 15: 256}
         cat = None
         for i in range(len(self.gen_layout)):
             if i in fuse_at and w > 0:
-                s = fuse_at[i]
-                c = self.channels[s]
+                s0 = fuse_at[i]                      # nominal scale: names; s: the actual feature size
+                s = s0 * R
+                c = self.channels[s0]
                 cat = torch.empty((B, s, s, 2 * c), device=dev, dtype=torch.float32)   # [enc | dec] for Fuse_sft_block
                 x = self._block('generator', i, self.gen_layout, x, out=cat[..., c:])
                 enc = compensate(s, out=cat[..., :c])
-                n = f'fuse_convs_dict.{s}'
+                n = f'fuse_convs_dict.{s0}'
                 e = self._res(n + '.encode_enc', cat, 2 * c, c)
                 ss = ops.conv2d(e, W[n + '.ss0'], pad=1, act='leaky')                  # [scale.0 | shift.0]
                 scale = ops.conv2d(ss[..., :c], W[n + '.scale.2'], pad=1)
@@ -512,7 +523,7 @@ class AppMotionCompFormer(ParamModule):
                 xf = ops.conv2d(ss[..., c:], W[n + '.shift.2'], pad=1, res=x, sft=(scale, float(w)))
                 if collect is not None:
                     collect[f'sft_{s}'] = xf.clone()                                   # (the next conv accumulates in place)
-                x = ops.conv2d(enc, W[f'fuse_ms_dict.{s}'], pad=1, res=xf, out=xf)
+                x = ops.conv2d(enc, W[f'fuse_ms_dict.{s0}'], pad=1, res=xf, out=xf)
                 if collect is not None:
                     collect[f'fused_{s}'] = x
             else:
@@ -534,18 +545,18 @@ class AppMotionCompFormer(ParamModule):
         heat = dense_motion.get('_driving_kp_heatmap_nhwc')
         if heat is None:
             heat = ops.nchw_to_nhwc(dense_motion['driving_kp_heatmap'].contiguous().float())
-        occ = dense_motion['occlusion_map'].contiguous().float().view(B, 64, 64)
+        occ = dense_motion['occlusion_map'].contiguous().float().view(B, self.fg, self.fg)
         collect = {}
         r = self.generate(feats, deformation, occ, heat, float(w), collect=collect)
         half = (deformation.shape[1] - 1.0) / 2.0
-        scales = [s for s in self.SCALES if f'warped_{s}' in collect]
+        scales = [s * self.R for s in self.SCALES if f'warped_{s * self.R}' in collect]
         before = [ops.nhwc_to_nchw(collect[f'warped_{s}']) for s in scales]
         after = [ops.nhwc_to_nchw(collect[f'app_{s}']) for s in scales]
         out = {
             'out': ops.nhwc_to_nchw(r['out']),
             '_out_nhwc': r['out'],
             'lq_feat': ops.nhwc_to_nchw(r['lq_feat']),
-            'out_occ': [o.view(B, 1, 64, 64) for o in r['out_occ']],
+            'out_occ': [o.view(B, 1, self.fg, self.fg) for o in r['out_occ']],
             'deformation_list': r['deformation_list'],
             'res_deform_list': [q[..., 0:2] / half for q in r['residuals']],
             # the reference computes the occluded final warp a third time for this list (:604,609-615,700,705-719): same values

@@ -287,9 +287,9 @@ extern "C" int sma_mha_fwd(const float* q, int ldq, const float* k, int ldk, con
     return SMA_ERR_UNSUPPORTED;
   if (kv_bstride & 3) return SMA_ERR_UNSUPPORTED;
   cudaStream_t st = as_stream(stream);
-  if (D == 4 && !key_mask && !(flags & 1) && (S % 8) == 0 && S * 32 <= 96 * 1024) {
+  if (D == 4 && !key_mask && !(flags & 1) && (S % 8) == 0 && S * 32 <= 192 * 1024) {       // K / V of one head in shared memory: 4096 keys (512x512 variant) = 128 KB
     static SmaDevOnce once;
-    if (int rc = sma_opt_in_smem(once, mha_d4_fast_kernel, 96 * 1024)) return rc;
+    if (int rc = sma_opt_in_smem(once, mha_d4_fast_kernel, 192 * 1024)) return rc;
     mha_d4_fast_kernel<<<dim3(cdiv(L, 128), heads, B), 128, S * 32, st>>>(q, ldq, k, ldk, v, ldv, kv_bstride, L, S, scale * 1.4426950408889634f, out, ldo);
     SMA_LAUNCH_CHECK();
     return SMA_OK;

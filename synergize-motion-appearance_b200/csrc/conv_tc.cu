@@ -266,6 +266,7 @@ struct Tc2P {
   int Ho, Wo, out_ld, act, res_ld, d2s;
   const float* aux; long long aux_bs; int aux_ld; float sft_w;   // SFT epilogue (aux != nullptr): y = res + sft_w * (res * aux + v), v = act(acc + bias)
   const float* wscale;        // F16 only: per-output-channel power-of-two factor that undoes the weight pre-scaling
+  float acc_corr;             // F16 only: 1 + 1.6e-8 * (adds into the main accumulator): undoes the mean truncation bias of the tensor core's fp32 accumulation
   int HoWo, cpt, taps, NT, ntiles_n, passes, tmem_cols;
   int fuse;                   // 3-pass, NT <= 128: the hi and lo weight images (adjacent in the ring) are read as ONE B tile of 2*NT rows, so
                               // a_hi*[b_hi | b_lo] is one MMA; its lo half lands in accumulator columns [NT, 2NT) and is added in the epilogue
@@ -338,7 +339,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const Tc2P p) {
         asm volatile("bar.sync 1, 128;" ::: "memory");
         for (int i = m; i < p.NT; i += 128) {
           int n = nt * p.NT + i; s_bias[i] = (p.bias && n < p.Cout) ? __ldg(p.bias + n) : 0.f;
-          if (F16) s_scale[i] = __ldg(p.wscale + n);
+          if (F16) s_scale[i] = __ldg(p.wscale + n) * p.acc_corr;
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");
         cur_nt = nt;
@@ -490,7 +491,10 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const Tc2P p) {
                 const uint64_t ko = (uint64_t)(k4 * 2);
                 if (p.fuse) {
                   tc_mma<F16>(d_tmem, dah + ko, dbh + ko, idesc2, acc);          // a_hi * [b_hi | b_lo]  (N = 2 NT)
-                  tc_mma<F16>(d_tmem, dal + ko, dbh + ko, idesc, 1u);            // a_lo * b_hi
+                  // a_lo * b_hi goes to the LO half of the accumulator (columns [NT, 2 NT), added in the epilogue with round-to-nearest):
+                  // the tensor core adds into its fp32 accumulator with truncation (measured: a bias of -1.6e-8 per add, relative), so
+                  // the main accumulator should see as few adds as possible - one per k-step instead of two
+                  tc_mma<F16>(d_tmem + (uint32_t)p.NT, dal + ko, dbh + ko, idesc, 1u);
                 } else if (three) {
                   tc_mma<F16>(d_tmem, dal + ko, dbh + ko, idesc, acc);
                   tc_mma<F16>(d_tmem, dah + ko, dbl + ko, idesc, 1u);
@@ -821,6 +825,12 @@ static int conv_tc2_try(const sma_conv_desc* d, cudaStream_t st, bool f16) {
   p.SA = SA; p.SB = SB;
   p.fuse = (p.passes == 3 && p.NT <= 128 && !(d->tc_variant & 128)) ? 1 : 0;       // tc_variant bit 7: keep the three separate MMAs (tests)
   p.acc_cols = p.fuse ? 2 * p.NT : p.NT;
+  // The tensor core adds every MMA result into its fp32 accumulator with truncation toward zero (tools/acc_bias.py: the relative error of a
+  // conv is a BIAS of -1.6e-8 per add for mixed-sign terms, the same on every shape from 36 to 864 adds, 10x the rounding noise of an fp32
+  // FFMA chain).  The epilogue multiplies the mean back in; what remains is the data-dependent part (partial sums that stay far below or
+  // above the random-walk average), at most the size of the correction itself (<= 1.4e-5 for the longest chain of this network).
+  const int main_adds = p.cpt * p.taps * 4 * (p.fuse ? 1 : p.passes);
+  p.acc_corr = (d->tc_variant & 256) ? 1.f : 1.f + 1.6e-8f * (float)main_adds;
   p.dbg = (d->tc_variant >> 1) & 7;
   int cols = 32; while (cols < 2 * p.acc_cols + ((p.NT & 31) ? 32 : 0)) cols <<= 1;      // the epilogue reads 32 columns at a time
   if (cols > 512) return SMA_ERR_UNSUPPORTED;

@@ -54,9 +54,23 @@ def test_state_dict_inventory_and_strict_load(inventory, weights):
 
 
 def test_unsupported_configs_raise():
-    bad = dict(CFG['network_g']); bad['img_size'] = 512
-    with pytest.raises(NotImplementedError):
-        S.build_network(bad)
+    for key, val in (('img_size', 384), ('nf', 32), ('split', 2), ('codebook_size_app', 1000)):
+        bad = dict(CFG['network_g']); bad[key] = val
+        with pytest.raises(NotImplementedError):
+            S.build_network(bad)
+
+
+def test_512_variant_inventory(inventory):
+    """BASELINE configs[3] (Config 4): the 512x512 variant has the reference's key inventory and shapes except the position
+    embeddings (one row per token of the 64x64 grid)."""
+    import sma_oracle as O
+    opt = dict(CFG['network_g']); opt['img_size'] = 512
+    g = S.build_network(opt)
+    sd = {k: list(v.shape) for k, v in g.state_dict().items()}
+    assert sd == O.variant_shapes(inventory['net_g'], 512)
+    assert sd['position_emb_app'] == [4096, 256] and sd['position_emb_motion'] == [4096, 32]
+    assert (g.tg, g.fg, g.L, g.R) == (64, 128, 4096, 2)
+    g.load_state_dict(O.synthetic_state_dict(O.variant_shapes(inventory['net_g'], 512), 0), strict=True)
 
 
 def test_c_abi_exports_every_declared_symbol():

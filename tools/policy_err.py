@@ -8,16 +8,20 @@ import sma_b200 as S
 import sma_oracle as O
 from conftest import CFG
 inv = json.load(open(os.path.join(ROOT, 'tests/golden/state_keys.json')))
-P_g, P_me = O.synthetic_state_dict(inv['net_g'], 0), O.synthetic_state_dict(inv['motion_estimator'], 1)
+SIZE = 512 if 'size512' in sys.argv else 256
+P_g, P_me = O.synthetic_state_dict(O.variant_shapes(inv['net_g'], SIZE), 0), O.synthetic_state_dict(inv['motion_estimator'], 1)
+CFG['network_g']['img_size'] = SIZE
 g = S.build_network(CFG['network_g']); me = S.build_network(CFG['network_motion_estimator'])
 g.load_state_dict(P_g); me.load_state_dict(P_me)
 g, me = g.eval().cuda(), me.eval().cuda()
+SIZE = 512 if 'size512' in sys.argv else 256
+sys.argv = [a for a in sys.argv if a != 'size512']
 seeds = [int(a) for a in sys.argv[1:] if a.isdigit()] or [77]
 policies = [a for a in sys.argv[1:] if not a.isdigit()] or ['exact', 'f16', 'f16+kp', 'f16+s1', 'f16+s3m', 'f16+kp+s1+s3m']
 idx = [0, 17, 38, 63]
 torch.set_num_threads(os.cpu_count())
 for seed in seeds:
-    src, drv = O.synthetic_frames(64, seed=seed)
+    src, drv = O.synthetic_frames(64, seed=seed, size=SIZE)
     sel = [drv[i] for i in idx]
     t0 = time.time()
     with torch.no_grad():
@@ -39,7 +43,7 @@ for seed in seeds:
         kp = me.estimate_kp(frames)
         kpn = S.normalize_kp(anim.kp_source, kp, anim.kp_initial, adapt_movement_scale=True, use_relative_movement=True, use_relative_jacobian=True, _scale=anim.scale)
         dmg = me.estimate_motion_w_kp(kp_source=anim.kp_source, kp_driving=kpn, source_image=anim.source)
-        r = g.generate(anim.feats, dmg['deformation'], dmg['occlusion_map'].view(4, 64, 64), dmg['_driving_kp_heatmap_nhwc'], 1.0)
+        r = g.generate(anim.feats, dmg['deformation'], dmg['occlusion_map'].view(4, 64 * SIZE // 256, 64 * SIZE // 256), dmg['_driving_kp_heatmap_nhwc'], 1.0)
         out = r['out'].permute(0, 3, 1, 2).cpu()
         e = (out - ref['out']).abs().amax(dim=(1, 2, 3))
         ekp = float((kp['value'].cpu() - kp_d['value']).abs().max()); ekj = float((kp['jacobian'].cpu() - kp_d['jacobian']).abs().max())
@@ -48,6 +52,6 @@ for seed in seeds:
         em = [float((a.cpu() - b).abs().max()) for a, b in zip(r['deformation_list'][1:], ref['deformation_list'][1:])]
         # the generator alone, fed with the ORACLE's dense motion (isolates KP / S1 from S3m / S3a / S4)
         heat = S.ops.nchw_to_nhwc(dm['driving_kp_heatmap'].cuda().contiguous())
-        r2 = g.generate(anim.feats, dm['deformation'].cuda(), dm['occlusion_map'].cuda().view(4, 64, 64), heat, 1.0)
+        r2 = g.generate(anim.feats, dm['deformation'].cuda(), dm['occlusion_map'].cuda().view(4, 64 * SIZE // 256, 64 * SIZE // 256), heat, 1.0)
         e2 = (r2['out'].permute(0, 3, 1, 2).cpu() - ref['out']).abs().amax(dim=(1, 2, 3))
         print(f'  {mode:16s} out {["%.2e" % float(v) for v in e]} | gen-only {["%.2e" % float(v) for v in e2]} | kp {ekp:.1e} jac {ekj:.1e} kpn {ekn:.1e} | deform {edef:.1e} occ {eocc:.1e} | m_com {["%.1e" % v for v in em]}', flush=True)
