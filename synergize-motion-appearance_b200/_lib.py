@@ -4,7 +4,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, 'csrc', 'libsma_b200.so')
+LIB_PATH = os.environ.get('SMA_B200_LIB') or os.path.join(HERE, 'csrc', 'libsma_b200.so')      # (the override is for kernel A/B experiments)
 
 c_f32p = C.c_void_p
 c_i64 = C.c_int64

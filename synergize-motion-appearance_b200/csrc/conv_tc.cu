@@ -256,7 +256,10 @@ constexpr int V2_PROD_WARPS = 8;                       // halo producers: enough
 constexpr int V2_THREADS = 192 + 32 * V2_PROD_WARPS;
 constexpr int V2_PGROUPS = 2;                          // producer groups working on alternate channel chunks (2x the latency budget each)
 constexpr int V2_PROWS = 4 * V2_PROD_WARPS / V2_PGROUPS;   // halo rows per pass of one group (8 lanes per 128-byte row)
-constexpr int V2_UNROLL = 6;                           // loads in flight per producer thread
+#ifndef SMA_V2_UNROLL
+#define SMA_V2_UNROLL 12             // (macro: tools/build_variants.sh A/B-tests it; 6 -> 12 = -11 % on the halo-latency-bound 128->64 3x3 @256^2)
+#endif
+constexpr int V2_UNROLL = SMA_V2_UNROLL;                          // loads in flight per producer thread
 constexpr int MAX_SA = 3, MAX_SB = 8;
 
 struct Tc2P {
@@ -527,6 +530,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const Tc2P p) {
         for (int j = 0; j < nblob; j++, jt++) {
           const int sb = jt % p.SB; const uint32_t phb = (jt / p.SB) & 1;
           mbar_wait(b_empty(sb), phb ^ 1u);
+          if (p.dbg & 1) { mbar_arrive(b_full(sb)); continue; }          // timing experiment: no weight traffic
           mbar_expect_tx(b_full(sb), bytes);
           bulk_g2s(b_ring + (uint32_t)sb * b_stage_bytes, src + (long long)j * b_stage_bytes, bytes, b_full(sb));
         }
@@ -557,6 +561,11 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const Tc2P p) {
         const int sa = it % p.SA; const uint32_t pha = (it / p.SA) & 1;
         const uint32_t a_hi = a_ring + (uint32_t)sa * p.a_stage_bytes, a_lo = a_hi + p.a_img_bytes;
         bool waited = false;
+        if (p.dbg & 2) {                                   // timing experiment: no halo loads / stores
+          mbar_wait(a_empty(sa), pha ^ 1u);
+          mbar_arrive(a_full(sa));
+          continue;
+        }
         if (!F16) {
           const int c = cc * KCH + cq * 4;
           float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
