@@ -215,51 +215,81 @@ __global__ void __launch_bounds__(128) mha_d4_kernel(const float* __restrict__ q
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ float ex2f_(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
+// QPT query rows per thread: the broadcast K / V shared-memory loads are shared by QPT independent dot-product / exp / accumulate chains
+// (ncu, round 2: the single-row version was latency-bound - short-scoreboard stalls 4.5 per issue at 35 % occupancy - not issue-bound)
+template <int QPT>
 __global__ void __launch_bounds__(128) mha_d4_fast_kernel(const float* __restrict__ q, int ldq, const float* __restrict__ k, int ldk,
                                                           const float* __restrict__ v, int ldv, long long kv_bs, int L, int S, float qscale,
                                                           float* __restrict__ out, int ldo) {
   extern __shared__ float4 kv_s[];
   float4* Ks = kv_s; float4* Vs = kv_s + S;
   const int h = blockIdx.y, b = blockIdx.z;
-  const int r = blockIdx.x * 128 + threadIdx.x;
+  const int r0 = blockIdx.x * (128 * QPT) + threadIdx.x;
   for (int f = threadIdx.x; f < S; f += 128) {
     Ks[f] = __ldg(reinterpret_cast<const float4*>(k + (long long)b * kv_bs + (long long)f * ldk + h * 4));
     Vs[f] = __ldg(reinterpret_cast<const float4*>(v + (long long)b * kv_bs + (long long)f * ldv + h * 4));
   }
-  float4 qv = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (r < L) qv = __ldg(reinterpret_cast<const float4*>(q + ((long long)b * L + r) * ldq + h * 4));
-  qv.x *= qscale; qv.y *= qscale; qv.z *= qscale; qv.w *= qscale;        // log2 units
+  float4 qv[QPT];
+#pragma unroll
+  for (int j = 0; j < QPT; j++) {
+    const int r = r0 + j * 128;
+    qv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (r < L) qv[j] = __ldg(reinterpret_cast<const float4*>(q + ((long long)b * L + r) * ldq + h * 4));
+    qv[j].x *= qscale; qv[j].y *= qscale; qv[j].z *= qscale; qv[j].w *= qscale;        // log2 units
+  }
   __syncthreads();
   constexpr float LAZY = 8.f;
-  float m_ref = -CUDART_INF_F;
+  float m_ref[QPT], l[QPT]; float4 o[QPT];
 #pragma unroll
-  for (int i = 0; i < 8; i++) { float4 kk = Ks[i]; m_ref = fmaxf(m_ref, fmaf(qv.w, kk.w, fmaf(qv.z, kk.z, fmaf(qv.y, kk.y, qv.x * kk.x)))); }
-  float l = 0.f; float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int j = 0; j < QPT; j++) {
+    m_ref[j] = -CUDART_INF_F; l[j] = 0.f; o[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < 8; i++) { float4 kk = Ks[i]; m_ref[j] = fmaxf(m_ref[j], fmaf(qv[j].w, kk.w, fmaf(qv[j].z, kk.z, fmaf(qv[j].y, kk.y, qv[j].x * kk.x)))); }
+  }
   for (int c0 = 0; c0 < S; c0 += 8) {
-    float t[8]; float tmax = -CUDART_INF_F;
+    float t[QPT][8]; float tmax[QPT];
+#pragma unroll
+    for (int j = 0; j < QPT; j++) tmax[j] = -CUDART_INF_F;
 #pragma unroll
     for (int i = 0; i < 8; i++) {
       const float4 kk = Ks[c0 + i];
-      t[i] = fmaf(qv.w, kk.w, fmaf(qv.z, kk.z, fmaf(qv.y, kk.y, fmaf(qv.x, kk.x, -m_ref))));
-      tmax = fmaxf(tmax, t[i]);
-    }
-    if (__any_sync(0xffffffffu, tmax > LAZY)) {        // rare after the first chunks
-      if (tmax > LAZY) {
-        const float corr = ex2f_(-tmax);
-        l *= corr; o.x *= corr; o.y *= corr; o.z *= corr; o.w *= corr; m_ref += tmax;
 #pragma unroll
-        for (int i = 0; i < 8; i++) t[i] -= tmax;
+      for (int j = 0; j < QPT; j++) {
+        t[j][i] = fmaf(qv[j].w, kk.w, fmaf(qv[j].z, kk.z, fmaf(qv[j].y, kk.y, fmaf(qv[j].x, kk.x, -m_ref[j]))));
+        tmax[j] = fmaxf(tmax[j], t[j][i]);
+      }
+    }
+    bool any = false;
+#pragma unroll
+    for (int j = 0; j < QPT; j++) any |= tmax[j] > LAZY;
+    if (__any_sync(0xffffffffu, any)) {        // rare after the first chunks
+#pragma unroll
+      for (int j = 0; j < QPT; j++) {
+        if (tmax[j] > LAZY) {
+          const float corr = ex2f_(-tmax[j]);
+          l[j] *= corr; o[j].x *= corr; o[j].y *= corr; o[j].z *= corr; o[j].w *= corr; m_ref[j] += tmax[j];
+#pragma unroll
+          for (int i = 0; i < 8; i++) t[j][i] -= tmax[j];
+        }
       }
     }
 #pragma unroll
     for (int i = 0; i < 8; i++) {
-      const float pr = ex2f_(t[i]); const float4 vv = Vs[c0 + i];
-      l += pr; o.x = fmaf(pr, vv.x, o.x); o.y = fmaf(pr, vv.y, o.y); o.z = fmaf(pr, vv.z, o.z); o.w = fmaf(pr, vv.w, o.w);
+      const float4 vv = Vs[c0 + i];
+#pragma unroll
+      for (int j = 0; j < QPT; j++) {
+        const float pr = ex2f_(t[j][i]);
+        l[j] += pr; o[j].x = fmaf(pr, vv.x, o[j].x); o[j].y = fmaf(pr, vv.y, o[j].y); o[j].z = fmaf(pr, vv.z, o[j].z); o[j].w = fmaf(pr, vv.w, o[j].w);
+      }
     }
   }
-  if (r < L) {
-    const float inv = 1.f / l;
-    *reinterpret_cast<float4*>(out + ((long long)b * L + r) * ldo + h * 4) = make_float4(o.x * inv, o.y * inv, o.z * inv, o.w * inv);
+#pragma unroll
+  for (int j = 0; j < QPT; j++) {
+    const int r = r0 + j * 128;
+    if (r < L) {
+      const float inv = 1.f / l[j];
+      *reinterpret_cast<float4*>(out + ((long long)b * L + r) * ldo + h * 4) = make_float4(o[j].x * inv, o[j].y * inv, o[j].z * inv, o[j].w * inv);
+    }
   }
 }
 
@@ -288,9 +318,14 @@ extern "C" int sma_mha_fwd(const float* q, int ldq, const float* k, int ldk, con
   if (kv_bstride & 3) return SMA_ERR_UNSUPPORTED;
   cudaStream_t st = as_stream(stream);
   if (D == 4 && !key_mask && !(flags & 1) && (S % 8) == 0 && S * 32 <= 192 * 1024) {       // K / V of one head in shared memory: 4096 keys (512x512 variant) = 128 KB
-    static SmaDevOnce once;
-    if (int rc = sma_opt_in_smem(once, mha_d4_fast_kernel, 192 * 1024)) return rc;
-    mha_d4_fast_kernel<<<dim3(cdiv(L, 128), heads, B), 128, S * 32, st>>>(q, ldq, k, ldk, v, ldv, kv_bstride, L, S, scale * 1.4426950408889634f, out, ldo);
+    static SmaDevOnce once2, once4;
+    if (L >= 2048) {      // long sequences (512x512 variant: 128 KB of K / V per CTA, one CTA per SM): four rows per thread
+      if (int rc = sma_opt_in_smem(once4, mha_d4_fast_kernel<4>, 192 * 1024)) return rc;
+      mha_d4_fast_kernel<4><<<dim3(cdiv(L, 512), heads, B), 128, S * 32, st>>>(q, ldq, k, ldk, v, ldv, kv_bstride, L, S, scale * 1.4426950408889634f, out, ldo);
+    } else {
+      if (int rc = sma_opt_in_smem(once2, mha_d4_fast_kernel<2>, 192 * 1024)) return rc;
+      mha_d4_fast_kernel<2><<<dim3(cdiv(L, 256), heads, B), 128, S * 32, st>>>(q, ldq, k, ldk, v, ldv, kv_bstride, L, S, scale * 1.4426950408889634f, out, ldo);
+    }
     SMA_LAUNCH_CHECK();
     return SMA_OK;
   }
