@@ -332,7 +332,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const Tc2P p) {
     const bool vec_ok = (p.out_ld & 3) == 0 && (p.out_bs & 3) == 0 && ((reinterpret_cast<uintptr_t>(p.y) & 15) == 0) &&
                         (!p.res || ((p.res_ld & 3) == 0 && (p.res_bs & 3) == 0 && (reinterpret_cast<uintptr_t>(p.res) & 15) == 0));
     const int Cq = p.d2s > 1 ? p.Cout / (p.d2s * p.d2s) : p.Cout;
-    const bool v8_ok = p.d2s <= 1 && (p.Cout & 7) == 0 && (p.out_ld & 7) == 0 && (p.out_bs & 7) == 0 && ((reinterpret_cast<uintptr_t>(p.y) & 31) == 0) &&
+    const bool v8_ok = (p.d2s <= 1 || (Cq & 7) == 0) && (p.Cout & 7) == 0 && (p.out_ld & 7) == 0 && (p.out_bs & 7) == 0 && ((reinterpret_cast<uintptr_t>(p.y) & 31) == 0) &&
                        (!p.res || ((p.res_ld & 7) == 0 && (p.res_bs & 7) == 0 && (reinterpret_cast<uintptr_t>(p.res) & 31) == 0));   // (the SFT epilogue is only dispatched here when this holds)
     int tcount = 0, cur_nt = -1;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tcount) {
@@ -407,7 +407,13 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const Tc2P p) {
                 o[0] += r0; o[1] += r1; o[2] += r2; o[3] += r3; o[4] += r4; o[5] += r5; o[6] += r6; o[7] += r7;
               }
             }
-            asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(yrow + n), "f"(o[0]), "f"(o[1]), "f"(o[2]), "f"(o[3]), "f"(o[4]), "f"(o[5]),
+            float* dst = yrow + n;
+            if (p.d2s > 1) {      // depth-to-space (un-patchify): the 8 columns lie inside one sub-pixel's channel block (Cq % 8 == 0)
+              const int qd = n / Cq, cval = n - qd * Cq, p1 = qd / p.d2s, p2 = qd - p1 * p.d2s;
+              const long long pix = (long long)(oy * p.d2s + p1) * (p.Wo * p.d2s) + (ox * p.d2s + p2);
+              dst = p.y + (long long)b * p.out_bs + pix * p.out_ld + cval;
+            }
+            asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst), "f"(o[0]), "f"(o[1]), "f"(o[2]), "f"(o[3]), "f"(o[4]), "f"(o[5]),
                          "f"(o[6]), "f"(o[7])
                          : "memory");
           }
