@@ -269,6 +269,7 @@ struct Tc2P {
   int Ho, Wo, out_ld, act, res_ld, d2s;
   const float* aux; long long aux_bs; int aux_ld; float sft_w;   // SFT epilogue (aux != nullptr): y = res + sft_w * (res * aux + v), v = act(acc + bias)
   const float* wscale;        // F16 only: per-output-channel power-of-two factor that undoes the weight pre-scaling
+  int res_pipe;               // host: the launch qualifies for the RES = 1 instantiation (residual, no activation, 256-bit eligible)
   float acc_corr;             // F16 only: 1 + 1.6e-8 * (adds into the main accumulator): undoes the mean truncation bias of the tensor core's fp32 accumulation
   int HoWo, cpt, taps, NT, ntiles_n, passes, tmem_cols;
   int fuse;                   // 3-pass, NT <= 128: the hi and lo weight images (adjacent in the ring) are read as ONE B tile of 2*NT rows, so
@@ -284,7 +285,8 @@ struct Tc2P {
 // F16: operands are split into two fp16 halves (hi = rn(x), lo = rn(x - hi); same 11-bit significand as tf32) and multiplied with
 // kind::f16 (K = 16 per instruction: twice the MACs per tensor-core cycle and per shared-memory byte of kind::tf32); a K-chunk
 // (one 128-byte swizzle row) is then 64 channels.
-template <int ACT, int PRE, int F16>
+// RES: 1 = the 256-bit epilogue with the residual prefetched one column block ahead (own instantiation: its register budget must not touch the others)
+template <int ACT, int PRE, int F16, int RES>
 __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const Tc2P p) {
   constexpr int KCH = F16 ? 64 : 32;                       // channels per K-chunk (128 bytes of operand)
   extern __shared__ uint8_t smem_raw[];
@@ -350,115 +352,220 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const Tc2P p) {
       int oy, ox, r; bool mok;
       if (p.flat) { r = ty0 + m; mok = r < p.HoWo; oy = r / p.Wo; ox = r - oy * p.Wo; }
       else { oy = ty0 + (m >> 3); ox = tx0 + (m & 7); mok = oy < p.Ho && ox < p.Wo; r = oy * p.Wo + ox; }
-      const int nbase = nt * p.NT;
-      mbar_wait(acc_full(ab), aph);
-      tc_fence_after();
-      for (int n0 = 0; n0 < p.NT && nbase + n0 < p.Cout; n0 += 32) {
-        uint32_t a[32];
-        const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(ab * p.acc_cols + n0);
-        tmem_ld32(taddr, a);
-        if (p.fuse) {                                  // a_hi * b_lo was accumulated NT columns further right
-          uint32_t a2[32];
-          tmem_ld32(taddr + (uint32_t)p.NT, a2);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; i++) a[i] = __float_as_uint(__uint_as_float(a[i]) + __uint_as_float(a2[i]));
-        } else {
-          tmem_ld_wait();
-        }
-        if (n0 + 32 >= p.NT || nbase + n0 + 32 >= p.Cout) {     // last column block: the accumulator may be overwritten while we store
-          tc_fence_before();
-          mbar_arrive(acc_empty(ab));
-        }
-        if (mok && !(p.dbg & 4) && v8_ok) {
-          // 256-bit residual loads / stores: every lane moves whole 32-byte sectors (with 128-bit accesses a warp-level instruction touches
-          // half of 32 different sectors, and the epilogue - not the MMAs - bounds the low-K layers)
-          float* yrow = p.y + (long long)b * p.out_bs + (long long)r * p.out_ld;
-          const float* rrow = p.res ? p.res + (long long)b * p.res_bs + (long long)r * p.res_ld : nullptr;
-          const float* arow = p.aux ? p.aux + (long long)b * p.aux_bs + (long long)r * p.aux_ld : nullptr;
-#pragma unroll
-          for (int q8 = 0; q8 < 4; q8++) {
-            const int n = nbase + n0 + q8 * 8;
-            if (n >= p.Cout) break;
-            float o[8];
-            const float4 b0 = *reinterpret_cast<const float4*>(&s_bias[n0 + q8 * 8]), b1 = *reinterpret_cast<const float4*>(&s_bias[n0 + q8 * 8 + 4]);
-            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-            if (F16) {
-              const float4 s0 = *reinterpret_cast<const float4*>(&s_scale[n0 + q8 * 8]), s1 = *reinterpret_cast<const float4*>(&s_scale[n0 + q8 * 8 + 4]);
-              const float ss[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-#pragma unroll
-              for (int t = 0; t < 8; t++) o[t] = sma_act(fmaf(__uint_as_float(a[q8 * 8 + t]), ss[t], bb[t]), ACT);
-            } else {
-#pragma unroll
-              for (int t = 0; t < 8; t++) o[t] = sma_act(__uint_as_float(a[q8 * 8 + t]) + bb[t], ACT);
-            }
-            if (rrow) {
-              float r0, r1, r2, r3, r4, r5, r6, r7;
-              asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];" : "=f"(r0), "=f"(r1), "=f"(r2), "=f"(r3), "=f"(r4), "=f"(r5), "=f"(r6), "=f"(r7)
-                           : "l"(rrow + n));
-              if (arow) {       // Fuse_sft_block tail (appmotioncodebook_arch.py:50-51): dec + w * (dec * scale + shift), this conv = shift
-                float a0, a1, a2, a3, a4, a5, a6, a7;
-                asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];" : "=f"(a0), "=f"(a1), "=f"(a2), "=f"(a3), "=f"(a4), "=f"(a5), "=f"(a6), "=f"(a7)
-                             : "l"(arow + n));
-                o[0] = r0 + p.sft_w * (r0 * a0 + o[0]); o[1] = r1 + p.sft_w * (r1 * a1 + o[1]); o[2] = r2 + p.sft_w * (r2 * a2 + o[2]);
-                o[3] = r3 + p.sft_w * (r3 * a3 + o[3]); o[4] = r4 + p.sft_w * (r4 * a4 + o[4]); o[5] = r5 + p.sft_w * (r5 * a5 + o[5]);
-                o[6] = r6 + p.sft_w * (r6 * a6 + o[6]); o[7] = r7 + p.sft_w * (r7 * a7 + o[7]);
-              } else {
-                o[0] += r0; o[1] += r1; o[2] += r2; o[3] += r3; o[4] += r4; o[5] += r5; o[6] += r6; o[7] += r7;
+      if constexpr (RES) {
+        const int nbase = nt * p.NT;
+        // 256-bit path for layers with a residual.  Loaded next to its use, every 8 columns of the residual exposed a full DRAM latency (32 per
+        // tile of a 256-column linear: the short-K transformer linears ran 4x below their MMA / HBM time).  Here (1) the residual row of the
+        // NEXT tile of this CTA is prefetched into L2 one tile ahead (two 128-byte lines per thread and 64 columns), and (2) the four loads of a
+        // 32-column block are issued together, before the accumulator block is read, so that one (L2) latency is exposed per block.
+        float* yrow = p.y + (long long)b * p.out_bs + (long long)r * p.out_ld;
+        const float* rrow = p.res + (long long)b * p.res_bs + (long long)(mok ? r : 0) * p.res_ld;       // (rows outside the image re-read row 0: unconditional loads)
+        const float* arow = p.aux ? p.aux + (long long)b * p.aux_bs + (long long)(mok ? r : 0) * p.aux_ld : nullptr;
+        float rc[32], rn[32];
+  #define SMA_LD_V8(A, O, ptr)                                                                                                          \
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"                                                                  \
+                 : "=f"(A[(O) + 0]), "=f"(A[(O) + 1]), "=f"(A[(O) + 2]), "=f"(A[(O) + 3]), "=f"(A[(O) + 4]), "=f"(A[(O) + 5]), "=f"(A[(O) + 6]), "=f"(A[(O) + 7]) \
+                 : "l"(ptr))
+        // (columns past Cout re-read column block 0: unconditional loads keep the arrays in registers)
+  #define SMA_LD_BLOCK(A, rowp, n0_)                                                                         \
+    {                                                                                                        \
+      _Pragma("unroll") for (int q8_ = 0; q8_ < 4; q8_++) {                                                  \
+        const int n_ = nbase + (n0_) + q8_ * 8;                                                              \
+        SMA_LD_V8(A, q8_ * 8, (rowp) + (n_ < p.Cout ? n_ : nbase));                                          \
+      }                                                                                                      \
+    }
+        {                                                // L2 prefetch of the next tile's residual (and SFT scale) row of this thread
+          const int tile2 = tile + (int)gridDim.x;
+          if (tile2 < p.total_tiles) {
+            int b2, ty2, tx2, nt2; decode(tile2, b2, ty2, tx2, nt2);
+            int r2; bool ok2;
+            if (p.flat) { r2 = ty2 + m; ok2 = r2 < p.HoWo; }
+            else { const int oy2 = ty2 + (m >> 3), ox2 = tx2 + (m & 7); ok2 = oy2 < p.Ho && ox2 < p.Wo; r2 = oy2 * p.Wo + ox2; }
+            if (ok2) {
+              const float* q = p.res + (long long)b2 * p.res_bs + (long long)r2 * p.res_ld + nt2 * p.NT;
+              const int nb2 = min(p.NT, p.Cout - nt2 * p.NT) * 4;
+              for (int o = 0; o < nb2; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(q) + o));
+              if (p.aux) {
+                const float* qa = p.aux + (long long)b2 * p.aux_bs + (long long)r2 * p.aux_ld + nt2 * p.NT;
+                for (int o = 0; o < nb2; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(qa) + o));
               }
             }
-            float* dst = yrow + n;
-            if (p.d2s > 1) {      // depth-to-space (un-patchify): the 8 columns lie inside one sub-pixel's channel block (Cq % 8 == 0)
-              const int qd = n / Cq, cval = n - qd * Cq, p1 = qd / p.d2s, p2 = qd - p1 * p.d2s;
-              const long long pix = (long long)(oy * p.d2s + p1) * (p.Wo * p.d2s) + (ox * p.d2s + p2);
-              dst = p.y + (long long)b * p.out_bs + pix * p.out_ld + cval;
-            }
-            asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst), "f"(o[0]), "f"(o[1]), "f"(o[2]), "f"(o[3]), "f"(o[4]), "f"(o[5]),
-                         "f"(o[6]), "f"(o[7])
-                         : "memory");
           }
-        } else if (mok && !(p.dbg & 4)) {
-#pragma unroll
-          for (int q = 0; q < 8; q++) {
-            const int n = nbase + n0 + q * 4;
-            if (n >= p.Cout) break;
-            float o[4];
-#pragma unroll
-            for (int t = 0; t < 4; t++) {
-              if (F16) o[t] = sma_act(fmaf(__uint_as_float(a[q * 4 + t]), s_scale[n0 + q * 4 + t], s_bias[n0 + q * 4 + t]), ACT);
-              else o[t] = sma_act(__uint_as_float(a[q * 4 + t]) + s_bias[n0 + q * 4 + t], ACT);
+        }
+        mbar_wait(acc_full(ab), aph);
+        tc_fence_after();
+        for (int n0 = 0; n0 < p.NT && nbase + n0 < p.Cout; n0 += 32) {
+          uint32_t a[32];
+          const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(ab * p.acc_cols + n0);
+          tmem_ld32(taddr, a);
+          if (p.fuse) {                                  // the lo products were accumulated NT columns further right (two halves: registers)
+  #pragma unroll
+            for (int hh = 0; hh < 2; hh++) {
+              uint32_t a2[16];
+              tmem_ld16(taddr + (uint32_t)(p.NT + hh * 16), a2);
+              tmem_ld_wait();
+  #pragma unroll
+              for (int i = 0; i < 16; i++) a[hh * 16 + i] = __float_as_uint(__uint_as_float(a[hh * 16 + i]) + __uint_as_float(a2[i]));
             }
-            if (vec_ok && n + 4 <= p.Cout && (Cq & 3) == 0) {
-              float* dst;
-              if (p.d2s > 1) {
-                int qd = n / Cq; int cval = n - qd * Cq; int p1 = qd / p.d2s, p2 = qd - p1 * p.d2s;
-                long long pix = (long long)(oy * p.d2s + p1) * (p.Wo * p.d2s) + (ox * p.d2s + p2);
-                dst = p.y + (long long)b * p.out_bs + pix * p.out_ld + cval;
+          } else {
+            tmem_ld_wait();
+          }
+          SMA_LD_BLOCK(rc, rrow, n0)                      // (after the lo half of the accumulator is folded in: register budget)
+          if (arow) SMA_LD_BLOCK(rn, arow, n0)
+          const bool last = n0 + 32 >= p.NT || nbase + n0 + 32 >= p.Cout;
+          if (last) {                                    // last column block: the accumulator may be overwritten while we store
+            tc_fence_before();
+            mbar_arrive(acc_empty(ab));
+          }
+          if (mok && !(p.dbg & 4)) {        // (RES = 1 is only dispatched for 256-bit-eligible launches)
+  #pragma unroll
+            for (int q8 = 0; q8 < 4; q8++) {
+              const int n = nbase + n0 + q8 * 8;
+              if (n >= p.Cout) break;
+              float o[8];
+              const float4 b0 = *reinterpret_cast<const float4*>(&s_bias[n0 + q8 * 8]), b1 = *reinterpret_cast<const float4*>(&s_bias[n0 + q8 * 8 + 4]);
+              const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+              if (F16) {
+                const float4 s0 = *reinterpret_cast<const float4*>(&s_scale[n0 + q8 * 8]), s1 = *reinterpret_cast<const float4*>(&s_scale[n0 + q8 * 8 + 4]);
+                const float ss[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+  #pragma unroll
+                for (int t = 0; t < 8; t++) o[t] = sma_act(fmaf(__uint_as_float(a[q8 * 8 + t]), ss[t], bb[t]), ACT);
               } else {
-                dst = p.y + (long long)b * p.out_bs + (long long)r * p.out_ld + n;
+  #pragma unroll
+                for (int t = 0; t < 8; t++) o[t] = sma_act(__uint_as_float(a[q8 * 8 + t]) + bb[t], ACT);
               }
-              if (p.res) {
-                float4 rr = __ldg(reinterpret_cast<const float4*>(p.res + (long long)b * p.res_bs + (long long)r * p.res_ld + n));
-                o[0] += rr.x; o[1] += rr.y; o[2] += rr.z; o[3] += rr.w;
+              if (arow) {         // Fuse_sft_block tail (appmotioncodebook_arch.py:50-51): dec + w * (dec * scale + shift), this conv = shift
+  #pragma unroll
+                for (int t = 0; t < 8; t++) o[t] = rc[q8 * 8 + t] + p.sft_w * (rc[q8 * 8 + t] * rn[q8 * 8 + t] + o[t]);
+              } else {
+  #pragma unroll
+                for (int t = 0; t < 8; t++) o[t] += rc[q8 * 8 + t];
               }
-              *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
-            } else {
-#pragma unroll
-              for (int t = 0; t < 4; t++) {
-                if (n + t >= p.Cout) break;
-                float val = o[t];
-                if (p.res) val += __ldg(p.res + (long long)b * p.res_bs + (long long)r * p.res_ld + n + t);
-                if (p.d2s > 1) {
-                  int nn = n + t; int qd = nn / Cq; int c2 = nn - qd * Cq; int p1 = qd / p.d2s, p2 = qd - p1 * p.d2s;
-                  long long pix = (long long)(oy * p.d2s + p1) * (p.Wo * p.d2s) + (ox * p.d2s + p2);
-                  p.y[(long long)b * p.out_bs + pix * p.out_ld + c2] = val;
+              float* dst = yrow + n;
+              if (p.d2s > 1) {      // depth-to-space (un-patchify): the 8 columns lie inside one sub-pixel's channel block (Cq % 8 == 0)
+                const int qd = n / Cq, cval = n - qd * Cq, p1 = qd / p.d2s, p2 = qd - p1 * p.d2s;
+                const long long pix = (long long)(oy * p.d2s + p1) * (p.Wo * p.d2s) + (ox * p.d2s + p2);
+                dst = p.y + (long long)b * p.out_bs + pix * p.out_ld + cval;
+              }
+              asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst), "f"(o[0]), "f"(o[1]), "f"(o[2]), "f"(o[3]), "f"(o[4]), "f"(o[5]),
+                           "f"(o[6]), "f"(o[7])
+                           : "memory");
+            }
+          }
+        }
+
+      } else {
+        const int nbase = nt * p.NT;
+        mbar_wait(acc_full(ab), aph);
+        tc_fence_after();
+        for (int n0 = 0; n0 < p.NT && nbase + n0 < p.Cout; n0 += 32) {
+          uint32_t a[32];
+          const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(ab * p.acc_cols + n0);
+          tmem_ld32(taddr, a);
+          if (p.fuse) {                                  // a_hi * b_lo was accumulated NT columns further right
+            uint32_t a2[32];
+            tmem_ld32(taddr + (uint32_t)p.NT, a2);
+            tmem_ld_wait();
+  #pragma unroll
+            for (int i = 0; i < 32; i++) a[i] = __float_as_uint(__uint_as_float(a[i]) + __uint_as_float(a2[i]));
+          } else {
+            tmem_ld_wait();
+          }
+          if (n0 + 32 >= p.NT || nbase + n0 + 32 >= p.Cout) {     // last column block: the accumulator may be overwritten while we store
+            tc_fence_before();
+            mbar_arrive(acc_empty(ab));
+          }
+          if (mok && !(p.dbg & 4) && v8_ok) {
+            // 256-bit residual loads / stores: every lane moves whole 32-byte sectors (with 128-bit accesses a warp-level instruction touches
+            // half of 32 different sectors, and the epilogue - not the MMAs - bounds the low-K layers)
+            float* yrow = p.y + (long long)b * p.out_bs + (long long)r * p.out_ld;
+            const float* rrow = p.res ? p.res + (long long)b * p.res_bs + (long long)r * p.res_ld : nullptr;
+            const float* arow = p.aux ? p.aux + (long long)b * p.aux_bs + (long long)r * p.aux_ld : nullptr;
+  #pragma unroll
+            for (int q8 = 0; q8 < 4; q8++) {
+              const int n = nbase + n0 + q8 * 8;
+              if (n >= p.Cout) break;
+              float o[8];
+              const float4 b0 = *reinterpret_cast<const float4*>(&s_bias[n0 + q8 * 8]), b1 = *reinterpret_cast<const float4*>(&s_bias[n0 + q8 * 8 + 4]);
+              const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+              if (F16) {
+                const float4 s0 = *reinterpret_cast<const float4*>(&s_scale[n0 + q8 * 8]), s1 = *reinterpret_cast<const float4*>(&s_scale[n0 + q8 * 8 + 4]);
+                const float ss[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+  #pragma unroll
+                for (int t = 0; t < 8; t++) o[t] = sma_act(fmaf(__uint_as_float(a[q8 * 8 + t]), ss[t], bb[t]), ACT);
+              } else {
+  #pragma unroll
+                for (int t = 0; t < 8; t++) o[t] = sma_act(__uint_as_float(a[q8 * 8 + t]) + bb[t], ACT);
+              }
+              if (rrow) {
+                float r0, r1, r2, r3, r4, r5, r6, r7;
+                asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];" : "=f"(r0), "=f"(r1), "=f"(r2), "=f"(r3), "=f"(r4), "=f"(r5), "=f"(r6), "=f"(r7)
+                             : "l"(rrow + n));
+                if (arow) {       // Fuse_sft_block tail (appmotioncodebook_arch.py:50-51): dec + w * (dec * scale + shift), this conv = shift
+                  float a0, a1, a2, a3, a4, a5, a6, a7;
+                  asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];" : "=f"(a0), "=f"(a1), "=f"(a2), "=f"(a3), "=f"(a4), "=f"(a5), "=f"(a6), "=f"(a7)
+                               : "l"(arow + n));
+                  o[0] = r0 + p.sft_w * (r0 * a0 + o[0]); o[1] = r1 + p.sft_w * (r1 * a1 + o[1]); o[2] = r2 + p.sft_w * (r2 * a2 + o[2]);
+                  o[3] = r3 + p.sft_w * (r3 * a3 + o[3]); o[4] = r4 + p.sft_w * (r4 * a4 + o[4]); o[5] = r5 + p.sft_w * (r5 * a5 + o[5]);
+                  o[6] = r6 + p.sft_w * (r6 * a6 + o[6]); o[7] = r7 + p.sft_w * (r7 * a7 + o[7]);
                 } else {
-                  p.y[(long long)b * p.out_bs + (long long)r * p.out_ld + n + t] = val;
+                  o[0] += r0; o[1] += r1; o[2] += r2; o[3] += r3; o[4] += r4; o[5] += r5; o[6] += r6; o[7] += r7;
+                }
+              }
+              float* dst = yrow + n;
+              if (p.d2s > 1) {      // depth-to-space (un-patchify): the 8 columns lie inside one sub-pixel's channel block (Cq % 8 == 0)
+                const int qd = n / Cq, cval = n - qd * Cq, p1 = qd / p.d2s, p2 = qd - p1 * p.d2s;
+                const long long pix = (long long)(oy * p.d2s + p1) * (p.Wo * p.d2s) + (ox * p.d2s + p2);
+                dst = p.y + (long long)b * p.out_bs + pix * p.out_ld + cval;
+              }
+              asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst), "f"(o[0]), "f"(o[1]), "f"(o[2]), "f"(o[3]), "f"(o[4]), "f"(o[5]),
+                           "f"(o[6]), "f"(o[7])
+                           : "memory");
+            }
+          } else if (mok && !(p.dbg & 4)) {
+  #pragma unroll
+            for (int q = 0; q < 8; q++) {
+              const int n = nbase + n0 + q * 4;
+              if (n >= p.Cout) break;
+              float o[4];
+  #pragma unroll
+              for (int t = 0; t < 4; t++) {
+                if (F16) o[t] = sma_act(fmaf(__uint_as_float(a[q * 4 + t]), s_scale[n0 + q * 4 + t], s_bias[n0 + q * 4 + t]), ACT);
+                else o[t] = sma_act(__uint_as_float(a[q * 4 + t]) + s_bias[n0 + q * 4 + t], ACT);
+              }
+              if (vec_ok && n + 4 <= p.Cout && (Cq & 3) == 0) {
+                float* dst;
+                if (p.d2s > 1) {
+                  int qd = n / Cq; int cval = n - qd * Cq; int p1 = qd / p.d2s, p2 = qd - p1 * p.d2s;
+                  long long pix = (long long)(oy * p.d2s + p1) * (p.Wo * p.d2s) + (ox * p.d2s + p2);
+                  dst = p.y + (long long)b * p.out_bs + pix * p.out_ld + cval;
+                } else {
+                  dst = p.y + (long long)b * p.out_bs + (long long)r * p.out_ld + n;
+                }
+                if (p.res) {
+                  float4 rr = __ldg(reinterpret_cast<const float4*>(p.res + (long long)b * p.res_bs + (long long)r * p.res_ld + n));
+                  o[0] += rr.x; o[1] += rr.y; o[2] += rr.z; o[3] += rr.w;
+                }
+                *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+              } else {
+  #pragma unroll
+                for (int t = 0; t < 4; t++) {
+                  if (n + t >= p.Cout) break;
+                  float val = o[t];
+                  if (p.res) val += __ldg(p.res + (long long)b * p.res_bs + (long long)r * p.res_ld + n + t);
+                  if (p.d2s > 1) {
+                    int nn = n + t; int qd = nn / Cq; int c2 = nn - qd * Cq; int p1 = qd / p.d2s, p2 = qd - p1 * p.d2s;
+                    long long pix = (long long)(oy * p.d2s + p1) * (p.Wo * p.d2s) + (ox * p.d2s + p2);
+                    p.y[(long long)b * p.out_bs + pix * p.out_ld + c2] = val;
+                  } else {
+                    p.y[(long long)b * p.out_bs + (long long)r * p.out_ld + n + t] = val;
+                  }
                 }
               }
             }
           }
         }
+
       }
     }
   } else if (warp == 4) {
@@ -764,20 +871,22 @@ extern "C" int sma_pack_conv_weight_tc16(const float* w_packed, int ldw, int Cou
 
 
 
-template <int ACT, int PRE, int F16>
+template <int ACT, int PRE, int F16, int RES = 0>
 static int launch_tc2_inst(const Tc2P& p, int grid, int smem, cudaStream_t st) {
   static SmaDevOnce once;             // per instantiation and per device
-  if (int rc = sma_opt_in_smem(once, conv_tc2_kernel<ACT, PRE, F16>, SMEM_DYN_MAX)) return rc;
-  conv_tc2_kernel<ACT, PRE, F16><<<grid, V2_THREADS, smem, st>>>(p);
+  if (int rc = sma_opt_in_smem(once, conv_tc2_kernel<ACT, PRE, F16, RES>, SMEM_DYN_MAX)) return rc;
+  conv_tc2_kernel<ACT, PRE, F16, RES><<<grid, V2_THREADS, smem, st>>>(p);
   SMA_LAUNCH_CHECK();
   return SMA_OK;
 }
 template <int ACT, int F16>
 static int launch_tc2_pre(int pre, const Tc2P& p, int grid, int smem, cudaStream_t st) {
   switch (pre) {
-    case -1: return launch_tc2_inst<ACT, -1, F16>(p, grid, smem, st);
+    case -1: return (ACT == SMA_ACT_NONE && F16 && p.res_pipe) ? launch_tc2_inst<ACT, -1, F16, (ACT == SMA_ACT_NONE && F16) ? 1 : 0>(p, grid, smem, st)
+                                                                : launch_tc2_inst<ACT, -1, F16>(p, grid, smem, st);
     case SMA_ACT_NONE: return launch_tc2_inst<ACT, SMA_ACT_NONE, F16>(p, grid, smem, st);
-    case SMA_ACT_SWISH: return launch_tc2_inst<ACT, SMA_ACT_SWISH, F16>(p, grid, smem, st);
+    case SMA_ACT_SWISH: return (ACT == SMA_ACT_NONE && F16 && p.res_pipe) ? launch_tc2_inst<ACT, SMA_ACT_SWISH, F16, (ACT == SMA_ACT_NONE && F16) ? 1 : 0>(p, grid, smem, st)
+                                                                           : launch_tc2_inst<ACT, SMA_ACT_SWISH, F16>(p, grid, smem, st);
     default: return SMA_ERR_UNSUPPORTED;     // other prologue activations: gather / CUDA-core kernels
   }
 }
@@ -844,6 +953,9 @@ static int conv_tc2_try(const sma_conv_desc* d, cudaStream_t st, bool f16) {
   // conv is a BIAS of -1.6e-8 per add for mixed-sign terms, the same on every shape from 36 to 864 adds, 10x the rounding noise of an fp32
   // FFMA chain).  The epilogue multiplies the mean back in; what remains is the data-dependent part (partial sums that stay far below or
   // above the random-walk average), at most the size of the correction itself (<= 1.4e-5 for the longest chain of this network).
+  p.res_pipe = (d->res && d->act == SMA_ACT_NONE && d->d2s <= 1 && (d->Cout & 7) == 0 && (d->out_ld & 7) == 0 && (d->out_bstride & 7) == 0 &&
+                (reinterpret_cast<uintptr_t>(d->y) & 31) == 0 && (d->res_ld & 7) == 0 && (d->res_bstride & 7) == 0 &&
+                (reinterpret_cast<uintptr_t>(d->res) & 31) == 0 && !(d->tc_variant & 512)) ? 1 : 0;
   const int main_adds = p.cpt * p.taps * 4 * (p.fuse ? 1 : p.passes);
   p.acc_corr = (d->tc_variant & 256) ? 1.f : 1.f + 1.6e-8f * (float)main_adds;
   p.dbg = (d->tc_variant >> 1) & 7;

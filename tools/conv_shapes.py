@@ -11,6 +11,7 @@ SHAPES = [  # B, Cin, H, Cout, k, pre, res, fast, weight in the step (launches)
     (64, 64, 256, 192, 1, False, False, True, 1), (64, 256, 32, 256, 3, True, True, False, 8), (64, 256, 64, 256, 3, False, False, True, 4),
     (64, 160, 64, 126, 3, False, False, True, 4), (64, 64, 256, 128, 3, False, False, False, 1), (64, 128, 64, 128, 3, True, True, False, 7),
     (64, 64, 256, 3, 3, True, False, False, 1), (64, 256, 32, 4096, 1, False, False, False, 1)]
+S.ops.TC_VARIANT = int(os.environ.get('TCV', '0'))
 flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')
 tot = 0.0
 rows = []
@@ -29,4 +30,4 @@ for (B, Cin, H, Cout, k, pre, res, fast, wgt) in SHAPES:
     ms = sorted(ts)[1]
     tot += ms * wgt
     rows.append(f'{ms:.3f}')
-print(os.environ.get('SMA_B200_LIB', 'default').split('/')[-1], f'weighted {tot:.2f} ms |', ' '.join(rows), flush=True)
+print('TCV', S.ops.TC_VARIANT, os.environ.get('SMA_B200_LIB', 'default').split('/')[-1], f'weighted {tot:.2f} ms |', ' '.join(rows), flush=True)
