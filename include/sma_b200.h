@@ -43,7 +43,7 @@ enum {
  *   F16X3  the same split with fp16 halves on kind::f16 (same 11-bit significands, twice the MACs per tensor cycle); weights are
  *          pre-scaled per output channel by a power of two, activations saturate at +-65504 and lose their lo half below 2^-25.
  *   TF32 / F16  single pass (hi*hi only): only for stages whose contribution to the 1e-3 output budget was measured negligible. */
-enum { SMA_PREC_EXACT = 0, SMA_PREC_TF32X3 = 1, SMA_PREC_TF32 = 2, SMA_PREC_F16X3 = 3, SMA_PREC_F16 = 4 };
+enum { SMA_PREC_EXACT = 0, SMA_PREC_TF32X3 = 1, SMA_PREC_TF32 = 2, SMA_PREC_F16X3 = 3, SMA_PREC_F16 = 4, SMA_PREC_F16X2 = 5 };
 
 enum { SMA_ACT_NONE = 0, SMA_ACT_RELU = 1, SMA_ACT_LEAKY02 = 2, SMA_ACT_GELU = 3, SMA_ACT_SIGMOID = 4,
        SMA_ACT_SWISH = 5 };

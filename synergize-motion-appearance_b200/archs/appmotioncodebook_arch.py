@@ -308,15 +308,15 @@ class AppMotionCompFormer(ParamModule):
         skip = x if cin == cout else ops.conv2d(x, W[name + '.conv_out'], fast=fast)
         return ops.conv2d(h, W[name + '.conv2'], pad=1, pre=(s2, h2, 'swish'), res=skip, out=out, fast=fast)
 
-    def _attn(self, name, x, out=None):
+    def _attn(self, name, x, out=None, fast=False):
         W = self._packed
         B, H, Wd, Cc = x.shape
         s, h = self._gn(name + '.norm', x)
-        qkv = ops.conv2d(x, W[name + '.qkv'], pre=(s, h, 'none')).view(B, H * Wd, 3 * Cc)
+        qkv = ops.conv2d(x, W[name + '.qkv'], pre=(s, h, 'none'), fast=fast).view(B, H * Wd, 3 * Cc)
         o = ops.mha(qkv[..., :Cc], qkv[..., Cc:2 * Cc], qkv[..., 2 * Cc:], heads=1, scale=float(int(Cc) ** (-0.5)))
-        return ops.conv2d(o.view(B, H, Wd, Cc), W[name + '.proj_out'], res=x, out=out)
+        return ops.conv2d(o.view(B, H, Wd, Cc), W[name + '.proj_out'], res=x, out=out, fast=fast)
 
-    def _block(self, prefix, i, layout, x, out=None):
+    def _block(self, prefix, i, layout, x, out=None, fast=False):
         kind, cin, cout = layout[i]
         n = f'{prefix}.blocks.{i}'
         W = self._packed
@@ -325,15 +325,15 @@ class AppMotionCompFormer(ParamModule):
             if i > 0 and layout[i - 1][0] == 'norm':          # GroupNorm (no activation) feeding the last conv
                 s, h = self._gn(f'{prefix}.blocks.{i - 1}', x)
                 pre = (s, h, 'none')
-            return ops.conv2d(x, W[n], pad=1, pre=pre, out=out)
+            return ops.conv2d(x, W[n], pad=1, pre=pre, out=out, fast=fast)
         if kind == 'res':
-            return self._res(n, x, cin, cout, out=out)
+            return self._res(n, x, cin, cout, out=out, fast=fast)
         if kind == 'attn':
-            return self._attn(n, x, out=out)
+            return self._attn(n, x, out=out, fast=fast)
         if kind == 'down':      # pad right/bottom by one, stride 2 (vqgan_arch.py:149-152)
-            return ops.conv2d(x, W[n + '.conv'], stride=2, pad_tl=(0, 0), out_hw=(x.shape[1] // 2, x.shape[2] // 2), out=out)
+            return ops.conv2d(x, W[n + '.conv'], stride=2, pad_tl=(0, 0), out_hw=(x.shape[1] // 2, x.shape[2] // 2), out=out, fast=fast)
         if kind == 'up':
-            return ops.conv2d(x, W[n + '.conv'], pad=1, upsample2=True, out=out)
+            return ops.conv2d(x, W[n + '.conv'], pad=1, upsample2=True, out=out, fast=fast)
         if kind == 'norm':
             return x              # folded into the next conv's operand load
         raise ValueError(kind)
@@ -448,19 +448,20 @@ class AppMotionCompFormer(ParamModule):
         B = feat.shape[0]
         tg, s0 = self.tg, s // self.R
         mask = ops.motion_ignore_mask(m_com, (tg, tg))
+        fa = ops.fast('s3a')
         if s0 == 32:
-            tok = ops.conv2d(feat, W['app_feat_emb_32'])
+            tok = ops.conv2d(feat, W['app_feat_emb_32'], fast=fa)
         else:
             p = s0 // 32
-            tok = ops.conv2d(feat, W[f'app_feat_emb_{s0}.1'], stride=p)
+            tok = ops.conv2d(feat, W[f'app_feat_emb_{s0}.1'], stride=p, fast=fa)
         tok = tok.view(B, self.L, self.Ea)
         n_ctx = self._n_ctx(self.n_codes_app, s0)
-        tok = self._transformer('app_block.0', tok, self.Ea, n_ctx, T['position_emb_app'], key_mask=mask)
-        tok = self._transformer('app_block.1', tok, self.Ea, n_ctx, T['position_emb_app'])
+        tok = self._transformer('app_block.0', tok, self.Ea, n_ctx, T['position_emb_app'], key_mask=mask, fast=fa)
+        tok = self._transformer('app_block.1', tok, self.Ea, n_ctx, T['position_emb_app'], fast=fa)
         tok = tok.view(B, tg, tg, self.Ea)
         if s0 == 32:
-            return ops.conv2d(tok, W['to_app_feat_32'], out=out)
-        return ops.conv2d(tok, W[f'to_app_feat_{s0}.0'], d2s=s0 // 32, out=out)
+            return ops.conv2d(tok, W['to_app_feat_32'], out=out, fast=fa)
+        return ops.conv2d(tok, W[f'to_app_feat_{s0}.0'], d2s=s0 // 32, out=out, fast=fa)
 
     # ------------------------------------------------------------------------------------------
     # the per-driving-frame body (appmotioncodebook_arch.py:556-764, inference=True)
@@ -507,27 +508,29 @@ class AppMotionCompFormer(ParamModule):
         lq_feat = x
         fuse_at = {9: 64, 12: 128, 15: 256}
         cat = None
+        fgen = ops.fast('gen')
         for i in range(len(self.gen_layout)):
             if i in fuse_at and w > 0:
                 s0 = fuse_at[i]                      # nominal scale: names; s: the actual feature size
                 s = s0 * R
                 c = self.channels[s0]
                 cat = torch.empty((B, s, s, 2 * c), device=dev, dtype=torch.float32)   # [enc | dec] for Fuse_sft_block
-                x = self._block('generator', i, self.gen_layout, x, out=cat[..., c:])
+                x = self._block('generator', i, self.gen_layout, x, out=cat[..., c:], fast=fgen)
                 enc = compensate(s, out=cat[..., :c])
                 n = f'fuse_convs_dict.{s0}'
-                e = self._res(n + '.encode_enc', cat, 2 * c, c)
-                ss = ops.conv2d(e, W[n + '.ss0'], pad=1, act='leaky')                  # [scale.0 | shift.0]
-                scale = ops.conv2d(ss[..., :c], W[n + '.scale.2'], pad=1)
+                fsft = ops.fast('sft')
+                e = self._res(n + '.encode_enc', cat, 2 * c, c, fast=fsft)
+                ss = ops.conv2d(e, W[n + '.ss0'], pad=1, act='leaky', fast=fsft)                  # [scale.0 | shift.0]
+                scale = ops.conv2d(ss[..., :c], W[n + '.scale.2'], pad=1, fast=fsft)
                 # dec + w * (dec * scale + shift) in the epilogue of the `shift.2` conv; the decoder half is read in place (channel slice of `cat`)
-                xf = ops.conv2d(ss[..., c:], W[n + '.shift.2'], pad=1, res=x, sft=(scale, float(w)))
+                xf = ops.conv2d(ss[..., c:], W[n + '.shift.2'], pad=1, res=x, sft=(scale, float(w)), fast=fsft)
                 if collect is not None:
                     collect[f'sft_{s}'] = xf.clone()                                   # (the next conv accumulates in place)
-                x = ops.conv2d(enc, W[f'fuse_ms_dict.{s0}'], pad=1, res=xf, out=xf)
+                x = ops.conv2d(enc, W[f'fuse_ms_dict.{s0}'], pad=1, res=xf, out=xf, fast=ops.fast('ms'))
                 if collect is not None:
                     collect[f'fused_{s}'] = x
             else:
-                x = self._block('generator', i, self.gen_layout, x)
+                x = self._block('generator', i, self.gen_layout, x, fast=fgen)
         return {'out': x, 'lq_feat': lq_feat, 'out_occ': occs, 'deformation_list': motions, 'residuals': residuals}
 
     # ------------------------------------------------------------------------------------------

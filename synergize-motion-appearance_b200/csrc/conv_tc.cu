@@ -610,10 +610,13 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const Tc2P p) {
                   // a_lo * b_hi goes to the LO half of the accumulator (columns [NT, 2 NT), added in the epilogue with round-to-nearest):
                   // the tensor core adds into its fp32 accumulator with truncation (measured: a bias of -1.6e-8 per add, relative), so
                   // the main accumulator should see as few adds as possible - one per k-step instead of two
-                  tc_mma<F16>(d_tmem + (uint32_t)p.NT, dal + ko, dbh + ko, idesc, 1u);
+                  if (three) tc_mma<F16>(d_tmem + (uint32_t)p.NT, dal + ko, dbh + ko, idesc, 1u);     // (2-product mode: the activations' lo halves are dropped)
                 } else if (three) {
                   tc_mma<F16>(d_tmem, dal + ko, dbh + ko, idesc, acc);
                   tc_mma<F16>(d_tmem, dah + ko, dbl + ko, idesc, 1u);
+                  tc_mma<F16>(d_tmem, dah + ko, dbh + ko, idesc, 1u);
+                } else if (p.passes == 2) {
+                  tc_mma<F16>(d_tmem, dah + ko, dbl + ko, idesc, acc);
                   tc_mma<F16>(d_tmem, dah + ko, dbh + ko, idesc, 1u);
                 } else {
                   tc_mma<F16>(d_tmem, dah + ko, dbh + ko, idesc, acc);
@@ -634,7 +637,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const Tc2P p) {
   } else if (warp == 5) {
     // =============================== weight loader ===============================
     if (lane == 0) {
-      const uint32_t bytes = (uint32_t)(p.passes == 3 ? b_stage_bytes : p.b_img_bytes);
+      const uint32_t bytes = (uint32_t)(p.passes >= 2 ? b_stage_bytes : p.b_img_bytes);
       int jt = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         const int nt = tile % p.ntiles_n;
@@ -927,7 +930,7 @@ static int conv_tc2_try(const sma_conv_desc* d, cudaStream_t st, bool f16) {
   p.pad_t = d->pad_t; p.pad_l = d->pad_l; p.up = d->upsample2 ? 1 : 0; p.pre_act = d->pre_act; p.Ho = d->Ho; p.Wo = d->Wo; p.out_ld = d->out_ld;
   p.act = d->act; p.res_ld = d->res_ld; p.d2s = d->d2s;
   p.HoWo = d->Ho * d->Wo; p.cpt = d->Cin / kch; p.taps = d->kh * d->kw;
-  p.passes = (d->precision == SMA_PREC_TF32 || d->precision == SMA_PREC_F16) ? 1 : 3;
+  p.passes = (d->precision == SMA_PREC_TF32 || d->precision == SMA_PREC_F16) ? 1 : (f16 && d->precision == SMA_PREC_F16X2) ? 2 : 3;
   p.flat = flat ? 1 : 0;
   if (flat) { p.tiles_x = 1; p.tiles_per_img = (p.HoWo + BM - 1) / BM; p.halo_w = 8; p.HP = BM; }
   else {
@@ -947,7 +950,7 @@ static int conv_tc2_try(const sma_conv_desc* d, cudaStream_t st, bool f16) {
   if (SB < 2) return SMA_ERR_UNSUPPORTED;
   if (SB > MAX_SB) SB = MAX_SB;
   p.SA = SA; p.SB = SB;
-  p.fuse = (p.passes == 3 && p.NT <= 128 && !(d->tc_variant & 128)) ? 1 : 0;       // tc_variant bit 7: keep the three separate MMAs (tests)
+  p.fuse = (p.passes >= 2 && p.NT <= 128 && !(d->tc_variant & 128)) ? 1 : 0;       // tc_variant bit 7: keep the three separate MMAs (tests)
   p.acc_cols = p.fuse ? 2 * p.NT : p.NT;
   // The tensor core adds every MMA result into its fp32 accumulator with truncation toward zero (tools/acc_bias.py: the relative error of a
   // conv is a BIAS of -1.6e-8 per add for mixed-sign terms, the same on every shape from 36 to 864 adds, 10x the rounding noise of an fp32
@@ -979,7 +982,7 @@ int sma_conv2d_tc_try(sma_conv_desc* d, cudaStream_t st) {
   const long long M = (long long)d->B * d->Ho * d->Wo;
   if (M < 64) return SMA_ERR_UNSUPPORTED;
   // plan_only: report the kernel (and the tf32 image tile) this launch would use if every weight image were available; nothing is launched
-  const bool want16 = (d->precision == SMA_PREC_F16X3 || d->precision == SMA_PREC_F16) && (d->plan_only || (d->w_tc16 && !(reinterpret_cast<uintptr_t>(d->w_tc16) & 15)));
+  const bool want16 = (d->precision == SMA_PREC_F16X3 || d->precision == SMA_PREC_F16 || d->precision == SMA_PREC_F16X2) && (d->plan_only || (d->w_tc16 && !(reinterpret_cast<uintptr_t>(d->w_tc16) & 15)));
   if (want16 && !(d->tc_variant & 1)) {
     int r2 = conv_tc2_try(d, st, true);
     if (r2 != SMA_ERR_UNSUPPORTED) { d->kernel_used = 3; return r2; }

@@ -214,7 +214,7 @@ def pack_conv_blockdiag(weights, biases) -> ConvW:
     return pack_conv(big, torch.cat([x.detach().float() for x in biases], dim=0))
 
 
-PREC = {'exact': 0, 'tf32x3': 1, 'tf32': 2, 'f16x3': 3, 'f16': 4}     # SMA_PREC_*
+PREC = {'exact': 0, 'tf32x3': 1, 'tf32': 2, 'f16x3': 3, 'f16': 4, 'f16x2': 5}     # SMA_PREC_*
 USE_TF32X3 = True        # let sma_conv2d_fwd pick a tcgen05 kernel where the shape allows (False: exact CUDA-core kernels everywhere)
 ALLOW_TF32_1PASS = True  # honour `fast=True` requests (single pass)
 USE_TS = False           # weights as the tensor-memory A operand (csrc/conv_ts.cu) where they fit in tensor memory; False: shared-memory-operand kernels
@@ -226,8 +226,12 @@ FAST_STAGES = {'s1', 's3m'}     # measured (tools/policy_err.py, gpurun_out/r2_p
                                 # image by up to 1.9e-3 on general frames (the round-1 fixture clip hid it); S1 costs 8e-5, S3m 3e-5 of the 1e-3 budget
 
 
-def fast(stage: str) -> bool:
-    return stage in FAST_STAGES
+X2_STAGES: set = set()          # stages whose convolutions drop the activations' lo halves (weights hi + lo x activation hi: SMA_PREC_F16X2)
+
+
+def fast(stage: str):
+    """-> the `fast` argument of conv2d for a stage: True = single pass, 'x2' = two products, False = fp32-faithful three products."""
+    return True if stage in FAST_STAGES else ('x2' if stage in X2_STAGES else False)
 
 
 TC_VARIANT = 0           # 0: library picks the tensor-core kernel variant; 1: force the gather kernel (tests)
@@ -295,8 +299,8 @@ def conv2d(x: torch.Tensor, cw: ConvW, *, stride: int = 1, pad: int = 0, pad_tl:
     if exact or not USE_TF32X3 or Cin % 32:
         d.precision = PREC['exact']
     else:
-        one = fast and ALLOW_TF32_1PASS
-        d.precision = (PREC['f16'] if one else PREC['f16x3']) if USE_F16 else (PREC['tf32'] if one else PREC['tf32x3'])
+        one = fast is True and ALLOW_TF32_1PASS
+        d.precision = (PREC['f16'] if one else (PREC['f16x2'] if fast == 'x2' else PREC['f16x3'])) if USE_F16 else (PREC['tf32'] if one else PREC['tf32x3'])
         if USE_TS:       # the tensor-memory-operand experiment: every image up front, the library picks
             d.w_tc, d.w_tc16, d.w_ts = _ptr(cw.image('tc', 0)), _ptr(cw.image('tc16')), _ptr(cw.image('ts'))
         else:
@@ -326,7 +330,7 @@ def conv2d(x: torch.Tensor, cw: ConvW, *, stride: int = 1, pad: int = 0, pad_tl:
                4.0 * (B * Hi * Wi * Cin + B * Ho * Wo * cw.Cout * (2 if res is not None else 1) + K * cw.Cout),
                f'conv B{B} {Hi}x{Wi} Cin{Cin} Cout{cw.Cout} k{cw.kh} s{stride}{" up" if upsample2 else ""}{" pre" if pre is not None else ""}') as pr:
         check(lib.sma_conv2d_fwd(C.byref(d), _stream()), f'sma_conv2d_fwd Cin={Cin} Cout={cw.Cout} k={cw.kh}x{cw.kw}')
-        pr.label += (' simt', ' tc-gather', ' tc-halo', ' tc-halo-f16', ' ts-f16')[d.kernel_used] + (' 1pass' if d.precision in (2, 4) else '')
+        pr.label += (' simt', ' tc-gather', ' tc-halo', ' tc-halo-f16', ' ts-f16')[d.kernel_used] + (' 1pass' if d.precision in (2, 4) else (' x2' if d.precision == 5 and d.kernel_used == 3 else ''))
     if planned is not None and d.kernel_used != planned[0]:
         raise _lib.SmaError(f'conv2d ran on kernel {d.kernel_used} but was planned on {planned[0]} (Cin={Cin} Cout={cw.Cout} k={cw.kh}): binding bug')
     global LAST_CONV_KERNEL

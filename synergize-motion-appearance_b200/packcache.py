@@ -61,7 +61,7 @@ def cache_dir_of(module) -> Optional[str]:
 def state_hash(module) -> str:
     """blake2b over (class, ABI version, packing policy, every state tensor's name / shape / bytes)."""
     h = hashlib.blake2b(digest_size=16)
-    policy = (module.__class__.__name__, _lib.load().sma_abi_version(), ops.USE_F16, ops.USE_TS, sorted(ops.FAST_STAGES))
+    policy = (module.__class__.__name__, _lib.load().sma_abi_version(), ops.USE_F16, ops.USE_TS, sorted(ops.FAST_STAGES), sorted(ops.X2_STAGES))
     h.update(repr(policy).encode())
     for k, v in sorted(module.state_dict().items()):
         t = v.detach().cpu().contiguous()

@@ -147,6 +147,24 @@ def test_conv2d_f16_split_dynamic_range(S, scale_w, scale_x, tol):
     assert float((err / mag).max()) < tol, (err / mag).max()        # measured: 2.5e-5 for the 1e-3-scale activations, < 1e-5 otherwise
 
 
+@pytest.mark.parametrize('Cin,Cout', [(64, 64), (128, 128), (256, 512)])
+def test_conv2d_two_product_mode_is_the_full_weight_times_the_fp16_rounded_activation(S, Cin, Cout):
+    """SMA_PREC_F16X2 (fast='x2'): weights hi + lo, activations hi only - i.e. exactly conv(rn_fp16(x), w) to fp32-faithful accuracy, on both the
+    fused [hi | lo] weight tile (Cout <= 128: ONE MMA per k-step) and the wide-tile path (two).  Not used by the default policy: measured
+    (profiles/r2_two_product_policy.md) every generator stage it was tried on leaves the 1e-3 budget."""
+    B, H, W, k = 2, 32, 24, 3
+    x = rnd(B, Cin, H, W, seed=1)
+    w = rnd(Cout, Cin, k, k, seed=2, scale=(Cin * k * k) ** -0.5)
+    b = rnd(Cout, seed=3, scale=0.1)
+    ref = F.conv2d(x.half().double(), w.double(), b.double(), padding=1)
+    full = F.conv2d(x.double(), w.double(), b.double(), padding=1)
+    y = S.ops.conv2d(nhwc(x), S.ops.pack_conv(w.cuda(), b.cuda()), pad=1, fast='x2')
+    assert S.ops.LAST_CONV_KERNEL == 3
+    err = float((nchw(y).double() - ref).abs().max())
+    assert err < 2e-5 + 1e-8 * Cin * k * k, err
+    assert float((nchw(y).double() - full).abs().max()) > 5 * err          # ... and it really dropped the lo halves
+
+
 def test_conv2d_concat_slices_patchify_and_bn_fold(S):
     """channel-slice views as input/output (torch.cat elimination), stride-p patch embedding, depth-to-space."""
     B, C, s, p = 2, 128, 64, 2

@@ -35,7 +35,8 @@ for seed in seeds:
     for mode in policies:
         S.ops.USE_TF32X3 = not mode.startswith('exact')
         S.ops.USE_F16 = mode.startswith('f16')
-        S.ops.FAST_STAGES = set(mode.split('+')[1:])
+        S.ops.FAST_STAGES = set(t for t in mode.split('+')[1:] if not t.startswith('x2:'))
+        S.ops.X2_STAGES = set(t[3:] for t in mode.split('+')[1:] if t.startswith('x2:'))
         g.clear_source_cache(); me.dense_motion_network.clear_source_cache()
         anim = S.ClipAnimator(g, me, src.unsqueeze(0).cuda(), drv[0].unsqueeze(0).cuda(), True, True, 1.0)
         frames = torch.stack(sel).cuda()
@@ -54,4 +55,4 @@ for seed in seeds:
         heat = S.ops.nchw_to_nhwc(dm['driving_kp_heatmap'].cuda().contiguous())
         r2 = g.generate(anim.feats, dm['deformation'].cuda(), dm['occlusion_map'].cuda().view(4, 64 * SIZE // 256, 64 * SIZE // 256), heat, 1.0)
         e2 = (r2['out'].permute(0, 3, 1, 2).cpu() - ref['out']).abs().amax(dim=(1, 2, 3))
-        print(f'  {mode:16s} out {["%.2e" % float(v) for v in e]} | gen-only {["%.2e" % float(v) for v in e2]} | kp {ekp:.1e} jac {ekj:.1e} kpn {ekn:.1e} | deform {edef:.1e} occ {eocc:.1e} | m_com {["%.1e" % v for v in em]}', flush=True)
+        print(f'  {mode:34s} out {["%.2e" % float(v) for v in e]} | gen-only {["%.2e" % float(v) for v in e2]} | kp {ekp:.1e} jac {ekj:.1e} kpn {ekn:.1e} | deform {edef:.1e} occ {eocc:.1e} | m_com {["%.1e" % v for v in em]}', flush=True)
