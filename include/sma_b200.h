@@ -42,7 +42,9 @@ enum {
  *   TF32X3 error-compensated split on tcgen05 kind::tf32: x = hi + lo, a*b ~= a_lo*b_hi + a_hi*b_lo + a_hi*b_hi (fp32-faithful).
  *   F16X3  the same split with fp16 halves on kind::f16 (same 11-bit significands, twice the MACs per tensor cycle); weights are
  *          pre-scaled per output channel by a power of two, activations saturate at +-65504 and lose their lo half below 2^-25.
- *   TF32 / F16  single pass (hi*hi only): only for stages whose contribution to the 1e-3 output budget was measured negligible. */
+ *   TF32 / F16  single pass (hi*hi only): only for stages whose contribution to the 1e-3 output budget was measured negligible.
+ *   F16X2  weights hi + lo, activations hi only (one MMA per k-step on the fused [hi | lo] weight tile); measured too coarse for every generator
+ *          stage (profiles/r2_two_product_policy.md): no stage of the shipped policy uses it. */
 enum { SMA_PREC_EXACT = 0, SMA_PREC_TF32X3 = 1, SMA_PREC_TF32 = 2, SMA_PREC_F16X3 = 3, SMA_PREC_F16 = 4, SMA_PREC_F16X2 = 5 };
 
 enum { SMA_ACT_NONE = 0, SMA_ACT_RELU = 1, SMA_ACT_LEAKY02 = 2, SMA_ACT_GELU = 3, SMA_ACT_SIGMOID = 4,
@@ -187,6 +189,11 @@ int sma_mha_e256_fwd(const float* q, int ldq, const float* k, int ldk, const flo
  * lowest-index ties -> idx (int64), zq = e[idx].  z:(N,E) row-major, codebook (n_codes,E). */
 int sma_vq_lookup_fwd(const float* z, int N, int E, const float* codebook, int n_codes, int64_t* idx,
                       float* zq, float* min_dist, sma_stream_t stream);
+/* Forward values of VectorQuantizer.forward's other returns (archs/vqgan_arch.py:76-80,88), the training-path pieces of SURVEY 8f(4):
+ * zq_st = z + (zq - z) (the straight-through tensor, may be NULL) and loss[0] = beta * mean((zq - z)^2) + mean((zq - z)^2) over n elements
+ * (a device scalar).  Deterministic two-stage sum; workspace: sma_vq_workspace_floats() floats. */
+int sma_vq_workspace_floats(void);
+int sma_vq_commit_fwd(const float* z, const float* zq, int64_t n, float beta, float* zq_st, float* workspace, float* loss, sma_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Motion-estimator heads and glue

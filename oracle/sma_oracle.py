@@ -259,6 +259,18 @@ def encode_source(P: SD, x: T) -> Dict[str, T]:
     return feats
 
 
+def encode_driving(P: SD, x: T) -> Dict[str, T]:
+    """AppMotionCompFormer.encode_driving (archs/appmotioncodebook_arch.py:364-371; the same taps feed app_codebook_loss, :433-439): features after
+    encoder blocks 2 / 5 / 8 and **11** - the '32' entry is the output of the first attention block at 32x32 (`fuse_encoder_block['32'] = 11`, :327),
+    NOT the latent the forward warps (that is the output of the last block)."""
+    feats = {}
+    for i, kind in enumerate(ENCODER_BLOCKS):
+        x = run_block(P, kind, f'encoder.blocks.{i}', x)
+        if i in (2, 5, 8, 11):
+            feats[str(x.shape[-1])] = x
+    return feats
+
+
 # ----------------------------------------------------------------------------------------------
 # codebook transformer layer + vector quantizer
 # ----------------------------------------------------------------------------------------------
@@ -315,6 +327,51 @@ def vq_lookup(codebook: T, z: T, scale: Optional[float] = None):
     return zq.permute(0, 3, 1, 2).contiguous(), loss, idx.unsqueeze(1), d.mean(), perplexity
 
 
+def vq_forward(codebook: T, z: T, scale: Optional[float] = None, beta: float = 0.25):
+    """What VectorQuantizer.forward RETURNS as its first two values (archs/vqgan_arch.py:76-80,88): the straight-through tensor
+    z + (z_q - z) (its forward value differs from z_q by one rounding) and the loss beta * mean((z_q - z)^2) + mean((z_q - z)^2)."""
+    zq, _, idx, _, _ = vq_lookup(codebook, z, scale)
+    loss = beta * torch.mean((zq - z) ** 2) + torch.mean((zq - z) ** 2)
+    return z + (zq - z), loss, idx
+
+
+def to_motion(P: SD, x: T) -> T:
+    """self.to_motion = Upsample, ResBlock, GroupNorm, conv3x3 32 -> 2 (archs/appmotioncodebook_arch.py:290-292)."""
+    x = upsample(P, 'to_motion.0', x)
+    x = res_block(P, 'to_motion.1', x)
+    return conv(P, 'to_motion.3', group_norm(P, 'to_motion.2', x), padding=1)
+
+
+def app_codebook_loss(P: SD, gt: T, beta: float = 0.25):
+    """AppMotionCompFormer.app_codebook_loss (archs/appmotioncodebook_arch.py:429-469), split = 1, shared codebook prefixes: the driving ("gt")
+    frame's encoder features are embedded to the 32x32 token grid, quantised against the first 256 k rows of the appearance codebook and mapped
+    back.  -> ([[app_recon, app_feat_original, quant_app, app_feat, feat_com] per scale 32, 64, 128, 256], [loss per scale])."""
+    feats = encode_driving(P, gt)
+    recon, losses = [], []
+    cb = P['quantize_app.embedding.weight']
+    for w in (32, 64, 128, 256):
+        f = feats[str(w)]
+        b, c = f.shape[:2]
+        if w == 32:
+            app_feat = conv(P, 'app_feat_emb_32', f)
+        else:
+            p = w // 32
+            x = f.view(b, c, 32, p, 32, p).permute(0, 2, 4, 3, 5, 1).reshape(b, 1024, p * p * c)          # Rearrange 'b c (h p1) (w p2) -> b (h w) (p1 p2 c)'
+            app_feat = F.linear(x, P[f'app_feat_emb_{w}.1.weight'], P[f'app_feat_emb_{w}.1.bias'])        # (b, 1024, 256)
+            app_feat = app_feat.permute(0, 2, 1).reshape(b, app_feat.shape[2], 32, 32)                    # Rearrange 'b n d -> b d n', then :452-453
+        quant, loss, _ = vq_forward(cb, app_feat, SCALE_K[w] / 4.0, beta)
+
+        def back(t):
+            if w == 32:
+                return conv(P, 'to_app_feat_32', t)
+            y = F.linear(t.reshape(b, t.shape[1], 1024).permute(0, 2, 1), P[f'to_app_feat_{w}.0.weight'], P[f'to_app_feat_{w}.0.bias'])
+            p = w // 32
+            return y.view(b, 32, 32, p, p, c).permute(0, 5, 1, 3, 2, 4).reshape(b, c, w, w)
+        recon.append([back(quant), back(app_feat), quant, app_feat, f])
+        losses.append(loss)
+    return recon, losses
+
+
 # ----------------------------------------------------------------------------------------------
 # AppMotionCompFormer forward (inference=True, w given)   archs/appmotioncodebook_arch.py:546-764
 # ----------------------------------------------------------------------------------------------
@@ -344,7 +401,7 @@ def occlude(feat: T, occ: T) -> T:
     return feat * resize_ac(occ, feat.shape[-2:])
 
 
-def motion_compensation(P: SD, flow_px: T, qfeat: T, warp0: T, s: int) -> T:
+def motion_compensation(P: SD, flow_px: T, qfeat: T, warp0: T, s: int, collect: Optional[dict] = None) -> T:
     """motion_codebook_compensation, inference branch (appmotioncodebook_arch.py:373-427) with
     BasicMotionEncoder (:129-147) and RefineFlow (:150-168).  flow_px:(B,64,64,2) in pixels.
     Returns (B,64,64,3): delta-flow (px) and delta-occlusion logit."""
@@ -353,6 +410,8 @@ def motion_compensation(P: SD, flow_px: T, qfeat: T, warp0: T, s: int) -> T:
     mf = conv(P, 'motion_emb.0', m, padding=1)
     mf = downsample(P, 'motion_emb.1', mf)
     mf = res_block(P, 'motion_emb.2', mf)                                          # (B,32,32,32)
+    if collect is not None:
+        collect[f'm_feat_{s}'] = mf
     q = conv(P, 'motion_query_enc_2', torch.cat([mf, resize_ac(qfeat, mf.shape[-2:])], dim=1))
     E = q.shape[1]
     R = h // 64                                                                    # 1 at 256x256, 2 for the 512x512 variant
@@ -444,7 +503,7 @@ def generator_forward(P: SD, src_feats: Dict[str, T], dm: Dict[str, T], w: float
         warp0 = warp_ac(feat_s, m_prev)
         ws_ = F.relu(conv(P, f'warped_source_enc_{s // R}', resize_ac(warp0, (tg, tg))))
         qf = conv(P, 'motion_query_enc_1', torch.cat([ws_, kp_feat], dim=1))
-        res = motion_compensation(P, (m_prev - grid) * half, qf, warp0, s)
+        res = motion_compensation(P, (m_prev - grid) * half, qf, warp0, s, collect)
         m_com = m_prev + res[..., 0:2] / half
         motions.append(m_com)
         occ = torch.sigmoid(occ_prev + res[..., 2:].permute(0, 3, 1, 2))
@@ -472,6 +531,27 @@ def generator_forward(P: SD, src_feats: Dict[str, T], dm: Dict[str, T], w: float
             if collect is not None:
                 collect[f'fused_{s}'] = x
     return {'out': x, 'lq_feat': lq_feat, 'out_occ': occs, 'deformation_list': motions}
+
+
+def generator_forward_train(P: SD, src_feats: Dict[str, T], dm: Dict[str, T], w: float = 1.0, gt: Optional[T] = None, beta: float = 0.25) -> Dict[str, T]:
+    """The VALUES AppMotionCompFormer.forward adds with inference=False (archs/appmotioncodebook_arch.py:379-386,424-427,580-587,641-662,
+    676-683,749-757): per scale the motion feature is quantised against the first 256 k rows of the motion codebook and decoded by `to_motion`
+    (`motion_recon_list`, in grid units; `codebook_loss_motion_list`), the un-fused decoder runs on lq_feat (`out_lr`), and with a ground-truth frame
+    `app_codebook_loss` (`app_recon_list`, `codebook_loss_app_list`).  Forward values only: gradients are outside the path."""
+    collect: dict = {}
+    out = generator_forward(P, src_feats, dm, w, collect)
+    half = (dm['deformation'].shape[1] - 1.) / 2.
+    R = dm['deformation'].shape[1] // 64
+    cb = P['quantize_motion.embedding.weight']
+    recon, losses = [], []
+    for s0 in (32, 64, 128, 256):
+        quant, loss, _ = vq_forward(cb, collect[f'm_feat_{s0 * R}'], SCALE_K[s0] / 4.0, beta)
+        recon.append(to_motion(P, quant).permute(0, 2, 3, 1) / half)
+        losses.append(loss)
+    out.update(out_lr=[decode_plain(P, out['lq_feat'])], motion_recon_list=recon, codebook_loss_motion_list=losses)
+    if gt is not None:
+        out['app_recon_list'], out['codebook_loss_app_list'] = app_codebook_loss(P, gt, beta)
+    return out
 
 
 def to_uint8(x: T, bgr: bool = False) -> np.ndarray:

@@ -5,7 +5,9 @@ on the VQGAN blocks of basicsr/archs/vqgan_arch.py): same constructor kwargs, sa
 same call `net_g(source, dense_motion, w=1, inference=True) -> dict` with the reference's full inference key set
 (`out`, `lq_feat`, `out_occ`, `deformation_list`, `res_deform_list`, `deform_feat_list`, `app_comp_list`,
 `app_before_comp_list`; `app_query_feat_list` / `app_comp_feat_list` with visualize_app_feat, `x_before_app_32` with
-vis_app_before_comp: appmotioncodebook_arch.py:745-764), plus `encode_driving` and the callable `generator`.  Inference only.
+vis_app_before_comp: appmotioncodebook_arch.py:745-764), plus `encode_driving`, `app_codebook_loss` and the callable `generator`.
+`inference=False` returns the forward VALUES of the training branch as well (`out_lr`, `motion_recon_list`, `codebook_loss_motion_list`, and with
+`gt` `app_recon_list` / `codebook_loss_app_list`: the VQ lookup runs inside the forward); there is no autograd graph - backward is outside the path.
 
 Design (B200-first, not a module-for-module port):
   * everything NHWC fp32; torch only allocates buffers; every op is a kernel from csrc/;
@@ -371,10 +373,64 @@ class AppMotionCompFormer(ParamModule):
             h = self._block('generator', i, self.gen_layout, h)
         return ops.nhwc_to_nchw(h)
 
+    @torch.no_grad()
+    def _encode_taps(self, x: torch.Tensor) -> Dict[int, torch.Tensor]:
+        """Encoder features after blocks 2 / 5 / 8 / 11 (NHWC), the taps of `encode_driving` and `app_codebook_loss`
+        (appmotioncodebook_arch.py:327,364-371,433-439): the 32x32 entry is the output of block 11 - the first attention block at that scale -
+        NOT the latent of the last block that `forward` warps."""
+        self._weights()
+        h = ops.nchw_to_nhwc(x.contiguous().float())
+        feats = {}
+        for i in range(12):
+            h = self._block('encoder', i, self.enc_layout, h)
+            if i in (2, 5, 8, 11):
+                feats[h.shape[2]] = h
+        return feats
+
     def encode_driving(self, x):
         """Reference API (appmotioncodebook_arch.py:364-371): NCHW feature dict keyed by resolution string."""
-        f = self.encode_source(x)
-        return {str(s): ops.nhwc_to_nchw(t) for s, t in f.items()}
+        return {str(s): ops.nhwc_to_nchw(t) for s, t in self._encode_taps(x).items()}
+
+    # ------------------------------------------------------------------------------------------
+    # training-path forward values (SURVEY 8f(4)): VQ lookups inside the forward, `to_motion`, `app_codebook_loss`.  No gradients.
+    # ------------------------------------------------------------------------------------------
+    def _to_motion(self, x: torch.Tensor) -> torch.Tensor:
+        """self.to_motion = Upsample, ResBlock, GroupNorm, conv3x3 Em -> 2 (appmotioncodebook_arch.py:290-292) on NHWC (B,tg,tg,Em) -> (B,fg,fg,2)."""
+        W, T = self._packed, self.tensors()
+        if 'to_motion.3' not in W:
+            for n in ('to_motion.0.conv', 'to_motion.1.conv1', 'to_motion.1.conv2', 'to_motion.3'):
+                W[n] = ops.pack_conv(T[n + '.weight'], T[n + '.bias'])
+        x = ops.conv2d(x, W['to_motion.0.conv'], pad=1, upsample2=True)
+        x = self._res('to_motion.1', x, self.Em, self.Em)
+        sc, sh = self._gn('to_motion.2', x)
+        return ops.conv2d(x, W['to_motion.3'], pad=1, pre=(sc, sh, 'none'))
+
+    @torch.no_grad()
+    def app_codebook_loss(self, x, weight=1, fuse_list=None):
+        """Reference API (appmotioncodebook_arch.py:429-469), forward values: x = the driving ("gt") frames (B,3,H,W) ->
+        ([[app_recon, app_feat_original, quant_app, app_feat, feat_com] per scale 32..256] (NCHW), [codebook loss per scale] (device scalars))."""
+        if self.R != 1:
+            raise NotImplementedError('app_codebook_loss: 256x256 only (the reference hard-codes the 32x32 token grid, :452-453)')
+        W, T = self._weights(), self.tensors()
+        feats = self._encode_taps(x)
+        codes = T['quantize_app.embedding.weight'].float().contiguous()
+        recon, losses = [], []
+        for s0 in self.SCALES:
+            f = feats[s0]
+            B = f.shape[0]
+            if s0 == 32:
+                emb = ops.conv2d(f, W['app_feat_emb_32'])
+            else:
+                emb = ops.conv2d(f, W[f'app_feat_emb_{s0}.1'], stride=s0 // 32)
+            quant, loss, _ = ops.vq_quantize(emb, codes, self._n_ctx(self.n_codes_app, s0), self.beta)
+
+            def back(t):
+                if s0 == 32:
+                    return ops.conv2d(t, W['to_app_feat_32'])
+                return ops.conv2d(t, W[f'to_app_feat_{s0}.0'], d2s=s0 // 32)
+            recon.append([ops.nhwc_to_nchw(v) for v in (back(quant), back(emb), quant, emb, f)])
+            losses.append(loss)
+        return recon, losses
 
     # ------------------------------------------------------------------------------------------
     # codebook transformer layer (appmotioncodebook_arch.py:88-126) on (B,1024,E) tokens
@@ -406,7 +462,7 @@ class AppMotionCompFormer(ParamModule):
     # ------------------------------------------------------------------------------------------
     # stage 3m: motion codebook compensation (appmotioncodebook_arch.py:373-427, 129-168)
     # ------------------------------------------------------------------------------------------
-    def _motion_comp(self, m_prev, occ_prev, warp0, qcat, s):
+    def _motion_comp(self, m_prev, occ_prev, warp0, qcat, s, collect=None):
         W, T = self._packed, self._T
         B = m_prev.shape[0]
         dev = m_prev.device
@@ -421,6 +477,8 @@ class AppMotionCompFormer(ParamModule):
         mf = ops.conv2d(mf, W['motion_emb.1.conv'], stride=2, pad_tl=(0, 0), out_hw=(tg, tg), fast=fs)
         ops_out = qcat[..., :Em]
         self._res('motion_emb.2', mf, Em, Em, out=ops_out, fast=fs)                        # qcat = [m_feat | query_feat]
+        if collect is not None and collect.get('_train'):
+            collect[f'm_feat_{s}'] = ops_out.contiguous()                                      # (the buffer is reused by the next scale)
         t = ops.conv2d(qcat, W['motion_query_enc_2'], fast=fs).view(B, self.L, Em)
         for i in range(2):
             t = self._transformer(f'motion_block.{i}', t, Em, self._n_ctx(self.n_codes_motion, s0), T['position_emb_motion'], fast=fs)
@@ -495,7 +553,7 @@ class AppMotionCompFormer(ParamModule):
             w32 = warp0 if s == tg else ops.resize_ac(warp0, (tg, tg))
             ops.conv2d(w32, W[f'warped_source_enc_{s // R}'], act='relu', out=qk[..., :Em])
             ops.conv2d(qk, W['motion_query_enc_1'], out=qcat[..., Em:])
-            m_com, occ, r = self._motion_comp(motions[-1], occ_prev, warp0, qcat, s)
+            m_com, occ, r = self._motion_comp(motions[-1], occ_prev, warp0, qcat, s, collect)
             motions.append(m_com); occs.append(occ); residuals.append(r)
             occ_prev = occ
             warped = ops.warp_occlude(f, m_com, occ)
@@ -538,8 +596,6 @@ class AppMotionCompFormer(ParamModule):
     # ------------------------------------------------------------------------------------------
     @torch.no_grad()
     def forward(self, x, dense_motion, w=1, inference=False, vis_app_before_comp=False, gt=None, visualize_app_feat=False):
-        if not inference:
-            raise NotImplementedError('the B200 path implements inference=True only (training losses are out of scope)')
         if isinstance(dense_motion['occlusion_map'], list):
             raise NotImplementedError('multi-mask occlusion lists are not part of options/test.yml')
         feats = self.encode_source(x)
@@ -549,7 +605,7 @@ class AppMotionCompFormer(ParamModule):
         if heat is None:
             heat = ops.nchw_to_nhwc(dense_motion['driving_kp_heatmap'].contiguous().float())
         occ = dense_motion['occlusion_map'].contiguous().float().view(B, self.fg, self.fg)
-        collect = {}
+        collect = {} if inference else {'_train': True}
         r = self.generate(feats, deformation, occ, heat, float(w), collect=collect)
         half = (deformation.shape[1] - 1.0) / 2.0
         scales = [s * self.R for s in self.SCALES if f'warped_{s * self.R}' in collect]
@@ -571,4 +627,17 @@ class AppMotionCompFormer(ParamModule):
             out['app_query_feat_list'], out['app_comp_feat_list'] = before, after
         if vis_app_before_comp:     # the plain decoder run on the un-compensated 32x32 feature (:654-655,661-662)
             out['x_before_app_32'] = self.decode_plain(before[0])
+        if not inference:
+            # forward VALUES of the training branch (:379-386,424-427,580-587,641-662,676-683,749-757); gradients are outside the path (no autograd graph)
+            codes = self._T['quantize_motion.embedding.weight'].float().contiguous()
+            recon, losses = [], []
+            for s0 in self.SCALES:
+                quant, loss, _ = ops.vq_quantize(collect[f'm_feat_{s0 * self.R}'], codes, self._n_ctx(self.n_codes_motion, s0), self.beta)
+                recon.append(self._to_motion(quant) / half)
+                losses.append(loss)
+            out['out_lr'] = [self.decode_plain(out['lq_feat'])]
+            out['motion_recon_list'] = recon
+            out['codebook_loss_motion_list'] = losses
+            if gt is not None:
+                out['app_recon_list'], out['codebook_loss_app_list'] = self.app_codebook_loss(gt)
         return out

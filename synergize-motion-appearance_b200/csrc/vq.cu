@@ -53,7 +53,43 @@ __global__ void __launch_bounds__(256) vq_lookup_kernel(const float* __restrict_
   }
 }
 
+// Forward values of what VectorQuantizer.forward returns besides the indices (archs/vqgan_arch.py:76-80): the straight-through tensor z + (z_q - z)
+// and the loss beta * mean((z_q - z)^2) + mean((z_q - z)^2).  Deterministic two-stage sum: per-block partials in a fixed order, then one block.
+constexpr int VQL_BLOCKS = 592, VQL_THREADS = 256;
+__global__ void __launch_bounds__(VQL_THREADS) vq_st_partial_kernel(const float* __restrict__ z, const float* __restrict__ zq, long long n,
+                                                                     float* __restrict__ st, float* __restrict__ partial) {
+  __shared__ float red[VQL_THREADS / 32];
+  float acc = 0.f;
+  for (long long i = (long long)blockIdx.x * VQL_THREADS + threadIdx.x; i < n; i += (long long)VQL_BLOCKS * VQL_THREADS) {
+    const float a = __ldg(z + i), d = __fsub_rn(__ldg(zq + i), a);
+    if (st) st[i] = __fadd_rn(a, d);
+    acc = fmaf(d, d, acc);
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) { float t = 0.f; for (int w = 0; w < VQL_THREADS / 32; w++) t += red[w]; partial[blockIdx.x] = t; }
+}
+__global__ void __launch_bounds__(32) vq_loss_final_kernel(const float* __restrict__ partial, long long n, float beta, float* __restrict__ loss) {
+  float t = 0.f;
+  for (int i = threadIdx.x; i < VQL_BLOCKS; i += 32) t += partial[i];
+  t = warp_sum(t);
+  if (threadIdx.x == 0) { const float m = t / (float)n; loss[0] = __fadd_rn(__fmul_rn(beta, m), m); }
+}
+
 }  // namespace
+
+extern "C" int sma_vq_workspace_floats(void) { return VQL_BLOCKS; }
+
+extern "C" int sma_vq_commit_fwd(const float* z, const float* zq, int64_t n, float beta, float* zq_st, float* workspace, float* loss, sma_stream_t stream) {
+  if (!z || !zq || !workspace || !loss || n <= 0) return SMA_ERR_BAD_ARG;
+  cudaStream_t st = as_stream(stream);
+  vq_st_partial_kernel<<<VQL_BLOCKS, VQL_THREADS, 0, st>>>(z, zq, (long long)n, zq_st, workspace);
+  SMA_LAUNCH_CHECK();
+  vq_loss_final_kernel<<<1, 32, 0, st>>>(workspace, (long long)n, beta, loss);
+  SMA_LAUNCH_CHECK();
+  return SMA_OK;
+}
 
 extern "C" int sma_vq_lookup_fwd(const float* z, int N, int E, const float* codebook, int n_codes, int64_t* idx, float* zq, float* min_dist,
                                  sma_stream_t stream) {

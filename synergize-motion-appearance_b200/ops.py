@@ -478,6 +478,20 @@ def vq_lookup(z: torch.Tensor, codebook: torch.Tensor, n_codes: Optional[int] = 
     return idx, zq, md
 
 
+def vq_quantize(z: torch.Tensor, codebook: torch.Tensor, n_codes: Optional[int] = None, beta: float = 0.25):
+    """VectorQuantizer.forward's forward values (archs/vqgan_arch.py:33-93) on channels-last rows: z (..., E) contiguous ->
+    (z + (zq - z) with z's shape, loss (0-dim device tensor), idx int64 (N,))."""
+    lib = _lib.load()
+    E = z.shape[-1]
+    zf = z.reshape(-1, E)
+    idx, zq, _ = vq_lookup(zf, codebook, n_codes)
+    st = torch.empty_like(zf)
+    ws = torch.empty((lib.sma_vq_workspace_floats() + 1,), device=z.device, dtype=torch.float32)
+    check(lib.sma_vq_commit_fwd(zf.data_ptr(), zq.data_ptr(), zf.numel(), float(beta), st.data_ptr(), ws.data_ptr(), ws[-1:].data_ptr(), _stream()),
+          'sma_vq_commit_fwd')
+    return st.view(z.shape), ws[-1], idx
+
+
 def antialias_down4(x_nchw: torch.Tensor, kernel13: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     lib = _lib.load()
     assert x_nchw.is_cuda and x_nchw.is_contiguous() and x_nchw.dtype == torch.float32

@@ -1,6 +1,10 @@
 """CPU: the oracle restatement against the fixtures produced by the live reference (oracle/make_golden.py)."""
+import os
+
 import numpy as np
 import torch
+
+from conftest import GOLD
 
 import sma_oracle as O
 
@@ -75,3 +79,25 @@ def test_oracle_caller_surface_matches_reference_fixture(weights):
     with torch.no_grad():
         recon = O.decode_plain(P_g, lq)
     assert float((recon[:, :, ::2, ::2] - fx['recon_s2']).abs().max()) < 2e-4
+
+
+def test_oracle_training_forward_matches_reference_fixture(weights, clip):
+    """The oracle's inference=False restatement and `encode_driving` against the outputs of the live reference (oracle/make_golden_train.py):
+    subsampled tensors and the eight codebook losses."""
+    fx = torch.load(os.path.join(GOLD, 'reference_train1.pt'))
+    src, drv = clip
+    P_g = weights[0]
+    dm = {k: fx[k] for k in ('deformation', 'occlusion_map', 'driving_kp_heatmap')}
+    with torch.no_grad():
+        out = O.generator_forward_train(P_g, O.encode_source(P_g, src.unsqueeze(0)), dm, 1.0, gt=drv[1].unsqueeze(0))
+        ed = O.encode_driving(P_g, drv[1].unsqueeze(0))
+    sub = lambda t: t[:, ::max(1, t.shape[1] // 16), ::max(1, t.shape[2] // 16), ::max(1, t.shape[3] // 16)]
+    assert float((out['out_lr'][0][:, :, ::4, ::4] - fx['out_lr_s4']).abs().max()) < 1e-5
+    for i in range(4):
+        assert float((out['motion_recon_list'][i] - fx['motion_recon_list'][i]).abs().max()) < 1e-5
+        assert abs(float(out['codebook_loss_motion_list'][i]) - fx['codebook_loss_motion_list'][i]) < 1e-5 * fx['codebook_loss_motion_list'][i]
+        assert abs(float(out['codebook_loss_app_list'][i]) - fx['codebook_loss_app_list'][i]) < 1e-5 * fx['codebook_loss_app_list'][i]
+        for j in range(5):
+            assert float((sub(out['app_recon_list'][i][j]) - fx['app_recon_s'][i][j]).abs().max()) < 1e-5, (i, j)
+    for k, v in ed.items():
+        assert float((sub(v) - fx['encode_driving_s'][k]).abs().max()) < 1e-5, k
