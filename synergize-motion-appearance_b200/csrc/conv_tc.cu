@@ -18,6 +18,7 @@
 // empty[s] (tcgen05.commit of the MMAs that read the slot).
 #include "sma_common.cuh"
 #include "tc_common.cuh"
+#include <cuda.h>          // CUtensorMap (types only: cuTensorMapEncodeTiled is resolved at run time through cudaGetDriverEntryPoint, no libcuda link)
 #include <cuda_fp16.h>
 
 namespace {
@@ -253,14 +254,20 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const TcP p) {
 //   warps 0-3 epilogue | warp 4 MMA issue + TMEM alloc | warp 5 weight loader | warps 6-13 halo producers
 // =================================================================================================================
 constexpr int V2_PROD_WARPS = 8;                       // halo producers: enough loads in flight to cover HBM latency
-constexpr int V2_THREADS = 192 + 32 * V2_PROD_WARPS;
+constexpr int V2_THREADS = 192 + 32 * V2_PROD_WARPS;       // 14 warps: 144 registers per thread (a 15th warp would cap them at 128)
+constexpr int V2_CONV_WARPS = V2_PROD_WARPS - 1;           // staged-input (TMA) mode: warps 6-12 convert, warp 13 issues the tensor loads
 constexpr int V2_PGROUPS = 2;                          // producer groups working on alternate channel chunks (2x the latency budget each)
 constexpr int V2_PROWS = 4 * V2_PROD_WARPS / V2_PGROUPS;   // halo rows per pass of one group (8 lanes per 128-byte row)
 #ifndef SMA_V2_UNROLL
 #define SMA_V2_UNROLL 12             // (macro: tools/build_variants.sh A/B-tests it; 6 -> 12 = -11 % on the halo-latency-bound 128->64 3x3 @256^2)
 #endif
 constexpr int V2_UNROLL = SMA_V2_UNROLL;                          // loads in flight per producer thread
-constexpr int MAX_SA = 3, MAX_SB = 8;
+constexpr int MAX_SA = 3, MAX_SB = 8, MAX_NS = 8;
+#ifdef SMA_COAL_EPILOGUE
+constexpr bool SMA_COAL_ENABLED = true;
+#else
+constexpr bool SMA_COAL_ENABLED = false;
+#endif
 
 struct Tc2P {
   const float* x; const float* wtc; const float* bias; const float* pre_scale; const float* pre_shift; const float* res; float* y;
@@ -278,6 +285,12 @@ struct Tc2P {
   int dbg;                    // timing experiments (results invalid): bit 2 = epilogue skips its residual loads and stores
   int flat, tiles_x, tiles_per_img, total_tiles;
   int halo_w, HP, a_img_bytes, a_stage_bytes, b_img_bytes, SA, SB;
+  // TMA-staged input (TMA = 1): warp 14 brings the fp32 halo of every (tile, 64-channel chunk) into a ring of NS shared-memory slots with
+  // cp.async.bulk.tensor (a 4-D map over (C, W, H, B): zero fill outside the image = the convolution's padding; flat 1x1 layers: a 3-D map over
+  // (C, pixels, B)), `parts` boxes of `slot_rows` halo rows each; the 8 producer warps convert slot by slot.  No thread waits on global memory.
+  int NS, parts, slot_rows, slot_bytes, rs /* image rows per box */, tma_b_fixed /* batch stride 0: always coordinate 0 */;
+  int coal;                   // RES = 2: 16 KB of shared memory after the staging slots for the coalescing epilogue (4 KB per epilogue warp)
+  alignas(64) CUtensorMap tmap;
 };
 
 // ACT: epilogue activation; PRE: -1 no prologue, else the prologue activation applied after scale/shift (compile-time so that the
@@ -286,11 +299,11 @@ struct Tc2P {
 // kind::f16 (K = 16 per instruction: twice the MACs per tensor-core cycle and per shared-memory byte of kind::tf32); a K-chunk
 // (one 128-byte swizzle row) is then 64 channels.
 // RES: 1 = the 256-bit epilogue with the residual prefetched one column block ahead (own instantiation: its register budget must not touch the others)
-template <int ACT, int PRE, int F16, int RES>
-__global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const Tc2P p) {
+template <int ACT, int PRE, int F16, int RES, int TMA>
+__global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const __grid_constant__ Tc2P p) {
   constexpr int KCH = F16 ? 64 : 32;                       // channels per K-chunk (128 bytes of operand)
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bars[2 * MAX_SA + 2 * MAX_SB + 4];
+  __shared__ __align__(8) uint64_t bars[2 * MAX_SA + 2 * MAX_SB + 4 + 2 * MAX_NS];
   __shared__ uint32_t tmem_slot;
   __shared__ __align__(16) float s_bias[256];              // bias of the current N tile (epilogue warps only)
   __shared__ __align__(16) float s_scale[F16 ? 256 : 4];   // F16: un-scaling factors of the current N tile
@@ -303,11 +316,16 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const Tc2P p) {
   auto b_empty = [&](int s) { return bar0 + 8u * (2 * MAX_SA + MAX_SB + s); };
   auto acc_full = [&](int s) { return bar0 + 8u * (2 * MAX_SA + 2 * MAX_SB + s); };
   auto acc_empty = [&](int s) { return bar0 + 8u * (2 * MAX_SA + 2 * MAX_SB + 2 + s); };
+  auto s_full = [&](int s) { return bar0 + 8u * (2 * MAX_SA + 2 * MAX_SB + 4 + s); };
+  auto s_empty = [&](int s) { return bar0 + 8u * (2 * MAX_SA + 2 * MAX_SB + 4 + MAX_NS + s); };
   const uint32_t a_ring = sbase, b_ring = sbase + (uint32_t)p.SA * p.a_stage_bytes;
   const int b_stage_bytes = 2 * p.b_img_bytes;
+  const uint32_t stg_ring = b_ring + (uint32_t)p.SB * b_stage_bytes;      // (TMA) fp32 staging slots; 1 KB aligned like everything before it
+  const uint32_t epi_ring = stg_ring + (uint32_t)p.NS * p.slot_bytes;      // (RES = 2) 4 x 4 KB transposition buffers of the epilogue warps
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < p.SA; s++) { mbar_init(a_full(s), 32 * V2_PROD_WARPS / V2_PGROUPS); mbar_init(a_empty(s), 1); }
+    for (int s = 0; s < p.SA; s++) { mbar_init(a_full(s), TMA ? 32 * V2_CONV_WARPS : 32 * V2_PROD_WARPS / V2_PGROUPS); mbar_init(a_empty(s), 1); }
+    if (TMA) for (int s = 0; s < p.NS; s++) { mbar_init(s_full(s), 1); mbar_init(s_empty(s), V2_CONV_WARPS); }
     for (int s = 0; s < p.SB; s++) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
     for (int s = 0; s < 2; s++) { mbar_init(acc_full(s), 1); mbar_init(acc_empty(s), 128); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -352,7 +370,128 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const Tc2P p) {
       int oy, ox, r; bool mok;
       if (p.flat) { r = ty0 + m; mok = r < p.HoWo; oy = r / p.Wo; ox = r - oy * p.Wo; }
       else { oy = ty0 + (m >> 3); ox = tx0 + (m & 7); mok = oy < p.Ho && ox < p.Wo; r = oy * p.Wo + ox; }
-      if constexpr (RES) {
+      if constexpr (RES == 2) {
+        // Coalescing epilogue (EXPERIMENT, compiled only with -DSMA_COAL_EPILOGUE; measured SLOWER than the register epilogue, see
+        // profiles/r2_tma_staging.md).  A thread owns one pixel ROW of the accumulator, so stored straight from registers a warp-level 256-bit
+        // store touches 32 different 128-byte lines (a quarter of each).  Here every warp transposes its 32 x 32 block through 4 KB of shared memory
+        // (16-byte chunks XOR-swizzled by the row: conflict-free both ways) so that 8 consecutive lanes read / write one whole 128-byte line of the
+        // residual / the output.  Hypothesis was that the line-by-line L1 processing of the scattered stores bounds the short-K layers; it does not:
+        // 1x1 64 -> 192 @256^2 takes 0.97 ms with the 256-bit row stores and 1.64 ms this way (the layer already moves 4.4 TB/s).
+        const int nbase = nt * p.NT;
+        const uint32_t stg = epi_ring + (uint32_t)warp * 4096u;
+        const int cc = lane & 7, rsub = lane >> 3;
+        if (p.res) {                                     // L2 prefetch of the next tile's residual (and SFT scale) row of this thread
+          const int tile2 = tile + (int)gridDim.x;
+          if (tile2 < p.total_tiles) {
+            int b2, ty2, tx2, nt2; decode(tile2, b2, ty2, tx2, nt2);
+            int r2; bool ok2;
+            if (p.flat) { r2 = ty2 + m; ok2 = r2 < p.HoWo; }
+            else { const int oy2 = ty2 + (m >> 3), ox2 = tx2 + (m & 7); ok2 = oy2 < p.Ho && ox2 < p.Wo; r2 = oy2 * p.Wo + ox2; }
+            if (ok2) {
+              const float* q = p.res + (long long)b2 * p.res_bs + (long long)r2 * p.res_ld + nt2 * p.NT;
+              const int nb2 = min(p.NT, p.Cout - nt2 * p.NT) * 4;
+              for (int o = 0; o < nb2; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(q) + o));
+              if (p.aux) {
+                const float* qa = p.aux + (long long)b2 * p.aux_bs + (long long)r2 * p.aux_ld + nt2 * p.NT;
+                for (int o = 0; o < nb2; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(qa) + o));
+              }
+            }
+          }
+        }
+        // the 8 rows this lane serves in the transposed domain are row_i = i * 4 + rsub of this warp's 32 (recomputed where used: registers)
+        auto row_of = [&](int i, bool& oki) -> int {
+          const int mi = warp * 32 + i * 4 + rsub;
+          if (p.flat) { const int ri = ty0 + mi; oki = ri < p.HoWo; return oki ? ri : 0; }
+          const int oyi = ty0 + (mi >> 3), oxi = tx0 + (mi & 7);
+          oki = oyi < p.Ho && oxi < p.Wo;
+          return oki ? oyi * p.Wo + oxi : 0;
+        };
+        // residual of one 32-column block: whole 128-byte lines per 8 lanes; issued one block ahead (the first before the accumulator wait)
+        auto load_res = [&](const float* base, long long bs, int ld, int n0_, float4 (&dst)[8]) {
+          const int n_ = nbase + n0_ + cc * 4;
+#pragma unroll
+          for (int i = 0; i < 8; i++) {
+            bool oki; const int ri = row_of(i, oki);
+            dst[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (oki && n_ < p.Cout) {
+              const float* q = base + (long long)b * bs + (long long)ri * ld + n_;
+              asm volatile("ld.global.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(dst[i].x), "=f"(dst[i].y), "=f"(dst[i].z), "=f"(dst[i].w) : "l"(q));
+            }
+          }
+        };
+        float4 rr[8];
+        const bool has_res = p.res != nullptr && !(p.dbg & 4);
+        if (has_res) load_res(p.res, p.res_bs, p.res_ld, 0, rr);
+        mbar_wait(acc_full(ab), aph);
+        tc_fence_after();
+        for (int n0 = 0; n0 < p.NT && nbase + n0 < p.Cout; n0 += 32) {
+          const bool last = n0 + 32 >= p.NT || nbase + n0 + 32 >= p.Cout;
+#pragma unroll
+          for (int hh = 0; hh < 2; hh++) {                  // two halves of 16 columns: accumulator -> (bias, un-scaling, activation) -> own row in shared memory
+            uint32_t a[16];
+            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(ab * p.acc_cols + n0 + hh * 16);
+            tmem_ld16(taddr, a);
+            if (p.fuse) {
+              uint32_t a2[16];
+              tmem_ld16(taddr + (uint32_t)p.NT, a2);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 16; i++) a[i] = __float_as_uint(__uint_as_float(a[i]) + __uint_as_float(a2[i]));
+            } else {
+              tmem_ld_wait();
+            }
+            if (last && hh == 1) {                         // last column block: the accumulator may be overwritten while we store
+              tc_fence_before();
+              mbar_arrive(acc_empty(ab));
+            }
+            if (!(p.dbg & 4)) {
+#pragma unroll
+              for (int c4 = 0; c4 < 4; c4++) {
+                const int cq4 = hh * 4 + c4;
+                const float4 b4 = *reinterpret_cast<const float4*>(&s_bias[n0 + cq4 * 4]);
+                float o0, o1, o2, o3;
+                if (F16) {
+                  const float4 s4 = *reinterpret_cast<const float4*>(&s_scale[n0 + cq4 * 4]);
+                  o0 = sma_act(fmaf(__uint_as_float(a[c4 * 4 + 0]), s4.x, b4.x), ACT); o1 = sma_act(fmaf(__uint_as_float(a[c4 * 4 + 1]), s4.y, b4.y), ACT);
+                  o2 = sma_act(fmaf(__uint_as_float(a[c4 * 4 + 2]), s4.z, b4.z), ACT); o3 = sma_act(fmaf(__uint_as_float(a[c4 * 4 + 3]), s4.w, b4.w), ACT);
+                } else {
+                  o0 = sma_act(__uint_as_float(a[c4 * 4 + 0]) + b4.x, ACT); o1 = sma_act(__uint_as_float(a[c4 * 4 + 1]) + b4.y, ACT);
+                  o2 = sma_act(__uint_as_float(a[c4 * 4 + 2]) + b4.z, ACT); o3 = sma_act(__uint_as_float(a[c4 * 4 + 3]) + b4.w, ACT);
+                }
+                sts128(stg + (uint32_t)lane * 128u + (uint32_t)((cq4 ^ (lane & 7)) << 4), o0, o1, o2, o3);
+              }
+            }
+          }
+          if (p.dbg & 4) continue;
+          __syncwarp();
+          const int n = nbase + n0 + cc * 4;               // the 4 columns this lane serves in the transposed domain
+#pragma unroll
+          for (int i = 0; i < 8; i++) {
+            const int rw = i * 4 + rsub;
+            bool oki; const int ri = row_of(i, oki);
+            float4 v;
+            asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                         : "r"(stg + (uint32_t)rw * 128u + (uint32_t)((cc ^ (rw & 7)) << 4)));
+            if (oki && n < p.Cout) {
+              if (has_res) {
+                if (p.aux) {        // Fuse_sft_block tail (appmotioncodebook_arch.py:50-51): dec + w * (dec * scale + shift), this conv = shift
+                  float4 sa;
+                  const float* q = p.aux + (long long)b * p.aux_bs + (long long)ri * p.aux_ld + n;
+                  asm volatile("ld.global.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(sa.x), "=f"(sa.y), "=f"(sa.z), "=f"(sa.w) : "l"(q));
+                  v.x = rr[i].x + p.sft_w * (rr[i].x * sa.x + v.x); v.y = rr[i].y + p.sft_w * (rr[i].y * sa.y + v.y);
+                  v.z = rr[i].z + p.sft_w * (rr[i].z * sa.z + v.z); v.w = rr[i].w + p.sft_w * (rr[i].w * sa.w + v.w);
+                } else {
+                  v.x += rr[i].x; v.y += rr[i].y; v.z += rr[i].z; v.w += rr[i].w;
+                }
+              }
+              float* dst = p.y + (long long)b * p.out_bs + (long long)ri * p.out_ld + n;
+              asm volatile("st.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(dst), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+            }
+          }
+          __syncwarp();
+          if (has_res && !last) load_res(p.res, p.res_bs, p.res_ld, n0 + 32, rr);      // next block's residual: in flight across its accumulator read
+        }
+      } else if constexpr (RES == 1) {
         const int nbase = nt * p.NT;
         // 256-bit path for layers with a residual.  Loaded next to its use, every 8 columns of the residual exposed a full DRAM latency (32 per
         // tile of a 256-column linear: the short-K transformer linears ran 4x below their MMA / HBM time).  Here (1) the residual row of the
@@ -653,6 +792,90 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const Tc2P p) {
       }
     }
     __syncwarp();
+  } else if (TMA && warp == 6 + V2_CONV_WARPS) {
+    // =============================== TMA issuer (staged-input mode) ===============================
+    if (lane == 0 && !(p.dbg & 2)) {
+      uint32_t ss = 0, phs = 0;
+      const uint64_t tm = reinterpret_cast<uint64_t>(&p.tmap);
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        int b, ty0, tx0, nt; decode(tile, b, ty0, tx0, nt);
+        if (p.tma_b_fixed) b = 0;
+        for (int cc = 0; cc < p.cpt; cc++) {
+          for (int part = 0; part < p.parts; part++) {
+            mbar_wait(s_empty(ss), phs ^ 1u);
+            mbar_expect_tx(s_full(ss), (uint32_t)p.slot_bytes);
+            const uint32_t dst = stg_ring + ss * (uint32_t)p.slot_bytes;
+            if (p.flat) {
+              asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                           ::"r"(dst), "l"(tm), "r"(cc * 64), "r"(ty0 + part * p.slot_rows), "r"(b), "r"(s_full(ss)) : "memory");
+            } else {
+              asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+                           ::"r"(dst), "l"(tm), "r"(cc * 64), "r"(tx0 - p.pad_l), "r"(ty0 - p.pad_t + part * p.rs), "r"(b), "r"(s_full(ss)) : "memory");
+            }
+            if (++ss == (uint32_t)p.NS) { ss = 0; phs ^= 1u; }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (TMA) {
+    // =============================== halo converters (staged-input mode): shared fp32 slot -> prologue -> fp16 hi / lo operand rows ===============================
+    const int ptid = threadIdx.x - 192; const int cq = ptid & 7; const int prow = ptid >> 3;      // 28 halo rows per pass of the 7 warps
+    const int swap = cq >> 2;                                   // lanes 4-7 read their two 16-byte halves in the opposite order: conflict-free LDS.128
+    const int Hv = p.Hi, Wv = p.Wi;
+    uint32_t ss = 0, phs = 0; int it = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      int b, ty0, tx0, nt; decode(tile, b, ty0, tx0, nt);
+      for (int cc = 0; cc < p.cpt; cc++, it++) {
+        const int sa = it % p.SA; const uint32_t pha = (it / p.SA) & 1;
+        const uint32_t a_hi = a_ring + (uint32_t)sa * p.a_stage_bytes, a_lo = a_hi + p.a_img_bytes;
+        const int c = cc * KCH + cq * 8;
+        float4 sc0 = make_float4(1.f, 1.f, 1.f, 1.f), sh0 = make_float4(0.f, 0.f, 0.f, 0.f), sc1 = sc0, sh1 = sh0;
+        if (PRE >= 0) {
+          sc0 = __ldg(reinterpret_cast<const float4*>(p.pre_scale + (long long)b * p.Cin + c));
+          sc1 = __ldg(reinterpret_cast<const float4*>(p.pre_scale + (long long)b * p.Cin + c + 4));
+          sh0 = __ldg(reinterpret_cast<const float4*>(p.pre_shift + (long long)b * p.Cin + c));
+          sh1 = __ldg(reinterpret_cast<const float4*>(p.pre_shift + (long long)b * p.Cin + c + 4));
+        }
+        mbar_wait(a_empty(sa), pha ^ 1u);
+        if (p.dbg & 2) { mbar_arrive(a_full(sa)); continue; }          // timing experiment: no halo traffic, no conversion
+        for (int part = 0; part < p.parts; part++) {
+          mbar_wait(s_full(ss), phs);
+          const uint32_t slot = stg_ring + ss * (uint32_t)p.slot_bytes;
+          for (int lr = prow; lr < p.slot_rows; lr += 4 * V2_CONV_WARPS) {
+            const int hp = part * p.slot_rows + lr;
+            if (hp >= p.HP) break;
+            const uint32_t src = slot + (uint32_t)lr * 256u + (uint32_t)cq * 32u;
+            float4 u0, u1;
+            asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(u0.x), "=f"(u0.y), "=f"(u0.z), "=f"(u0.w) : "r"(src + (uint32_t)swap * 16u));
+            asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(u1.x), "=f"(u1.y), "=f"(u1.z), "=f"(u1.w) : "r"(src + 16u - (uint32_t)swap * 16u));
+            float4 t0 = swap ? u1 : u0, t1 = swap ? u0 : u1;
+            if (PRE >= 0) {
+              bool ok;                                         // zero padding applies AFTER the normalisation: pixels outside the image stay zero
+              if (p.flat) ok = ty0 + hp < p.HoWo;
+              else { const int hy = hp / p.halo_w, hx = hp - hy * p.halo_w; ok = (unsigned)(ty0 + hy - p.pad_t) < (unsigned)Hv && (unsigned)(tx0 + hx - p.pad_l) < (unsigned)Wv; }
+              if (ok) {
+                t0.x = pre_act_fast(fmaf(t0.x, sc0.x, sh0.x), PRE); t0.y = pre_act_fast(fmaf(t0.y, sc0.y, sh0.y), PRE);
+                t0.z = pre_act_fast(fmaf(t0.z, sc0.z, sh0.z), PRE); t0.w = pre_act_fast(fmaf(t0.w, sc0.w, sh0.w), PRE);
+                t1.x = pre_act_fast(fmaf(t1.x, sc1.x, sh1.x), PRE); t1.y = pre_act_fast(fmaf(t1.y, sc1.y, sh1.y), PRE);
+                t1.z = pre_act_fast(fmaf(t1.z, sc1.z, sh1.z), PRE); t1.w = pre_act_fast(fmaf(t1.w, sc1.w, sh1.w), PRE);
+              }
+            }
+            const uint32_t off = (uint32_t)hp * 128u + (uint32_t)((cq ^ (hp & 7)) << 4);
+            uint32_t h0, h1, h2, h3, l0, l1, l2, l3;
+            split_f16x2(t0.x, t0.y, h0, l0); split_f16x2(t0.z, t0.w, h1, l1);
+            split_f16x2(t1.x, t1.y, h2, l2); split_f16x2(t1.z, t1.w, h3, l3);
+            sts128u(a_hi + off, h0, h1, h2, h3);
+            if (p.passes == 3) sts128u(a_lo + off, l0, l1, l2, l3);
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(s_empty(ss));              // this warp is done reading the slot
+          if (++ss == (uint32_t)p.NS) { ss = 0; phs ^= 1u; }
+        }
+        fence_async_smem();
+        mbar_arrive(a_full(sa));
+      }
+    }
   } else {
     // =============================== halo producers ===============================
     const int pgroup = (threadIdx.x - 192) / (32 * V2_PROD_WARPS / V2_PGROUPS);
@@ -874,22 +1097,50 @@ extern "C" int sma_pack_conv_weight_tc16(const float* w_packed, int ldw, int Cou
 
 
 
-template <int ACT, int PRE, int F16, int RES = 0>
-static int launch_tc2_inst(const Tc2P& p, int grid, int smem, cudaStream_t st) {
+// cuTensorMapEncodeTiled through the runtime's driver entry point query (the library does not link libcuda: it must load on a GPU-less box)
+typedef CUresult (*SmaEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                     const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static SmaEncodeTiledFn sma_tmap_encoder() {
+  static std::atomic<void*> cached{nullptr};
+  void* f = cached.load(std::memory_order_acquire);
+  if (f) return reinterpret_cast<SmaEncodeTiledFn>(f);
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess || !f) return nullptr;
+  cached.store(f, std::memory_order_release);
+  return reinterpret_cast<SmaEncodeTiledFn>(f);
+}
+
+template <int ACT, int PRE, int F16, int RES, int TMA>
+static int launch_tc2_inst2(const Tc2P& p, int grid, int smem, cudaStream_t st) {
   static SmaDevOnce once;             // per instantiation and per device
-  if (int rc = sma_opt_in_smem(once, conv_tc2_kernel<ACT, PRE, F16, RES>, SMEM_DYN_MAX)) return rc;
-  conv_tc2_kernel<ACT, PRE, F16, RES><<<grid, V2_THREADS, smem, st>>>(p);
+  if (int rc = sma_opt_in_smem(once, conv_tc2_kernel<ACT, PRE, F16, RES, TMA>, SMEM_DYN_MAX)) return rc;
+  conv_tc2_kernel<ACT, PRE, F16, RES, TMA><<<grid, V2_THREADS, smem, st>>>(p);
   SMA_LAUNCH_CHECK();
   return SMA_OK;
+}
+template <int ACT, int PRE, int F16, int RES = 0>
+static int launch_tc2_inst(const Tc2P& p, int grid, int smem, cudaStream_t st) {
+  if (F16 && p.NS > 0) return launch_tc2_inst2<ACT, PRE, F16, RES, F16 ? 1 : 0>(p, grid, smem, st);
+  return launch_tc2_inst2<ACT, PRE, F16, RES, 0>(p, grid, smem, st);
+}
+template <int ACT, int PRE, int F16>
+static int launch_tc2_res(const Tc2P& p, int grid, int smem, cudaStream_t st) {
+  if constexpr (F16 != 0) {
+#ifdef SMA_COAL_EPILOGUE     // negative result, kept for the record (profiles/r2_tma_staging.md): off by default, not even instantiated
+    if (p.coal) return launch_tc2_inst<ACT, PRE, 1, 2>(p, grid, smem, st);            // coalescing epilogue (shared-memory transposition)
+#endif
+    if constexpr (ACT == SMA_ACT_NONE && (PRE == -1 || PRE == SMA_ACT_SWISH)) {
+      if (p.res_pipe) return launch_tc2_inst<ACT, PRE, 1, 1>(p, grid, smem, st);       // no room for it (256-column 3x3 tiles): register epilogue with the residual pipeline
+    }
+  }
+  return launch_tc2_inst<ACT, PRE, F16, 0>(p, grid, smem, st);
 }
 template <int ACT, int F16>
 static int launch_tc2_pre(int pre, const Tc2P& p, int grid, int smem, cudaStream_t st) {
   switch (pre) {
-    case -1: return (ACT == SMA_ACT_NONE && F16 && p.res_pipe) ? launch_tc2_inst<ACT, -1, F16, (ACT == SMA_ACT_NONE && F16) ? 1 : 0>(p, grid, smem, st)
-                                                                : launch_tc2_inst<ACT, -1, F16>(p, grid, smem, st);
-    case SMA_ACT_NONE: return launch_tc2_inst<ACT, SMA_ACT_NONE, F16>(p, grid, smem, st);
-    case SMA_ACT_SWISH: return (ACT == SMA_ACT_NONE && F16 && p.res_pipe) ? launch_tc2_inst<ACT, SMA_ACT_SWISH, F16, (ACT == SMA_ACT_NONE && F16) ? 1 : 0>(p, grid, smem, st)
-                                                                           : launch_tc2_inst<ACT, SMA_ACT_SWISH, F16>(p, grid, smem, st);
+    case -1: return launch_tc2_res<ACT, -1, F16>(p, grid, smem, st);
+    case SMA_ACT_NONE: return launch_tc2_res<ACT, SMA_ACT_NONE, F16>(p, grid, smem, st);
+    case SMA_ACT_SWISH: return launch_tc2_res<ACT, SMA_ACT_SWISH, F16>(p, grid, smem, st);
     default: return SMA_ERR_UNSUPPORTED;     // other prologue activations: gather / CUDA-core kernels
   }
 }
@@ -945,7 +1196,28 @@ static int conv_tc2_try(const sma_conv_desc* d, cudaStream_t st, bool f16) {
   p.b_img_bytes = p.NT * 128;                    // NT rows of one 128-byte K-chunk (32 tf32 or 64 fp16)
   const int b_stage = 2 * p.b_img_bytes;
   int SA = 2;
-  int SB = (SMEM_LIMIT - SA * p.a_stage_bytes) / b_stage;
+  // TMA-staged input: stride 1, no fused upsample, 1x1 / 3x3, 16-byte aligned strides; as many staging slots as leave the weight ring >= 3 stages
+  // (2 for the 256-column tiles); layers where that is not possible (3x3 with 128 / 256-column tiles) keep the register-staged producers
+  p.NS = 0; p.parts = p.slot_rows = p.slot_bytes = p.rs = 0; p.tma_b_fixed = d->in_bstride == 0 ? 1 : 0;
+  // coalescing epilogue (RES = 2): 256-bit-eligible NHWC output, no depth-to-space, 16 KB of shared memory beside at least two weight stages
+  int budget = SMEM_LIMIT - SA * p.a_stage_bytes;
+  p.coal = (SMA_COAL_ENABLED && f16 && !(d->tc_variant & 2048) && d->d2s <= 1 && (d->Cout & 7) == 0 && (d->out_ld & 7) == 0 && (d->out_bstride & 7) == 0 &&
+            (reinterpret_cast<uintptr_t>(d->y) & 31) == 0 &&
+            (!d->res || ((d->res_ld & 7) == 0 && (d->res_bstride & 7) == 0 && (reinterpret_cast<uintptr_t>(d->res) & 31) == 0)) &&
+            (!d->aux || ((d->aux_ld & 7) == 0 && (d->aux_bstride & 7) == 0 && (reinterpret_cast<uintptr_t>(d->aux) & 31) == 0)) &&
+            budget - 16384 >= 2 * b_stage) ? 1 : 0;
+  if (p.coal) budget -= 16384;
+  if (f16 && !(d->tc_variant & 1024) && !d->upsample2 && d->kh == d->kw && (d->kh == 1 || d->kh == 3) && (d->in_bstride & 3) == 0) {
+    if (flat) { p.parts = 4; p.rs = 0; p.slot_rows = 32; }
+    else { p.parts = d->kh == 3 ? 3 : 2; p.rs = (16 + d->kh - 1) / p.parts; p.slot_rows = p.halo_w * p.rs; }
+    p.slot_bytes = p.slot_rows * 256;
+    const int sb_min = p.NT <= 128 ? 3 : 2;
+    int NS = 2 * p.parts < MAX_NS ? 2 * p.parts : MAX_NS;
+    while (NS >= 2 && (budget - NS * p.slot_bytes) / b_stage < sb_min) NS--;
+    // single pass: the MMAs of a chunk are 3x shorter, so less than a whole chunk (+1 box) in flight exposes the load latency: register path instead
+    p.NS = (NS >= 2 && NS > p.parts / 2 && (p.passes == 3 || NS > p.parts)) ? NS : 0;
+  }
+  int SB = (budget - p.NS * p.slot_bytes) / b_stage;
   // (a single A stage is not an option: the two producer groups could then be two barrier phases apart - parity aliasing)
   if (SB < 2) return SMA_ERR_UNSUPPORTED;
   if (SB > MAX_SB) SB = MAX_SB;
@@ -965,8 +1237,30 @@ static int conv_tc2_try(const sma_conv_desc* d, cudaStream_t st, bool f16) {
   int cols = 32; while (cols < 2 * p.acc_cols + ((p.NT & 31) ? 32 : 0)) cols <<= 1;      // the epilogue reads 32 columns at a time
   if (cols > 512) return SMA_ERR_UNSUPPORTED;
   p.tmem_cols = cols;
-  const int smem = SA * p.a_stage_bytes + SB * b_stage + 1024;
+  const int smem = SA * p.a_stage_bytes + SB * b_stage + p.NS * p.slot_bytes + (p.coal ? 16384 : 0) + 1024;
   if (d->plan_only) return SMA_OK;
+  if (p.NS > 0) {
+    SmaEncodeTiledFn enc = sma_tmap_encoder();
+    if (!enc) return SMA_ERR_CUDA;
+    const cuuint64_t nb = d->in_bstride == 0 ? 1 : (cuuint64_t)d->B;
+    const cuuint64_t bstride_bytes = d->in_bstride == 0 ? (cuuint64_t)d->Hi * d->Wi * d->in_ld * 4ull : (cuuint64_t)d->in_bstride * 4ull;
+    const cuuint32_t ones[4] = {1, 1, 1, 1};
+    CUresult cr;
+    if (flat) {
+      const cuuint64_t gdim[3] = {(cuuint64_t)d->Cin, (cuuint64_t)p.HoWo, nb};
+      const cuuint64_t gstr[2] = {(cuuint64_t)d->in_ld * 4ull, bstride_bytes};
+      const cuuint32_t box[3] = {64, (cuuint32_t)p.slot_rows, 1};
+      cr = enc(&p.tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(d->x), gdim, gstr, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    } else {
+      const cuuint64_t gdim[4] = {(cuuint64_t)d->Cin, (cuuint64_t)d->Wi, (cuuint64_t)d->Hi, nb};
+      const cuuint64_t gstr[3] = {(cuuint64_t)d->in_ld * 4ull, (cuuint64_t)d->Wi * d->in_ld * 4ull, bstride_bytes};
+      const cuuint32_t box[4] = {64, (cuuint32_t)p.halo_w, (cuuint32_t)p.rs, 1};
+      cr = enc(&p.tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(d->x), gdim, gstr, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    }
+    if (cr != CUDA_SUCCESS) return SMA_ERR_CUDA;
+  }
   const int g_num_sms = sma_num_sms();
   if (g_num_sms <= 0) return SMA_ERR_CUDA;
   const int grid = p.total_tiles < g_num_sms ? p.total_tiles : g_num_sms;

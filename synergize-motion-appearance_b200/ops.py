@@ -11,6 +11,8 @@ import ctypes as C
 from dataclasses import dataclass
 from typing import Optional, Tuple
 
+import os
+
 import torch
 
 from . import _lib
@@ -234,7 +236,7 @@ def fast(stage: str):
     return True if stage in FAST_STAGES else ('x2' if stage in X2_STAGES else False)
 
 
-TC_VARIANT = 0           # 0: library picks the tensor-core kernel variant; 1: force the gather kernel (tests)
+TC_VARIANT = int(os.environ.get('SMA_TC_VARIANT', '0'))           # (env override: A/B experiments on one box) 0: library picks the tensor-core kernel variant; 1: force the gather kernel (tests)
 LAST_CONV_KERNEL = -1    # which kernel the last conv2d ran on: 0 CUDA-core, 1 tcgen05 gather, 2 tcgen05 persistent halo (tf32), 3 (fp16), 4 fp16 with weights in tensor memory
 
 

@@ -1,0 +1,18 @@
+import sys, os
+sys.path.insert(0, '/root/repo')
+import torch
+import sma_b200 as S
+def t(B, Cin, H, Cout, k, pad, res, var):
+    x = torch.randn(B, H, H, Cin, device='cuda'); w = torch.randn(Cout, Cin, k, k, device='cuda') * (Cin * k * k) ** -0.5
+    cw = S.ops.pack_conv(w, torch.randn(Cout, device='cuda'))
+    r = torch.randn(B, H, H, Cout, device='cuda') if res else None
+    S.ops.TC_VARIANT = var
+    y = S.ops.conv2d(x, cw, pad=pad, res=r)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(); e0.record()
+    for _ in range(5): S.ops.conv2d(x, cw, pad=pad, out=y, res=r)
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / 5
+for shp in [(64, 64, 256, 192, 1, 0, False), (64, 64, 256, 64, 3, 1, True)]:
+    for var, name in [(0, 'coal+tma'), (8, 'coal+tma no-epi-mem'), (2048, 'old epi + tma'), (2048 + 8, 'old epi no-epi-mem'), (1024, 'coal, reg producers')]:
+        print(shp, name, '%.3f ms' % t(*shp, var), flush=True)

@@ -11,7 +11,7 @@ def run(B, Cin, H, Cout, k, pad, pre=False, res=False):
     prek = (torch.ones(B, Cin, device='cuda'), torch.zeros(B, Cin, device='cuda'), 'swish') if pre else None
     r = torch.randn(B, H, H, Cout, device='cuda') if res else None
     out = []
-    for fast in (False, True):
+    for fast in (False,):
         for dbg, name in ((0, 'all on'), (2, 'no weights'), (4, 'no halo'), (8, 'no epilogue'), (6, 'no weights, no halo'), (14, 'MMA only')):
             S.ops.TC_VARIANT = dbg
             y = S.ops.conv2d(x, cw, pad=pad, fast=fast, pre=prek, res=r)
@@ -24,5 +24,5 @@ def run(B, Cin, H, Cout, k, pad, pre=False, res=False):
     S.ops.TC_VARIANT = 0
     print(f'B{B} Cin{Cin} H{H} Cout{Cout} k{k} pre={pre} res={res}\n   ' + '\n   '.join(out), flush=True)
 
-for a in [(64, 64, 256, 64, 3, 1, True, True), (64, 128, 128, 128, 3, 1, True, True), (64, 256, 64, 256, 3, 1), (64, 128, 256, 64, 3, 1, True), (64, 256, 32, 512, 3, 1), (64, 128, 256, 64, 1, 0), (64, 256, 32, 256, 1, 0)]:
+for a in [(64, 64, 256, 64, 3, 1, True, True), (64, 64, 256, 64, 3, 1, False, True), (64, 128, 128, 128, 3, 1, True, True), (64, 128, 256, 64, 3, 1, True), (64, 128, 256, 64, 1, 0), (64, 64, 256, 192, 1, 0), (64, 256, 32, 256, 1, 0, False, True)]:
     run(*a)
