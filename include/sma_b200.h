@@ -226,6 +226,10 @@ int sma_dense_motion_prep(const float* src64, int h, int w, const float* kp_src_
 int sma_dense_motion_head(const float* logits, int ld, int h, int w, const float* kp_src_v, const float* kp_src_j,
                           const float* kp_drv_v, const float* kp_drv_j, int B, int K, float* deformation,
                           float* occlusion, float* mask_out, sma_stream_t stream);
+/* im2col of a few-channel NHWC map (row pitch ld): out (B,H,W,Kp) with out[..][(ky*k+kx)*C + c] = x[.., y+ky-pad, x+kx-pad, c], zeros outside
+ * the image and for columns >= k*k*C; turns the 7x7 conv over the 2-channel flow (archs/appmotioncodebook_arch.py:136,142) into one 1x1 conv of
+ * depth Kp = 128 instead of 49 taps of a zero-padded 32-channel chunk. */
+int sma_im2col_small(const float* x, int B, int H, int W, int ld, int C, int k, int pad, float* out, int Kp, sma_stream_t stream);
 /* flow glue of AppMotionCompFormer.forward (archs/appmotioncodebook_arch.py:562-601,689-710) */
 int sma_flow_to_px(const float* m, int B, int h, int w, float* flow_px, int out_ld, sma_stream_t stream);
 /* res: (B,h,w,res_ld) with columns 0,1 = delta-flow in pixels, 2 = delta-occlusion logit */

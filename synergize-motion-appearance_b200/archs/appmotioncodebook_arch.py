@@ -265,11 +265,15 @@ class AppMotionCompFormer(ParamModule):
                 [T[f'fuse_convs_dict.{s}.{b}.0.bias'] for b in ('scale', 'shift')])
             pc(f'fuse_convs_dict.{s}.scale.2'); pc(f'fuse_convs_dict.{s}.shift.2'); pc(f'fuse_ms_dict.{s}')
         # the 2-channel pixel-unit flow is kept in a 32-channel zero-padded buffer: both convs reading it run on the tensor cores
-        for n in ('motion_emb.0', 'BasicMotionEncoder.convf1'):
-            W[n] = ops.pack_conv(T[n + '.weight'], T[n + '.bias'], pad_cin=32)
+        W['motion_emb.0'] = ops.pack_conv(T['motion_emb.0.weight'], T['motion_emb.0.bias'], pad_cin=32)
+        # the 7x7 conv over the same 2 channels is unfolded instead (ops.im2col_small): one 1x1 conv of depth 128 instead of 49 taps x 32 padded channels
+        W['BasicMotionEncoder.convf1'] = ops.pack_conv_unfolded(T['BasicMotionEncoder.convf1.weight'], T['BasicMotionEncoder.convf1.bias'], 128)
         pc('motion_emb.1.conv'); pres('motion_emb.2', self.Em, self.Em)
+        # 160 input channels -> 192 (zero weights; the [cor | flo] buffer carries a zero tail): Cin % 64 == 0 puts the layer on the fp16 kernel
+        # (K = 16 per tensor-core instruction instead of the tf32 kernel's 8)
+        W['BasicMotionEncoder.conv'] = ops.pack_conv(T['BasicMotionEncoder.conv.weight'], T['BasicMotionEncoder.conv.bias'], pad_cin=192)
         for n in ('BasicMotionEncoder.convc1', 'BasicMotionEncoder.convc2',
-                  'BasicMotionEncoder.convf2', 'BasicMotionEncoder.conv', 'refine.convc1',
+                  'BasicMotionEncoder.convf2', 'refine.convc1',
                   'driving_kp_enc', 'motion_query_enc_1', 'motion_query_enc_2'):
             pc(n)
         # the two 3x3 output convs of RefineFlow read different halves of one buffer: one block-diagonal launch
@@ -483,11 +487,12 @@ class AppMotionCompFormer(ParamModule):
         for i in range(2):
             t = self._transformer(f'motion_block.{i}', t, Em, self._n_ctx(self.n_codes_motion, s0), T['position_emb_motion'], fast=fs)
         mfeat = ops.resize_ac(t.view(B, tg, tg, Em), (fg, fg))
-        cf = torch.empty((B, fg, fg, 160), device=dev, dtype=torch.float32)       # [cor 96 | flo 64]
+        cf = torch.empty((B, fg, fg, 192), device=dev, dtype=torch.float32)       # [cor 96 | flo 64 | zero 32]
+        cf[..., 160:].zero_()
         cor = ops.conv2d(mfeat, W['BasicMotionEncoder.convc1'], act='relu', fast=fs)
         ops.conv2d(cor, W['BasicMotionEncoder.convc2'], pad=1, act='relu', out=cf[..., :96], fast=fs)
-        flo = ops.conv2d(flow_px, W['BasicMotionEncoder.convf1'], pad=3, act='relu', fast=fs)
-        ops.conv2d(flo, W['BasicMotionEncoder.convf2'], pad=1, act='relu', out=cf[..., 96:], fast=fs)
+        flo = ops.conv2d(ops.im2col_small(flow_px, 2, 7, 3, 128), W['BasicMotionEncoder.convf1'], act='relu', fast=fs)
+        ops.conv2d(flo, W['BasicMotionEncoder.convf2'], pad=1, act='relu', out=cf[..., 96:160], fast=fs)
         ops.conv2d(cf, W['BasicMotionEncoder.conv'], pad=1, act='relu', out=z[..., :126], fast=fs)
         ctx = ops.conv2d(warp0, W[f'to_context.{int(math.log2(s0)) - 5}'], act='relu', fast=fs)
         if s != fg:

@@ -820,6 +820,8 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const __grid_co
     __syncwarp();
   } else if (TMA) {
     // =============================== halo converters (staged-input mode): shared fp32 slot -> prologue -> fp16 hi / lo operand rows ===============================
+    // (A/B'd: moving the two sleeping roles - weight loader, TMA issuer - onto the MMA warp's scheduler so that no converter competes with the MMA
+    //  thread for issue slots is 1-2 % SLOWER: spreading the converters evenly over the four schedulers matters more)
     const int ptid = threadIdx.x - 192; const int cq = ptid & 7; const int prow = ptid >> 3;      // 28 halo rows per pass of the 7 warps
     const int swap = cq >> 2;                                   // lanes 4-7 read their two 16-byte halves in the opposite order: conflict-free LDS.128
     const int Hv = p.Hi, Wv = p.Wi;

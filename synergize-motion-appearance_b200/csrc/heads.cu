@@ -352,6 +352,37 @@ extern "C" int sma_dense_motion_head(const float* logits, int ld, int h, int w, 
   dense_motion_head_kernel<<<nblocks((long long)B * h * w, 128), 128, 0, as_stream(s)>>>(logits, ld, h, w, sv, sj, dv, dj, B, K, deform, occ, mask_out);
   SMA_LAUNCH_CHECK(); return SMA_OK;
 }
+// im2col of a few-channel map (the 2-channel pixel-unit flow feeding the 7x7 BasicMotionEncoder.convf1, appmotioncodebook_arch.py:136,142): as an
+// implicit GEMM the conv would contract over kh*kw taps of a 32-channel zero-padded chunk each (1568 K values for 98 real ones); unfolded to
+// K = k*k*C (padded to `Kp`) it is ONE 128-deep 1x1 conv on the tensor cores.  out[b][y][x][(ky*k+kx)*C + c] = x[b][y+ky-pad][x+kx-pad][c], zero
+// outside the image and for columns >= k*k*C.  One thread per (pixel, 4 columns).
+__global__ void im2col_small_kernel(const float* __restrict__ x, int B, int H, int W, int ld, int C, int k, int pad, float* __restrict__ out, int Kp) {
+  const int kq = Kp >> 2;
+  const long long total = (long long)B * H * W * kq;
+  const int KK = k * k * C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int q = (int)(i % kq); long long pix = i / kq;
+    const int px = (int)(pix % W); const int py = (int)((pix / W) % H); const long long b = pix / ((long long)W * H);
+    float v[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const int col = q * 4 + j;
+      v[j] = 0.f;
+      if (col < KK) {
+        const int tap = col / C, c = col - tap * C; const int ky = tap / k, kx = tap - ky * k;
+        const int iy = py + ky - pad, ix = px + kx - pad;
+        if ((unsigned)iy < (unsigned)H && (unsigned)ix < (unsigned)W) v[j] = __ldg(x + ((b * H + iy) * W + ix) * ld + c);
+      }
+    }
+    *reinterpret_cast<float4*>(out + pix * Kp + q * 4) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+}
+extern "C" int sma_im2col_small(const float* x, int B, int H, int W, int ld, int C, int k, int pad, float* out, int Kp, sma_stream_t s) {
+  if (!x || !out || B <= 0 || H <= 0 || W <= 0 || C <= 0 || k <= 0 || pad < 0 || ld < C || (Kp & 3) || Kp < k * k * C) return SMA_ERR_BAD_ARG;
+  if (reinterpret_cast<uintptr_t>(out) & 15) return SMA_ERR_BAD_ARG;
+  im2col_small_kernel<<<nblocks((long long)B * H * W * (Kp >> 2)), 256, 0, as_stream(s)>>>(x, B, H, W, ld, C, k, pad, out, Kp);
+  SMA_LAUNCH_CHECK(); return SMA_OK;
+}
 extern "C" int sma_flow_to_px(const float* m, int B, int h, int w, float* o, int ld, sma_stream_t s) {
   if (!m || !o || B <= 0 || h <= 1 || w <= 1 || ld < 2) return SMA_ERR_BAD_ARG;
   flow_to_px_kernel<<<nblocks((long long)B * h * w), 256, 0, as_stream(s)>>>(m, B, h, w, o, ld);

@@ -601,6 +601,24 @@ def flow_to_px(m: torch.Tensor, out: torch.Tensor):
     return out
 
 
+def im2col_small(x: torch.Tensor, C: int, k: int, pad: int, Kp: int) -> torch.Tensor:
+    """x (B,H,W,>=C) channels-last view (the first C channels are used) -> (B,H,W,Kp), column (ky*k+kx)*C + c; zero padded."""
+    lib = _lib.load()
+    B, H, W, _, bs, ld = _nhwc(x)
+    assert bs == H * W * ld
+    out = torch.empty((B, H, W, Kp), device=x.device, dtype=torch.float32)
+    check(lib.sma_im2col_small(x.data_ptr(), B, H, W, ld, C, k, pad, out.data_ptr(), Kp, _stream()), 'sma_im2col_small')
+    return out
+
+
+def pack_conv_unfolded(weight: torch.Tensor, bias: Optional[torch.Tensor], Kp: int) -> 'ConvW':
+    """OIHW weight of a few-channel conv -> the (O, Kp) linear weight over im2col_small's columns ((ky*k+kx)*C + c)."""
+    O, Cc, kh, kw = weight.shape
+    w2 = torch.zeros((O, Kp), device=weight.device, dtype=torch.float32)
+    w2[:, :kh * kw * Cc] = weight.detach().float().permute(0, 2, 3, 1).reshape(O, kh * kw * Cc)
+    return pack_conv(w2, bias)
+
+
 def flow_update(m_prev: torch.Tensor, occ_prev: torch.Tensor, res: torch.Tensor):
     lib = _lib.load()
     B, h, w, _ = m_prev.shape

@@ -165,6 +165,22 @@ def test_conv2d_two_product_mode_is_the_full_weight_times_the_fp16_rounded_activ
     assert float((nchw(y).double() - full).abs().max()) > 5 * err          # ... and it really dropped the lo halves
 
 
+def test_unfolded_few_channel_conv_matches_torch(S):
+    """The 7x7 conv over the 2-channel flow (BasicMotionEncoder.convf1, appmotioncodebook_arch.py:136,142) as im2col (sma_im2col_small, bit-exact data
+    movement with zero padding) + one 1x1 conv of depth 128."""
+    B, H, W = 2, 20, 28
+    x = rnd(B, 2, H, W, seed=1)
+    w = rnd(128, 2, 7, 7, seed=2, scale=98 ** -0.5); b = rnd(128, seed=3, scale=0.1)
+    buf = torch.zeros(B, H, W, 32, device='cuda'); buf[..., :2] = nhwc(x)
+    cols = S.ops.im2col_small(buf, 2, 7, 3, 128)
+    ref_cols = F.unfold(x, 7, padding=3).view(B, 2, 49, H, W).permute(0, 3, 4, 2, 1).reshape(B, H, W, 98)      # column (ky*7+kx)*2 + c
+    assert torch.equal(cols[..., :98].cpu(), ref_cols) and float(cols[..., 98:].abs().max()) == 0.0
+    y = S.ops.conv2d(cols, S.ops.pack_conv_unfolded(w.cuda(), b.cuda(), 128), act='relu')
+    ref = F.relu(F.conv2d(x.double(), w.double(), b.double(), padding=3))
+    assert S.ops.LAST_CONV_KERNEL == 3
+    assert float((nchw(y).double() - ref).abs().max()) < 2e-5
+
+
 def test_conv2d_concat_slices_patchify_and_bn_fold(S):
     """channel-slice views as input/output (torch.cat elimination), stride-p patch embedding, depth-to-space."""
     B, C, s, p = 2, 128, 64, 2
