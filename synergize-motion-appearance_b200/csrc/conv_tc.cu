@@ -254,8 +254,11 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const TcP p) {
 //   warps 0-3 epilogue | warp 4 MMA issue + TMEM alloc | warp 5 weight loader | warps 6-13 halo producers
 // =================================================================================================================
 constexpr int V2_PROD_WARPS = 8;                       // halo producers: enough loads in flight to cover HBM latency
-constexpr int V2_THREADS = 192 + 32 * V2_PROD_WARPS;       // 14 warps: 144 registers per thread (a 15th warp would cap them at 128)
-constexpr int V2_CONV_WARPS = V2_PROD_WARPS - 1;           // staged-input (TMA) mode: warps 6-12 convert, warp 13 issues the tensor loads
+constexpr int V2_THREADS = 192 + 32 * V2_PROD_WARPS;       // register-staged mode, 14 warps: 4 epilogue | MMA | weight loader | 8 halo producers
+// staged-input (TMA) mode, 16 warps: 8 epilogue (two per tensor-memory lane quarter, alternate 32-column blocks) | MMA | copy issuer (one thread drives
+// the weight ring and the TMA staging ring) | 6 converters
+constexpr int V2_CONV_WARPS = 6;
+constexpr int V2_THREADS_TMA = 512;
 constexpr int V2_PGROUPS = 2;                          // producer groups working on alternate channel chunks (2x the latency budget each)
 constexpr int V2_PROWS = 4 * V2_PROD_WARPS / V2_PGROUPS;   // halo rows per pass of one group (8 lanes per 128-byte row)
 #ifndef SMA_V2_UNROLL
@@ -263,11 +266,7 @@ constexpr int V2_PROWS = 4 * V2_PROD_WARPS / V2_PGROUPS;   // halo rows per pass
 #endif
 constexpr int V2_UNROLL = SMA_V2_UNROLL;                          // loads in flight per producer thread
 constexpr int MAX_SA = 3, MAX_SB = 8, MAX_NS = 8;
-#ifdef SMA_COAL_EPILOGUE
-constexpr bool SMA_COAL_ENABLED = true;
-#else
-constexpr bool SMA_COAL_ENABLED = false;
-#endif
+
 
 struct Tc2P {
   const float* x; const float* wtc; const float* bias; const float* pre_scale; const float* pre_shift; const float* res; float* y;
@@ -289,7 +288,6 @@ struct Tc2P {
   // cp.async.bulk.tensor (a 4-D map over (C, W, H, B): zero fill outside the image = the convolution's padding; flat 1x1 layers: a 3-D map over
   // (C, pixels, B)), `parts` boxes of `slot_rows` halo rows each; the 8 producer warps convert slot by slot.  No thread waits on global memory.
   int NS, parts, slot_rows, slot_bytes, rs /* image rows per box */, tma_b_fixed /* batch stride 0: always coordinate 0 */;
-  int coal;                   // RES = 2: 16 KB of shared memory after the staging slots for the coalescing epilogue (4 KB per epilogue warp)
   alignas(64) CUtensorMap tmap;
 };
 
@@ -300,8 +298,10 @@ struct Tc2P {
 // (one 128-byte swizzle row) is then 64 channels.
 // RES: 1 = the 256-bit epilogue with the residual prefetched one column block ahead (own instantiation: its register budget must not touch the others)
 template <int ACT, int PRE, int F16, int RES, int TMA>
-__global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const __grid_constant__ Tc2P p) {
-  constexpr int KCH = F16 ? 64 : 32;                       // channels per K-chunk (128 bytes of operand)
+__global__ void __launch_bounds__(TMA ? V2_THREADS_TMA : V2_THREADS, 1) conv_tc2_kernel(const __grid_constant__ Tc2P p) {
+  constexpr int KCH = F16 ? 64 : 32;
+  // warp roles: [0, EPW) epilogue, W_MMA, W_MMA + 1 weight loader, then (TMA) the tensor-load issuer and the converters, else the 8 halo producers
+  constexpr int EPW = TMA ? 8 : 4, W_MMA = EPW, W_LOAD = EPW + 1, W_CONV0 = EPW + 2;                       // channels per K-chunk (128 bytes of operand)
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[2 * MAX_SA + 2 * MAX_SB + 4 + 2 * MAX_NS];
   __shared__ uint32_t tmem_slot;
@@ -321,16 +321,15 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const __grid_co
   const uint32_t a_ring = sbase, b_ring = sbase + (uint32_t)p.SA * p.a_stage_bytes;
   const int b_stage_bytes = 2 * p.b_img_bytes;
   const uint32_t stg_ring = b_ring + (uint32_t)p.SB * b_stage_bytes;      // (TMA) fp32 staging slots; 1 KB aligned like everything before it
-  const uint32_t epi_ring = stg_ring + (uint32_t)p.NS * p.slot_bytes;      // (RES = 2) 4 x 4 KB transposition buffers of the epilogue warps
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.SA; s++) { mbar_init(a_full(s), TMA ? 32 * V2_CONV_WARPS : 32 * V2_PROD_WARPS / V2_PGROUPS); mbar_init(a_empty(s), 1); }
     if (TMA) for (int s = 0; s < p.NS; s++) { mbar_init(s_full(s), 1); mbar_init(s_empty(s), V2_CONV_WARPS); }
     for (int s = 0; s < p.SB; s++) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
-    for (int s = 0; s < 2; s++) { mbar_init(acc_full(s), 1); mbar_init(acc_empty(s), 128); }
+    for (int s = 0; s < 2; s++) { mbar_init(acc_full(s), 1); mbar_init(acc_empty(s), 32 * EPW); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 4) {
+  if (warp == W_MMA) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(p.tmem_cols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -346,9 +345,12 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const __grid_co
     if (p.flat) { ty0 = t * BM; tx0 = 0; } else { int tyi = t / p.tiles_x; ty0 = tyi * 16; tx0 = (t - tyi * p.tiles_x) * 8; }
   };
 
-  if (warp < 4) {
+  if (warp < EPW) {
     // =============================== epilogue ===============================
-    const int m = warp * 32 + lane;
+    // warp w reads tensor-memory lanes 32 (w % 4) .. +31 (= tile rows); with 8 warps, warp w and w + 4 share a lane quarter and take alternate
+    // 32-column blocks: the per-tile instruction stream of an epilogue thread halves (it was as long as the MMAs of a tile)
+    const int wq = warp & 3, half = warp >> 2;
+    const int m = wq * 32 + lane;
     const bool vec_ok = (p.out_ld & 3) == 0 && (p.out_bs & 3) == 0 && ((reinterpret_cast<uintptr_t>(p.y) & 15) == 0) &&
                         (!p.res || ((p.res_ld & 3) == 0 && (p.res_bs & 3) == 0 && (reinterpret_cast<uintptr_t>(p.res) & 15) == 0));
     const int Cq = p.d2s > 1 ? p.Cout / (p.d2s * p.d2s) : p.Cout;
@@ -358,9 +360,9 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const __grid_co
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tcount) {
       int b, ty0, tx0, nt; decode(tile, b, ty0, tx0, nt);
       const int ab = tcount & 1; const uint32_t aph = (tcount >> 1) & 1;
-      if (nt != cur_nt) {                           // (re)stage the bias slice of this N tile; named barrier 1 = the 4 epilogue warps
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        for (int i = m; i < p.NT; i += 128) {
+      if (nt != cur_nt) {                           // (re)stage the bias slice of this N tile; named barrier 1 = the epilogue warps
+        asm volatile("bar.sync 1, %0;" ::"r"(32 * EPW) : "memory");
+        for (int i = threadIdx.x; i < p.NT; i += 32 * EPW) {
           int n = nt * p.NT + i; s_bias[i] = (p.bias && n < p.Cout) ? __ldg(p.bias + n) : 0.f;
           if (F16) s_scale[i] = __ldg(p.wscale + n) * p.acc_corr;
         }
@@ -370,128 +372,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const __grid_co
       int oy, ox, r; bool mok;
       if (p.flat) { r = ty0 + m; mok = r < p.HoWo; oy = r / p.Wo; ox = r - oy * p.Wo; }
       else { oy = ty0 + (m >> 3); ox = tx0 + (m & 7); mok = oy < p.Ho && ox < p.Wo; r = oy * p.Wo + ox; }
-      if constexpr (RES == 2) {
-        // Coalescing epilogue (EXPERIMENT, compiled only with -DSMA_COAL_EPILOGUE; measured SLOWER than the register epilogue, see
-        // profiles/r2_tma_staging.md).  A thread owns one pixel ROW of the accumulator, so stored straight from registers a warp-level 256-bit
-        // store touches 32 different 128-byte lines (a quarter of each).  Here every warp transposes its 32 x 32 block through 4 KB of shared memory
-        // (16-byte chunks XOR-swizzled by the row: conflict-free both ways) so that 8 consecutive lanes read / write one whole 128-byte line of the
-        // residual / the output.  Hypothesis was that the line-by-line L1 processing of the scattered stores bounds the short-K layers; it does not:
-        // 1x1 64 -> 192 @256^2 takes 0.97 ms with the 256-bit row stores and 1.64 ms this way (the layer already moves 4.4 TB/s).
-        const int nbase = nt * p.NT;
-        const uint32_t stg = epi_ring + (uint32_t)warp * 4096u;
-        const int cc = lane & 7, rsub = lane >> 3;
-        if (p.res) {                                     // L2 prefetch of the next tile's residual (and SFT scale) row of this thread
-          const int tile2 = tile + (int)gridDim.x;
-          if (tile2 < p.total_tiles) {
-            int b2, ty2, tx2, nt2; decode(tile2, b2, ty2, tx2, nt2);
-            int r2; bool ok2;
-            if (p.flat) { r2 = ty2 + m; ok2 = r2 < p.HoWo; }
-            else { const int oy2 = ty2 + (m >> 3), ox2 = tx2 + (m & 7); ok2 = oy2 < p.Ho && ox2 < p.Wo; r2 = oy2 * p.Wo + ox2; }
-            if (ok2) {
-              const float* q = p.res + (long long)b2 * p.res_bs + (long long)r2 * p.res_ld + nt2 * p.NT;
-              const int nb2 = min(p.NT, p.Cout - nt2 * p.NT) * 4;
-              for (int o = 0; o < nb2; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(q) + o));
-              if (p.aux) {
-                const float* qa = p.aux + (long long)b2 * p.aux_bs + (long long)r2 * p.aux_ld + nt2 * p.NT;
-                for (int o = 0; o < nb2; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(qa) + o));
-              }
-            }
-          }
-        }
-        // the 8 rows this lane serves in the transposed domain are row_i = i * 4 + rsub of this warp's 32 (recomputed where used: registers)
-        auto row_of = [&](int i, bool& oki) -> int {
-          const int mi = warp * 32 + i * 4 + rsub;
-          if (p.flat) { const int ri = ty0 + mi; oki = ri < p.HoWo; return oki ? ri : 0; }
-          const int oyi = ty0 + (mi >> 3), oxi = tx0 + (mi & 7);
-          oki = oyi < p.Ho && oxi < p.Wo;
-          return oki ? oyi * p.Wo + oxi : 0;
-        };
-        // residual of one 32-column block: whole 128-byte lines per 8 lanes; issued one block ahead (the first before the accumulator wait)
-        auto load_res = [&](const float* base, long long bs, int ld, int n0_, float4 (&dst)[8]) {
-          const int n_ = nbase + n0_ + cc * 4;
-#pragma unroll
-          for (int i = 0; i < 8; i++) {
-            bool oki; const int ri = row_of(i, oki);
-            dst[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (oki && n_ < p.Cout) {
-              const float* q = base + (long long)b * bs + (long long)ri * ld + n_;
-              asm volatile("ld.global.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(dst[i].x), "=f"(dst[i].y), "=f"(dst[i].z), "=f"(dst[i].w) : "l"(q));
-            }
-          }
-        };
-        float4 rr[8];
-        const bool has_res = p.res != nullptr && !(p.dbg & 4);
-        if (has_res) load_res(p.res, p.res_bs, p.res_ld, 0, rr);
-        mbar_wait(acc_full(ab), aph);
-        tc_fence_after();
-        for (int n0 = 0; n0 < p.NT && nbase + n0 < p.Cout; n0 += 32) {
-          const bool last = n0 + 32 >= p.NT || nbase + n0 + 32 >= p.Cout;
-#pragma unroll
-          for (int hh = 0; hh < 2; hh++) {                  // two halves of 16 columns: accumulator -> (bias, un-scaling, activation) -> own row in shared memory
-            uint32_t a[16];
-            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(ab * p.acc_cols + n0 + hh * 16);
-            tmem_ld16(taddr, a);
-            if (p.fuse) {
-              uint32_t a2[16];
-              tmem_ld16(taddr + (uint32_t)p.NT, a2);
-              tmem_ld_wait();
-#pragma unroll
-              for (int i = 0; i < 16; i++) a[i] = __float_as_uint(__uint_as_float(a[i]) + __uint_as_float(a2[i]));
-            } else {
-              tmem_ld_wait();
-            }
-            if (last && hh == 1) {                         // last column block: the accumulator may be overwritten while we store
-              tc_fence_before();
-              mbar_arrive(acc_empty(ab));
-            }
-            if (!(p.dbg & 4)) {
-#pragma unroll
-              for (int c4 = 0; c4 < 4; c4++) {
-                const int cq4 = hh * 4 + c4;
-                const float4 b4 = *reinterpret_cast<const float4*>(&s_bias[n0 + cq4 * 4]);
-                float o0, o1, o2, o3;
-                if (F16) {
-                  const float4 s4 = *reinterpret_cast<const float4*>(&s_scale[n0 + cq4 * 4]);
-                  o0 = sma_act(fmaf(__uint_as_float(a[c4 * 4 + 0]), s4.x, b4.x), ACT); o1 = sma_act(fmaf(__uint_as_float(a[c4 * 4 + 1]), s4.y, b4.y), ACT);
-                  o2 = sma_act(fmaf(__uint_as_float(a[c4 * 4 + 2]), s4.z, b4.z), ACT); o3 = sma_act(fmaf(__uint_as_float(a[c4 * 4 + 3]), s4.w, b4.w), ACT);
-                } else {
-                  o0 = sma_act(__uint_as_float(a[c4 * 4 + 0]) + b4.x, ACT); o1 = sma_act(__uint_as_float(a[c4 * 4 + 1]) + b4.y, ACT);
-                  o2 = sma_act(__uint_as_float(a[c4 * 4 + 2]) + b4.z, ACT); o3 = sma_act(__uint_as_float(a[c4 * 4 + 3]) + b4.w, ACT);
-                }
-                sts128(stg + (uint32_t)lane * 128u + (uint32_t)((cq4 ^ (lane & 7)) << 4), o0, o1, o2, o3);
-              }
-            }
-          }
-          if (p.dbg & 4) continue;
-          __syncwarp();
-          const int n = nbase + n0 + cc * 4;               // the 4 columns this lane serves in the transposed domain
-#pragma unroll
-          for (int i = 0; i < 8; i++) {
-            const int rw = i * 4 + rsub;
-            bool oki; const int ri = row_of(i, oki);
-            float4 v;
-            asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
-                         : "r"(stg + (uint32_t)rw * 128u + (uint32_t)((cc ^ (rw & 7)) << 4)));
-            if (oki && n < p.Cout) {
-              if (has_res) {
-                if (p.aux) {        // Fuse_sft_block tail (appmotioncodebook_arch.py:50-51): dec + w * (dec * scale + shift), this conv = shift
-                  float4 sa;
-                  const float* q = p.aux + (long long)b * p.aux_bs + (long long)ri * p.aux_ld + n;
-                  asm volatile("ld.global.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(sa.x), "=f"(sa.y), "=f"(sa.z), "=f"(sa.w) : "l"(q));
-                  v.x = rr[i].x + p.sft_w * (rr[i].x * sa.x + v.x); v.y = rr[i].y + p.sft_w * (rr[i].y * sa.y + v.y);
-                  v.z = rr[i].z + p.sft_w * (rr[i].z * sa.z + v.z); v.w = rr[i].w + p.sft_w * (rr[i].w * sa.w + v.w);
-                } else {
-                  v.x += rr[i].x; v.y += rr[i].y; v.z += rr[i].z; v.w += rr[i].w;
-                }
-              }
-              float* dst = p.y + (long long)b * p.out_bs + (long long)ri * p.out_ld + n;
-              asm volatile("st.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(dst), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
-            }
-          }
-          __syncwarp();
-          if (has_res && !last) load_res(p.res, p.res_bs, p.res_ld, n0 + 32, rr);      // next block's residual: in flight across its accumulator read
-        }
-      } else if constexpr (RES == 1) {
+      if constexpr (RES == 1) {
         const int nbase = nt * p.NT;
         // 256-bit path for layers with a residual.  Loaded next to its use, every 8 columns of the residual exposed a full DRAM latency (32 per
         // tile of a 256-column linear: the short-K transformer linears ran 4x below their MMA / HBM time).  Here (1) the residual row of the
@@ -515,7 +396,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const __grid_co
     }
         {                                                // L2 prefetch of the next tile's residual (and SFT scale) row of this thread
           const int tile2 = tile + (int)gridDim.x;
-          if (tile2 < p.total_tiles) {
+          if (tile2 < p.total_tiles && half == 0) {
             int b2, ty2, tx2, nt2; decode(tile2, b2, ty2, tx2, nt2);
             int r2; bool ok2;
             if (p.flat) { r2 = ty2 + m; ok2 = r2 < p.HoWo; }
@@ -533,9 +414,13 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const __grid_co
         }
         mbar_wait(acc_full(ab), aph);
         tc_fence_after();
-        for (int n0 = 0; n0 < p.NT && nbase + n0 < p.Cout; n0 += 32) {
+        if (half * 32 >= p.NT || nbase + half * 32 >= p.Cout) {      // (8 warps) no column block for this half: release the accumulator right away
+          tc_fence_before();
+          mbar_arrive(acc_empty(ab));
+        }
+        for (int n0 = half * 32; n0 < p.NT && nbase + n0 < p.Cout; n0 += 8 * EPW) {
           uint32_t a[32];
-          const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(ab * p.acc_cols + n0);
+          const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(ab * p.acc_cols + n0);
           tmem_ld32(taddr, a);
           if (p.fuse) {                                  // the lo products were accumulated NT columns further right (two halves: registers)
   #pragma unroll
@@ -551,7 +436,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const __grid_co
           }
           SMA_LD_BLOCK(rc, rrow, n0)                      // (after the lo half of the accumulator is folded in: register budget)
           if (arow) SMA_LD_BLOCK(rn, arow, n0)
-          const bool last = n0 + 32 >= p.NT || nbase + n0 + 32 >= p.Cout;
+          const bool last = n0 + 8 * EPW >= p.NT || nbase + n0 + 8 * EPW >= p.Cout;      // this warp's last column block
           if (last) {                                    // last column block: the accumulator may be overwritten while we store
             tc_fence_before();
             mbar_arrive(acc_empty(ab));
@@ -597,9 +482,13 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const __grid_co
         const int nbase = nt * p.NT;
         mbar_wait(acc_full(ab), aph);
         tc_fence_after();
-        for (int n0 = 0; n0 < p.NT && nbase + n0 < p.Cout; n0 += 32) {
+        if (half * 32 >= p.NT || nbase + half * 32 >= p.Cout) {      // (8 warps) no column block for this half: release the accumulator right away
+          tc_fence_before();
+          mbar_arrive(acc_empty(ab));
+        }
+        for (int n0 = half * 32; n0 < p.NT && nbase + n0 < p.Cout; n0 += 8 * EPW) {
           uint32_t a[32];
-          const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(ab * p.acc_cols + n0);
+          const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(ab * p.acc_cols + n0);
           tmem_ld32(taddr, a);
           if (p.fuse) {                                  // a_hi * b_lo was accumulated NT columns further right
             uint32_t a2[32];
@@ -610,7 +499,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const __grid_co
           } else {
             tmem_ld_wait();
           }
-          if (n0 + 32 >= p.NT || nbase + n0 + 32 >= p.Cout) {     // last column block: the accumulator may be overwritten while we store
+          if (n0 + 8 * EPW >= p.NT || nbase + n0 + 8 * EPW >= p.Cout) {     // this warp's last column block: the accumulator may be overwritten while we store
             tc_fence_before();
             mbar_arrive(acc_empty(ab));
           }
@@ -707,7 +596,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const __grid_co
 
       }
     }
-  } else if (warp == 4) {
+  } else if (warp == W_MMA) {
     // =============================== MMA issuer (whole warp converged, one elected lane issues) ===============================
     // fp32 accumulate; A/B format 2 = tf32 (kind::tf32) or 0 = fp16 (kind::f16); K-major A and B
     const uint32_t idesc = (1u << 4) | (F16 ? 0u : ((2u << 7) | (2u << 10))) | ((uint32_t)(p.NT >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
@@ -773,9 +662,62 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const __grid_co
       }
     }
     __syncwarp();
-  } else if (warp == 5) {
+  } else if (warp == W_LOAD) {
     // =============================== weight loader ===============================
-    if (lane == 0) {
+    if (TMA && lane == 0) {
+      // staged-input mode: ONE thread feeds both rings.  It polls the two "slot free" barriers without blocking on either (a blocked weight slot
+      // must not hold back a free staging slot and vice versa), so that a 16th warp is not needed for the tensor loads (16 warps = 128 registers).
+      const uint32_t bytes = (uint32_t)(p.passes >= 2 ? b_stage_bytes : p.b_img_bytes);
+      const uint64_t tm = reinterpret_cast<uint64_t>(&p.tmap);
+      const int nblob = p.cpt * p.taps;
+      auto test = [&](uint32_t bar, uint32_t parity) -> bool {
+        uint32_t ok;
+        asm volatile("{\n.reg .pred p;\nmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        return ok != 0;
+      };
+      // weight cursor
+      int wt = blockIdx.x, wj = 0; uint32_t wsb = 0, wph = 0;
+      // staging cursor
+      int st_ = blockIdx.x, scc = 0, spart = 0; uint32_t ss = 0, phs = 0;
+      int sb_, sty0, stx0, snt; decode(st_ < p.total_tiles ? st_ : 0, sb_, sty0, stx0, snt);
+      bool wdone = wt >= p.total_tiles, sdone = st_ >= p.total_tiles || (p.dbg & 2);
+      while (!wdone || !sdone) {
+        bool progressed = false;
+        if (!sdone && test(s_empty(ss), phs ^ 1u)) {
+          mbar_expect_tx(s_full(ss), (uint32_t)p.slot_bytes);
+          const uint32_t dst = stg_ring + ss * (uint32_t)p.slot_bytes;
+          const int bc = p.tma_b_fixed ? 0 : sb_;
+          if (p.flat) {
+            asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                         ::"r"(dst), "l"(tm), "r"(scc * 64), "r"(sty0 + spart * p.slot_rows), "r"(bc), "r"(s_full(ss)) : "memory");
+          } else {
+            asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+                         ::"r"(dst), "l"(tm), "r"(scc * 64), "r"(stx0 - p.pad_l), "r"(sty0 - p.pad_t + spart * p.rs), "r"(bc), "r"(s_full(ss)) : "memory");
+          }
+          if (++ss == (uint32_t)p.NS) { ss = 0; phs ^= 1u; }
+          if (++spart == p.parts) {
+            spart = 0;
+            if (++scc == p.cpt) {
+              scc = 0; st_ += gridDim.x;
+              if (st_ >= p.total_tiles) sdone = true; else decode(st_, sb_, sty0, stx0, snt);
+            }
+          }
+          progressed = true;
+        }
+        if (!wdone && test(b_empty(wsb), wph ^ 1u)) {
+          if (p.dbg & 1) mbar_arrive(b_full(wsb));                        // timing experiment: no weight traffic
+          else {
+            const char* src = reinterpret_cast<const char*>(p.wtc) + ((long long)(wt % p.ntiles_n) * nblob + wj) * b_stage_bytes;
+            mbar_expect_tx(b_full(wsb), bytes);
+            bulk_g2s(b_ring + wsb * (uint32_t)b_stage_bytes, src, bytes, b_full(wsb));
+          }
+          if (++wsb == (uint32_t)p.SB) { wsb = 0; wph ^= 1u; }
+          if (++wj == nblob) { wj = 0; wt += gridDim.x; if (wt >= p.total_tiles) wdone = true; }
+          progressed = true;
+        }
+        if (!progressed) __nanosleep(32);
+      }
+    } else if (!TMA && lane == 0) {
       const uint32_t bytes = (uint32_t)(p.passes >= 2 ? b_stage_bytes : p.b_img_bytes);
       int jt = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -792,37 +734,11 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const __grid_co
       }
     }
     __syncwarp();
-  } else if (TMA && warp == 6 + V2_CONV_WARPS) {
-    // =============================== TMA issuer (staged-input mode) ===============================
-    if (lane == 0 && !(p.dbg & 2)) {
-      uint32_t ss = 0, phs = 0;
-      const uint64_t tm = reinterpret_cast<uint64_t>(&p.tmap);
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        int b, ty0, tx0, nt; decode(tile, b, ty0, tx0, nt);
-        if (p.tma_b_fixed) b = 0;
-        for (int cc = 0; cc < p.cpt; cc++) {
-          for (int part = 0; part < p.parts; part++) {
-            mbar_wait(s_empty(ss), phs ^ 1u);
-            mbar_expect_tx(s_full(ss), (uint32_t)p.slot_bytes);
-            const uint32_t dst = stg_ring + ss * (uint32_t)p.slot_bytes;
-            if (p.flat) {
-              asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-                           ::"r"(dst), "l"(tm), "r"(cc * 64), "r"(ty0 + part * p.slot_rows), "r"(b), "r"(s_full(ss)) : "memory");
-            } else {
-              asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
-                           ::"r"(dst), "l"(tm), "r"(cc * 64), "r"(tx0 - p.pad_l), "r"(ty0 - p.pad_t + part * p.rs), "r"(b), "r"(s_full(ss)) : "memory");
-            }
-            if (++ss == (uint32_t)p.NS) { ss = 0; phs ^= 1u; }
-          }
-        }
-      }
-    }
-    __syncwarp();
   } else if (TMA) {
     // =============================== halo converters (staged-input mode): shared fp32 slot -> prologue -> fp16 hi / lo operand rows ===============================
     // (A/B'd: moving the two sleeping roles - weight loader, TMA issuer - onto the MMA warp's scheduler so that no converter competes with the MMA
     //  thread for issue slots is 1-2 % SLOWER: spreading the converters evenly over the four schedulers matters more)
-    const int ptid = threadIdx.x - 192; const int cq = ptid & 7; const int prow = ptid >> 3;      // 28 halo rows per pass of the 7 warps
+    const int ptid = threadIdx.x - 32 * W_CONV0; const int cq = ptid & 7; const int prow = ptid >> 3;      // 24 halo rows per pass of the 6 warps
     const int swap = cq >> 2;                                   // lanes 4-7 read their two 16-byte halves in the opposite order: conflict-free LDS.128
     const int Hv = p.Hi, Wv = p.Wi;
     uint32_t ss = 0, phs = 0; int it = 0;
@@ -841,12 +757,13 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const __grid_co
         }
         mbar_wait(a_empty(sa), pha ^ 1u);
         if (p.dbg & 2) { mbar_arrive(a_full(sa)); continue; }          // timing experiment: no halo traffic, no conversion
+        int hp = prow;                                           // this thread's rows run on across the boxes of the chunk: prow, prow + 24, ...
         for (int part = 0; part < p.parts; part++) {
           mbar_wait(s_full(ss), phs);
           const uint32_t slot = stg_ring + ss * (uint32_t)p.slot_bytes;
-          for (int lr = prow; lr < p.slot_rows; lr += 4 * V2_CONV_WARPS) {
-            const int hp = part * p.slot_rows + lr;
-            if (hp >= p.HP) break;
+          const int hp_end = min((part + 1) * p.slot_rows, p.HP);
+          for (; hp < hp_end; hp += 4 * V2_CONV_WARPS) {
+            const int lr = hp - part * p.slot_rows;
             const uint32_t src = slot + (uint32_t)lr * 256u + (uint32_t)cq * 32u;
             float4 u0, u1;
             asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(u0.x), "=f"(u0.y), "=f"(u0.z), "=f"(u0.w) : "r"(src + (uint32_t)swap * 16u));
@@ -998,7 +915,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) conv_tc2_kernel(const __grid_co
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == W_MMA) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
   }
@@ -1116,7 +1033,7 @@ template <int ACT, int PRE, int F16, int RES, int TMA>
 static int launch_tc2_inst2(const Tc2P& p, int grid, int smem, cudaStream_t st) {
   static SmaDevOnce once;             // per instantiation and per device
   if (int rc = sma_opt_in_smem(once, conv_tc2_kernel<ACT, PRE, F16, RES, TMA>, SMEM_DYN_MAX)) return rc;
-  conv_tc2_kernel<ACT, PRE, F16, RES, TMA><<<grid, V2_THREADS, smem, st>>>(p);
+  conv_tc2_kernel<ACT, PRE, F16, RES, TMA><<<grid, TMA ? V2_THREADS_TMA : V2_THREADS, smem, st>>>(p);
   SMA_LAUNCH_CHECK();
   return SMA_OK;
 }
@@ -1128,9 +1045,6 @@ static int launch_tc2_inst(const Tc2P& p, int grid, int smem, cudaStream_t st) {
 template <int ACT, int PRE, int F16>
 static int launch_tc2_res(const Tc2P& p, int grid, int smem, cudaStream_t st) {
   if constexpr (F16 != 0) {
-#ifdef SMA_COAL_EPILOGUE     // negative result, kept for the record (profiles/r2_tma_staging.md): off by default, not even instantiated
-    if (p.coal) return launch_tc2_inst<ACT, PRE, 1, 2>(p, grid, smem, st);            // coalescing epilogue (shared-memory transposition)
-#endif
     if constexpr (ACT == SMA_ACT_NONE && (PRE == -1 || PRE == SMA_ACT_SWISH)) {
       if (p.res_pipe) return launch_tc2_inst<ACT, PRE, 1, 1>(p, grid, smem, st);       // no room for it (256-column 3x3 tiles): register epilogue with the residual pipeline
     }
@@ -1201,14 +1115,7 @@ static int conv_tc2_try(const sma_conv_desc* d, cudaStream_t st, bool f16) {
   // TMA-staged input: stride 1, no fused upsample, 1x1 / 3x3, 16-byte aligned strides; as many staging slots as leave the weight ring >= 3 stages
   // (2 for the 256-column tiles); layers where that is not possible (3x3 with 128 / 256-column tiles) keep the register-staged producers
   p.NS = 0; p.parts = p.slot_rows = p.slot_bytes = p.rs = 0; p.tma_b_fixed = d->in_bstride == 0 ? 1 : 0;
-  // coalescing epilogue (RES = 2): 256-bit-eligible NHWC output, no depth-to-space, 16 KB of shared memory beside at least two weight stages
   int budget = SMEM_LIMIT - SA * p.a_stage_bytes;
-  p.coal = (SMA_COAL_ENABLED && f16 && !(d->tc_variant & 2048) && d->d2s <= 1 && (d->Cout & 7) == 0 && (d->out_ld & 7) == 0 && (d->out_bstride & 7) == 0 &&
-            (reinterpret_cast<uintptr_t>(d->y) & 31) == 0 &&
-            (!d->res || ((d->res_ld & 7) == 0 && (d->res_bstride & 7) == 0 && (reinterpret_cast<uintptr_t>(d->res) & 31) == 0)) &&
-            (!d->aux || ((d->aux_ld & 7) == 0 && (d->aux_bstride & 7) == 0 && (reinterpret_cast<uintptr_t>(d->aux) & 31) == 0)) &&
-            budget - 16384 >= 2 * b_stage) ? 1 : 0;
-  if (p.coal) budget -= 16384;
   if (f16 && !(d->tc_variant & 1024) && !d->upsample2 && d->kh == d->kw && (d->kh == 1 || d->kh == 3) && (d->in_bstride & 3) == 0) {
     if (flat) { p.parts = 4; p.rs = 0; p.slot_rows = 32; }
     else { p.parts = d->kh == 3 ? 3 : 2; p.rs = (16 + d->kh - 1) / p.parts; p.slot_rows = p.halo_w * p.rs; }
@@ -1239,7 +1146,7 @@ static int conv_tc2_try(const sma_conv_desc* d, cudaStream_t st, bool f16) {
   int cols = 32; while (cols < 2 * p.acc_cols + ((p.NT & 31) ? 32 : 0)) cols <<= 1;      // the epilogue reads 32 columns at a time
   if (cols > 512) return SMA_ERR_UNSUPPORTED;
   p.tmem_cols = cols;
-  const int smem = SA * p.a_stage_bytes + SB * b_stage + p.NS * p.slot_bytes + (p.coal ? 16384 : 0) + 1024;
+  const int smem = SA * p.a_stage_bytes + SB * b_stage + p.NS * p.slot_bytes + 1024;
   if (d->plan_only) return SMA_OK;
   if (p.NS > 0) {
     SmaEncodeTiledFn enc = sma_tmap_encoder();
