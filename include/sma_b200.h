@@ -103,6 +103,11 @@ typedef struct sma_conv_desc {
    * this conv is `shift.2`, aux the output of `scale.2`, res the decoder feature.  Persistent tensor-core kernel only (SMA_ERR_UNSUPPORTED
    * otherwise: use sma_sft_combine). */
   const float* aux;  int64_t aux_bstride;  int aux_ld;  float sft_w;
+  /* GroupNorm statistics of the OUTPUT fused into the epilogue (the next layer's GroupNorm would otherwise re-read the tensor from HBM): with
+     gn_want != 0 the persistent tensor-core kernel writes per (frame, 32-row chunk, channel pair) partial sums {sum, sum of squares} into
+     gn_partial (B * gn_chunks * Cout floats) where the 256-bit epilogue runs; gn_chunks is an OUTPUT (also of a plan_only call): 0 = this launch
+     cannot produce them (other kernel / layout): the caller runs sma_groupnorm_stats on y instead.  Finish with sma_groupnorm_finalize_pairs. */
+  int gn_want;  float* gn_partial;  int gn_chunks;
 } sma_conv_desc;
 
 int sma_conv2d_fwd(sma_conv_desc* d, sma_stream_t stream);
@@ -140,6 +145,9 @@ int sma_debug_conv_ts_prof(long long* cycles_ns /* 8 values: cycles, ns, cycles 
 int sma_groupnorm_stats(const float* x, int B, int HW, int C, int64_t bstride, int ld, int groups, float eps,
                         const float* gamma, const float* beta, float* partial, float* scale, float* shift,
                         sma_stream_t stream);
+/* second half of the fused form: partial sums written by sma_conv2d_fwd (sma_conv_desc.gn_partial, nchunk = gn_chunks) -> scale/shift */
+int sma_groupnorm_finalize_pairs(const float* partial, int B, int nchunk, int C, int groups, int HW, float eps,
+                                 const float* gamma, const float* beta, float* scale, float* shift, sma_stream_t stream);
 /* y = act(x*scale[b,c]+shift[b,c]) elementwise (used where no conv follows, e.g. AttnBlock input) */
 int sma_affine_act(const float* x, int B, int HW, int C, int64_t bstride, int ld, const float* scale,
                    const float* shift, int act, float* y, int64_t y_bstride, int y_ld, sma_stream_t stream);

@@ -24,6 +24,7 @@ class ConvDesc(C.Structure):
         ('res', C.c_void_p), ('res_bstride', c_i64), ('res_ld', C.c_int),
         ('d2s', C.c_int), ('out_nchw', C.c_int), ('precision', C.c_int), ('w_tc', C.c_void_p), ('w_tc16', C.c_void_p), ('w_ts', C.c_void_p), ('tc_variant', C.c_int), ('kernel_used', C.c_int),
         ('w_tc_nt', C.c_int), ('plan_only', C.c_int), ('aux', C.c_void_p), ('aux_bstride', c_i64), ('aux_ld', C.c_int), ('sft_w', C.c_float),
+        ('gn_want', C.c_int), ('gn_partial', C.c_void_p), ('gn_chunks', C.c_int),
     ]
 
 
@@ -45,6 +46,7 @@ SIGNATURES = {
     'sma_pack_conv_weight_ts': ([_V, _I, _I, _I, _I, _I, _V, _V], C.c_int),
     'sma_debug_conv_ts_prof': ([_V], C.c_int),
     'sma_groupnorm_stats': ([_V, _I, _I, _I, _L, _I, _I, _F, _V, _V, _V, _V, _V, _V], C.c_int),
+    'sma_groupnorm_finalize_pairs': ([_V, _I, _I, _I, _I, _I, _F, _V, _V, _V, _V, _V], C.c_int),
     'sma_affine_act': ([_V, _I, _I, _I, _L, _I, _V, _V, _I, _V, _L, _I, _V], C.c_int),
     'sma_layernorm': ([_V, _I, _I, _V, _V, _F, _V, _I, _V, _V, _V], C.c_int),
     'sma_warp_occlude_fwd': ([_V, _L, _I, _I, _I, _I, _V, _V, _I, _I, _V, _V], C.c_int),

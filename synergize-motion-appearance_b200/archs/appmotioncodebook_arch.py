@@ -306,43 +306,72 @@ class AppMotionCompFormer(ParamModule):
     def _gn(self, name, x):
         return ops.groupnorm_stats(x, self._T[name + '.weight'], self._T[name + '.bias'], 32, 1e-6)
 
-    def _res(self, name, x, cin, cout, out=None, fast=False):
-        W = self._packed
-        s1, h1 = self._gn(name + '.norm1', x)
-        h = ops.conv2d(x, W[name + '.conv1'], pad=1, pre=(s1, h1, 'swish'), fast=fast)
-        s2, h2 = self._gn(name + '.norm2', h)
-        skip = x if cin == cout else ops.conv2d(x, W[name + '.conv_out'], fast=fast)
-        return ops.conv2d(h, W[name + '.conv2'], pad=1, pre=(s2, h2, 'swish'), res=skip, out=out, fast=fast)
+    def _gnp(self, name):
+        """(gamma, beta) of a GroupNorm: passed as conv2d(gn=...) so that the producing convolution's epilogue delivers the statistics."""
+        return self._T[name + '.weight'], self._T[name + '.bias']
 
-    def _attn(self, name, x, out=None, fast=False):
+    # Every block takes `stats` (GroupNorm scale / shift of its input, already produced by the previous convolution's epilogue, or None) and `want`
+    # ((gamma, beta) of the GroupNorm that will read its output, or None) and returns y, or (y, stats of y) when `want` is given.
+    def _res(self, name, x, cin, cout, out=None, fast=False, stats=None, want=None):
+        W = self._packed
+        s1, h1 = stats if stats is not None else self._gn(name + '.norm1', x)
+        h, (s2, h2) = ops.conv2d(x, W[name + '.conv1'], pad=1, pre=(s1, h1, 'swish'), fast=fast, gn=self._gnp(name + '.norm2'))
+        skip = x if cin == cout else ops.conv2d(x, W[name + '.conv_out'], fast=fast)
+        return ops.conv2d(h, W[name + '.conv2'], pad=1, pre=(s2, h2, 'swish'), res=skip, out=out, fast=fast, gn=want)
+
+    def _attn(self, name, x, out=None, fast=False, stats=None, want=None):
         W = self._packed
         B, H, Wd, Cc = x.shape
-        s, h = self._gn(name + '.norm', x)
+        s, h = stats if stats is not None else self._gn(name + '.norm', x)
         qkv = ops.conv2d(x, W[name + '.qkv'], pre=(s, h, 'none'), fast=fast).view(B, H * Wd, 3 * Cc)
         o = ops.mha(qkv[..., :Cc], qkv[..., Cc:2 * Cc], qkv[..., 2 * Cc:], heads=1, scale=float(int(Cc) ** (-0.5)))
-        return ops.conv2d(o.view(B, H, Wd, Cc), W[name + '.proj_out'], res=x, out=out, fast=fast)
+        return ops.conv2d(o.view(B, H, Wd, Cc), W[name + '.proj_out'], res=x, out=out, fast=fast, gn=want)
 
-    def _block(self, prefix, i, layout, x, out=None, fast=False):
+    def _block(self, prefix, i, layout, x, out=None, fast=False, stats=None, want=None):
         kind, cin, cout = layout[i]
         n = f'{prefix}.blocks.{i}'
         W = self._packed
         if kind == 'conv':
             pre = None
             if i > 0 and layout[i - 1][0] == 'norm':          # GroupNorm (no activation) feeding the last conv
-                s, h = self._gn(f'{prefix}.blocks.{i - 1}', x)
+                s, h = stats if stats is not None else self._gn(f'{prefix}.blocks.{i - 1}', x)
                 pre = (s, h, 'none')
-            return ops.conv2d(x, W[n], pad=1, pre=pre, out=out, fast=fast)
+            return ops.conv2d(x, W[n], pad=1, pre=pre, out=out, fast=fast, gn=want)
         if kind == 'res':
-            return self._res(n, x, cin, cout, out=out, fast=fast)
+            return self._res(n, x, cin, cout, out=out, fast=fast, stats=stats, want=want)
         if kind == 'attn':
-            return self._attn(n, x, out=out, fast=fast)
+            return self._attn(n, x, out=out, fast=fast, stats=stats, want=want)
         if kind == 'down':      # pad right/bottom by one, stride 2 (vqgan_arch.py:149-152)
-            return ops.conv2d(x, W[n + '.conv'], stride=2, pad_tl=(0, 0), out_hw=(x.shape[1] // 2, x.shape[2] // 2), out=out, fast=fast)
+            return ops.conv2d(x, W[n + '.conv'], stride=2, pad_tl=(0, 0), out_hw=(x.shape[1] // 2, x.shape[2] // 2), out=out, fast=fast, gn=want)
         if kind == 'up':
-            return ops.conv2d(x, W[n + '.conv'], pad=1, upsample2=True, out=out, fast=fast)
-        if kind == 'norm':
-            return x              # folded into the next conv's operand load
+            return ops.conv2d(x, W[n + '.conv'], pad=1, upsample2=True, out=out, fast=fast, gn=want)
         raise ValueError(kind)
+
+    def _want_after(self, prefix, layout, i):
+        """(gamma, beta) of the GroupNorm that reads the output of block i (the first norm of block i + 1), or None."""
+        if i + 1 >= len(layout):
+            return None
+        kind = layout[i + 1][0]
+        n = f'{prefix}.blocks.{i + 1}'
+        if kind == 'res':
+            return self._gnp(n + '.norm1')
+        if kind == 'attn':
+            return self._gnp(n + '.norm')
+        if kind == 'norm':
+            return self._gnp(n)
+        return None
+
+    def _chain(self, prefix, layout, x, start, stop, stats=None, taps=None, fast=False):
+        """Blocks [start, stop) in sequence, each convolution producing the GroupNorm statistics its successor needs.  -> (x, stats of x or None)"""
+        for i in range(start, stop):
+            if layout[i][0] == 'norm':                        # folded into the next conv's operand load; the statistics pass through
+                continue
+            want = self._want_after(prefix, layout, i)
+            r = self._block(prefix, i, layout, x, fast=fast, stats=stats, want=want)
+            x, stats = r if want is not None else (r, None)
+            if taps is not None and i in taps:
+                taps[i] = x
+        return x, stats
 
     # ------------------------------------------------------------------------------------------
     # per-source work: encoder features (cached)
@@ -359,11 +388,9 @@ class AppMotionCompFormer(ParamModule):
         if c is not None and c[0] is x and c[1] == x._version:
             return c[2]
         h = ops.nchw_to_nhwc(x.contiguous().float())
-        feats = {}
-        for i in range(len(self.enc_layout)):
-            h = self._block('encoder', i, self.enc_layout, h)
-            if i in (2, 5, 8):
-                feats[h.shape[2]] = h
+        taps = {2: None, 5: None, 8: None}
+        h, _ = self._chain('encoder', self.enc_layout, h, 0, len(self.enc_layout), taps=taps)
+        feats = {t.shape[2]: t for t in taps.values()}
         feats[h.shape[2]] = h
         self._src_cache = (x, x._version, feats)
         return feats
@@ -373,8 +400,7 @@ class AppMotionCompFormer(ParamModule):
         """(B,256,32,32) NCHW latent -> (B,3,256,256): the 19 decoder blocks without the multi-scale fusion."""
         self._weights()
         h = ops.nchw_to_nhwc(x.contiguous().float())
-        for i in range(len(self.gen_layout)):
-            h = self._block('generator', i, self.gen_layout, h)
+        h, _ = self._chain('generator', self.gen_layout, h, 0, len(self.gen_layout))
         return ops.nhwc_to_nchw(h)
 
     @torch.no_grad()
@@ -384,12 +410,9 @@ class AppMotionCompFormer(ParamModule):
         NOT the latent of the last block that `forward` warps."""
         self._weights()
         h = ops.nchw_to_nhwc(x.contiguous().float())
-        feats = {}
-        for i in range(12):
-            h = self._block('encoder', i, self.enc_layout, h)
-            if i in (2, 5, 8, 11):
-                feats[h.shape[2]] = h
-        return feats
+        taps = {2: None, 5: None, 8: None, 11: None}
+        self._chain('encoder', self.enc_layout, h, 0, 12, taps=taps)
+        return {t.shape[2]: t for t in taps.values()}
 
     def encode_driving(self, x):
         """Reference API (appmotioncodebook_arch.py:364-371): NCHW feature dict keyed by resolution string."""
@@ -572,13 +595,17 @@ class AppMotionCompFormer(ParamModule):
         fuse_at = {9: 64, 12: 128, 15: 256}
         cat = None
         fgen = ops.fast('gen')
+        stats = None                                     # GroupNorm scale / shift of x, when the convolution that produced x delivered them
         for i in range(len(self.gen_layout)):
+            if self.gen_layout[i][0] == 'norm':
+                continue
+            want = self._want_after('generator', self.gen_layout, i)
             if i in fuse_at and w > 0:
                 s0 = fuse_at[i]                      # nominal scale: names; s: the actual feature size
                 s = s0 * R
                 c = self.channels[s0]
                 cat = torch.empty((B, s, s, 2 * c), device=dev, dtype=torch.float32)   # [enc | dec] for Fuse_sft_block
-                x = self._block('generator', i, self.gen_layout, x, out=cat[..., c:], fast=fgen)
+                x = self._block('generator', i, self.gen_layout, x, out=cat[..., c:], fast=fgen, stats=stats)
                 enc = compensate(s, out=cat[..., :c])
                 n = f'fuse_convs_dict.{s0}'
                 fsft = ops.fast('sft')
@@ -589,11 +616,13 @@ class AppMotionCompFormer(ParamModule):
                 xf = ops.conv2d(ss[..., c:], W[n + '.shift.2'], pad=1, res=x, sft=(scale, float(w)), fast=fsft)
                 if collect is not None:
                     collect[f'sft_{s}'] = xf.clone()                                   # (the next conv accumulates in place)
-                x = ops.conv2d(enc, W[f'fuse_ms_dict.{s0}'], pad=1, res=xf, out=xf, fast=ops.fast('ms'))
+                r = ops.conv2d(enc, W[f'fuse_ms_dict.{s0}'], pad=1, res=xf, out=xf, fast=ops.fast('ms'), gn=want)
+                x, stats = r if want is not None else (r, None)
                 if collect is not None:
                     collect[f'fused_{s}'] = x
             else:
-                x = self._block('generator', i, self.gen_layout, x, fast=fgen)
+                r = self._block('generator', i, self.gen_layout, x, fast=fgen, stats=stats, want=want)
+                x, stats = r if want is not None else (r, None)
         return {'out': x, 'lq_feat': lq_feat, 'out_occ': occs, 'deformation_list': motions, 'residuals': residuals}
 
     # ------------------------------------------------------------------------------------------

@@ -253,6 +253,7 @@ extern "C" int sma_conv2d_fwd(sma_conv_desc* d, sma_stream_t stream) {
   if (d->d2s > 1 && (d->res || d->out_nchw || d->Cout % (d->d2s * d->d2s))) return SMA_ERR_UNSUPPORTED;
   if ((long long)d->B * d->Ho * d->Wo > 0x7fffffffLL) return SMA_ERR_UNSUPPORTED;
   cudaStream_t st = as_stream(stream);
+  d->gn_chunks = 0;                                   // set by the persistent tensor-core kernel when it produces the fused GroupNorm partial sums
   if (d->precision != SMA_PREC_EXACT) {
     int r = sma_conv2d_ts_try(d, st);
     if (r != SMA_ERR_UNSUPPORTED) { d->kernel_used = 4; return r; }

@@ -240,6 +240,39 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const TcP p) {
 }
 
 
+
+// GroupNorm statistics of the tile a convolution has just computed (fused producer-side: the standalone statistics pass re-reads every normalised
+// tensor from HBM, 15 GB per 64-frame step).  The 8 consecutive channels o[0..7] of this lane's pixel row (zero for rows outside the image) are
+// reduced over the warp's 32 rows as 4 channel PAIRS x {sum, sum of squares}: a transposing butterfly - three rounds that halve the number of
+// values while exchanging them across the lane bits 4, 3, 2, then two plain rounds - 9 shuffles for the 8 values; lane 4j ends up with value j
+// (j < 4: sum of pair j, j >= 4: sum of squares of pair j - 4) and stores it.  `dst` = partial row of this (frame, 32-row chunk) + 2 * first pair.
+__device__ __forceinline__ void gn_pairs_reduce_store(const float (&o)[8], bool mok, int lane, float* dst) {
+  float v[8];
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    const float x0 = mok ? o[2 * j] : 0.f, x1 = mok ? o[2 * j + 1] : 0.f;
+    v[j] = x0 + x1; v[4 + j] = fmaf(x0, x0, x1 * x1);
+  }
+  const bool h16 = (lane & 16) != 0, h8 = (lane & 8) != 0, h4 = (lane & 4) != 0;
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const float keep = h16 ? v[4 + i] : v[i], send = h16 ? v[i] : v[4 + i];
+    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+#pragma unroll
+  for (int i = 0; i < 2; i++) {
+    const float keep = h8 ? v[2 + i] : v[i], send = h8 ? v[i] : v[2 + i];
+    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+  {
+    const float keep = h4 ? v[1] : v[0], send = h4 ? v[0] : v[1];
+    v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+  v[0] += __shfl_xor_sync(0xffffffffu, v[0], 2);
+  v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+  if ((lane & 3) == 0) { const int j = lane >> 2; dst[(j & 3) * 2 + (j >> 2)] = v[0]; }
+}
+
 // =================================================================================================================
 // v2: persistent, halo-resident kernel for stride-1 convolutions (1x1, 3x3, 7x7; optional fused nearest-x2 upsample).
 //
@@ -281,6 +314,7 @@ struct Tc2P {
   int fuse;                   // 3-pass, NT <= 128: the hi and lo weight images (adjacent in the ring) are read as ONE B tile of 2*NT rows, so
                               // a_hi*[b_hi | b_lo] is one MMA; its lo half lands in accumulator columns [NT, 2NT) and is added in the epilogue
   int acc_cols;               // TMEM columns per accumulator (NT or 2*NT)
+  float* gnp; int gn_chunks;  // fused GroupNorm partial sums: [frame][chunk = 4 * tile-in-image + lane quarter][Cout / 2 pairs][sum, sum of squares]; nullptr: off
   int dbg;                    // timing experiments (results invalid): bit 2 = epilogue skips its residual loads and stores
   int flat, tiles_x, tiles_per_img, total_tiles;
   int halo_w, HP, a_img_bytes, a_stage_bytes, b_img_bytes, SA, SB;
@@ -339,6 +373,7 @@ __global__ void __launch_bounds__(TMA ? V2_THREADS_TMA : V2_THREADS, 1) conv_tc2
   const uint32_t tmem_base = tmem_slot;
 
   // tile -> (image b, first output row / column or first flat pixel, N tile)
+  auto tile_in_img = [&](int tile) { const int mt = tile / p.ntiles_n; return mt - (mt / p.tiles_per_img) * p.tiles_per_img; };
   auto decode = [&](int tile, int& b, int& ty0, int& tx0, int& nt) {
     nt = tile % p.ntiles_n; int mt = tile / p.ntiles_n;
     b = mt / p.tiles_per_img; int t = mt - b * p.tiles_per_img;
@@ -441,7 +476,7 @@ __global__ void __launch_bounds__(TMA ? V2_THREADS_TMA : V2_THREADS, 1) conv_tc2
             tc_fence_before();
             mbar_arrive(acc_empty(ab));
           }
-          if (mok && !(p.dbg & 4)) {        // (RES = 1 is only dispatched for 256-bit-eligible launches)
+          if ((mok || p.gnp) && !(p.dbg & 4)) {        // (RES = 1 is only dispatched for 256-bit-eligible launches; with fused statistics every lane runs the shuffles)
   #pragma unroll
             for (int q8 = 0; q8 < 4; q8++) {
               const int n = nbase + n0 + q8 * 8;
@@ -465,12 +500,14 @@ __global__ void __launch_bounds__(TMA ? V2_THREADS_TMA : V2_THREADS, 1) conv_tc2
   #pragma unroll
                 for (int t = 0; t < 8; t++) o[t] += rc[q8 * 8 + t];
               }
+              if (p.gnp) gn_pairs_reduce_store(o, mok, lane, p.gnp + (((long long)b * p.gn_chunks + tile_in_img(tile) * 4 + wq) * (p.Cout >> 1) + (n >> 1)) * 2);
               float* dst = yrow + n;
               if (p.d2s > 1) {      // depth-to-space (un-patchify): the 8 columns lie inside one sub-pixel's channel block (Cq % 8 == 0)
                 const int qd = n / Cq, cval = n - qd * Cq, p1 = qd / p.d2s, p2 = qd - p1 * p.d2s;
                 const long long pix = (long long)(oy * p.d2s + p1) * (p.Wo * p.d2s) + (ox * p.d2s + p2);
                 dst = p.y + (long long)b * p.out_bs + pix * p.out_ld + cval;
               }
+              if (mok)
               asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst), "f"(o[0]), "f"(o[1]), "f"(o[2]), "f"(o[3]), "f"(o[4]), "f"(o[5]),
                            "f"(o[6]), "f"(o[7])
                            : "memory");
@@ -503,12 +540,13 @@ __global__ void __launch_bounds__(TMA ? V2_THREADS_TMA : V2_THREADS, 1) conv_tc2
             tc_fence_before();
             mbar_arrive(acc_empty(ab));
           }
-          if (mok && !(p.dbg & 4) && v8_ok) {
+          if ((mok || p.gnp) && !(p.dbg & 4) && v8_ok) {
             // 256-bit residual loads / stores: every lane moves whole 32-byte sectors (with 128-bit accesses a warp-level instruction touches
             // half of 32 different sectors, and the epilogue - not the MMAs - bounds the low-K layers)
-            float* yrow = p.y + (long long)b * p.out_bs + (long long)r * p.out_ld;
-            const float* rrow = p.res ? p.res + (long long)b * p.res_bs + (long long)r * p.res_ld : nullptr;
-            const float* arow = p.aux ? p.aux + (long long)b * p.aux_bs + (long long)r * p.aux_ld : nullptr;
+            const int rs_ = mok ? r : 0;                      // (fused statistics: rows outside the image run along with row 0 and store nothing)
+            float* yrow = p.y + (long long)b * p.out_bs + (long long)rs_ * p.out_ld;
+            const float* rrow = p.res ? p.res + (long long)b * p.res_bs + (long long)rs_ * p.res_ld : nullptr;
+            const float* arow = p.aux ? p.aux + (long long)b * p.aux_bs + (long long)rs_ * p.aux_ld : nullptr;
   #pragma unroll
             for (int q8 = 0; q8 < 4; q8++) {
               const int n = nbase + n0 + q8 * 8;
@@ -540,12 +578,14 @@ __global__ void __launch_bounds__(TMA ? V2_THREADS_TMA : V2_THREADS, 1) conv_tc2
                   o[0] += r0; o[1] += r1; o[2] += r2; o[3] += r3; o[4] += r4; o[5] += r5; o[6] += r6; o[7] += r7;
                 }
               }
+              if (p.gnp) gn_pairs_reduce_store(o, mok, lane, p.gnp + (((long long)b * p.gn_chunks + tile_in_img(tile) * 4 + wq) * (p.Cout >> 1) + (n >> 1)) * 2);
               float* dst = yrow + n;
               if (p.d2s > 1) {      // depth-to-space (un-patchify): the 8 columns lie inside one sub-pixel's channel block (Cq % 8 == 0)
                 const int qd = n / Cq, cval = n - qd * Cq, p1 = qd / p.d2s, p2 = qd - p1 * p.d2s;
                 const long long pix = (long long)(oy * p.d2s + p1) * (p.Wo * p.d2s) + (ox * p.d2s + p2);
                 dst = p.y + (long long)b * p.out_bs + pix * p.out_ld + cval;
               }
+              if (mok)
               asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst), "f"(o[0]), "f"(o[1]), "f"(o[2]), "f"(o[3]), "f"(o[4]), "f"(o[5]),
                            "f"(o[6]), "f"(o[7])
                            : "memory");
@@ -1074,7 +1114,7 @@ static int launch_tc2(int act, int pre, const Tc2P& p, int grid, int smem, cudaS
 }
 
 // persistent halo kernel (stride 1); returns SMA_ERR_UNSUPPORTED when not eligible
-static int conv_tc2_try(const sma_conv_desc* d, cudaStream_t st, bool f16) {
+static int conv_tc2_try(sma_conv_desc* d, cudaStream_t st, bool f16) {
   const int kch = f16 ? 64 : KC;
   if (d->Cin % kch) return SMA_ERR_UNSUPPORTED;
   if (d->aux) {      // SFT epilogue: only on the 256-bit epilogue path, with a residual (the decoder feature) of the same geometry
@@ -1143,10 +1183,21 @@ static int conv_tc2_try(const sma_conv_desc* d, cudaStream_t st, bool f16) {
   const int main_adds = p.cpt * p.taps * 4 * (p.fuse ? 1 : p.passes);
   p.acc_corr = (d->tc_variant & 256) ? 1.f : 1.f + 1.6e-8f * (float)main_adds;
   p.dbg = (d->tc_variant >> 1) & 7;
+  // fused GroupNorm partial sums: only where the 256-bit epilogue runs (every lane then walks the same column blocks) and the output is the whole
+  // normalised tensor (no depth-to-space); the caller learns through gn_chunks (0 = not produced: it runs sma_groupnorm_stats instead)
+  {
+    const bool v8 = d->d2s <= 1 && (d->Cout & 7) == 0 && (d->out_ld & 7) == 0 && (d->out_bstride & 7) == 0 && (reinterpret_cast<uintptr_t>(d->y) & 31) == 0 &&
+                    (!d->res || ((d->res_ld & 7) == 0 && (d->res_bstride & 7) == 0 && (reinterpret_cast<uintptr_t>(d->res) & 31) == 0));
+    const bool want = d->gn_want != 0 && v8 && !d->out_nchw;
+    p.gn_chunks = want ? p.tiles_per_img * 4 : 0;
+    p.gnp = (want && !d->plan_only) ? d->gn_partial : nullptr;
+    if (want && !d->plan_only && !d->gn_partial) return SMA_ERR_BAD_ARG;
+  }
   int cols = 32; while (cols < 2 * p.acc_cols + ((p.NT & 31) ? 32 : 0)) cols <<= 1;      // the epilogue reads 32 columns at a time
   if (cols > 512) return SMA_ERR_UNSUPPORTED;
   p.tmem_cols = cols;
   const int smem = SA * p.a_stage_bytes + SB * b_stage + p.NS * p.slot_bytes + 1024;
+  d->gn_chunks = p.gn_chunks;                 // (past the last point where this kernel can decline the launch)
   if (d->plan_only) return SMA_OK;
   if (p.NS > 0) {
     SmaEncodeTiledFn enc = sma_tmap_encoder();

@@ -79,15 +79,16 @@ __global__ void gn_partial4_kernel(const float* __restrict__ x, int HW, int C, l
   }
 }
 
-// one block per (b, group): combine chunk partials in fp64, emit scale/shift per channel
+// one block per (b, group): combine chunk partials in fp64, emit scale/shift per channel.  `per` = channels per partial entry: 1 (the standalone
+// statistics pass) or 2 (channel pairs: the partial sums a convolution's epilogue produced, conv_tc.cu gn_pairs_reduce_store)
 __global__ void gn_finalize_kernel(const float* __restrict__ partial, int nchunk, int C, int groups, int HW, float eps,
-                                   const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ scale, float* __restrict__ shift) {
+                                   const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ scale, float* __restrict__ shift, int per) {
   const int g = blockIdx.x, b = blockIdx.y;
-  const int cg = C / groups;
+  const int cg = C / groups, eg = cg / per, Cp = C / per;
   double s = 0.0, q = 0.0;
-  for (int i = threadIdx.x; i < nchunk * cg; i += blockDim.x) {
-    int chunk = i / cg, c = g * cg + i % cg;
-    const float* o = partial + (((long long)b * nchunk + chunk) * C + c) * 2;
+  for (int i = threadIdx.x; i < nchunk * eg; i += blockDim.x) {
+    int chunk = i / eg, c = g * eg + i % eg;
+    const float* o = partial + (((long long)b * nchunk + chunk) * Cp + c) * 2;
     s += (double)o[0]; q += (double)o[1];
   }
   __shared__ double sh[2][32];
@@ -159,7 +160,15 @@ extern "C" int sma_groupnorm_stats(const float* x, int B, int HW, int C, int64_t
   if (vec) gn_partial4_kernel<<<dim3(nchunk, B), 256, 0, as_stream(stream)>>>(x, HW, C, bstride, ld, partial, nchunk);
   else gn_partial_kernel<<<dim3(nchunk, B), 256, 512 * sizeof(float), as_stream(stream)>>>(x, HW, C, bstride, ld, partial, nchunk);
   SMA_LAUNCH_CHECK();
-  gn_finalize_kernel<<<dim3(groups, B), 128, 0, as_stream(stream)>>>(partial, nchunk, C, groups, HW, eps, gamma, beta, scale, shift);
+  gn_finalize_kernel<<<dim3(groups, B), 128, 0, as_stream(stream)>>>(partial, nchunk, C, groups, HW, eps, gamma, beta, scale, shift, 1);
+  SMA_LAUNCH_CHECK();
+  return SMA_OK;
+}
+
+extern "C" int sma_groupnorm_finalize_pairs(const float* partial, int B, int nchunk, int C, int groups, int HW, float eps, const float* gamma,
+                                            const float* beta, float* scale, float* shift, sma_stream_t stream) {
+  if (!partial || !scale || !shift || B <= 0 || nchunk <= 0 || HW <= 0 || C <= 0 || groups <= 0 || C % groups || ((C / groups) & 1)) return SMA_ERR_BAD_ARG;
+  gn_finalize_kernel<<<dim3(groups, B), 256, 0, as_stream(stream)>>>(partial, nchunk, C, groups, HW, eps, gamma, beta, scale, shift, 2);
   SMA_LAUNCH_CHECK();
   return SMA_OK;
 }

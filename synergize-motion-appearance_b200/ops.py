@@ -221,6 +221,7 @@ USE_TF32X3 = True        # let sma_conv2d_fwd pick a tcgen05 kernel where the sh
 ALLOW_TF32_1PASS = True  # honour `fast=True` requests (single pass)
 USE_TS = False           # weights as the tensor-memory A operand (csrc/conv_ts.cu) where they fit in tensor memory; False: shared-memory-operand kernels
 USE_MH_F16 = True        # 8-head E=256 attention: fp16-split kernel with pre-split tile images (csrc/attn_mh.cu); False: tf32 kernel (attn_tc.cu)
+FUSE_GN = os.environ.get('SMA_NO_FUSE_GN', '0') != '1'           # (env: A/B on one box) GroupNorm partial sums of a conv's output from its own epilogue (conv2d(gn=...)); False: always the standalone statistics pass
 USE_F16 = True           # split operands into fp16 halves (kind::f16, 2x the tensor rate of kind::tf32) where Cin % 64 == 0
 # Per-stage precision policy: stages listed here run their convolutions as single-pass TF32 (3x fewer tensor-core
 # instructions); everything else is fp32-faithful 3xTF32.  See DESIGN.md section 4 for the measured error budget.
@@ -244,11 +245,13 @@ def conv2d(x: torch.Tensor, cw: ConvW, *, stride: int = 1, pad: int = 0, pad_tl:
            out: Optional[torch.Tensor] = None, out_hw: Optional[Tuple[int, int]] = None, act: str = 'none',
            pre: Optional[Tuple[torch.Tensor, torch.Tensor, str]] = None, res: Optional[torch.Tensor] = None,
            upsample2: bool = False, d2s: int = 0, out_nchw: bool = False, exact: bool = False, fast: bool = False,
-           sft: Optional[Tuple[torch.Tensor, float]] = None) -> torch.Tensor:
+           sft: Optional[Tuple[torch.Tensor, float]] = None, gn: Optional[Tuple[torch.Tensor, torch.Tensor]] = None):
     """`exact`: force the CUDA-core fp32 kernel; `fast`: allow single-pass TF32 on the tensor cores (layers whose
     contribution to the output error budget was measured to be negligible); default: 3xTF32 (fp32-faithful).
     `sft=(scale, w)`: Fuse_sft_block tail, y = res + w*(res*scale + conv(x)) (needs `res`): fused into the epilogue of the persistent
-    tensor-core kernel; launches that cannot run there (exact mode, odd shapes) do conv -> sma_sft_combine instead."""
+    tensor-core kernel; launches that cannot run there (exact mode, odd shapes) do conv -> sma_sft_combine instead.
+    `gn=(gamma, beta)`: also return the GroupNorm(32, eps 1e-6) scale / shift of the OUTPUT, `(y, (scale, shift))`: the partial sums come out of the
+    convolution's epilogue where the persistent tensor-core kernel runs (no second pass over y), else from groupnorm_stats(y)."""
     lib = _lib.load()
     B, Hi, Wi, Cin, ibs, ild = _nhwc(x)
     if Cin != cw.Cin:
@@ -307,20 +310,28 @@ def conv2d(x: torch.Tensor, cw: ConvW, *, stride: int = 1, pad: int = 0, pad_tl:
             d.w_tc, d.w_tc16, d.w_ts = _ptr(cw.image('tc', 0)), _ptr(cw.image('tc16')), _ptr(cw.image('ts'))
         else:
             # ask the library which kernel this launch will run on (nothing is launched), then pack / fetch exactly the image it reads
+            d.gn_want = 1 if (gn is not None and FUSE_GN and sft is None and d.out_ld == cw.Cout and cw.Cout % 64 == 0) else 0      # (pairs must not straddle the 32 groups)
             key = (B, Hi, Wi, stride, pt, pl, upsample2, Ho, Wo, out_nchw, d2s, d.precision, TC_VARIANT, x.data_ptr() & 15, ild & 3, ibs & 3,
-                   pre is not None, sft is not None, 0 if res is None else (d.res_ld & 7, d.res_bstride & 7), d.out_ld & 7, d.out_bstride & 7)
+                   pre is not None, sft is not None, 0 if res is None else (d.res_ld & 7, d.res_bstride & 7), d.out_ld & 7, d.out_bstride & 7,
+                   d.gn_want, out.data_ptr() & 31, 0 if res is None else res.data_ptr() & 31)
             if cw.plans is None:
                 cw.plans = {}
             planned = cw.plans.get(key)
             if planned is None:
                 d.plan_only = 1
                 check(lib.sma_conv2d_fwd(C.byref(d), _stream()), 'sma_conv2d_fwd(plan)')
-                planned = cw.plans[key] = (d.kernel_used, d.w_tc_nt)
+                planned = cw.plans[key] = (d.kernel_used, d.w_tc_nt, d.gn_chunks)
                 d.plan_only, d.kernel_used, d.w_tc_nt = 0, -1, 0
             if planned[0] in (1, 2):
                 d.w_tc, d.w_tc_nt = _ptr(cw.image('tc', planned[1])), planned[1]
             elif planned[0] == 3:
                 d.w_tc16 = _ptr(cw.image('tc16'))
+            gn_partial = None
+            if d.gn_want and planned[2] > 0:
+                gn_partial = torch.empty((B * planned[2] * cw.Cout,), device=x.device, dtype=torch.float32)
+                d.gn_partial = gn_partial.data_ptr()
+            else:
+                d.gn_want = 0
     if sft is not None and (planned is None or planned[0] not in (2, 3)):
         # unfused form: the CUDA-core / gather kernels have no SFT epilogue
         shift = conv2d(x, cw, stride=stride, pad=pad, pad_tl=pad_tl, out_hw=out_hw, act=act, pre=pre, upsample2=upsample2, exact=exact, fast=fast)
@@ -337,6 +348,14 @@ def conv2d(x: torch.Tensor, cw: ConvW, *, stride: int = 1, pad: int = 0, pad_tl:
         raise _lib.SmaError(f'conv2d ran on kernel {d.kernel_used} but was planned on {planned[0]} (Cin={Cin} Cout={cw.Cout} k={cw.kh}): binding bug')
     global LAST_CONV_KERNEL
     LAST_CONV_KERNEL = d.kernel_used
+    if gn is not None:
+        if d.gn_want and d.gn_chunks > 0:
+            scale = torch.empty((B, cw.Cout), device=x.device, dtype=torch.float32)
+            shift = torch.empty((B, cw.Cout), device=x.device, dtype=torch.float32)
+            check(lib.sma_groupnorm_finalize_pairs(gn_partial.data_ptr(), B, d.gn_chunks, cw.Cout, 32, Ho * Wo, 1e-6, gn[0].data_ptr(), gn[1].data_ptr(),
+                                                   scale.data_ptr(), shift.data_ptr(), _stream()), 'sma_groupnorm_finalize_pairs')
+            return out, (scale, shift)
+        return out, groupnorm_stats(out, gn[0], gn[1], 32, 1e-6)
     return out
 
 

@@ -181,6 +181,38 @@ def test_unfolded_few_channel_conv_matches_torch(S):
     assert float((nchw(y).double() - ref).abs().max()) < 2e-5
 
 
+@pytest.mark.parametrize('B,Cin,Cout,H,W,k,res,pre', [(2, 64, 64, 40, 24, 3, True, True), (1, 128, 128, 32, 32, 3, False, True), (2, 256, 256, 32, 32, 1, True, False),
+                                                     (3, 64, 64, 45, 27, 3, False, False), (1, 128, 256, 16, 16, 3, False, False), (1, 64, 17, 16, 16, 3, False, False)])
+def test_conv2d_fused_groupnorm_statistics(S, B, Cin, Cout, H, W, k, res, pre):
+    """conv2d(gn=(gamma, beta)): the GroupNorm(32, 1e-6) scale / shift of the OUTPUT from partial sums produced in the convolution's own epilogue
+    (no second pass over the tensor) against the standalone statistics pass and a float64 torch GroupNorm of the same output; partial tiles,
+    residual, prologue, 1x1 and 3x3, and a shape that cannot be fused (Cout = 17: falls back to the standalone pass)."""
+    x = rnd(B, Cin, H, W, seed=1); w = rnd(Cout, Cin, k, k, seed=2, scale=(Cin * k * k) ** -0.5); b = rnd(Cout, seed=3, scale=0.1)
+    G = 32 if Cout % 32 == 0 else 1
+    gamma, beta = (1 + 0.1 * rnd(Cout, seed=7)).cuda(), (0.1 * rnd(Cout, seed=8)).cuda()
+    r = nhwc(rnd(B, Cout, H, W, seed=6)) if res else None
+    prek = ((1 + 0.1 * rnd(B, Cin, seed=4)).cuda(), (0.1 * rnd(B, Cin, seed=5)).cuda(), 'swish') if pre else None
+    cw = S.ops.pack_conv(w.cuda(), b.cuda())
+    if G == 1:
+        y = S.ops.conv2d(nhwc(x), cw, pad=k // 2, pre=prek, res=r)
+        return                                                   # (GroupNorm(32) does not apply; the gn= path needs Cout % 32 == 0)
+    y, (sc, sh) = S.ops.conv2d(nhwc(x), cw, pad=k // 2, pre=prek, res=r, gn=(gamma, beta))
+    launches_fused = S.kernel_launch_count() if hasattr(S, 'kernel_launch_count') else None
+    sc2, sh2 = S.ops.groupnorm_stats(y, gamma, beta, 32, 1e-6)
+    yd = nchw(y).double()
+    gn = F.group_norm(yd, 32, gamma.cpu().double(), beta.cpu().double(), eps=1e-6)
+    got = yd * sc.cpu().double().view(B, Cout, 1, 1) + sh.cpu().double().view(B, Cout, 1, 1)
+    assert float((got - gn).abs().max()) < 2e-5 * max(1.0, float(gn.abs().max()))
+    assert float((sc - sc2).abs().max()) < 1e-5 * float(sc2.abs().max()) and float((sh - sh2).abs().max()) < 2e-5 * max(1.0, float(sh2.abs().max()))
+    saved = S.ops.FUSE_GN
+    S.ops.FUSE_GN = False
+    try:
+        y3, (sc3, sh3) = S.ops.conv2d(nhwc(x), cw, pad=k // 2, pre=prek, res=r, gn=(gamma, beta))
+    finally:
+        S.ops.FUSE_GN = saved
+    assert torch.equal(y3, y) and torch.equal(sc3, sc2)
+
+
 def test_conv2d_concat_slices_patchify_and_bn_fold(S):
     """channel-slice views as input/output (torch.cat elimination), stride-p patch embedding, depth-to-space."""
     B, C, s, p = 2, 128, 64, 2
