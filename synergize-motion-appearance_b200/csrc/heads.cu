@@ -356,31 +356,42 @@ extern "C" int sma_dense_motion_head(const float* logits, int ld, int h, int w, 
 // implicit GEMM the conv would contract over kh*kw taps of a 32-channel zero-padded chunk each (1568 K values for 98 real ones); unfolded to
 // K = k*k*C (padded to `Kp`) it is ONE 128-deep 1x1 conv on the tensor cores.  out[b][y][x][(ky*k+kx)*C + c] = x[b][y+ky-pad][x+kx-pad][c], zero
 // outside the image and for columns >= k*k*C.  One thread per (pixel, 4 columns).
-__global__ void im2col_small_kernel(const float* __restrict__ x, int B, int H, int W, int ld, int C, int k, int pad, float* __restrict__ out, int Kp) {
-  const int kq = Kp >> 2;
-  const long long total = (long long)B * H * W * kq;
-  const int KK = k * k * C;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int q = (int)(i % kq); long long pix = i / kq;
-    const int px = (int)(pix % W); const int py = (int)((pix / W) % H); const long long b = pix / ((long long)W * H);
+// block = 8 x 32 output pixels of one frame: the (8 + k - 1) x (32 + k - 1) x C input halo is staged in shared memory once, then every thread writes
+// float4 groups of the unfolded rows (the kernel is bound by the HBM writes of the (B,H,W,Kp) result)
+__global__ void __launch_bounds__(256) im2col_small_kernel(const float* __restrict__ x, int B, int H, int W, int ld, int C, int k, int pad, float* __restrict__ out, int Kp,
+                                                         int tiles_x, int tiles_y) {
+  extern __shared__ float sh[];                       // [(8 + k - 1)][(32 + k - 1)][C]
+  const int t = blockIdx.x; const int b = t / (tiles_x * tiles_y); const int tr = t - b * tiles_x * tiles_y;
+  const int ty0 = (tr / tiles_x) * 8, tx0 = (tr % tiles_x) * 32;
+  const int hw = 32 + k - 1, hh = 8 + k - 1;
+  for (int i = threadIdx.x; i < hh * hw * C; i += 256) {
+    const int c = i % C; const int px = (i / C) % hw; const int py = i / (C * hw);
+    const int iy = ty0 + py - pad, ix = tx0 + px - pad;
+    sh[i] = ((unsigned)iy < (unsigned)H && (unsigned)ix < (unsigned)W) ? __ldg(x + (((long long)b * H + iy) * W + ix) * ld + c) : 0.f;
+  }
+  __syncthreads();
+  const int KK = k * k * C, kq = Kp >> 2;
+  for (int i = threadIdx.x; i < 256 * kq; i += 256) {
+    const int q = i % kq; const int p = i / kq; const int py = p >> 5, px = p & 31;
+    const int oy = ty0 + py, ox = tx0 + px;
+    if (oy >= H || ox >= W) continue;
     float v[4];
 #pragma unroll
     for (int j = 0; j < 4; j++) {
       const int col = q * 4 + j;
       v[j] = 0.f;
-      if (col < KK) {
-        const int tap = col / C, c = col - tap * C; const int ky = tap / k, kx = tap - ky * k;
-        const int iy = py + ky - pad, ix = px + kx - pad;
-        if ((unsigned)iy < (unsigned)H && (unsigned)ix < (unsigned)W) v[j] = __ldg(x + ((b * H + iy) * W + ix) * ld + c);
-      }
+      if (col < KK) { const int tap = col / C, c = col - tap * C; const int ky = tap / k, kx = tap - ky * k; v[j] = sh[((py + ky) * hw + (px + kx)) * C + c]; }
     }
-    *reinterpret_cast<float4*>(out + pix * Kp + q * 4) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(out + (((long long)b * H + oy) * W + ox) * Kp + q * 4) = make_float4(v[0], v[1], v[2], v[3]);
   }
 }
 extern "C" int sma_im2col_small(const float* x, int B, int H, int W, int ld, int C, int k, int pad, float* out, int Kp, sma_stream_t s) {
   if (!x || !out || B <= 0 || H <= 0 || W <= 0 || C <= 0 || k <= 0 || pad < 0 || ld < C || (Kp & 3) || Kp < k * k * C) return SMA_ERR_BAD_ARG;
   if (reinterpret_cast<uintptr_t>(out) & 15) return SMA_ERR_BAD_ARG;
-  im2col_small_kernel<<<nblocks((long long)B * H * W * (Kp >> 2)), 256, 0, as_stream(s)>>>(x, B, H, W, ld, C, k, pad, out, Kp);
+  const int smem = (8 + k - 1) * (32 + k - 1) * C * (int)sizeof(float);
+  if (smem > 48 * 1024) return SMA_ERR_UNSUPPORTED;
+  const int tiles_x = (W + 31) / 32, tiles_y = (H + 7) / 8;
+  im2col_small_kernel<<<B * tiles_x * tiles_y, 256, smem, as_stream(s)>>>(x, B, H, W, ld, C, k, pad, out, Kp, tiles_x, tiles_y);
   SMA_LAUNCH_CHECK(); return SMA_OK;
 }
 extern "C" int sma_flow_to_px(const float* m, int B, int h, int w, float* o, int ld, sma_stream_t s) {
