@@ -322,6 +322,7 @@ struct Tc2P {
   // cp.async.bulk.tensor (a 4-D map over (C, W, H, B): zero fill outside the image = the convolution's padding; flat 1x1 layers: a 3-D map over
   // (C, pixels, B)), `parts` boxes of `slot_rows` halo rows each; the 8 producer warps convert slot by slot.  No thread waits on global memory.
   int NS, parts, slot_rows, slot_bytes, rs /* image rows per box */, tma_b_fixed /* batch stride 0: always coordinate 0 */;
+  int patch;                  // > 0: patch-embedding conv (kernel = stride = patch, no padding) as a strided gather: a 5-D map over (C, px, X, py, B*Y); chunk = (channel chunk, tap)
   alignas(64) CUtensorMap tmap;
 };
 
@@ -727,7 +728,12 @@ __global__ void __launch_bounds__(TMA ? V2_THREADS_TMA : V2_THREADS, 1) conv_tc2
           mbar_expect_tx(s_full(ss), (uint32_t)p.slot_bytes);
           const uint32_t dst = stg_ring + ss * (uint32_t)p.slot_bytes;
           const int bc = p.tma_b_fixed ? 0 : sb_;
-          if (p.flat) {
+          if (p.patch) {            // chunk scc = (channel chunk, tap (py, px)); box = 32 consecutive tokens (one token row or a part of it)
+            const int pp = p.patch * p.patch, cch = scc / pp, tap = scc - cch * pp, py = tap / p.patch, px = tap - py * p.patch;
+            const int tok = sty0 + spart * 32, tyy = tok / p.Wo, txx = tok - tyy * p.Wo;
+            asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
+                         ::"r"(dst), "l"(tm), "r"(cch * 64), "r"(px), "r"(txx), "r"(py), "r"(sb_ * p.Ho + tyy), "r"(s_full(ss)) : "memory");
+          } else if (p.flat) {
             asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
                          ::"r"(dst), "l"(tm), "r"(scc * 64), "r"(sty0 + spart * p.slot_rows), "r"(bc), "r"(s_full(ss)) : "memory");
           } else {
@@ -1123,8 +1129,13 @@ static int conv_tc2_try(sma_conv_desc* d, cudaStream_t st, bool f16) {
                     (d->aux_ld & 7) == 0 && (d->aux_bstride & 7) == 0 && (reinterpret_cast<uintptr_t>(d->aux) & 31) == 0;
     if (!ok) return SMA_ERR_UNSUPPORTED;
   }
-  if (d->stride != 1 || (d->kh != d->kw && !(d->kh == 1 || d->kw == 1))) return SMA_ERR_UNSUPPORTED;
-  const bool flat = d->kh == 1 && d->kw == 1 && !d->upsample2 && d->pad_t == 0 && d->pad_l == 0 && d->Ho == d->Hi && d->Wo == d->Wi;
+  // patch embedding (appmotioncodebook_arch.py:222,229,236: Rearrange + Linear = a p x p conv of stride p): every tap's operand tile is a strided gather of
+  // the input, which a 5-D tensor map expresses directly; runs as a flat GEMM over the tokens with (channel chunk, tap) as the K chunks (staged-input mode only)
+  const bool patch = f16 && d->stride >= 2 && d->stride == d->kh && d->kh == d->kw && !d->upsample2 && d->pad_t == 0 && d->pad_l == 0 && !d->pre_scale &&
+                     d->Hi == d->Ho * d->kh && d->Wi == d->Wo * d->kw && (d->Wo % 32) == 0 && ((d->Ho * d->Wo) % BM) == 0 &&
+                     (d->B == 1 || d->in_bstride == (int64_t)d->Hi * d->Wi * d->in_ld) && !(d->tc_variant & 1024);
+  if (!patch && (d->stride != 1 || (d->kh != d->kw && !(d->kh == 1 || d->kw == 1)))) return SMA_ERR_UNSUPPORTED;
+  const bool flat = patch || (d->kh == 1 && d->kw == 1 && !d->upsample2 && d->pad_t == 0 && d->pad_l == 0 && d->Ho == d->Hi && d->Wo == d->Wi);
   if (!flat && (d->Ho < 8 || d->Wo < 4)) return SMA_ERR_UNSUPPORTED;      // tiny feature maps: the gather kernel packs images into one tile
   Tc2P p;
   p.x = d->x; p.bias = d->bias; p.pre_scale = d->pre_scale; p.pre_shift = d->pre_shift; p.res = d->res; p.y = d->y;
@@ -1137,6 +1148,8 @@ static int conv_tc2_try(sma_conv_desc* d, cudaStream_t st, bool f16) {
   p.pad_t = d->pad_t; p.pad_l = d->pad_l; p.up = d->upsample2 ? 1 : 0; p.pre_act = d->pre_act; p.Ho = d->Ho; p.Wo = d->Wo; p.out_ld = d->out_ld;
   p.act = d->act; p.res_ld = d->res_ld; p.d2s = d->d2s;
   p.HoWo = d->Ho * d->Wo; p.cpt = d->Cin / kch; p.taps = d->kh * d->kw;
+  p.patch = patch ? d->kh : 0;
+  if (patch) { p.cpt *= p.taps; p.taps = 1; p.kh = p.kw = 1; }       // the kernel sees a 1x1 conv over Cin * p * p channels (weight image order: channel chunk outer, tap inner)
   p.passes = (d->precision == SMA_PREC_TF32 || d->precision == SMA_PREC_F16) ? 1 : (f16 && d->precision == SMA_PREC_F16X2) ? 2 : 3;
   p.flat = flat ? 1 : 0;
   if (flat) { p.tiles_x = 1; p.tiles_per_img = (p.HoWo + BM - 1) / BM; p.halo_w = 8; p.HP = BM; }
@@ -1156,8 +1169,9 @@ static int conv_tc2_try(sma_conv_desc* d, cudaStream_t st, bool f16) {
   // (2 for the 256-column tiles); layers where that is not possible (3x3 with 128 / 256-column tiles) keep the register-staged producers
   p.NS = 0; p.parts = p.slot_rows = p.slot_bytes = p.rs = 0; p.tma_b_fixed = d->in_bstride == 0 ? 1 : 0;
   int budget = SMEM_LIMIT - SA * p.a_stage_bytes;
-  if (f16 && !(d->tc_variant & 1024) && !d->upsample2 && d->kh == d->kw && (d->kh == 1 || d->kh == 3) && (d->in_bstride & 3) == 0) {
-    if (flat) { p.parts = 4; p.rs = 0; p.slot_rows = 32; }
+  if (f16 && !(d->tc_variant & 1024) && !d->upsample2 && (patch || (d->kh == d->kw && (d->kh == 1 || d->kh == 3))) && (d->in_bstride & 3) == 0) {
+    if (patch) { p.parts = 4; p.rs = 0; p.slot_rows = 32; }                        // 32 consecutive tokens of one token row per box
+    else if (flat) { p.parts = 4; p.rs = 0; p.slot_rows = 32; }
     else { p.parts = d->kh == 3 ? 3 : 2; p.rs = (16 + d->kh - 1) / p.parts; p.slot_rows = p.halo_w * p.rs; }
     p.slot_bytes = p.slot_rows * 256;
     const int sb_min = p.NT <= 128 ? 3 : 2;
@@ -1166,6 +1180,7 @@ static int conv_tc2_try(sma_conv_desc* d, cudaStream_t st, bool f16) {
     // single pass: the MMAs of a chunk are 3x shorter, so less than a whole chunk (+1 box) in flight exposes the load latency: register path instead
     p.NS = (NS >= 2 && NS > p.parts / 2 && (p.passes == 3 || NS > p.parts)) ? NS : 0;
   }
+  if (patch && p.NS == 0) return SMA_ERR_UNSUPPORTED;          // (the register-staged producers have no strided gather: gather kernel instead)
   int SB = (budget - p.NS * p.slot_bytes) / b_stage;
   // (a single A stage is not an option: the two producer groups could then be two barrier phases apart - parity aliasing)
   if (SB < 2) return SMA_ERR_UNSUPPORTED;
@@ -1206,7 +1221,14 @@ static int conv_tc2_try(sma_conv_desc* d, cudaStream_t st, bool f16) {
     const cuuint64_t bstride_bytes = d->in_bstride == 0 ? (cuuint64_t)d->Hi * d->Wi * d->in_ld * 4ull : (cuuint64_t)d->in_bstride * 4ull;
     const cuuint32_t ones[4] = {1, 1, 1, 1};
     CUresult cr;
-    if (flat) {
+    if (patch) {
+      const cuuint64_t P = (cuuint64_t)d->kh, ld4 = (cuuint64_t)d->in_ld * 4ull;
+      const cuuint64_t gdim[5] = {(cuuint64_t)d->Cin, P, (cuuint64_t)d->Wo, P, (cuuint64_t)d->B * d->Ho};       // (channel, px, token x, py, frame * token rows + token y)
+      const cuuint64_t gstr[4] = {ld4, P * ld4, (cuuint64_t)d->Wi * ld4, P * (cuuint64_t)d->Wi * ld4};
+      const cuuint32_t box[5] = {64, 1, 32, 1, 1}, ones5[5] = {1, 1, 1, 1, 1};
+      cr = enc(&p.tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float*>(d->x), gdim, gstr, box, ones5, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    } else if (flat) {
       const cuuint64_t gdim[3] = {(cuuint64_t)d->Cin, (cuuint64_t)p.HoWo, nb};
       const cuuint64_t gstr[2] = {(cuuint64_t)d->in_ld * 4ull, bstride_bytes};
       const cuuint32_t box[3] = {64, (cuuint32_t)p.slot_rows, 1};

@@ -213,6 +213,19 @@ def test_conv2d_fused_groupnorm_statistics(S, B, Cin, Cout, H, W, k, res, pre):
     assert torch.equal(y3, y) and torch.equal(sc3, sc2)
 
 
+@pytest.mark.parametrize('p,Cin,tg', [(2, 128, 32), (4, 128, 32), (8, 64, 32), (2, 64, 64)])
+def test_patch_embedding_conv_as_tensor_map_gather(S, p, Cin, tg):
+    """Patch embedding (Rearrange 'b c (h p1) (w p2) -> b (h w) (p1 p2 c)' + Linear, appmotioncodebook_arch.py:222,229,236) = a p x p conv of stride p: on the
+    fp16 staged-input kernel every (channel chunk, tap) operand tile is a strided gather through a 5-D tensor map; against an fp64 torch conv, two frames."""
+    B, Cout = 2, 256
+    x = rnd(B, Cin, tg * p, tg * p, seed=1); w = rnd(Cout, Cin, p, p, seed=2, scale=(Cin * p * p) ** -0.5); b = rnd(Cout, seed=3, scale=0.1)
+    ref = F.conv2d(x.double(), w.double(), b.double(), stride=p)
+    y = S.ops.conv2d(nhwc(x), S.ops.pack_conv(w.cuda(), b.cuda()), stride=p)
+    assert S.ops.LAST_CONV_KERNEL == 3, S.ops.LAST_CONV_KERNEL              # the fp16 persistent kernel, not the tf32 gather kernel
+    err = float((nchw(y).double() - ref).abs().max())
+    assert err < 2e-5 + 1e-8 * Cin * p * p, err
+
+
 def test_conv2d_concat_slices_patchify_and_bn_fold(S):
     """channel-slice views as input/output (torch.cat elimination), stride-p patch embedding, depth-to-space."""
     B, C, s, p = 2, 128, 64, 2
