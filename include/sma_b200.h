@@ -194,9 +194,10 @@ int sma_mha_e256_fwd(const float* q, int ldq, const float* k, int ldk, const flo
                      int B, int L, int S, float scale, const uint8_t* key_mask, void* workspace, float* out, int ldo, sma_stream_t stream);
 
 /* VectorQuantizer lookup (archs/vqgan_arch.py:33-73): d = fl(fl(|z|^2+|e|^2) - 2 z.e), argmin with
- * lowest-index ties -> idx (int64), zq = e[idx].  z:(N,E) row-major, codebook (n_codes,E). */
+ * lowest-index ties -> idx (int64), zq = e[idx].  z:(N,E) row-major, codebook (n_codes,E).  workspace: n_codes floats (|e|^2) or NULL; with it,
+ * N >= 512 rows run as an exact-fp32 register-tiled GEMM (bit-identical distances and indices, ~20x the warp-per-row form). */
 int sma_vq_lookup_fwd(const float* z, int N, int E, const float* codebook, int n_codes, int64_t* idx,
-                      float* zq, float* min_dist, sma_stream_t stream);
+                      float* zq, float* min_dist, float* workspace, sma_stream_t stream);
 /* Forward values of VectorQuantizer.forward's other returns (archs/vqgan_arch.py:76-80,88), the training-path pieces of SURVEY 8f(4):
  * zq_st = z + (zq - z) (the straight-through tensor, may be NULL) and loss[0] = beta * mean((zq - z)^2) + mean((zq - z)^2) over n elements
  * (a device scalar).  Deterministic two-stage sum; workspace: sma_vq_workspace_floats() floats. */

@@ -56,7 +56,7 @@ SIGNATURES = {
     'sma_attn256_fwd': ([_V, _I, _V, _I, _V, _I, _L, _L, _I, _I, _I, _F, _V, _V, _I, _V], C.c_int),
     'sma_mha_e256_workspace_bytes': ([_I, _I, _I, _I], C.c_int64),
     'sma_mha_e256_fwd': ([_V, _I, _V, _I, _V, _I, _L, _L, _I, _I, _I, _F, _V, _V, _V, _I, _V], C.c_int),
-    'sma_vq_lookup_fwd': ([_V, _I, _I, _V, _I, _V, _V, _V, _V], C.c_int),
+    'sma_vq_lookup_fwd': ([_V, _I, _I, _V, _I, _V, _V, _V, _V, _V], C.c_int),
     'sma_vq_workspace_floats': ([], C.c_int),
     'sma_vq_commit_fwd': ([_V, _V, _L, _F, _V, _V, _V, _V], C.c_int),
     'sma_antialias_down4': ([_V, _I, _I, _I, _I, _V, _V, _I, _V], C.c_int),

@@ -221,6 +221,7 @@ USE_TF32X3 = True        # let sma_conv2d_fwd pick a tcgen05 kernel where the sh
 ALLOW_TF32_1PASS = True  # honour `fast=True` requests (single pass)
 USE_TS = False           # weights as the tensor-memory A operand (csrc/conv_ts.cu) where they fit in tensor memory; False: shared-memory-operand kernels
 USE_MH_F16 = True        # 8-head E=256 attention: fp16-split kernel with pre-split tile images (csrc/attn_mh.cu); False: tf32 kernel (attn_tc.cu)
+VQ_TILED = True          # large-N VQ lookups as the register-tiled exact-fp32 GEMM (bit-identical); False: warp-per-row kernel
 FUSE_GN = os.environ.get('SMA_NO_FUSE_GN', '0') != '1'           # (env: A/B on one box) GroupNorm partial sums of a conv's output from its own epilogue (conv2d(gn=...)); False: always the standalone statistics pass
 USE_F16 = True           # split operands into fp16 halves (kind::f16, 2x the tensor rate of kind::tf32) where Cin % 64 == 0
 # Per-stage precision policy: stages listed here run their convolutions as single-pass TF32 (3x fewer tensor-core
@@ -494,7 +495,8 @@ def vq_lookup(z: torch.Tensor, codebook: torch.Tensor, n_codes: Optional[int] = 
     idx = torch.empty((N,), device=z.device, dtype=torch.int64)
     zq = torch.empty_like(z)
     md = torch.empty((N,), device=z.device, dtype=torch.float32)
-    check(lib.sma_vq_lookup_fwd(z.data_ptr(), N, E, codebook.data_ptr(), n, idx.data_ptr(), zq.data_ptr(), md.data_ptr(), _stream()),
+    ws = torch.empty((n,), device=z.device, dtype=torch.float32) if VQ_TILED else None
+    check(lib.sma_vq_lookup_fwd(z.data_ptr(), N, E, codebook.data_ptr(), n, idx.data_ptr(), zq.data_ptr(), md.data_ptr(), _ptr(ws), _stream()),
           'sma_vq_lookup_fwd')
     return idx, zq, md
 

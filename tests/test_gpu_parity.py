@@ -264,7 +264,7 @@ def test_conv2d_bad_arguments_return_status(S):
     d = S._lib.ConvDesc()
     assert lib.sma_conv2d_fwd(ctypes.byref(d), None) == -1          # null pointers -> SMA_ERR_BAD_ARG
     assert lib.sma_conv2d_fwd(None, None) == -1
-    assert lib.sma_vq_lookup_fwd(None, 0, 0, None, 0, None, None, None, None) == -1
+    assert lib.sma_vq_lookup_fwd(None, 0, 0, None, 0, None, None, None, None, None) == -1
     assert lib.sma_warp_occlude_fwd(None, 0, 1, 4, 4, 4, None, None, 4, 4, None, None) == -1
     z = torch.zeros(8, 48, device='cuda'); cb = torch.zeros(16, 48, device='cuda')
     with pytest.raises(RuntimeError):                               # unsupported embedding width -> status -2 -> raise
@@ -418,6 +418,29 @@ def test_vq_lookup_indices_bit_exact(S, E, init):
         # idempotence: quantising code vectors returns the same codes
         idx2, _, _ = S.ops.vq_lookup(zq, cb.cuda(), n)
         assert torch.equal(idx2.cpu(), idx)
+
+
+def test_vq_lookup_tiled_kernel_is_bit_identical_to_the_warp_per_row_kernel(S, weights):
+    """Large-N lookups run as a register-tiled exact-fp32 GEMM (12x the warp-per-row kernel on 65 536 x 1024 x 256): the same fmaf chains, the same
+    tie-breaking - indices, gathered rows AND minimum distances must be bit-identical, on both codebooks, prefix splits, ragged N and exact ties."""
+    for key, E in (('quantize_app.embedding.weight', 256), ('quantize_motion.embedding.weight', 32)):
+        cb = weights[0][key].cuda().contiguous()
+        for N, n in ((4096, 1024), (1000, 768), (513, 256), (2048, 300)):
+            z = (rnd(N, E, seed=N) * 0.8).cuda()
+            z[7] = cb[5]; z[8] = cb[5]                       # exact zero distances
+            saved = S.ops.VQ_TILED
+            try:
+                S.ops.VQ_TILED = True; a = S.ops.vq_lookup(z, cb, n)
+                S.ops.VQ_TILED = False; b = S.ops.vq_lookup(z, cb, n)
+            finally:
+                S.ops.VQ_TILED = saved
+            for u, v in zip(a, b):
+                assert torch.equal(u, v), (key, N, n)
+    cb2 = torch.zeros(1024, 256, device='cuda'); cb2[::2] = 1.0          # every even code identical, every odd code identical: lowest index wins
+    z = torch.ones(1024, 256, device='cuda') * 0.9
+    S.ops.VQ_TILED = True
+    idx, _, _ = S.ops.vq_lookup(z, cb2, 1024)
+    assert int(idx.min()) == 0 and int(idx.max()) == 0
 
 
 def test_vq_lookup_ties_lowest_index_and_ragged(S):
