@@ -174,7 +174,8 @@ int sma_resize_bilinear_ac(const float* x, int B, int Hi, int Wi, int C, int64_t
  * single-head AttnBlock, archs/vqgan_arch.py:233-248).  q:(B,L,*) k,v:(B or shared,S,*) ;
  * head h occupies columns [h*D,(h+1)*D).  key_mask (B,S) uint8, 1 = ignore (may be NULL).
  * D in {4,32,256}.  D in {4,32} with L % 128 == 0 and S % 64 == 0 runs on the tensor cores (tcgen05, 3xTF32 for both
- * contractions); flags bit 0 forces the exact-fp32 CUDA-core kernel.
+ * contractions); flags bit 0 forces the exact-fp32 CUDA-core kernel; flags bit 1 allows, for D = 4 without a mask, the register-level mma form
+ * (fp32-faithful hi/lo scores, P rounded to fp16: ~3e-4 absolute on unit-scale values; for stages whose error budget allows it, here S3m).
  * ------------------------------------------------------------------------------------------- */
 int sma_mha_fwd(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv,
                 int64_t kv_bstride, int B, int L, int S, int heads, int D, float scale,

@@ -475,12 +475,12 @@ class AppMotionCompFormer(ParamModule):
         qkv = torch.empty((B, L, 3 * E), device=t.device, dtype=torch.float32)
         ops.linear(uq, W[name + '.self_in'].cols(0, 2 * E), out=qkv[..., :2 * E], fast=fast)
         ops.linear(u, W[name + '.self_in'].cols(2 * E, E), out=qkv[..., 2 * E:], fast=fast)
-        a = ops.mha(qkv[..., :E], qkv[..., E:2 * E], qkv[..., 2 * E:], heads=self.n_head, key_mask=key_mask)
+        a = ops.mha(qkv[..., :E], qkv[..., E:2 * E], qkv[..., 2 * E:], heads=self.n_head, key_mask=key_mask, fast=fast)
         t = ops.linear(a, W[name + '.self_out'], res=t, fast=fast)
         _, uq = ops.layernorm(t, T[name + '.norm2.weight'], T[name + '.norm2.bias'], pos, want_y=False)
         qc = ops.linear(uq, W[name + '.cross_in'].cols(0, E), fast=fast)
         kv = W[name + '.ctx_kv']
-        a = ops.mha(qc, kv[:n_ctx, :E], kv[:n_ctx, E:], heads=self.n_head)
+        a = ops.mha(qc, kv[:n_ctx, :E], kv[:n_ctx, E:], heads=self.n_head, fast=fast)
         t = ops.linear(a, W[name + '.cross_out'], res=t, fast=fast)
         u, _ = ops.layernorm(t, T[name + '.norm3.weight'], T[name + '.norm3.bias'])
         f = ops.conv2d(u.view(B, tg, tg, E), W[name + '.conv1'], pad=1, act='gelu', fast=fast)

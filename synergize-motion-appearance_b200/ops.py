@@ -221,6 +221,7 @@ USE_TF32X3 = True        # let sma_conv2d_fwd pick a tcgen05 kernel where the sh
 ALLOW_TF32_1PASS = True  # honour `fast=True` requests (single pass)
 USE_TS = False           # weights as the tensor-memory A operand (csrc/conv_ts.cu) where they fit in tensor memory; False: shared-memory-operand kernels
 USE_MH_F16 = True        # 8-head E=256 attention: fp16-split kernel with pre-split tile images (csrc/attn_mh.cu); False: tf32 kernel (attn_tc.cu)
+MHA_D4_MMA = os.environ.get('SMA_NO_D4_MMA', '0') != '1'      # head-dim-4 attention of single-pass stages (S3m) as register-level mma with P in fp16 (csrc/attn.cu)
 VQ_TILED = True          # large-N VQ lookups as the register-tiled exact-fp32 GEMM (bit-identical); False: warp-per-row kernel
 FUSE_GN = os.environ.get('SMA_NO_FUSE_GN', '0') != '1'           # (env: A/B on one box) GroupNorm partial sums of a conv's output from its own epilogue (conv2d(gn=...)); False: always the standalone statistics pass
 USE_F16 = True           # split operands into fp16 halves (kind::f16, 2x the tensor rate of kind::tf32) where Cin % 64 == 0
@@ -437,7 +438,7 @@ def resize_ac(x: torch.Tensor, size: Tuple[int, int], out: Optional[torch.Tensor
 
 
 def mha(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, key_mask: Optional[torch.Tensor] = None,
-        scale: Optional[float] = None, out: Optional[torch.Tensor] = None, exact: bool = False) -> torch.Tensor:
+        scale: Optional[float] = None, out: Optional[torch.Tensor] = None, exact: bool = False, fast: bool = False) -> torch.Tensor:
     """q (B,L,E-view) ; k,v (B,S,E-view) or (S,E-view) shared by all frames.  Views may be column slices."""
     lib = _lib.load()
     B, L, E = q.shape
@@ -466,7 +467,7 @@ def mha(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, key_mask:
         return out
     with _Prof('mha', 4.0 * B * L * S * E, 4.0 * (2 * B * L * E + 2 * (B if kvbs else 1) * S * E), f'mha B{B} L{L} S{S} h{heads} D{D}'):
         check(lib.sma_mha_fwd(q.data_ptr(), q.stride(1), k.data_ptr(), ldk, v.data_ptr(), ldv, kvbs, B, L, S, heads, D, scale,
-                              _ptr(key_mask), out.data_ptr(), out.stride(1), 1 if (exact or not USE_TF32X3) else 0, _stream()), f'sma_mha_fwd D={D}')
+                              _ptr(key_mask), out.data_ptr(), out.stride(1), 1 if (exact or not USE_TF32X3) else (2 if (fast is True and MHA_D4_MMA) else 0), _stream()), f'sma_mha_fwd D={D}')
     return out
 
 

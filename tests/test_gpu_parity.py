@@ -376,6 +376,29 @@ def test_mha_core(S, E, heads, S_kv, shared, masked, exact):
     assert float((got.cpu().double() - ref).abs().max()) < (2e-5 if exact else 1e-4)
 
 
+@pytest.mark.parametrize('S_kv,shared,qs', [(1024, False, 1.0), (256, True, 1.0), (768, True, 3.0)])
+def test_mha_d4_register_mma_form(S, S_kv, shared, qs):
+    """Head-dim-4 attention of the single-pass stages (S3m) as warp-level mma with the whole hi / lo split packed into K = 16 (fp32-faithful scores)
+    and P rounded to fp16: against fp64 torch on unit-scale inputs (qs = 3 spreads the scores so that the lazy maximum moves); tolerance = the
+    fp16 rounding of P (2^-12 relative per term)."""
+    B, L, E, heads = 2, 1024, 32, 8
+    q = rnd(B, L, E, seed=1) * qs
+    k = rnd(S_kv, E, seed=2) if shared else rnd(B, S_kv, E, seed=2)
+    v = rnd(S_kv, E, seed=3) if shared else rnd(B, S_kv, E, seed=3)
+    kk = k.unsqueeze(0).expand(B, -1, -1) if shared else k
+    vv = v.unsqueeze(0).expand(B, -1, -1) if shared else v
+    qh = q.double().view(B, L, heads, 4).transpose(1, 2) * 0.5
+    ref = (torch.softmax(qh @ kk.double().reshape(B, S_kv, heads, 4).transpose(1, 2).transpose(-1, -2), -1) @
+           vv.double().reshape(B, S_kv, heads, 4).transpose(1, 2)).transpose(1, 2).reshape(B, L, E)
+    got = S.ops.mha(q.cuda(), k.cuda(), v.cuda(), heads, fast=True)
+    exact = S.ops.mha(q.cuda(), k.cuda(), v.cuda(), heads)
+    err = (got.cpu().double() - ref).abs()
+    # (peaked rows - qs = 3 - keep the full 2^-12 of their dominant term: |v| up to ~4 -> 1e-3; diffuse rows average it away)
+    assert float(err.max()) < (1e-3 if qs == 1.0 else 3e-3) and float(err.mean()) < (3e-5 if qs == 1.0 else 1.5e-4), (float(err.max()), float(err.mean()))
+    assert float((exact.cpu().double() - ref).abs().max()) < 1e-4
+    assert not torch.equal(got, exact)                       # ... and the two calls really ran different kernels
+
+
 @pytest.mark.parametrize('B,L,S_kv,qs', [(3, 1024, 1024, 1.0), (1, 256, 512, 1.0), (2, 1024, 1024, 6.0)])
 def test_attn256_tensor_core_kernel(S, B, L, S_kv, qs):
     """AttnBlock attention on tcgen05 (csrc/attn256.cu) called directly; qs = 6 makes the scores spread over ~+-100 so that the lazy
