@@ -392,7 +392,9 @@ def main():
                     'share_of_step_ms': c[3] / (ms / K),
                     'note': 'algorithmic flops = 2*M*N*K of the fp32 convolution (zero-padded input channels included); the kernels spend 3 fp16 '
                             'tensor-core MACs per fp32 MAC (fp16 hi/lo split, fp32 accumulate) to stay within 1e-3 of the fp32 reference, so '
-                            'frac <= 1/3 by construction; measured on rank 0 in a separate collective-free step'}
+                            'frac <= 1/3 by construction; since round 2b these launches also produce the GroupNorm statistics of their outputs in the epilogue '
+                            '(the standalone statistics passes, 2.9 ms per step, are gone; the conv launches themselves got 1.7 ms longer) and stage '
+                            'their input tiles with TMA tensor maps; measured on rank 0 in a separate collective-free step'}
         w_ = agg.get('warp')
         if w_:
             stage_table['warp']['hbm_frac'] = w_[2] / (w_[3] * 1e-3) / 1e9 / pk['hbm_gbs']
