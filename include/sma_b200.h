@@ -108,6 +108,10 @@ typedef struct sma_conv_desc {
      gn_partial (B * gn_chunks * Cout floats) where the 256-bit epilogue runs; gn_chunks is an OUTPUT (also of a plan_only call): 0 = this launch
      cannot produce them (other kernel / layout): the caller runs sma_groupnorm_stats on y instead.  Finish with sma_groupnorm_finalize_pairs. */
   int gn_want;  float* gn_partial;  int gn_chunks;
+  /* second input tensor (may be NULL): input channels [Cin1, Cin) are read from x2 (same B, Hi, Wi; row pitch in2_ld, batch stride in2_bstride), i.e.
+     conv(x, w[:, :Cin1]) + conv(x2, w[:, Cin1:]) in one accumulator - Fuse_sft_block's shift conv and the fuse_ms conv of the same scale
+     (appmotioncodebook_arch.py:50-51,737-738).  TMA-staged fp16 kernel only (else SMA_ERR_UNSUPPORTED: run the two convolutions). */
+  const float* x2;  int64_t in2_bstride;  int in2_ld;  int Cin1;
 } sma_conv_desc;
 
 int sma_conv2d_fwd(sma_conv_desc* d, sma_stream_t stream);

@@ -21,6 +21,7 @@ Design (B200-first, not a module-for-module port):
   * the third (duplicate) warp per scale that only feeds `deform_feat_list` is not computed.
 """
 import math
+import os
 import weakref
 from typing import Dict, List, Optional, Tuple
 
@@ -124,6 +125,7 @@ class AppMotionCompFormer(ParamModule):
         gen.__class__ = _PlainDecoder
         object.__setattr__(gen, '_owner', weakref.ref(self))      # not a registered sub-module: no cycle in the module tree
         self._src_cache = None
+        self._two_tensor_ok = os.environ.get('SMA_NO_TWO', '0') != '1'      # (env: A/B on one box)
         if ae_path is not None:
             self.load_state_dict(torch.load(ae_path, map_location='cpu')['params_ema'])
         for module in (fix_modules or []):
@@ -264,6 +266,10 @@ class AppMotionCompFormer(ParamModule):
                 [T[f'fuse_convs_dict.{s}.{b}.0.weight'] for b in ('scale', 'shift')],
                 [T[f'fuse_convs_dict.{s}.{b}.0.bias'] for b in ('scale', 'shift')])
             pc(f'fuse_convs_dict.{s}.scale.2'); pc(f'fuse_convs_dict.{s}.shift.2'); pc(f'fuse_ms_dict.{s}')
+            # shift.2 over the SFT branch and fuse_ms over the compensated feature write the same tensor (w = 1): one conv over two input tensors
+            W[f'fuse_convs_dict.{s}.shift2ms'] = ops.pack_conv(
+                torch.cat([T[f'fuse_convs_dict.{s}.shift.2.weight'], T[f'fuse_ms_dict.{s}.weight']], dim=1),
+                T[f'fuse_convs_dict.{s}.shift.2.bias'] + T[f'fuse_ms_dict.{s}.bias'])
         # the 2-channel pixel-unit flow is kept in a 32-channel zero-padded buffer: both convs reading it run on the tensor cores
         W['motion_emb.0'] = ops.pack_conv(T['motion_emb.0.weight'], T['motion_emb.0.bias'], pad_cin=32)
         # the 7x7 conv over the same 2 channels is unfolded instead (ops.im2col_small): one 1x1 conv of depth 128 instead of 49 taps x 32 padded channels
@@ -613,10 +619,18 @@ class AppMotionCompFormer(ParamModule):
                 ss = ops.conv2d(e, W[n + '.ss0'], pad=1, act='leaky', fast=fsft)                  # [scale.0 | shift.0]
                 scale = ops.conv2d(ss[..., :c], W[n + '.scale.2'], pad=1, fast=fsft)
                 # dec + w * (dec * scale + shift) in the epilogue of the `shift.2` conv; the decoder half is read in place (channel slice of `cat`)
-                xf = ops.conv2d(ss[..., c:], W[n + '.shift.2'], pad=1, res=x, sft=(scale, float(w)), fast=fsft)
-                if collect is not None:
-                    collect[f'sft_{s}'] = xf.clone()                                   # (the next conv accumulates in place)
-                r = ops.conv2d(enc, W[f'fuse_ms_dict.{s0}'], pad=1, res=xf, out=xf, fast=ops.fast('ms'), gn=want)
+                r = None
+                if collect is None and float(w) == 1.0 and self._two_tensor_ok and fsft == ops.fast('ms') and (n + '.shift2ms') in W:
+                    # dec + (dec * scale + shift) + fuse_ms(enc) with shift + fuse_ms in ONE accumulator: the SFT result is never written and re-read
+                    try:
+                        r = ops.conv2d(ss[..., c:], W[n + '.shift2ms'], pad=1, res=x, sft=(scale, 1.0), fast=fsft, x2=enc, gn=want)
+                    except ops._lib.SmaError:
+                        self._two_tensor_ok = False                                    # (layout the staged-input kernel declines: two convolutions from now on)
+                if r is None:
+                    xf = ops.conv2d(ss[..., c:], W[n + '.shift.2'], pad=1, res=x, sft=(scale, float(w)), fast=fsft)
+                    if collect is not None:
+                        collect[f'sft_{s}'] = xf.clone()                               # (the next conv accumulates in place)
+                    r = ops.conv2d(enc, W[f'fuse_ms_dict.{s0}'], pad=1, res=xf, out=xf, fast=ops.fast('ms'), gn=want)
                 x, stats = r if want is not None else (r, None)
                 if collect is not None:
                     collect[f'fused_{s}'] = x

@@ -324,6 +324,8 @@ struct Tc2P {
   int NS, parts, slot_rows, slot_bytes, rs /* image rows per box */, tma_b_fixed /* batch stride 0: always coordinate 0 */;
   int patch;                  // > 0: patch-embedding conv (kernel = stride = patch, no padding) as a strided gather: a 5-D map over (C, px, X, py, B*Y); chunk = (channel chunk, tap)
   alignas(64) CUtensorMap tmap;
+  alignas(64) CUtensorMap tmap2;   // second input tensor (cpt1 < cpt): channel chunks [cpt1, cpt) are read from it (two convolutions over different tensors summed in one accumulator)
+  int cpt1;
 };
 
 // ACT: epilogue activation; PRE: -1 no prologue, else the prologue activation applied after scale/shift (compile-time so that the
@@ -709,7 +711,7 @@ __global__ void __launch_bounds__(TMA ? V2_THREADS_TMA : V2_THREADS, 1) conv_tc2
       // staged-input mode: ONE thread feeds both rings.  It polls the two "slot free" barriers without blocking on either (a blocked weight slot
       // must not hold back a free staging slot and vice versa), so that a 16th warp is not needed for the tensor loads (16 warps = 128 registers).
       const uint32_t bytes = (uint32_t)(p.passes >= 2 ? b_stage_bytes : p.b_img_bytes);
-      const uint64_t tm = reinterpret_cast<uint64_t>(&p.tmap);
+      const uint64_t tm1 = reinterpret_cast<uint64_t>(&p.tmap), tm2 = reinterpret_cast<uint64_t>(&p.tmap2);
       const int nblob = p.cpt * p.taps;
       auto test = [&](uint32_t bar, uint32_t parity) -> bool {
         uint32_t ok;
@@ -728,6 +730,9 @@ __global__ void __launch_bounds__(TMA ? V2_THREADS_TMA : V2_THREADS, 1) conv_tc2
           mbar_expect_tx(s_full(ss), (uint32_t)p.slot_bytes);
           const uint32_t dst = stg_ring + ss * (uint32_t)p.slot_bytes;
           const int bc = p.tma_b_fixed ? 0 : sb_;
+          const bool second = scc >= p.cpt1;                 // chunk of the second input tensor
+          const uint64_t tm = second ? tm2 : tm1;
+          const int ch0 = (second ? scc - p.cpt1 : scc) * 64;
           if (p.patch) {            // chunk scc = (channel chunk, tap (py, px)); box = 32 consecutive tokens (one token row or a part of it)
             const int pp = p.patch * p.patch, cch = scc / pp, tap = scc - cch * pp, py = tap / p.patch, px = tap - py * p.patch;
             const int tok = sty0 + spart * 32, tyy = tok / p.Wo, txx = tok - tyy * p.Wo;
@@ -735,10 +740,10 @@ __global__ void __launch_bounds__(TMA ? V2_THREADS_TMA : V2_THREADS, 1) conv_tc2
                          ::"r"(dst), "l"(tm), "r"(cch * 64), "r"(px), "r"(txx), "r"(py), "r"(sb_ * p.Ho + tyy), "r"(s_full(ss)) : "memory");
           } else if (p.flat) {
             asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-                         ::"r"(dst), "l"(tm), "r"(scc * 64), "r"(sty0 + spart * p.slot_rows), "r"(bc), "r"(s_full(ss)) : "memory");
+                         ::"r"(dst), "l"(tm), "r"(ch0), "r"(sty0 + spart * p.slot_rows), "r"(bc), "r"(s_full(ss)) : "memory");
           } else {
             asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
-                         ::"r"(dst), "l"(tm), "r"(scc * 64), "r"(stx0 - p.pad_l), "r"(sty0 - p.pad_t + spart * p.rs), "r"(bc), "r"(s_full(ss)) : "memory");
+                         ::"r"(dst), "l"(tm), "r"(ch0), "r"(stx0 - p.pad_l), "r"(sty0 - p.pad_t + spart * p.rs), "r"(bc), "r"(s_full(ss)) : "memory");
           }
           if (++ss == (uint32_t)p.NS) { ss = 0; phs ^= 1u; }
           if (++spart == p.parts) {
@@ -1150,6 +1155,13 @@ static int conv_tc2_try(sma_conv_desc* d, cudaStream_t st, bool f16) {
   p.HoWo = d->Ho * d->Wo; p.cpt = d->Cin / kch; p.taps = d->kh * d->kw;
   p.patch = patch ? d->kh : 0;
   if (patch) { p.cpt *= p.taps; p.taps = 1; p.kh = p.kw = 1; }       // the kernel sees a 1x1 conv over Cin * p * p channels (weight image order: channel chunk outer, tap inner)
+  p.cpt1 = p.cpt;
+  if (d->x2) {        // two input tensors: staged-input mode only, plain inputs (no prologue), both channel counts multiples of 64, same geometry
+    if (!f16 || patch || flat || d->pre_scale || d->upsample2 || d->Cin1 <= 0 || d->Cin1 >= d->Cin || (d->Cin1 % 64) || ((d->Cin - d->Cin1) % 64) ||
+        (d->in2_ld & 3) || (d->in2_bstride & 3) || d->in2_bstride == 0 || d->in_bstride == 0 || (reinterpret_cast<uintptr_t>(d->x2) & 15))
+      return SMA_ERR_UNSUPPORTED;
+    p.cpt1 = d->Cin1 / 64;
+  }
   p.passes = (d->precision == SMA_PREC_TF32 || d->precision == SMA_PREC_F16) ? 1 : (f16 && d->precision == SMA_PREC_F16X2) ? 2 : 3;
   p.flat = flat ? 1 : 0;
   if (flat) { p.tiles_x = 1; p.tiles_per_img = (p.HoWo + BM - 1) / BM; p.halo_w = 8; p.HP = BM; }
@@ -1180,7 +1192,7 @@ static int conv_tc2_try(sma_conv_desc* d, cudaStream_t st, bool f16) {
     // single pass: the MMAs of a chunk are 3x shorter, so less than a whole chunk (+1 box) in flight exposes the load latency: register path instead
     p.NS = (NS >= 2 && NS > p.parts / 2 && (p.passes == 3 || NS > p.parts)) ? NS : 0;
   }
-  if (patch && p.NS == 0) return SMA_ERR_UNSUPPORTED;          // (the register-staged producers have no strided gather: gather kernel instead)
+  if ((patch || d->x2) && p.NS == 0) return SMA_ERR_UNSUPPORTED;          // (the register-staged producers have no strided gather: gather kernel instead)
   int SB = (budget - p.NS * p.slot_bytes) / b_stage;
   // (a single A stage is not an option: the two producer groups could then be two barrier phases apart - parity aliasing)
   if (SB < 2) return SMA_ERR_UNSUPPORTED;
@@ -1235,11 +1247,18 @@ static int conv_tc2_try(sma_conv_desc* d, cudaStream_t st, bool f16) {
       cr = enc(&p.tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(d->x), gdim, gstr, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE,
                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     } else {
-      const cuuint64_t gdim[4] = {(cuuint64_t)d->Cin, (cuuint64_t)d->Wi, (cuuint64_t)d->Hi, nb};
+      const cuuint64_t c1 = d->x2 ? (cuuint64_t)d->Cin1 : (cuuint64_t)d->Cin;
+      const cuuint64_t gdim[4] = {c1, (cuuint64_t)d->Wi, (cuuint64_t)d->Hi, nb};
       const cuuint64_t gstr[3] = {(cuuint64_t)d->in_ld * 4ull, (cuuint64_t)d->Wi * d->in_ld * 4ull, bstride_bytes};
       const cuuint32_t box[4] = {64, (cuuint32_t)p.halo_w, (cuuint32_t)p.rs, 1};
       cr = enc(&p.tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(d->x), gdim, gstr, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE,
                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (cr == CUDA_SUCCESS && d->x2) {
+        const cuuint64_t gdim2[4] = {(cuuint64_t)(d->Cin - d->Cin1), (cuuint64_t)d->Wi, (cuuint64_t)d->Hi, (cuuint64_t)d->B};
+        const cuuint64_t gstr2[3] = {(cuuint64_t)d->in2_ld * 4ull, (cuuint64_t)d->Wi * d->in2_ld * 4ull, (cuuint64_t)d->in2_bstride * 4ull};
+        cr = enc(&p.tmap2, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(d->x2), gdim2, gstr2, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                 CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      }
     }
     if (cr != CUDA_SUCCESS) return SMA_ERR_CUDA;
   }
@@ -1269,7 +1288,7 @@ int sma_conv2d_tc_try(sma_conv_desc* d, cudaStream_t st) {
     int r2 = conv_tc2_try(d, st, false);
     if (r2 != SMA_ERR_UNSUPPORTED) { d->kernel_used = 2; if (d->plan_only) d->w_tc_nt = nt_default; return r2; }
   }
-  if (d->aux) return SMA_ERR_UNSUPPORTED;
+  if (d->aux || d->x2) return SMA_ERR_UNSUPPORTED;
   // gather kernel: one CTA per (128 rows, NT columns).  Few rows (tiny feature maps: the hourglass bottlenecks) would leave most SMs idle
   // with the widest tile, so the image may be packed with a narrower NT (more CTAs, each streaming a quarter of the weights).
   int NTg = d->w_tc_nt ? d->w_tc_nt : nt_default;

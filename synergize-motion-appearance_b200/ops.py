@@ -247,15 +247,23 @@ def conv2d(x: torch.Tensor, cw: ConvW, *, stride: int = 1, pad: int = 0, pad_tl:
            out: Optional[torch.Tensor] = None, out_hw: Optional[Tuple[int, int]] = None, act: str = 'none',
            pre: Optional[Tuple[torch.Tensor, torch.Tensor, str]] = None, res: Optional[torch.Tensor] = None,
            upsample2: bool = False, d2s: int = 0, out_nchw: bool = False, exact: bool = False, fast: bool = False,
-           sft: Optional[Tuple[torch.Tensor, float]] = None, gn: Optional[Tuple[torch.Tensor, torch.Tensor]] = None):
+           sft: Optional[Tuple[torch.Tensor, float]] = None, gn: Optional[Tuple[torch.Tensor, torch.Tensor]] = None,
+           x2: Optional[torch.Tensor] = None):
     """`exact`: force the CUDA-core fp32 kernel; `fast`: allow single-pass TF32 on the tensor cores (layers whose
     contribution to the output error budget was measured to be negligible); default: 3xTF32 (fp32-faithful).
     `sft=(scale, w)`: Fuse_sft_block tail, y = res + w*(res*scale + conv(x)) (needs `res`): fused into the epilogue of the persistent
     tensor-core kernel; launches that cannot run there (exact mode, odd shapes) do conv -> sma_sft_combine instead.
     `gn=(gamma, beta)`: also return the GroupNorm(32, eps 1e-6) scale / shift of the OUTPUT, `(y, (scale, shift))`: the partial sums come out of the
-    convolution's epilogue where the persistent tensor-core kernel runs (no second pass over y), else from groupnorm_stats(y)."""
+    convolution's epilogue where the persistent tensor-core kernel runs (no second pass over y), else from groupnorm_stats(y).
+    `x2`: second input tensor of the same geometry; `cw` holds the weights of both (input channels of x first): conv(x, w1) + conv(x2, w2) in one
+    accumulator (staged-input fp16 kernel only; raises SmaError(unsupported) otherwise - callers keep a two-convolution form)."""
     lib = _lib.load()
     B, Hi, Wi, Cin, ibs, ild = _nhwc(x)
+    Cin1 = Cin
+    if x2 is not None:
+        B2, H2, W2, C2, ibs2, ild2 = _nhwc(x2)
+        assert (B2, H2, W2) == (B, Hi, Wi), (tuple(x2.shape), tuple(x.shape))
+        Cin = Cin1 + C2
     if Cin != cw.Cin:
         raise _lib.SmaError(f'conv2d: input has {Cin} channels, weight expects {cw.Cin}')
     pt, pl = (pad, pad) if pad_tl is None else pad_tl
@@ -270,6 +278,8 @@ def conv2d(x: torch.Tensor, cw: ConvW, *, stride: int = 1, pad: int = 0, pad_tl:
     d.w, d.ldw, d.bias = cw.w.data_ptr(), cw.w.stride(0), _ptr(cw.bias)
     d.Cout, d.kh, d.kw, d.stride, d.pad_t, d.pad_l = cw.Cout, cw.kh, cw.kw, stride, pt, pl
     d.upsample2 = 1 if upsample2 else 0
+    if x2 is not None:
+        d.x2, d.in2_bstride, d.in2_ld, d.Cin1 = x2.data_ptr(), ibs2, ild2, Cin1
     if pre is not None:
         d.pre_scale, d.pre_shift, d.pre_act = pre[0].data_ptr(), pre[1].data_ptr(), ACT[pre[2]]
     if out_nchw:
@@ -312,10 +322,11 @@ def conv2d(x: torch.Tensor, cw: ConvW, *, stride: int = 1, pad: int = 0, pad_tl:
             d.w_tc, d.w_tc16, d.w_ts = _ptr(cw.image('tc', 0)), _ptr(cw.image('tc16')), _ptr(cw.image('ts'))
         else:
             # ask the library which kernel this launch will run on (nothing is launched), then pack / fetch exactly the image it reads
-            d.gn_want = 1 if (gn is not None and FUSE_GN and sft is None and d.out_ld == cw.Cout and cw.Cout % 64 == 0) else 0      # (pairs must not straddle the 32 groups)
+            d.gn_want = 1 if (gn is not None and FUSE_GN and d.out_ld == cw.Cout and cw.Cout % 64 == 0) else 0      # (pairs must not straddle the 32 groups)
             key = (B, Hi, Wi, stride, pt, pl, upsample2, Ho, Wo, out_nchw, d2s, d.precision, TC_VARIANT, x.data_ptr() & 15, ild & 3, ibs & 3,
                    pre is not None, sft is not None, 0 if res is None else (d.res_ld & 7, d.res_bstride & 7), d.out_ld & 7, d.out_bstride & 7,
-                   d.gn_want, out.data_ptr() & 31, 0 if res is None else res.data_ptr() & 31)
+                   d.gn_want, out.data_ptr() & 31, 0 if res is None else res.data_ptr() & 31,
+                   None if x2 is None else (Cin1, ild2 & 3, ibs2 & 3, x2.data_ptr() & 15))
             if cw.plans is None:
                 cw.plans = {}
             planned = cw.plans.get(key)
@@ -334,6 +345,8 @@ def conv2d(x: torch.Tensor, cw: ConvW, *, stride: int = 1, pad: int = 0, pad_tl:
                 d.gn_partial = gn_partial.data_ptr()
             else:
                 d.gn_want = 0
+    if x2 is not None and (planned is None or planned[0] != 3):
+        raise _lib.SmaError('conv2d(x2=...): the two-tensor input needs the staged-input fp16 kernel (unsupported shape / layout): run the two convolutions')
     if sft is not None and (planned is None or planned[0] not in (2, 3)):
         # unfused form: the CUDA-core / gather kernels have no SFT epilogue
         shift = conv2d(x, cw, stride=stride, pad=pad, pad_tl=pad_tl, out_hw=out_hw, act=act, pre=pre, upsample2=upsample2, exact=exact, fast=fast)

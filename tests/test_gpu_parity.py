@@ -226,6 +226,46 @@ def test_patch_embedding_conv_as_tensor_map_gather(S, p, Cin, tg):
     assert err < 2e-5 + 1e-8 * Cin * p * p, err
 
 
+def test_conv2d_two_input_tensors_in_one_accumulator(S):
+    """conv2d(x, cw, x2=...): conv(x, w[:, :C1]) + conv(x2, w[:, C1:]) accumulated in one tile (Fuse_sft_block's shift conv + the fuse_ms conv of the same scale),
+    with the SFT tail and a residual, x a channel slice of a wider buffer; against two fp64 torch convolutions."""
+    B, c, H, W = 2, 64, 40, 24
+    wide = rnd(B, 2 * c, H, W, seed=1); x2 = rnd(B, c, H, W, seed=2)
+    w1 = rnd(c, c, 3, 3, seed=3, scale=(c * 9) ** -0.5); w2 = rnd(c, c, 3, 3, seed=4, scale=(c * 9) ** -0.5)
+    b1, b2 = rnd(c, seed=5, scale=0.1), rnd(c, seed=6, scale=0.1)
+    dec, scale = rnd(B, c, H, W, seed=7), rnd(B, c, H, W, seed=8)
+    x1 = wide[:, c:]
+    conv = F.conv2d(x1.double(), w1.double(), b1.double(), padding=1) + F.conv2d(x2.double(), w2.double(), b2.double(), padding=1)
+    ref = dec.double() + (dec.double() * scale.double() + conv)
+    cw = S.ops.pack_conv(torch.cat([w1, w2], dim=1).cuda(), (b1 + b2).cuda())
+    y = S.ops.conv2d(nhwc(wide)[..., c:], cw, pad=1, res=nhwc(dec), sft=(nhwc(scale), 1.0), x2=nhwc(x2))
+    assert S.ops.LAST_CONV_KERNEL == 3
+    assert float((nchw(y).double() - ref).abs().max()) < 3e-5 * max(1.0, float(ref.abs().max()))
+    y2, (sc, sh) = S.ops.conv2d(nhwc(wide)[..., c:], cw, pad=1, res=nhwc(dec), sft=(nhwc(scale), 1.0), x2=nhwc(x2),
+                               gn=((1 + 0.1 * rnd(c, seed=9)).cuda(), (0.1 * rnd(c, seed=10)).cuda()))
+    sc2, sh2 = S.ops.groupnorm_stats(y2, (1 + 0.1 * rnd(c, seed=9)).cuda(), (0.1 * rnd(c, seed=10)).cuda(), 32, 1e-6)
+    assert torch.equal(y2, y) and float((sc - sc2).abs().max()) < 1e-5 * float(sc2.abs().max())
+
+
+def test_generator_fused_shift_and_fuse_ms_matches_two_convolutions(S, nets, clip, golden):
+    """generate() with the shift.2 + fuse_ms pair as one two-tensor convolution against the two-convolution form (same kernels otherwise)."""
+    g, me = nets
+    src, drv = clip
+    dm = {'deformation': golden['deformation1'].cuda(), 'occlusion_map': golden['occlusion1'].cuda()}
+    heat = S.ops.nchw_to_nhwc(O.gaussian_heatmaps(golden['kp_norm1_value'], 64, 64).cuda().contiguous())
+    feats = g.encode_source(src.unsqueeze(0).cuda())
+    outs = []
+    for ok in (True, False, True, False):                   # (the first round packs weight images lazily: its launch counts are not the steady state)
+        g._two_tensor_ok = ok
+        n0 = S.ops.launch_count()
+        outs.append((g.generate(feats, dm['deformation'], dm['occlusion_map'].view(1, 64, 64), heat, 1.0)['out'].clone(), S.ops.launch_count() - n0))
+    g._two_tensor_ok = True
+    outs = outs[2:]
+    assert outs[0][1] == outs[1][1] - 3                      # three convolution launches fewer (one per fused scale)
+    assert float((outs[0][0] - outs[1][0]).abs().max()) < 2e-5
+    assert float((nchw(outs[0][0]) - golden['out1']).abs().max()) < 1e-3
+
+
 def test_conv2d_concat_slices_patchify_and_bn_fold(S):
     """channel-slice views as input/output (torch.cat elimination), stride-p patch embedding, depth-to-space."""
     B, C, s, p = 2, 128, 64, 2
