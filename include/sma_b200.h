@@ -171,6 +171,12 @@ int sma_warp_occlude_fwd(const float* feat, int64_t feat_bstride, int B, int H, 
 /* bilinear align_corners=True resize of an NHWC tensor (F.interpolate call sites :390,414,418,571,671) */
 int sma_resize_bilinear_ac(const float* x, int B, int Hi, int Wi, int C, int64_t in_bstride, int in_ld,
                            float* y, int Ho, int Wo, int64_t out_bstride, int out_ld, sma_stream_t stream);
+/* A pointwise layer followed by a bilinear (align_corners=True) down-sampling, evaluated only where it is sampled: gather the 4 neighbours of every
+ * output sample into g (B, 2Ho, 2Wo, C) [g[2i+a][2j+b] = x[i_a(i)][j_b(j)]], run the layer on g, blend (B, 2Ho, 2Wo, C') -> y (B, Ho, Wo, C') with the weights and
+ * arithmetic order of sma_resize_bilinear_ac for an (Hi, Wi) source: bit-identical to layer-then-resize for a 1x1 conv + activation
+ * (to_context at the 256x256 scale, archs/appmotioncodebook_arch.py:416-418: a quarter of the pixels). */
+int sma_gather_bilinear4(const float* x, int B, int Hi, int Wi, int C, int64_t in_bstride, int in_ld, float* g, int Ho, int Wo, sma_stream_t stream);
+int sma_blend_bilinear4(const float* g, int B, int Hi, int Wi, int C, float* y, int Ho, int Wo, int64_t out_bstride, int out_ld, sma_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Stage 3: multi-head attention core softmax(Q K^T * scale [+mask]) V on projected tensors

@@ -52,6 +52,8 @@ SIGNATURES = {
     'sma_layernorm': ([_V, _I, _I, _V, _V, _F, _V, _I, _V, _V, _V], C.c_int),
     'sma_warp_occlude_fwd': ([_V, _L, _I, _I, _I, _I, _V, _V, _I, _I, _V, _V], C.c_int),
     'sma_resize_bilinear_ac': ([_V, _I, _I, _I, _I, _L, _I, _V, _I, _I, _L, _I, _V], C.c_int),
+    'sma_gather_bilinear4': ([_V, _I, _I, _I, _I, _L, _I, _V, _I, _I, _V], C.c_int),
+    'sma_blend_bilinear4': ([_V, _I, _I, _I, _I, _V, _I, _I, _L, _I, _V], C.c_int),
     'sma_mha_fwd': ([_V, _I, _V, _I, _V, _I, _L, _I, _I, _I, _I, _I, _F, _V, _V, _I, _I, _V], C.c_int),
     'sma_attn256_workspace_bytes': ([_I, _I, _I], C.c_int64),
     'sma_attn256_fwd': ([_V, _I, _V, _I, _V, _I, _L, _L, _I, _I, _I, _F, _V, _V, _I, _V], C.c_int),

@@ -523,9 +523,13 @@ class AppMotionCompFormer(ParamModule):
         flo = ops.conv2d(ops.im2col_small(flow_px, 2, 7, 3, 128), W['BasicMotionEncoder.convf1'], act='relu', fast=fs)
         ops.conv2d(flo, W['BasicMotionEncoder.convf2'], pad=1, act='relu', out=cf[..., 96:160], fast=fs)
         ops.conv2d(cf, W['BasicMotionEncoder.conv'], pad=1, act='relu', out=z[..., :126], fast=fs)
-        ctx = ops.conv2d(warp0, W[f'to_context.{int(math.log2(s0)) - 5}'], act='relu', fast=fs)
-        if s != fg:
-            ctx = ops.resize_ac(ctx, (fg, fg))
+        wc = W[f'to_context.{int(math.log2(s0)) - 5}']
+        if s >= 4 * fg:        # relu(conv1x1) then a 4x bilinear down-sampling: evaluate the pointwise layer only at the sampled neighbours (a quarter of the pixels), bit-identical
+            ctx = ops.blend_bil4(ops.conv2d(ops.gather_bil4(warp0, (fg, fg)), wc, act='relu', fast=fs), (s, s))
+        else:
+            ctx = ops.conv2d(warp0, wc, act='relu', fast=fs)
+            if s != fg:
+                ctx = ops.resize_ac(ctx, (fg, fg))
         ops.conv2d(ctx, W['refine.convc1'], pad=1, act='relu', out=z[..., 128:], fast=fs)
         f = ops.conv2d(z, W['refine.conv1o1'], pad=1, act='relu', fast=fs)                 # [flow branch 128 | occlusion branch 128]
         r = torch.empty((B, fg, fg, 4), device=dev, dtype=torch.float32)

@@ -125,7 +125,56 @@ __global__ void resize_ac4_kernel(const float* __restrict__ x, int Hi, int Wi, i
   }
 }
 
+// A pointwise layer (1x1 conv + activation) followed by a bilinear down-sampling only needs the layer at the four neighbours of every output
+// sample: gather those (out[2i + a][2j + b] = x[i_a(i)][j_b(j)], a / b = the lower / upper neighbour), run the layer on the 2Ho x 2Wo gather,
+// then blend with the SAME weights and arithmetic order as resize_ac4_kernel - bit-identical to layer-at-full-resolution + resize when the
+// layer treats pixels independently.  to_context at the 256^2 scale (appmotioncodebook_arch.py:416-418): a quarter of the pixels.
+__global__ void gather_bil4_kernel(const float* __restrict__ x, int Hi, int Wi, int C4, long long ibs, int ild, float* __restrict__ y, int Ho, int Wo, long long total) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % C4) * 4; long long pp = i / C4; int gx = (int)(pp % (2 * Wo)); long long t = pp / (2 * Wo); int gy = (int)(t % (2 * Ho)); int b = (int)(t / (2 * Ho));
+    const Bil by = bil_ac(gy >> 1, Hi, Ho), bx = bil_ac(gx >> 1, Wi, Wo);
+    const int iy = (gy & 1) ? by.i1 : by.i0, ix = (gx & 1) ? bx.i1 : bx.i0;
+    *reinterpret_cast<float4*>(y + (pp * C4) * 4 + c) = __ldg(reinterpret_cast<const float4*>(x + (long long)b * ibs + ((long long)iy * Wi + ix) * ild + c));
+  }
+}
+__global__ void blend_bil4_kernel(const float* __restrict__ g, int Hi, int Wi, int C4, float* __restrict__ y, int Ho, int Wo, long long obs, int old_, long long total) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % C4) * 4; long long pp = i / C4; int ox = (int)(pp % Wo); long long t = pp / Wo; int oy = (int)(t % Ho); int b = (int)(t / Ho);
+    const Bil by = bil_ac(oy, Hi, Ho), bx = bil_ac(ox, Wi, Wo);
+    const float* gb = g + ((((long long)b * 2 * Ho + 2 * oy) * (2 * Wo) + 2 * ox) * C4) * 4 + c;
+    const long long rowp = (long long)2 * Wo * C4 * 4;
+    const float4 v00 = __ldg(reinterpret_cast<const float4*>(gb)), v01 = __ldg(reinterpret_cast<const float4*>(gb + C4 * 4));
+    const float4 v10 = __ldg(reinterpret_cast<const float4*>(gb + rowp)), v11 = __ldg(reinterpret_cast<const float4*>(gb + rowp + C4 * 4));
+    const float w0y = 1.f - by.w1, w0x = 1.f - bx.w1;
+    float4 o;
+    o.x = w0y * (w0x * v00.x + bx.w1 * v01.x) + by.w1 * (w0x * v10.x + bx.w1 * v11.x);
+    o.y = w0y * (w0x * v00.y + bx.w1 * v01.y) + by.w1 * (w0x * v10.y + bx.w1 * v11.y);
+    o.z = w0y * (w0x * v00.z + bx.w1 * v01.z) + by.w1 * (w0x * v10.z + bx.w1 * v11.z);
+    o.w = w0y * (w0x * v00.w + bx.w1 * v01.w) + by.w1 * (w0x * v10.w + bx.w1 * v11.w);
+    *reinterpret_cast<float4*>(y + (long long)b * obs + ((long long)oy * Wo + ox) * old_ + c) = o;
+  }
+}
+
 }  // namespace
+
+extern "C" int sma_gather_bilinear4(const float* x, int B, int Hi, int Wi, int C, int64_t ibs, int ild, float* g, int Ho, int Wo, sma_stream_t stream) {
+  if (!x || !g || B <= 0 || Hi <= 0 || Wi <= 0 || C <= 0 || Ho <= 0 || Wo <= 0) return SMA_ERR_BAD_ARG;
+  if ((C & 3) || (ild & 3) || (ibs & 3) || ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(g)) & 15)) return SMA_ERR_UNSUPPORTED;
+  long long total = (long long)B * 4 * Ho * Wo * (C / 4);
+  long long blocks = (total + 255) / 256; if (blocks > kNumSMs * 32) blocks = kNumSMs * 32;
+  gather_bil4_kernel<<<(int)blocks, 256, 0, as_stream(stream)>>>(x, Hi, Wi, C / 4, ibs, ild, g, Ho, Wo, total);
+  SMA_LAUNCH_CHECK();
+  return SMA_OK;
+}
+extern "C" int sma_blend_bilinear4(const float* g, int B, int Hi, int Wi, int C, float* y, int Ho, int Wo, int64_t obs, int old_, sma_stream_t stream) {
+  if (!g || !y || B <= 0 || Hi <= 0 || Wi <= 0 || C <= 0 || Ho <= 0 || Wo <= 0) return SMA_ERR_BAD_ARG;
+  if ((C & 3) || (old_ & 3) || (obs & 3) || ((reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(y)) & 15)) return SMA_ERR_UNSUPPORTED;
+  long long total = (long long)B * Ho * Wo * (C / 4);
+  long long blocks = (total + 255) / 256; if (blocks > kNumSMs * 32) blocks = kNumSMs * 32;
+  blend_bil4_kernel<<<(int)blocks, 256, 0, as_stream(stream)>>>(g, Hi, Wi, C / 4, y, Ho, Wo, obs, old_, total);
+  SMA_LAUNCH_CHECK();
+  return SMA_OK;
+}
 
 extern "C" int sma_warp_occlude_fwd(const float* feat, int64_t fbs, int B, int H, int W, int C, const float* flow, const float* occ,
                                     int hf, int wf, float* out, sma_stream_t stream) {

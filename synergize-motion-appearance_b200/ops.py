@@ -450,6 +450,29 @@ def resize_ac(x: torch.Tensor, size: Tuple[int, int], out: Optional[torch.Tensor
     return out
 
 
+def gather_bil4(x: torch.Tensor, size: Tuple[int, int]) -> torch.Tensor:
+    """(B,Hi,Wi,C) -> (B,2Ho,2Wo,C): the four bilinear (align_corners=True) neighbours of every sample of a resize to `size`."""
+    lib = _lib.load()
+    B, Hi, Wi, Cc, ibs, ild = _nhwc(x)
+    Ho, Wo = size
+    g = torch.empty((B, 2 * Ho, 2 * Wo, Cc), device=x.device, dtype=torch.float32)
+    check(lib.sma_gather_bilinear4(x.data_ptr(), B, Hi, Wi, Cc, ibs, ild, g.data_ptr(), Ho, Wo, _stream()), 'sma_gather_bilinear4')
+    return g
+
+
+def blend_bil4(g: torch.Tensor, src_hw: Tuple[int, int], out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """(B,2Ho,2Wo,C) gathered neighbours (after a pointwise layer) -> (B,Ho,Wo,C): the bilinear blend of a resize from `src_hw`."""
+    lib = _lib.load()
+    assert g.is_contiguous()
+    B, H2, W2, Cc = g.shape
+    Ho, Wo = H2 // 2, W2 // 2
+    if out is None:
+        out = torch.empty((B, Ho, Wo, Cc), device=g.device, dtype=torch.float32)
+    _, _, _, _, obs, old = _nhwc(out)
+    check(lib.sma_blend_bilinear4(g.data_ptr(), B, src_hw[0], src_hw[1], Cc, out.data_ptr(), Ho, Wo, obs, old, _stream()), 'sma_blend_bilinear4')
+    return out
+
+
 def mha(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, key_mask: Optional[torch.Tensor] = None,
         scale: Optional[float] = None, out: Optional[torch.Tensor] = None, exact: bool = False, fast: bool = False) -> torch.Tensor:
     """q (B,L,E-view) ; k,v (B,S,E-view) or (S,E-view) shared by all frames.  Views may be column slices."""

@@ -266,6 +266,19 @@ def test_generator_fused_shift_and_fuse_ms_matches_two_convolutions(S, nets, cli
     assert float((nchw(outs[0][0]) - golden['out1']).abs().max()) < 1e-3
 
 
+def test_pointwise_layer_evaluated_only_where_the_resize_samples_it(S):
+    """relu(conv1x1(x)) followed by a 4x bilinear (align_corners=True) down-sampling == gather the four neighbours of every sample, run the layer on the gather,
+    blend with the resize kernel's weights and arithmetic order: bit-identical (to_context at the 256x256 scale)."""
+    B, C, Hs, Ho, Cout = 2, 64, 128, 32, 192
+    x = nhwc(rnd(B, C, Hs, Hs, seed=1))
+    cw = S.ops.pack_conv(rnd(Cout, C, 1, 1, seed=2, scale=C ** -0.5).cuda(), rnd(Cout, seed=3, scale=0.1).cuda())
+    full = S.ops.resize_ac(S.ops.conv2d(x, cw, act='relu'), (Ho, Ho))
+    g = S.ops.gather_bil4(x, (Ho, Ho))
+    assert tuple(g.shape) == (B, 2 * Ho, 2 * Ho, C)
+    sparse = S.ops.blend_bil4(S.ops.conv2d(g, cw, act='relu'), (Hs, Hs))
+    assert torch.equal(full, sparse)
+
+
 def test_conv2d_concat_slices_patchify_and_bn_fold(S):
     """channel-slice views as input/output (torch.cat elimination), stride-p patch embedding, depth-to-space."""
     B, C, s, p = 2, 128, 64, 2
