@@ -168,6 +168,11 @@ int sma_layernorm(const float* x, int rows, int E, const float* gamma, const flo
  * ------------------------------------------------------------------------------------------- */
 int sma_warp_occlude_fwd(const float* feat, int64_t feat_bstride, int B, int H, int W, int C,
                          const float* flow, const float* occ, int hf, int wf, float* out, sma_stream_t stream);
+/* the same warp evaluated only at the pixels a following bilinear (align_corners=True) down-sampling to (Hg, Wg) reads: out (B, 2Hg, 2Wg, C),
+ * out[2i+a][2j+b] = warp at pixel (i_a(i), j_b(j)) - the layout sma_blend_bilinear4 consumes (Hg = Wg = 0: the full warp).  At the 256x256 scale
+ * the un-occluded query warp is only ever sampled (by the 32x32 query resize and by to_context's 64x64 resize): it is never materialised. */
+int sma_warp_occlude_gather_fwd(const float* feat, int64_t feat_bstride, int B, int H, int W, int C, const float* flow, const float* occ,
+                                int hf, int wf, int Hg, int Wg, float* out, sma_stream_t stream);
 /* bilinear align_corners=True resize of an NHWC tensor (F.interpolate call sites :390,414,418,571,671) */
 int sma_resize_bilinear_ac(const float* x, int B, int Hi, int Wi, int C, int64_t in_bstride, int in_ld,
                            float* y, int Ho, int Wo, int64_t out_bstride, int out_ld, sma_stream_t stream);

@@ -51,6 +51,7 @@ SIGNATURES = {
     'sma_affine_act': ([_V, _I, _I, _I, _L, _I, _V, _V, _I, _V, _L, _I, _V], C.c_int),
     'sma_layernorm': ([_V, _I, _I, _V, _V, _F, _V, _I, _V, _V, _V], C.c_int),
     'sma_warp_occlude_fwd': ([_V, _L, _I, _I, _I, _I, _V, _V, _I, _I, _V, _V], C.c_int),
+    'sma_warp_occlude_gather_fwd': ([_V, _L, _I, _I, _I, _I, _V, _V, _I, _I, _I, _I, _V, _V], C.c_int),
     'sma_resize_bilinear_ac': ([_V, _I, _I, _I, _I, _L, _I, _V, _I, _I, _L, _I, _V], C.c_int),
     'sma_gather_bilinear4': ([_V, _I, _I, _I, _I, _L, _I, _V, _I, _I, _V], C.c_int),
     'sma_blend_bilinear4': ([_V, _I, _I, _I, _I, _V, _I, _I, _L, _I, _V], C.c_int),

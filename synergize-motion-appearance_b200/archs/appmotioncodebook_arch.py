@@ -495,7 +495,7 @@ class AppMotionCompFormer(ParamModule):
     # ------------------------------------------------------------------------------------------
     # stage 3m: motion codebook compensation (appmotioncodebook_arch.py:373-427, 129-168)
     # ------------------------------------------------------------------------------------------
-    def _motion_comp(self, m_prev, occ_prev, warp0, qcat, s, collect=None):
+    def _motion_comp(self, m_prev, occ_prev, warp0, qcat, s, collect=None, warp0g=None):
         W, T = self._packed, self._T
         B = m_prev.shape[0]
         dev = m_prev.device
@@ -525,7 +525,8 @@ class AppMotionCompFormer(ParamModule):
         ops.conv2d(cf, W['BasicMotionEncoder.conv'], pad=1, act='relu', out=z[..., :126], fast=fs)
         wc = W[f'to_context.{int(math.log2(s0)) - 5}']
         if s >= 4 * fg:        # relu(conv1x1) then a 4x bilinear down-sampling: evaluate the pointwise layer only at the sampled neighbours (a quarter of the pixels), bit-identical
-            ctx = ops.blend_bil4(ops.conv2d(ops.gather_bil4(warp0, (fg, fg)), wc, act='relu', fast=fs), (s, s))
+            g4 = warp0g if warp0g is not None else ops.gather_bil4(warp0, (fg, fg))
+            ctx = ops.blend_bil4(ops.conv2d(g4, wc, act='relu', fast=fs), (s, s))
         else:
             ctx = ops.conv2d(warp0, wc, act='relu', fast=fs)
             if s != fg:
@@ -587,11 +588,19 @@ class AppMotionCompFormer(ParamModule):
         def compensate(s, out=None):
             nonlocal occ_prev
             f = src(s)
-            warp0 = ops.warp_occlude(f, motions[-1], None)
-            w32 = warp0 if s == tg else ops.resize_ac(warp0, (tg, tg))
+            if collect is None and s >= 4 * fg:
+                # the un-occluded query warp of this scale is only ever SAMPLED (32x32 query resize, to_context's 64x64 resize): evaluate it at those
+                # samples' neighbours instead of materialising s x s pixels (bit-identical: the blend uses the resize kernel's weights and order)
+                warp0 = None
+                w32 = ops.blend_bil4(ops.warp_occlude_gather(f, motions[-1], None, (tg, tg)), (s, s))
+                warp0g = ops.warp_occlude_gather(f, motions[-1], None, (fg, fg))
+            else:
+                warp0 = ops.warp_occlude(f, motions[-1], None)
+                w32 = warp0 if s == tg else ops.resize_ac(warp0, (tg, tg))
+                warp0g = None
             ops.conv2d(w32, W[f'warped_source_enc_{s // R}'], act='relu', out=qk[..., :Em])
             ops.conv2d(qk, W['motion_query_enc_1'], out=qcat[..., Em:])
-            m_com, occ, r = self._motion_comp(motions[-1], occ_prev, warp0, qcat, s, collect)
+            m_com, occ, r = self._motion_comp(motions[-1], occ_prev, warp0, qcat, s, collect, warp0g=warp0g)
             motions.append(m_com); occs.append(occ); residuals.append(r)
             occ_prev = occ
             warped = ops.warp_occlude(f, m_com, occ)

@@ -37,10 +37,15 @@ __device__ __forceinline__ F8 ldg256(const float* p) {
 template <int VEC>
 __global__ void warp_occlude_kernel(const float* __restrict__ feat, long long fbs, int B, int H, int W, int C,
                                     const float* __restrict__ flow, const float* __restrict__ occ, int hf, int wf,
-                                    float* __restrict__ out, long long total4) {
+                                    float* __restrict__ out, long long total4, int Hg, int Wg) {
   const int C4 = C / VEC;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
-    int c4 = (int)(i % C4); long long pp = i / C4; int x = (int)(pp % W); long long t = pp / W; int y = (int)(t % H); int b = (int)(t / H);
+    int c4 = (int)(i % C4); long long pp = i / C4; int x, y, b;
+    if (Hg) {      // gathered output (B, 2 Hg, 2 Wg, C): only the pixels a following bilinear down-sampling to Hg x Wg reads (its four neighbours per sample)
+      const int qx = (int)(pp % (2 * Wg)); const long long t = pp / (2 * Wg); const int qy = (int)(t % (2 * Hg)); b = (int)(t / (2 * Hg));
+      const Bil sy = bil_ac(qy >> 1, H, Hg), sx = bil_ac(qx >> 1, W, Wg);
+      y = (qy & 1) ? sy.i1 : sy.i0; x = (qx & 1) ? sx.i1 : sx.i0;
+    } else { x = (int)(pp % W); const long long t = pp / W; y = (int)(t % H); b = (int)(t / H); }
     // resized flow / occlusion at (y,x)
     float gx, gy, oc = 1.f;
     if (hf == H && wf == W) {
@@ -176,17 +181,28 @@ extern "C" int sma_blend_bilinear4(const float* g, int B, int Hi, int Wi, int C,
   return SMA_OK;
 }
 
+extern "C" int sma_warp_occlude_gather_fwd(const float* feat, int64_t fbs, int B, int H, int W, int C, const float* flow, const float* occ,
+                                           int hf, int wf, int Hg, int Wg, float* out, sma_stream_t stream);
 extern "C" int sma_warp_occlude_fwd(const float* feat, int64_t fbs, int B, int H, int W, int C, const float* flow, const float* occ,
                                     int hf, int wf, float* out, sma_stream_t stream) {
   if (!feat || !flow || !out || B <= 0 || H <= 1 || W <= 1 || C <= 0 || hf <= 1 || wf <= 1) return SMA_ERR_BAD_ARG;
   if ((C & 3) || (fbs & 3) || ((reinterpret_cast<uintptr_t>(feat) | reinterpret_cast<uintptr_t>(out)) & 15) ||
       (reinterpret_cast<uintptr_t>(flow) & 7))
     return SMA_ERR_UNSUPPORTED;
+  return sma_warp_occlude_gather_fwd(feat, fbs, B, H, W, C, flow, occ, hf, wf, 0, 0, out, stream);
+}
+
+extern "C" int sma_warp_occlude_gather_fwd(const float* feat, int64_t fbs, int B, int H, int W, int C, const float* flow, const float* occ,
+                                           int hf, int wf, int Hg, int Wg, float* out, sma_stream_t stream) {
+  if (!feat || !flow || !out || B <= 0 || H <= 1 || W <= 1 || C <= 0 || hf <= 1 || wf <= 1 || Hg < 0 || Wg < 0 || (Hg == 0) != (Wg == 0)) return SMA_ERR_BAD_ARG;
+  if ((C & 3) || (fbs & 3) || ((reinterpret_cast<uintptr_t>(feat) | reinterpret_cast<uintptr_t>(out)) & 15) ||
+      (reinterpret_cast<uintptr_t>(flow) & 7))
+    return SMA_ERR_UNSUPPORTED;
   const bool v8 = (C & 7) == 0 && (fbs & 7) == 0 && ((reinterpret_cast<uintptr_t>(feat) | reinterpret_cast<uintptr_t>(out)) & 31) == 0;
-  long long total4 = (long long)B * H * W * (C / (v8 ? 8 : 4));
+  long long total4 = (long long)B * (Hg ? 4LL * Hg * Wg : (long long)H * W) * (C / (v8 ? 8 : 4));
   long long blocks = (total4 + 255) / 256; if (blocks > kNumSMs * 32) blocks = kNumSMs * 32;
-  if (v8) warp_occlude_kernel<8><<<(int)blocks, 256, 0, as_stream(stream)>>>(feat, fbs, B, H, W, C, flow, occ, hf, wf, out, total4);
-  else warp_occlude_kernel<4><<<(int)blocks, 256, 0, as_stream(stream)>>>(feat, fbs, B, H, W, C, flow, occ, hf, wf, out, total4);
+  if (v8) warp_occlude_kernel<8><<<(int)blocks, 256, 0, as_stream(stream)>>>(feat, fbs, B, H, W, C, flow, occ, hf, wf, out, total4, Hg, Wg);
+  else warp_occlude_kernel<4><<<(int)blocks, 256, 0, as_stream(stream)>>>(feat, fbs, B, H, W, C, flow, occ, hf, wf, out, total4, Hg, Wg);
   SMA_LAUNCH_CHECK();
   return SMA_OK;
 }

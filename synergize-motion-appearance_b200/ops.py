@@ -450,6 +450,19 @@ def resize_ac(x: torch.Tensor, size: Tuple[int, int], out: Optional[torch.Tensor
     return out
 
 
+def warp_occlude_gather(feat: torch.Tensor, flow: torch.Tensor, occ: Optional[torch.Tensor], size: Tuple[int, int]) -> torch.Tensor:
+    """warp_occlude evaluated only at the four bilinear neighbours of every sample of a later resize to `size`: (B,2Ho,2Wo,C), the layout blend_bil4 consumes."""
+    lib = _lib.load()
+    B, H, W, Cc, bs, ld = _nhwc(feat)
+    assert ld == Cc and flow.is_contiguous() and flow.shape[0] == B
+    hf, wf = flow.shape[1], flow.shape[2]
+    out = torch.empty((B, 2 * size[0], 2 * size[1], Cc), device=feat.device, dtype=torch.float32)
+    with _Prof('warp', 11.0 * B * 4 * size[0] * size[1] * Cc, 8.0 * B * 4 * size[0] * size[1] * Cc):
+        check(lib.sma_warp_occlude_gather_fwd(feat.data_ptr(), bs, B, H, W, Cc, flow.data_ptr(), _ptr(occ), hf, wf, size[0], size[1], out.data_ptr(), _stream()),
+              'sma_warp_occlude_gather_fwd')
+    return out
+
+
 def gather_bil4(x: torch.Tensor, size: Tuple[int, int]) -> torch.Tensor:
     """(B,Hi,Wi,C) -> (B,2Ho,2Wo,C): the four bilinear (align_corners=True) neighbours of every sample of a resize to `size`."""
     lib = _lib.load()

@@ -374,6 +374,20 @@ def test_warp_occlude_matches_oracle(S, C, s):
     assert float((got1 - ref1).abs().max()) < tol
 
 
+def test_warp_evaluated_only_at_the_samples_of_a_later_resize(S):
+    """sma_warp_occlude_gather_fwd: the warp at the four neighbours of every sample of a later bilinear down-sampling == gather of the full warp
+    (bit-identical), and blending it == resizing the full warp (bit-identical): the 256x256 query warp is never materialised."""
+    B, C, s, ho = 2, 64, 128, 32
+    feat = nhwc(rnd(1, C, s, s, seed=1)).expand(B, -1, -1, -1)
+    flow = (O.coord_grid(64, 64).unsqueeze(0) + 0.05 * rnd(B, 64, 64, 2, seed=2)).contiguous().cuda()
+    occ = torch.rand(B, 64, 64, generator=torch.Generator().manual_seed(3)).cuda()
+    for oc in (None, occ):
+        full = S.ops.warp_occlude(feat, flow, oc)
+        g = S.ops.warp_occlude_gather(feat, flow, oc, (ho, ho))
+        assert torch.equal(g, S.ops.gather_bil4(full, (ho, ho)))
+        assert torch.equal(S.ops.blend_bil4(g, (s, s)), S.ops.resize_ac(full, (ho, ho)))
+
+
 def test_warp_identity_and_linearity_full_size(S):
     """Size-independent properties at the BASELINE batch (64 frames): identity flow reproduces the source bit-for-bit,
     out-of-range flow gives zeros, and the warp is linear in the features."""
