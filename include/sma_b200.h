@@ -112,6 +112,9 @@ typedef struct sma_conv_desc {
      conv(x, w[:, :Cin1]) + conv(x2, w[:, Cin1:]) in one accumulator - Fuse_sft_block's shift conv and the fuse_ms conv of the same scale
      (appmotioncodebook_arch.py:50-51,737-738).  TMA-staged fp16 kernel only (else SMA_ERR_UNSUPPORTED: run the two convolutions). */
   const float* x2;  int64_t in2_bstride;  int in2_ld;  int Cin1;
+  int x2_k1;                     /* 1: x2 enters through a 1x1 conv (the centre tap only): a ResBlock's conv2 (k x k over x, with its GroupNorm prologue, which then
+                                    applies to x alone) + its 1x1 skip conv over the block input (archs/vqgan_arch.py:185-191).  The weight image is then packed
+                                    as a 1x1 conv over the rows [x: channel chunk outer, tap inner, 64 channels][x2: 64-channel chunks] */
 } sma_conv_desc;
 
 int sma_conv2d_fwd(sma_conv_desc* d, sma_stream_t stream);

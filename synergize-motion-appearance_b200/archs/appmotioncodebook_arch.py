@@ -126,6 +126,7 @@ class AppMotionCompFormer(ParamModule):
         object.__setattr__(gen, '_owner', weakref.ref(self))      # not a registered sub-module: no cycle in the module tree
         self._src_cache = None
         self._two_tensor_ok = os.environ.get('SMA_NO_TWO', '0') != '1'      # (env: A/B on one box)
+        self._skip_fused_ok = os.environ.get('SMA_NO_SKIPFUSE', '0') != '1'
         if ae_path is not None:
             self.load_state_dict(torch.load(ae_path, map_location='cpu')['params_ema'])
         for module in (fix_modules or []):
@@ -322,6 +323,15 @@ class AppMotionCompFormer(ParamModule):
         W = self._packed
         s1, h1 = stats if stats is not None else self._gn(name + '.norm1', x)
         h, (s2, h2) = ops.conv2d(x, W[name + '.conv1'], pad=1, pre=(s1, h1, 'swish'), fast=fast, gn=self._gnp(name + '.norm2'))
+        if cin != cout and self._skip_fused_ok and cin % 64 == 0 and cout % 64 == 0 and cout <= 128:
+            # conv2 (3x3 over h, GroupNorm + swish prologue) and the 1x1 skip conv over the block input in ONE accumulator: the skip tensor is never written / re-read
+            key = name + '.conv2+skip'
+            if key not in W:
+                W[key] = ops.pack_conv_plus_1x1(W[name + '.conv2'], W[name + '.conv_out'])
+            try:
+                return ops.conv2d(h, W[key], pad=1, pre=(s2, h2, 'swish'), x2=x, x2_1x1=True, out=out, fast=fast, gn=want)
+            except ops._lib.SmaError:
+                self._skip_fused_ok = False                  # (a layout the staged-input kernel declines: two convolutions from now on)
         skip = x if cin == cout else ops.conv2d(x, W[name + '.conv_out'], fast=fast)
         return ops.conv2d(h, W[name + '.conv2'], pad=1, pre=(s2, h2, 'swish'), res=skip, out=out, fast=fast, gn=want)
 

@@ -326,6 +326,10 @@ struct Tc2P {
   alignas(64) CUtensorMap tmap;
   alignas(64) CUtensorMap tmap2;   // second input tensor (cpt1 < cpt): channel chunks [cpt1, cpt) are read from it (two convolutions over different tensors summed in one accumulator)
   int cpt1;
+  int pre_ld;                 // row pitch of pre_scale / pre_shift (= channels of the first input tensor)
+  int x2_center;              // the second tensor's chunks contribute through the CENTRE tap only (a 1x1 conv over x2 added to a k x k conv over x: a ResBlock's
+                              // conv2 + its 1x1 skip conv); the weight image then holds one blob per such chunk; nblob = weight blobs per (tile, N tile)
+  int nblob;
 };
 
 // ACT: epilogue activation; PRE: -1 no prologue, else the prologue activation applied after scale/shift (compile-time so that the
@@ -665,8 +669,10 @@ __global__ void __launch_bounds__(TMA ? V2_THREADS_TMA : V2_THREADS, 1) conv_tc2
           const uint64_t dah0 = a_desc_hi_bits | (uint64_t)((a_hi & 0x3FFFFu) >> 4);
           const uint64_t dal0 = a_desc_hi_bits | (uint64_t)(((a_hi + (uint32_t)p.a_img_bytes) & 0x3FFFFu) >> 4);
           uint32_t roff = 0;
+          const bool centre_only = p.x2_center && cc >= p.cpt1;
           for (int ky = 0; ky < p.kh; ky++, roff += row_step) {
             for (int kx = 0; kx < p.kw; kx++) {
+              if (centre_only && (ky != p.pad_t || kx != p.pad_l)) continue;
               mbar_wait(b_full(sb), phb);
               tc_fence_after();
               const uint64_t toff = (uint64_t)(roff + (uint32_t)kx * 8u);
@@ -712,7 +718,7 @@ __global__ void __launch_bounds__(TMA ? V2_THREADS_TMA : V2_THREADS, 1) conv_tc2
       // must not hold back a free staging slot and vice versa), so that a 16th warp is not needed for the tensor loads (16 warps = 128 registers).
       const uint32_t bytes = (uint32_t)(p.passes >= 2 ? b_stage_bytes : p.b_img_bytes);
       const uint64_t tm1 = reinterpret_cast<uint64_t>(&p.tmap), tm2 = reinterpret_cast<uint64_t>(&p.tmap2);
-      const int nblob = p.cpt * p.taps;
+      const int nblob = p.nblob;
       auto test = [&](uint32_t bar, uint32_t parity) -> bool {
         uint32_t ok;
         asm volatile("{\n.reg .pred p;\nmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
@@ -773,8 +779,8 @@ __global__ void __launch_bounds__(TMA ? V2_THREADS_TMA : V2_THREADS, 1) conv_tc2
       int jt = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         const int nt = tile % p.ntiles_n;
-        const char* src = reinterpret_cast<const char*>(p.wtc) + (long long)nt * p.cpt * p.taps * b_stage_bytes;
-        const int nblob = p.cpt * p.taps;
+        const char* src = reinterpret_cast<const char*>(p.wtc) + (long long)nt * p.nblob * b_stage_bytes;
+        const int nblob = p.nblob;
         for (int j = 0; j < nblob; j++, jt++) {
           const int sb = jt % p.SB; const uint32_t phb = (jt / p.SB) & 1;
           mbar_wait(b_empty(sb), phb ^ 1u);
@@ -799,12 +805,13 @@ __global__ void __launch_bounds__(TMA ? V2_THREADS_TMA : V2_THREADS, 1) conv_tc2
         const int sa = it % p.SA; const uint32_t pha = (it / p.SA) & 1;
         const uint32_t a_hi = a_ring + (uint32_t)sa * p.a_stage_bytes, a_lo = a_hi + p.a_img_bytes;
         const int c = cc * KCH + cq * 8;
+        const bool pro = PRE >= 0 && cc < p.cpt1;                // the prologue belongs to the first input tensor (pre_scale / pre_shift are (B, Cin1))
         float4 sc0 = make_float4(1.f, 1.f, 1.f, 1.f), sh0 = make_float4(0.f, 0.f, 0.f, 0.f), sc1 = sc0, sh1 = sh0;
-        if (PRE >= 0) {
-          sc0 = __ldg(reinterpret_cast<const float4*>(p.pre_scale + (long long)b * p.Cin + c));
-          sc1 = __ldg(reinterpret_cast<const float4*>(p.pre_scale + (long long)b * p.Cin + c + 4));
-          sh0 = __ldg(reinterpret_cast<const float4*>(p.pre_shift + (long long)b * p.Cin + c));
-          sh1 = __ldg(reinterpret_cast<const float4*>(p.pre_shift + (long long)b * p.Cin + c + 4));
+        if (pro) {
+          sc0 = __ldg(reinterpret_cast<const float4*>(p.pre_scale + (long long)b * p.pre_ld + c));
+          sc1 = __ldg(reinterpret_cast<const float4*>(p.pre_scale + (long long)b * p.pre_ld + c + 4));
+          sh0 = __ldg(reinterpret_cast<const float4*>(p.pre_shift + (long long)b * p.pre_ld + c));
+          sh1 = __ldg(reinterpret_cast<const float4*>(p.pre_shift + (long long)b * p.pre_ld + c + 4));
         }
         mbar_wait(a_empty(sa), pha ^ 1u);
         if (p.dbg & 2) { mbar_arrive(a_full(sa)); continue; }          // timing experiment: no halo traffic, no conversion
@@ -820,7 +827,7 @@ __global__ void __launch_bounds__(TMA ? V2_THREADS_TMA : V2_THREADS, 1) conv_tc2
             asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(u0.x), "=f"(u0.y), "=f"(u0.z), "=f"(u0.w) : "r"(src + (uint32_t)swap * 16u));
             asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(u1.x), "=f"(u1.y), "=f"(u1.z), "=f"(u1.w) : "r"(src + 16u - (uint32_t)swap * 16u));
             float4 t0 = swap ? u1 : u0, t1 = swap ? u0 : u1;
-            if (PRE >= 0) {
+            if (pro) {
               bool ok;                                         // zero padding applies AFTER the normalisation: pixels outside the image stay zero
               if (p.flat) ok = ty0 + hp < p.HoWo;
               else { const int hy = hp / p.halo_w, hx = hp - hy * p.halo_w; ok = (unsigned)(ty0 + hy - p.pad_t) < (unsigned)Hv && (unsigned)(tx0 + hx - p.pad_l) < (unsigned)Wv; }
@@ -1157,11 +1164,14 @@ static int conv_tc2_try(sma_conv_desc* d, cudaStream_t st, bool f16) {
   if (patch) { p.cpt *= p.taps; p.taps = 1; p.kh = p.kw = 1; }       // the kernel sees a 1x1 conv over Cin * p * p channels (weight image order: channel chunk outer, tap inner)
   p.cpt1 = p.cpt;
   if (d->x2) {        // two input tensors: staged-input mode only, plain inputs (no prologue), both channel counts multiples of 64, same geometry
-    if (!f16 || patch || flat || d->pre_scale || d->upsample2 || d->Cin1 <= 0 || d->Cin1 >= d->Cin || (d->Cin1 % 64) || ((d->Cin - d->Cin1) % 64) ||
+    if (!f16 || patch || flat || (d->pre_scale && !d->x2_k1) || d->upsample2 || d->Cin1 <= 0 || d->Cin1 >= d->Cin || (d->Cin1 % 64) || ((d->Cin - d->Cin1) % 64) ||
         (d->in2_ld & 3) || (d->in2_bstride & 3) || d->in2_bstride == 0 || d->in_bstride == 0 || (reinterpret_cast<uintptr_t>(d->x2) & 15))
       return SMA_ERR_UNSUPPORTED;
     p.cpt1 = d->Cin1 / 64;
   }
+  p.pre_ld = d->x2 ? d->Cin1 : d->Cin;
+  p.x2_center = (d->x2 && d->x2_k1) ? 1 : 0;
+  p.nblob = p.x2_center ? p.cpt1 * p.taps + (p.cpt - p.cpt1) : p.cpt * p.taps;
   p.passes = (d->precision == SMA_PREC_TF32 || d->precision == SMA_PREC_F16) ? 1 : (f16 && d->precision == SMA_PREC_F16X2) ? 2 : 3;
   p.flat = flat ? 1 : 0;
   if (flat) { p.tiles_x = 1; p.tiles_per_img = (p.HoWo + BM - 1) / BM; p.halo_w = 8; p.HP = BM; }
@@ -1207,7 +1217,7 @@ static int conv_tc2_try(sma_conv_desc* d, cudaStream_t st, bool f16) {
   p.res_pipe = (d->res && d->act == SMA_ACT_NONE && d->d2s <= 1 && (d->Cout & 7) == 0 && (d->out_ld & 7) == 0 && (d->out_bstride & 7) == 0 &&
                 (reinterpret_cast<uintptr_t>(d->y) & 31) == 0 && (d->res_ld & 7) == 0 && (d->res_bstride & 7) == 0 &&
                 (reinterpret_cast<uintptr_t>(d->res) & 31) == 0 && !(d->tc_variant & 512)) ? 1 : 0;
-  const int main_adds = p.cpt * p.taps * 4 * (p.fuse ? 1 : p.passes);
+  const int main_adds = p.nblob * 4 * (p.fuse ? 1 : p.passes);
   p.acc_corr = (d->tc_variant & 256) ? 1.f : 1.f + 1.6e-8f * (float)main_adds;
   p.dbg = (d->tc_variant >> 1) & 7;
   // fused GroupNorm partial sums: only where the 256-bit epilogue runs (every lane then walks the same column blocks) and the output is the whole

@@ -89,6 +89,7 @@ class ConvW:
     plans: Optional[dict] = None             # launch signature -> (kernel, nt) as reported by the library's plan mode
     _slices: Optional[dict] = None           # cache of cols() results
     dirty: bool = False                      # an image was packed since the last packcache save
+    pack_dims: Optional[tuple] = None        # (Cin, kh, kw) the tensor-core image packers see when they differ from the conv geometry (pack_conv_plus_1x1)
 
     def image(self, kind: str, nt: int = 0) -> Optional[torch.Tensor]:
         global PACK_EVENTS
@@ -148,11 +149,12 @@ def _pack_tc(cw: 'ConvW', nt: int = 0) -> Optional[torch.Tensor]:
 
 def _pack_tc16(cw: 'ConvW') -> Optional[torch.Tensor]:
     lib = _lib.load()
-    n = lib.sma_conv_weight_tc16_floats(cw.Cout, cw.Cin, cw.kh, cw.kw)
+    Cin, kh, kw = cw.pack_dims or (cw.Cin, cw.kh, cw.kw)
+    n = lib.sma_conv_weight_tc16_floats(cw.Cout, Cin, kh, kw)
     if n <= 0:
         return None
     out = torch.empty((n,), device=cw.w.device, dtype=torch.float32)
-    check(lib.sma_pack_conv_weight_tc16(cw.w.data_ptr(), cw.w.stride(0), cw.Cout, cw.Cin, cw.kh, cw.kw, out.data_ptr(), _stream()),
+    check(lib.sma_pack_conv_weight_tc16(cw.w.data_ptr(), cw.w.stride(0), cw.Cout, Cin, kh, kw, out.data_ptr(), _stream()),
           'sma_pack_conv_weight_tc16')
     return out
 
@@ -194,6 +196,18 @@ def pack_conv(weight: torch.Tensor, bias: Optional[torch.Tensor], bn: Optional[d
     check(lib.sma_pack_conv_weight(_ptr(w), _ptr(b), Cout, Cin, kh, kw, _ptr(g), _ptr(be), _ptr(mu), _ptr(var), eps,
                                    _ptr(wp), ldw, _ptr(bo), _stream()), 'sma_pack_conv_weight')
     return ConvW(wp, None if bo is None else bo[:Cout], Cout, Cin, kh, kw)
+
+
+def pack_conv_plus_1x1(cw3: ConvW, cw1: ConvW) -> ConvW:
+    """A k x k conv over x (cw3) and a 1x1 conv over x2 (cw1) summed in one accumulator (conv2d(..., x2=, x2_1x1=True)): a ResBlock's conv2 + its skip
+    conv.  The weight rows are laid out in the order the kernel consumes them - x: 64-channel chunk outer, tap inner; then x2's 64-channel chunks - and
+    packed as ONE 1x1 conv of that depth, so that both parts share the per-output-channel power-of-two scaling of the fp16 image."""
+    assert cw1.kh == 1 and cw1.kw == 1 and cw3.Cout == cw1.Cout and cw3.Cin % 64 == 0 and cw1.Cin % 64 == 0
+    taps, c = cw3.kh * cw3.kw, cw3.Cin
+    idx = torch.cat([t * c + cc * 64 + torch.arange(64) for cc in range(c // 64) for t in range(taps)]).to(cw3.w.device)
+    w = torch.cat([cw3.w.index_select(0, idx), cw1.w], dim=0).contiguous()
+    bias = None if (cw3.bias is None and cw1.bias is None) else ((0 if cw3.bias is None else cw3.bias) + (0 if cw1.bias is None else cw1.bias)).contiguous()
+    return ConvW(w, bias, cw3.Cout, cw3.Cin + cw1.Cin, cw3.kh, cw3.kw, pack_dims=(w.shape[0], 1, 1))
 
 
 def pack_conv_cat(weights, biases, pad_cin: int = 0) -> ConvW:
@@ -248,7 +262,7 @@ def conv2d(x: torch.Tensor, cw: ConvW, *, stride: int = 1, pad: int = 0, pad_tl:
            pre: Optional[Tuple[torch.Tensor, torch.Tensor, str]] = None, res: Optional[torch.Tensor] = None,
            upsample2: bool = False, d2s: int = 0, out_nchw: bool = False, exact: bool = False, fast: bool = False,
            sft: Optional[Tuple[torch.Tensor, float]] = None, gn: Optional[Tuple[torch.Tensor, torch.Tensor]] = None,
-           x2: Optional[torch.Tensor] = None):
+           x2: Optional[torch.Tensor] = None, x2_1x1: bool = False):
     """`exact`: force the CUDA-core fp32 kernel; `fast`: allow single-pass TF32 on the tensor cores (layers whose
     contribution to the output error budget was measured to be negligible); default: 3xTF32 (fp32-faithful).
     `sft=(scale, w)`: Fuse_sft_block tail, y = res + w*(res*scale + conv(x)) (needs `res`): fused into the epilogue of the persistent
@@ -279,7 +293,7 @@ def conv2d(x: torch.Tensor, cw: ConvW, *, stride: int = 1, pad: int = 0, pad_tl:
     d.Cout, d.kh, d.kw, d.stride, d.pad_t, d.pad_l = cw.Cout, cw.kh, cw.kw, stride, pt, pl
     d.upsample2 = 1 if upsample2 else 0
     if x2 is not None:
-        d.x2, d.in2_bstride, d.in2_ld, d.Cin1 = x2.data_ptr(), ibs2, ild2, Cin1
+        d.x2, d.in2_bstride, d.in2_ld, d.Cin1, d.x2_k1 = x2.data_ptr(), ibs2, ild2, Cin1, 1 if x2_1x1 else 0
     if pre is not None:
         d.pre_scale, d.pre_shift, d.pre_act = pre[0].data_ptr(), pre[1].data_ptr(), ACT[pre[2]]
     if out_nchw:
@@ -326,7 +340,7 @@ def conv2d(x: torch.Tensor, cw: ConvW, *, stride: int = 1, pad: int = 0, pad_tl:
             key = (B, Hi, Wi, stride, pt, pl, upsample2, Ho, Wo, out_nchw, d2s, d.precision, TC_VARIANT, x.data_ptr() & 15, ild & 3, ibs & 3,
                    pre is not None, sft is not None, 0 if res is None else (d.res_ld & 7, d.res_bstride & 7), d.out_ld & 7, d.out_bstride & 7,
                    d.gn_want, out.data_ptr() & 31, 0 if res is None else res.data_ptr() & 31,
-                   None if x2 is None else (Cin1, ild2 & 3, ibs2 & 3, x2.data_ptr() & 15))
+                   None if x2 is None else (Cin1, ild2 & 3, ibs2 & 3, x2.data_ptr() & 15, x2_1x1))
             if cw.plans is None:
                 cw.plans = {}
             planned = cw.plans.get(key)

@@ -72,7 +72,7 @@ def state_hash(module) -> str:
 
 def _convw_to_blob(cw: ops.ConvW) -> dict:
     return {'__convw__': True, 'w': cw.w.detach().cpu(), 'bias': None if cw.bias is None else cw.bias.detach().cpu(),
-            'dims': (cw.Cout, cw.Cin, cw.kh, cw.kw),
+            'dims': (cw.Cout, cw.Cin, cw.kh, cw.kw), 'pack_dims': cw.pack_dims,
             'images': {k: (None if t is None else t.detach().cpu()) for k, t in (cw.images or {}).items()},
             'plans': dict(cw.plans or {}),
             'slices': {k: {'images': {ik: (None if t is None else t.detach().cpu()) for ik, t in (c.images or {}).items()}, 'plans': dict(c.plans or {})}
@@ -83,7 +83,7 @@ def _convw_from_blob(b: dict, dev) -> ops.ConvW:
     w = b['w'].to(dev)
     Cout, Cin, kh, kw = b['dims']
     bias = None if b['bias'] is None else b['bias'].to(dev)
-    cw = ops.ConvW(w, bias, Cout, Cin, kh, kw)
+    cw = ops.ConvW(w, bias, Cout, Cin, kh, kw, pack_dims=b.get('pack_dims'))
     cw.images = {k: (None if t is None else t.to(dev)) for k, t in b['images'].items()}
     cw.plans = dict(b['plans'])
     for (start, n), sb in b['slices'].items():

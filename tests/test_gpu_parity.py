@@ -247,6 +247,23 @@ def test_conv2d_two_input_tensors_in_one_accumulator(S):
     assert torch.equal(y2, y) and float((sc - sc2).abs().max()) < 1e-5 * float(sc2.abs().max())
 
 
+def test_resblock_conv2_plus_1x1_skip_in_one_accumulator(S):
+    """conv2d(h, pack_conv_plus_1x1(conv2, conv_out), pre=GroupNorm+swish, x2=x, x2_1x1=True): a ResBlock's 3x3 conv2 over the normalised h and its 1x1 skip conv over
+    the block input x in one accumulator (the prologue applies to h only; x2's chunks use the centre tap only); against fp64 torch; partial tiles; with statistics."""
+    B, cin, cout, H, W = 2, 128, 64, 40, 24
+    h = rnd(B, cout, H, W, seed=1); x = rnd(B, cin, H, W, seed=2)
+    w2 = rnd(cout, cout, 3, 3, seed=3, scale=(cout * 9) ** -0.5); wo = rnd(cout, cin, 1, 1, seed=4, scale=cin ** -0.5)
+    b2, bo = rnd(cout, seed=5, scale=0.1), rnd(cout, seed=6, scale=0.1)
+    sc, sh = 1 + 0.1 * rnd(B, cout, seed=7), 0.1 * rnd(B, cout, seed=8)
+    hn = h.double() * sc.double().view(B, cout, 1, 1) + sh.double().view(B, cout, 1, 1)
+    hn = hn * torch.sigmoid(hn)
+    ref = F.conv2d(hn, w2.double(), b2.double(), padding=1) + F.conv2d(x.double(), wo.double(), bo.double())
+    cw = S.ops.pack_conv_plus_1x1(S.ops.pack_conv(w2.cuda(), b2.cuda()), S.ops.pack_conv(wo.cuda(), bo.cuda()))
+    y = S.ops.conv2d(nhwc(h), cw, pad=1, pre=(sc.cuda(), sh.cuda(), 'swish'), x2=nhwc(x), x2_1x1=True)
+    assert S.ops.LAST_CONV_KERNEL == 3
+    assert float((nchw(y).double() - ref).abs().max()) < 3e-5 * max(1.0, float(ref.abs().max()))
+
+
 def test_generator_fused_shift_and_fuse_ms_matches_two_convolutions(S, nets, clip, golden):
     """generate() with the shift.2 + fuse_ms pair as one two-tensor convolution against the two-convolution form (same kernels otherwise)."""
     g, me = nets
