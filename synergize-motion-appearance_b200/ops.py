@@ -367,7 +367,7 @@ def conv2d(x: torch.Tensor, cw: ConvW, *, stride: int = 1, pad: int = 0, pad_tl:
         dec = res if res.is_contiguous() else affine_act(res, None, None)
         sc = sft[0] if sft[0].is_contiguous() else affine_act(sft[0], None, None)
         return sft_combine(dec, sc, shift, float(sft[1]), out=out if (out is not None and out.is_contiguous()) else None)
-    K = cw.kh * cw.kw * Cin
+    K = cw.kh * cw.kw * Cin if not (x2 is not None and x2_1x1) else cw.kh * cw.kw * Cin1 + (Cin - Cin1)      # (the second tensor enters through one tap)
     with _Prof('conv', 2.0 * B * Ho * Wo * K * cw.Cout,
                4.0 * (B * Hi * Wi * Cin + B * Ho * Wo * cw.Cout * (2 if res is not None else 1) + K * cw.Cout),
                f'conv B{B} {Hi}x{Wi} Cin{Cin} Cout{cw.Cout} k{cw.kh} s{stride}{" up" if upsample2 else ""}{" pre" if pre is not None else ""}') as pr:
