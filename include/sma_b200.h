@@ -152,9 +152,12 @@ int sma_debug_conv_ts_prof(long long* cycles_ns /* 8 values: cycles, ns, cycles 
 int sma_groupnorm_stats(const float* x, int B, int HW, int C, int64_t bstride, int ld, int groups, float eps,
                         const float* gamma, const float* beta, float* partial, float* scale, float* shift,
                         sma_stream_t stream);
-/* second half of the fused form: partial sums written by sma_conv2d_fwd (sma_conv_desc.gn_partial, nchunk = gn_chunks) -> scale/shift */
-int sma_groupnorm_finalize_pairs(const float* partial, int B, int nchunk, int C, int groups, int HW, float eps,
-                                 const float* gamma, const float* beta, float* scale, float* shift, sma_stream_t stream);
+/* second half of the fused form: partial sums written by sma_conv2d_fwd (sma_conv_desc.gn_partial, nchunk = gn_chunks) -> scale/shift rows of pitch out_ld
+ * (>= C: the statistics of one half of a concatenated tensor land in their columns of the consumer's (B, 2C) buffers - the groups of GroupNorm(32) over
+ * [enc | dec] do not straddle the halves).  fold > 1: the producer was a depth-to-space convolution with fold = d2s^2 sub-pixel column blocks of C channels
+ * (its Cout = fold * C; HW = its own output rows). */
+int sma_groupnorm_finalize_pairs(const float* partial, int B, int nchunk, int C, int groups, int HW, int fold, float eps,
+                                 const float* gamma, const float* beta, float* scale, float* shift, int out_ld, sma_stream_t stream);
 /* y = act(x*scale[b,c]+shift[b,c]) elementwise (used where no conv follows, e.g. AttnBlock input) */
 int sma_affine_act(const float* x, int B, int HW, int C, int64_t bstride, int ld, const float* scale,
                    const float* shift, int act, float* y, int64_t y_bstride, int y_ld, sma_stream_t stream);

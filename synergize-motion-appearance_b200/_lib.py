@@ -47,7 +47,7 @@ SIGNATURES = {
     'sma_pack_conv_weight_ts': ([_V, _I, _I, _I, _I, _I, _V, _V], C.c_int),
     'sma_debug_conv_ts_prof': ([_V], C.c_int),
     'sma_groupnorm_stats': ([_V, _I, _I, _I, _L, _I, _I, _F, _V, _V, _V, _V, _V, _V], C.c_int),
-    'sma_groupnorm_finalize_pairs': ([_V, _I, _I, _I, _I, _I, _F, _V, _V, _V, _V, _V], C.c_int),
+    'sma_groupnorm_finalize_pairs': ([_V, _I, _I, _I, _I, _I, _I, _F, _V, _V, _V, _V, _I, _V], C.c_int),
     'sma_affine_act': ([_V, _I, _I, _I, _L, _I, _V, _V, _I, _V, _L, _I, _V], C.c_int),
     'sma_layernorm': ([_V, _I, _I, _V, _V, _F, _V, _I, _V, _V, _V], C.c_int),
     'sma_warp_occlude_fwd': ([_V, _L, _I, _I, _I, _I, _V, _V, _I, _I, _V, _V], C.c_int),

@@ -550,7 +550,7 @@ class AppMotionCompFormer(ParamModule):
     # ------------------------------------------------------------------------------------------
     # stage 3a: appearance codebook compensation (appmotioncodebook_arch.py:472-544)
     # ------------------------------------------------------------------------------------------
-    def _app_comp(self, feat, m_com, s, out=None):
+    def _app_comp(self, feat, m_com, s, out=None, gn=None):
         W, T = self._packed, self._T
         B = feat.shape[0]
         tg, s0 = self.tg, s // self.R
@@ -568,7 +568,8 @@ class AppMotionCompFormer(ParamModule):
         tok = tok.view(B, tg, tg, self.Ea)
         if s0 == 32:
             return ops.conv2d(tok, W['to_app_feat_32'], out=out, fast=fa)
-        return ops.conv2d(tok, W[f'to_app_feat_{s0}.0'], d2s=s0 // 32, out=out, fast=fa)
+        r = ops.conv2d(tok, W[f'to_app_feat_{s0}.0'], d2s=s0 // 32, out=out, fast=fa, gn=gn)      # (gn: GroupNorm statistics of the un-patchified output, for Fuse_sft_block)
+        return r[0] if gn is not None else r
 
     # ------------------------------------------------------------------------------------------
     # the per-driving-frame body (appmotioncodebook_arch.py:556-764, inference=True)
@@ -595,7 +596,7 @@ class AppMotionCompFormer(ParamModule):
         qcat = torch.empty((B, tg, tg, 2 * Em), device=dev, dtype=torch.float32)   # [motion feat | query feat]
         ops.conv2d(ops.resize_ac(kp_heat_nhwc, (tg, tg)), W['driving_kp_enc'], act='relu', out=qk[..., Em:])
 
-        def compensate(s, out=None):
+        def compensate(s, out=None, gn=None):
             nonlocal occ_prev
             f = src(s)
             if collect is None and s >= 4 * fg:
@@ -614,7 +615,7 @@ class AppMotionCompFormer(ParamModule):
             motions.append(m_com); occs.append(occ); residuals.append(r)
             occ_prev = occ
             warped = ops.warp_occlude(f, m_com, occ)
-            enc = self._app_comp(warped, m_com, s, out=out)
+            enc = self._app_comp(warped, m_com, s, out=out, gn=gn)
             if collect is not None:
                 collect[f'warp0_{s}'], collect[f'warped_{s}'], collect[f'app_{s}'] = warp0, warped, enc
             return enc
@@ -634,11 +635,16 @@ class AppMotionCompFormer(ParamModule):
                 s = s0 * R
                 c = self.channels[s0]
                 cat = torch.empty((B, s, s, 2 * c), device=dev, dtype=torch.float32)   # [enc | dec] for Fuse_sft_block
-                x = self._block('generator', i, self.gen_layout, x, out=cat[..., c:], fast=fgen, stats=stats)
-                enc = compensate(s, out=cat[..., :c])
                 n = f'fuse_convs_dict.{s0}'
+                # GroupNorm(32) over [enc | dec] = 16 groups per half, none straddling: each half's statistics come out of the epilogue of the
+                # convolution that writes it (the decoder block's last conv; the un-patchifying conv of the appearance compensation)
+                g1, b1 = self._gnp(n + '.encode_enc.norm1')
+                sc_cat = torch.empty((B, 2 * c), device=dev, dtype=torch.float32); sh_cat = torch.empty((B, 2 * c), device=dev, dtype=torch.float32)
+                x = self._block('generator', i, self.gen_layout, x, out=cat[..., c:], fast=fgen, stats=stats,
+                                want=(g1[c:], b1[c:], 16, sc_cat[:, c:], sh_cat[:, c:]))[0]
+                enc = compensate(s, out=cat[..., :c], gn=(g1[:c], b1[:c], 16, sc_cat[:, :c], sh_cat[:, :c]))
                 fsft = ops.fast('sft')
-                e = self._res(n + '.encode_enc', cat, 2 * c, c, fast=fsft)
+                e = self._res(n + '.encode_enc', cat, 2 * c, c, fast=fsft, stats=(sc_cat, sh_cat))
                 ss = ops.conv2d(e, W[n + '.ss0'], pad=1, act='leaky', fast=fsft)                  # [scale.0 | shift.0]
                 scale = ops.conv2d(ss[..., :c], W[n + '.scale.2'], pad=1, fast=fsft)
                 # dec + w * (dec * scale + shift) in the epilogue of the `shift.2` conv; the decoder half is read in place (channel slice of `cat`)

@@ -1223,7 +1223,8 @@ static int conv_tc2_try(sma_conv_desc* d, cudaStream_t st, bool f16) {
   // fused GroupNorm partial sums: only where the 256-bit epilogue runs (every lane then walks the same column blocks) and the output is the whole
   // normalised tensor (no depth-to-space); the caller learns through gn_chunks (0 = not produced: it runs sma_groupnorm_stats instead)
   {
-    const bool v8 = d->d2s <= 1 && (d->Cout & 7) == 0 && (d->out_ld & 7) == 0 && (d->out_bstride & 7) == 0 && (reinterpret_cast<uintptr_t>(d->y) & 31) == 0 &&
+    const int Cq_ = d->d2s > 1 ? d->Cout / (d->d2s * d->d2s) : d->Cout;
+    const bool v8 = (d->d2s <= 1 || (Cq_ & 7) == 0) && (d->Cout & 7) == 0 && (d->out_ld & 7) == 0 && (d->out_bstride & 7) == 0 && (reinterpret_cast<uintptr_t>(d->y) & 31) == 0 &&
                     (!d->res || ((d->res_ld & 7) == 0 && (d->res_bstride & 7) == 0 && (reinterpret_cast<uintptr_t>(d->res) & 31) == 0));
     const bool want = d->gn_want != 0 && v8 && !d->out_nchw;
     p.gn_chunks = want ? p.tiles_per_img * 4 : 0;

@@ -369,27 +369,30 @@ __global__ void __launch_bounds__(256) im2col_small_kernel(const float* __restri
     const int iy = ty0 + py - pad, ix = tx0 + px - pad;
     sh[i] = ((unsigned)iy < (unsigned)H && (unsigned)ix < (unsigned)W) ? __ldg(x + (((long long)b * H + iy) * W + ix) * ld + c) : 0.f;
   }
-  __syncthreads();
+  // column -> offset inside the staged halo (relative to the pixel's top-left tap), -1 for the zero padding columns: one table per block
+  __shared__ __align__(16) int off[256];
   const int KK = k * k * C, kq = Kp >> 2;
+  for (int col = threadIdx.x; col < Kp && col < 256; col += 256) {
+    int o = -1;
+    if (col < KK) { const int tap = col / C, c = col - tap * C; const int ky = tap / k, kx = tap - ky * k; o = (ky * hw + kx) * C + c; }
+    off[col] = o;
+  }
+  __syncthreads();
   for (int i = threadIdx.x; i < 256 * kq; i += 256) {
     const int q = i % kq; const int p = i / kq; const int py = p >> 5, px = p & 31;
     const int oy = ty0 + py, ox = tx0 + px;
     if (oy >= H || ox >= W) continue;
-    float v[4];
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-      const int col = q * 4 + j;
-      v[j] = 0.f;
-      if (col < KK) { const int tap = col / C, c = col - tap * C; const int ky = tap / k, kx = tap - ky * k; v[j] = sh[((py + ky) * hw + (px + kx)) * C + c]; }
-    }
-    *reinterpret_cast<float4*>(out + (((long long)b * H + oy) * W + ox) * Kp + q * 4) = make_float4(v[0], v[1], v[2], v[3]);
+    const float* base = sh + (py * hw + px) * C;
+    const int4 o4 = *reinterpret_cast<const int4*>(&off[q * 4]);
+    const float4 v = make_float4(o4.x >= 0 ? base[o4.x] : 0.f, o4.y >= 0 ? base[o4.y] : 0.f, o4.z >= 0 ? base[o4.z] : 0.f, o4.w >= 0 ? base[o4.w] : 0.f);
+    *reinterpret_cast<float4*>(out + (((long long)b * H + oy) * W + ox) * Kp + q * 4) = v;
   }
 }
 extern "C" int sma_im2col_small(const float* x, int B, int H, int W, int ld, int C, int k, int pad, float* out, int Kp, sma_stream_t s) {
   if (!x || !out || B <= 0 || H <= 0 || W <= 0 || C <= 0 || k <= 0 || pad < 0 || ld < C || (Kp & 3) || Kp < k * k * C) return SMA_ERR_BAD_ARG;
   if (reinterpret_cast<uintptr_t>(out) & 15) return SMA_ERR_BAD_ARG;
   const int smem = (8 + k - 1) * (32 + k - 1) * C * (int)sizeof(float);
-  if (smem > 48 * 1024) return SMA_ERR_UNSUPPORTED;
+  if (smem > 40 * 1024 || Kp > 256) return SMA_ERR_UNSUPPORTED;
   const int tiles_x = (W + 31) / 32, tiles_y = (H + 7) / 8;
   im2col_small_kernel<<<B * tiles_x * tiles_y, 256, smem, as_stream(s)>>>(x, B, H, W, ld, C, k, pad, out, Kp, tiles_x, tiles_y);
   SMA_LAUNCH_CHECK(); return SMA_OK;

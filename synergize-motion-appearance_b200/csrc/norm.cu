@@ -80,15 +80,18 @@ __global__ void gn_partial4_kernel(const float* __restrict__ x, int HW, int C, l
 }
 
 // one block per (b, group): combine chunk partials in fp64, emit scale/shift per channel.  `per` = channels per partial entry: 1 (the standalone
-// statistics pass) or 2 (channel pairs: the partial sums a convolution's epilogue produced, conv_tc.cu gn_pairs_reduce_store)
+// statistics pass) or 2 (channel pairs: the partial sums a convolution's epilogue produced, conv_tc.cu gn_pairs_reduce_store).  `fold` > 1: the
+// producer was a depth-to-space (un-patchify) convolution whose `fold` sub-pixel column blocks of C channels each all belong to the same C output
+// channels (partial row = fold * C / per entries; HW counts the PRODUCER's rows, so a group holds HW * fold * cg values).  Output rows have pitch out_ld.
 __global__ void gn_finalize_kernel(const float* __restrict__ partial, int nchunk, int C, int groups, int HW, float eps,
-                                   const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ scale, float* __restrict__ shift, int per) {
+                                   const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ scale, float* __restrict__ shift, int per,
+                                   int fold, int out_ld) {
   const int g = blockIdx.x, b = blockIdx.y;
-  const int cg = C / groups, eg = cg / per, Cp = C / per;
+  const int cg = C / groups, eg = cg / per, Cp = C / per, rowp = Cp * fold;
   double s = 0.0, q = 0.0;
-  for (int i = threadIdx.x; i < nchunk * eg; i += blockDim.x) {
-    int chunk = i / eg, c = g * eg + i % eg;
-    const float* o = partial + (((long long)b * nchunk + chunk) * Cp + c) * 2;
+  for (int i = threadIdx.x; i < nchunk * fold * eg; i += blockDim.x) {
+    const int e = i % eg; const int t = i / eg; const int f = t % fold, chunk = t / fold;
+    const float* o = partial + (((long long)b * nchunk + chunk) * rowp + f * Cp + g * eg + e) * 2;
     s += (double)o[0]; q += (double)o[1];
   }
   __shared__ double sh[2][32];
@@ -98,7 +101,7 @@ __global__ void gn_finalize_kernel(const float* __restrict__ partial, int nchunk
   if (threadIdx.x == 0) {
     double ss = 0, qq = 0;
     for (int i = 0; i < (int)(blockDim.x >> 5); i++) { ss += sh[0][i]; qq += sh[1][i]; }
-    double n = (double)HW * cg; double mean = ss / n; double var = qq / n - mean * mean; if (var < 0) var = 0;
+    double n = (double)HW * fold * cg; double mean = ss / n; double var = qq / n - mean * mean; if (var < 0) var = 0;
     sh[0][0] = mean; sh[1][0] = 1.0 / sqrt(var + (double)eps);
   }
   __syncthreads();
@@ -107,7 +110,7 @@ __global__ void gn_finalize_kernel(const float* __restrict__ partial, int nchunk
     int c = g * cg + i;
     float ga = gamma ? gamma[c] : 1.f, be = beta ? beta[c] : 0.f;
     float sc = ga * rstd;
-    scale[(long long)b * C + c] = sc; shift[(long long)b * C + c] = be - mean * sc;
+    scale[(long long)b * out_ld + c] = sc; shift[(long long)b * out_ld + c] = be - mean * sc;
   }
 }
 
@@ -160,15 +163,15 @@ extern "C" int sma_groupnorm_stats(const float* x, int B, int HW, int C, int64_t
   if (vec) gn_partial4_kernel<<<dim3(nchunk, B), 256, 0, as_stream(stream)>>>(x, HW, C, bstride, ld, partial, nchunk);
   else gn_partial_kernel<<<dim3(nchunk, B), 256, 512 * sizeof(float), as_stream(stream)>>>(x, HW, C, bstride, ld, partial, nchunk);
   SMA_LAUNCH_CHECK();
-  gn_finalize_kernel<<<dim3(groups, B), 128, 0, as_stream(stream)>>>(partial, nchunk, C, groups, HW, eps, gamma, beta, scale, shift, 1);
+  gn_finalize_kernel<<<dim3(groups, B), 128, 0, as_stream(stream)>>>(partial, nchunk, C, groups, HW, eps, gamma, beta, scale, shift, 1, 1, C);
   SMA_LAUNCH_CHECK();
   return SMA_OK;
 }
 
-extern "C" int sma_groupnorm_finalize_pairs(const float* partial, int B, int nchunk, int C, int groups, int HW, float eps, const float* gamma,
-                                            const float* beta, float* scale, float* shift, sma_stream_t stream) {
-  if (!partial || !scale || !shift || B <= 0 || nchunk <= 0 || HW <= 0 || C <= 0 || groups <= 0 || C % groups || ((C / groups) & 1)) return SMA_ERR_BAD_ARG;
-  gn_finalize_kernel<<<dim3(groups, B), 256, 0, as_stream(stream)>>>(partial, nchunk, C, groups, HW, eps, gamma, beta, scale, shift, 2);
+extern "C" int sma_groupnorm_finalize_pairs(const float* partial, int B, int nchunk, int C, int groups, int HW, int fold, float eps, const float* gamma,
+                                            const float* beta, float* scale, float* shift, int out_ld, sma_stream_t stream) {
+  if (!partial || !scale || !shift || B <= 0 || nchunk <= 0 || HW <= 0 || C <= 0 || groups <= 0 || C % groups || ((C / groups) & 1) || fold < 1 || out_ld < C) return SMA_ERR_BAD_ARG;
+  gn_finalize_kernel<<<dim3(groups, B), 256, 0, as_stream(stream)>>>(partial, nchunk, C, groups, HW, eps, gamma, beta, scale, shift, 2, fold, out_ld);
   SMA_LAUNCH_CHECK();
   return SMA_OK;
 }

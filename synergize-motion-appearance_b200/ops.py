@@ -336,7 +336,9 @@ def conv2d(x: torch.Tensor, cw: ConvW, *, stride: int = 1, pad: int = 0, pad_tl:
             d.w_tc, d.w_tc16, d.w_ts = _ptr(cw.image('tc', 0)), _ptr(cw.image('tc16')), _ptr(cw.image('ts'))
         else:
             # ask the library which kernel this launch will run on (nothing is launched), then pack / fetch exactly the image it reads
-            d.gn_want = 1 if (gn is not None and FUSE_GN and d.out_ld == cw.Cout and cw.Cout % 64 == 0) else 0      # (pairs must not straddle the 32 groups)
+            gn_C = cw.Cout // (d2s * d2s) if d2s > 1 else cw.Cout                  # channels of the normalised tensor (a depth-to-space conv folds d2s^2 column blocks)
+            gn_groups = gn[2] if (gn is not None and len(gn) > 2) else 32
+            d.gn_want = 1 if (gn is not None and FUSE_GN and not out_nchw and gn_C % (2 * gn_groups) == 0) else 0      # (pairs must not straddle the groups)
             key = (B, Hi, Wi, stride, pt, pl, upsample2, Ho, Wo, out_nchw, d2s, d.precision, TC_VARIANT, x.data_ptr() & 15, ild & 3, ibs & 3,
                    pre is not None, sft is not None, 0 if res is None else (d.res_ld & 7, d.res_bstride & 7), d.out_ld & 7, d.out_bstride & 7,
                    d.gn_want, out.data_ptr() & 31, 0 if res is None else res.data_ptr() & 31,
@@ -378,13 +380,20 @@ def conv2d(x: torch.Tensor, cw: ConvW, *, stride: int = 1, pad: int = 0, pad_tl:
     global LAST_CONV_KERNEL
     LAST_CONV_KERNEL = d.kernel_used
     if gn is not None:
+        # gn = (gamma, beta[, groups[, scale_out, shift_out]]): the optional outputs are (B, C) column slices of wider buffers (the two halves of a
+        # concatenated tensor are normalised with separate statistics: GroupNorm's groups do not straddle them)
+        groups = gn[2] if len(gn) > 2 else 32
+        C_gn = cw.Cout // (d2s * d2s) if d2s > 1 else cw.Cout
+        scale = gn[3] if len(gn) > 3 else torch.empty((B, C_gn), device=x.device, dtype=torch.float32)
+        shift = gn[4] if len(gn) > 4 else torch.empty((B, C_gn), device=x.device, dtype=torch.float32)
         if d.gn_want and d.gn_chunks > 0:
-            scale = torch.empty((B, cw.Cout), device=x.device, dtype=torch.float32)
-            shift = torch.empty((B, cw.Cout), device=x.device, dtype=torch.float32)
-            check(lib.sma_groupnorm_finalize_pairs(gn_partial.data_ptr(), B, d.gn_chunks, cw.Cout, 32, Ho * Wo, 1e-6, gn[0].data_ptr(), gn[1].data_ptr(),
-                                                   scale.data_ptr(), shift.data_ptr(), _stream()), 'sma_groupnorm_finalize_pairs')
-            return out, (scale, shift)
-        return out, groupnorm_stats(out, gn[0], gn[1], 32, 1e-6)
+            check(lib.sma_groupnorm_finalize_pairs(gn_partial.data_ptr(), B, d.gn_chunks, C_gn, groups, Ho * Wo, d2s * d2s if d2s > 1 else 1, 1e-6,
+                                                   gn[0].data_ptr(), gn[1].data_ptr(), scale.data_ptr(), shift.data_ptr(), scale.stride(0), _stream()),
+                  'sma_groupnorm_finalize_pairs')
+        else:
+            sc_, sh_ = groupnorm_stats(out, gn[0], gn[1], groups, 1e-6)
+            scale.copy_(sc_); shift.copy_(sh_)
+        return out, (scale, shift)
     return out
 
 

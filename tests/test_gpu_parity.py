@@ -296,6 +296,23 @@ def test_pointwise_layer_evaluated_only_where_the_resize_samples_it(S):
     assert torch.equal(full, sparse)
 
 
+def test_groupnorm_statistics_of_a_concatenation_from_its_two_producers(S):
+    """GroupNorm(32) over [enc | dec] (Fuse_sft_block's input): 16 groups per half, none straddling, so each half's scale / shift comes out of the epilogue of the
+    convolution that writes that half - a depth-to-space (un-patchify) conv for enc (its d2s^2 sub-pixel column blocks fold onto the same channels) and a plain
+    conv with a residual for dec - into column slices of one (B, 2c) buffer; against the standalone statistics pass over the concatenated tensor."""
+    B, c, s, p = 2, 64, 64, 2
+    tok = nhwc(rnd(B, 256, s // p, s // p, seed=1)); h = nhwc(rnd(B, c, s, s, seed=2)); r = nhwc(rnd(B, c, s, s, seed=3))
+    w_un = S.ops.pack_conv(rnd(c * p * p, 256, 1, 1, seed=4, scale=256 ** -0.5).cuda(), rnd(c * p * p, seed=5, scale=0.1).cuda())
+    w_dec = S.ops.pack_conv(rnd(c, c, 3, 3, seed=6, scale=(9 * c) ** -0.5).cuda(), rnd(c, seed=7, scale=0.1).cuda())
+    gamma, beta = (1 + 0.1 * rnd(2 * c, seed=8)).cuda(), (0.1 * rnd(2 * c, seed=9)).cuda()
+    cat = torch.empty(B, s, s, 2 * c, device='cuda')
+    sc = torch.empty(B, 2 * c, device='cuda'); sh = torch.empty(B, 2 * c, device='cuda')
+    S.ops.conv2d(tok, w_un, d2s=p, out=cat[..., :c], gn=(gamma[:c], beta[:c], 16, sc[:, :c], sh[:, :c]))
+    S.ops.conv2d(h, w_dec, pad=1, res=r, out=cat[..., c:], gn=(gamma[c:], beta[c:], 16, sc[:, c:], sh[:, c:]))
+    sc2, sh2 = S.ops.groupnorm_stats(cat, gamma, beta, 32, 1e-6)
+    assert float((sc - sc2).abs().max()) < 1e-5 * float(sc2.abs().max()) and float((sh - sh2).abs().max()) < 2e-5 * max(1.0, float(sh2.abs().max()))
+
+
 def test_conv2d_concat_slices_patchify_and_bn_fold(S):
     """channel-slice views as input/output (torch.cat elimination), stride-p patch embedding, depth-to-space."""
     B, C, s, p = 2, 128, 64, 2
