@@ -290,8 +290,10 @@ class AppMotionCompFormer(ParamModule):
                                                 [T['refine.conv1.bias'], T['refine.convo1.bias']])
         for i, s in enumerate(self.SCALES):
             pc(f'to_context.{i}'); pc(f'warped_source_enc_{s}')
-        for blk, E, cb in (('motion_block', self.Em, 'quantize_motion.embedding.weight'), ('app_block', self.Ea, 'quantize_app.embedding.weight')):
+        for blk, E, cb, pe in (('motion_block', self.Em, 'quantize_motion.embedding.weight', 'position_emb_motion'),
+                               ('app_block', self.Ea, 'quantize_app.embedding.weight', 'position_emb_app')):
             codes = T[cb].float().contiguous()
+            pos64 = T[pe].double()
             for i in range(2):
                 n = f'{blk}.{i}'
                 W[n + '.self_in'] = ops.pack_conv(T[n + '.self_attn.in_proj_weight'], T[n + '.self_attn.in_proj_bias'])
@@ -299,6 +301,13 @@ class AppMotionCompFormer(ParamModule):
                 W[n + '.self_out'] = ops.pack_conv(T[n + '.self_attn.out_proj.weight'], T[n + '.self_attn.out_proj.bias'])
                 W[n + '.cross_out'] = ops.pack_conv(T[n + '.cross_attn.out_proj.weight'], T[n + '.cross_attn.out_proj.bias'])
                 pc(n + '.conv1'); pc(n + '.conv2')
+                # (LN(x) + pos) W^T = LN(x) W^T + pos W^T: the positional term of the q / k projections is frame-invariant - one (L, 3E) per-token bias
+                # [pos Wq^T | pos Wk^T | 0] added as a batch-stride-0 residual lets ONE linear produce q | k | v from LN(x) (and LayerNorm write one tensor)
+                wi = T[n + '.self_attn.in_proj_weight'].double(); wc = T[n + '.cross_attn.in_proj_weight'].double()
+                pq = torch.zeros((pos64.shape[0], 3 * E), device=codes.device, dtype=torch.float32)
+                pq[:, :2 * E] = (pos64 @ wi[:2 * E].t()).float()
+                W[n + '.pos_qkv'] = pq
+                W[n + '.pos_q2'] = (pos64 @ wc[:E].t()).float().contiguous()
                 # codebook keys/values are frame-invariant: project all rows once (prefix-sliceable for the split)
                 kv = ops.linear(codes.view(1, -1, E), W[n + '.cross_in'].cols(E, 2 * E), exact=True)
                 W[n + '.ctx_kv'] = kv[0]                              # (n_codes, 2E): K | V
@@ -486,15 +495,23 @@ class AppMotionCompFormer(ParamModule):
     def _transformer(self, name, t, E, n_ctx, pos, key_mask=None, fast=False):
         W, T = self._packed, self._T
         B = t.shape[0]
-        u, uq = ops.layernorm(t, T[name + '.norm1.weight'], T[name + '.norm1.bias'], pos)
         L, tg = self.L, self.tg
-        qkv = torch.empty((B, L, 3 * E), device=t.device, dtype=torch.float32)
-        ops.linear(uq, W[name + '.self_in'].cols(0, 2 * E), out=qkv[..., :2 * E], fast=fast)
-        ops.linear(u, W[name + '.self_in'].cols(2 * E, E), out=qkv[..., 2 * E:], fast=fast)
+        if (name + '.pos_qkv') in W:
+            u, _ = ops.layernorm(t, T[name + '.norm1.weight'], T[name + '.norm1.bias'])
+            qkv = ops.linear(u, W[name + '.self_in'], res=W[name + '.pos_qkv'].unsqueeze(0).expand(B, -1, -1), fast=fast)
+        else:       # (a pack cache written before the positional term was folded)
+            u, uq = ops.layernorm(t, T[name + '.norm1.weight'], T[name + '.norm1.bias'], pos)
+            qkv = torch.empty((B, L, 3 * E), device=t.device, dtype=torch.float32)
+            ops.linear(uq, W[name + '.self_in'].cols(0, 2 * E), out=qkv[..., :2 * E], fast=fast)
+            ops.linear(u, W[name + '.self_in'].cols(2 * E, E), out=qkv[..., 2 * E:], fast=fast)
         a = ops.mha(qkv[..., :E], qkv[..., E:2 * E], qkv[..., 2 * E:], heads=self.n_head, key_mask=key_mask, fast=fast)
         t = ops.linear(a, W[name + '.self_out'], res=t, fast=fast)
-        _, uq = ops.layernorm(t, T[name + '.norm2.weight'], T[name + '.norm2.bias'], pos, want_y=False)
-        qc = ops.linear(uq, W[name + '.cross_in'].cols(0, E), fast=fast)
+        if (name + '.pos_q2') in W:
+            u2, _ = ops.layernorm(t, T[name + '.norm2.weight'], T[name + '.norm2.bias'])
+            qc = ops.linear(u2, W[name + '.cross_in'].cols(0, E), res=W[name + '.pos_q2'].unsqueeze(0).expand(B, -1, -1), fast=fast)
+        else:
+            _, uq = ops.layernorm(t, T[name + '.norm2.weight'], T[name + '.norm2.bias'], pos, want_y=False)
+            qc = ops.linear(uq, W[name + '.cross_in'].cols(0, E), fast=fast)
         kv = W[name + '.ctx_kv']
         a = ops.mha(qc, kv[:n_ctx, :E], kv[:n_ctx, E:], heads=self.n_head, fast=fast)
         t = ops.linear(a, W[name + '.cross_out'], res=t, fast=fast)
