@@ -112,6 +112,10 @@ typedef struct sma_conv_desc {
      conv(x, w[:, :Cin1]) + conv(x2, w[:, Cin1:]) in one accumulator - Fuse_sft_block's shift conv and the fuse_ms conv of the same scale
      (appmotioncodebook_arch.py:50-51,737-738).  TMA-staged fp16 kernel only (else SMA_ERR_UNSUPPORTED: run the two convolutions). */
   const float* x2;  int64_t in2_bstride;  int in2_ld;  int Cin1;
+  /* split_ws != NULL: a flat 1x1 layer producing q (Cout = 256) or q | k | v (Cout = 768) of an E = 256 attention writes the attention kernels' fp16 hi / lo
+     operand images (the layout of sma_mha_e256_fwd / sma_attn256_fwd's workspace; q pre-scaled by split_qscale = softmax scale * log2 e) instead of fp32 rows:
+     y is not written; call the attention with presplit = 1 (q) or 2 (q, k, v).  Persistent tensor-core kernel only (else SMA_ERR_UNSUPPORTED). */
+  void* split_ws;  float split_qscale;
   int x2_k1;                     /* 1: x2 enters through a 1x1 conv (the centre tap only): a ResBlock's conv2 (k x k over x, with its GroupNorm prologue, which then
                                     applies to x alone) + its 1x1 skip conv over the block input (archs/vqgan_arch.py:185-191).  The weight image is then packed
                                     as a 1x1 conv over the rows [x: channel chunk outer, tap inner, 64 channels][x2: 64-channel chunks] */
@@ -207,13 +211,16 @@ int sma_mha_fwd(const float* q, int ldq, const float* k, int ldk, const float* v
  * streams them with bulk copies.  L % 128 == 0, S % 64 == 0; q:(B,L,256) k,v:(B,S,256) views with row strides ld*. */
 int64_t sma_attn256_workspace_bytes(int B, int L, int S);
 int sma_attn256_fwd(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv, int64_t q_bstride, int64_t kv_bstride,
-                    int B, int L, int S, float scale, void* workspace, float* out, int ldo, sma_stream_t stream);
+                    int B, int L, int S, float scale, void* workspace, float* out, int ldo,
+                    int presplit /* != 0: q, k, v images already in workspace (sma_conv_desc.split_ws with Cout = 768); S == L */, sma_stream_t stream);
 
 /* 8-head attention with E = 256 (head dim 32: the appearance TransformerLayer) on the tensor cores (csrc/attn_mh.cu), same scheme as
  * sma_attn256_fwd; kv_bstride == 0: k, v (the codebook projections) are shared by every frame.  key_mask (B,S) uint8 or NULL. */
 int64_t sma_mha_e256_workspace_bytes(int B, int kvB, int L, int S);
 int sma_mha_e256_fwd(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv, int64_t q_bstride, int64_t kv_bstride,
-                     int B, int L, int S, float scale, const uint8_t* key_mask, void* workspace, float* out, int ldo, sma_stream_t stream);
+                     int B, int L, int S, float scale, const uint8_t* key_mask, void* workspace, float* out, int ldo,
+                     int presplit /* 0: split q,k,v here; 1: q images already in workspace (sma_conv_desc.split_ws); 2: q,k,v images already there */,
+                     sma_stream_t stream);
 
 /* VectorQuantizer lookup (archs/vqgan_arch.py:33-73): d = fl(fl(|z|^2+|e|^2) - 2 z.e), argmin with
  * lowest-index ties -> idx (int64), zq = e[idx].  z:(N,E) row-major, codebook (n_codes,E).  workspace: n_codes floats (|e|^2) or NULL; with it,

@@ -25,7 +25,7 @@ class ConvDesc(C.Structure):
         ('d2s', C.c_int), ('out_nchw', C.c_int), ('precision', C.c_int), ('w_tc', C.c_void_p), ('w_tc16', C.c_void_p), ('w_ts', C.c_void_p), ('tc_variant', C.c_int), ('kernel_used', C.c_int),
         ('w_tc_nt', C.c_int), ('plan_only', C.c_int), ('aux', C.c_void_p), ('aux_bstride', c_i64), ('aux_ld', C.c_int), ('sft_w', C.c_float),
         ('gn_want', C.c_int), ('gn_partial', C.c_void_p), ('gn_chunks', C.c_int),
-        ('x2', C.c_void_p), ('in2_bstride', c_i64), ('in2_ld', C.c_int), ('Cin1', C.c_int), ('x2_k1', C.c_int),
+        ('x2', C.c_void_p), ('in2_bstride', c_i64), ('in2_ld', C.c_int), ('Cin1', C.c_int), ('split_ws', C.c_void_p), ('split_qscale', C.c_float), ('x2_k1', C.c_int),
     ]
 
 
@@ -57,9 +57,9 @@ SIGNATURES = {
     'sma_blend_bilinear4': ([_V, _I, _I, _I, _I, _V, _I, _I, _L, _I, _V], C.c_int),
     'sma_mha_fwd': ([_V, _I, _V, _I, _V, _I, _L, _I, _I, _I, _I, _I, _F, _V, _V, _I, _I, _V], C.c_int),
     'sma_attn256_workspace_bytes': ([_I, _I, _I], C.c_int64),
-    'sma_attn256_fwd': ([_V, _I, _V, _I, _V, _I, _L, _L, _I, _I, _I, _F, _V, _V, _I, _V], C.c_int),
+    'sma_attn256_fwd': ([_V, _I, _V, _I, _V, _I, _L, _L, _I, _I, _I, _F, _V, _V, _I, _I, _V], C.c_int),
     'sma_mha_e256_workspace_bytes': ([_I, _I, _I, _I], C.c_int64),
-    'sma_mha_e256_fwd': ([_V, _I, _V, _I, _V, _I, _L, _L, _I, _I, _I, _F, _V, _V, _V, _I, _V], C.c_int),
+    'sma_mha_e256_fwd': ([_V, _I, _V, _I, _V, _I, _L, _L, _I, _I, _I, _F, _V, _V, _V, _I, _I, _V], C.c_int),
     'sma_vq_lookup_fwd': ([_V, _I, _I, _V, _I, _V, _V, _V, _V, _V], C.c_int),
     'sma_vq_workspace_floats': ([], C.c_int),
     'sma_vq_commit_fwd': ([_V, _V, _L, _F, _V, _V, _V, _V], C.c_int),

@@ -127,6 +127,7 @@ class AppMotionCompFormer(ParamModule):
         self._src_cache = None
         self._two_tensor_ok = os.environ.get('SMA_NO_TWO', '0') != '1'      # (env: A/B on one box)
         self._skip_fused_ok = os.environ.get('SMA_NO_SKIPFUSE', '0') != '1'
+        self._split_ok = True
         if ae_path is not None:
             self.load_state_dict(torch.load(ae_path, map_location='cpu')['params_ema'])
         for module in (fix_modules or []):
@@ -348,8 +349,18 @@ class AppMotionCompFormer(ParamModule):
         W = self._packed
         B, H, Wd, Cc = x.shape
         s, h = stats if stats is not None else self._gn(name + '.norm', x)
-        qkv = ops.conv2d(x, W[name + '.qkv'], pre=(s, h, 'none'), fast=fast).view(B, H * Wd, 3 * Cc)
-        o = ops.mha(qkv[..., :Cc], qkv[..., Cc:2 * Cc], qkv[..., 2 * Cc:], heads=1, scale=float(int(Cc) ** (-0.5)))
+        o = None
+        if Cc == 256 and (H * Wd) % 128 == 0 and ops.SPLIT_FUSE and ops.USE_TF32X3 and self._split_ok:
+            # the qkv conv writes the attention kernel's fp16 hi / lo operand images in its epilogue (no fp32 q | k | v, no split pass)
+            ws = ops.attn256_workspace(B, H * Wd, x.device)
+            try:
+                ops.conv2d(x, W[name + '.qkv'], pre=(s, h, 'none'), fast=fast, attn_split=(ws, float(int(Cc) ** (-0.5))))
+                o = ops.attn256_presplit(ws, B, H * Wd)
+            except ops._lib.SmaError:
+                self._split_ok = False
+        if o is None:
+            qkv = ops.conv2d(x, W[name + '.qkv'], pre=(s, h, 'none'), fast=fast).view(B, H * Wd, 3 * Cc)
+            o = ops.mha(qkv[..., :Cc], qkv[..., Cc:2 * Cc], qkv[..., 2 * Cc:], heads=1, scale=float(int(Cc) ** (-0.5)))
         return ops.conv2d(o.view(B, H, Wd, Cc), W[name + '.proj_out'], res=x, out=out, fast=fast, gn=want)
 
     def _block(self, prefix, i, layout, x, out=None, fast=False, stats=None, want=None):
@@ -496,7 +507,20 @@ class AppMotionCompFormer(ParamModule):
         W, T = self._packed, self._T
         B = t.shape[0]
         L, tg = self.L, self.tg
-        if (name + '.pos_qkv') in W:
+        # E = 256: the projections write the attention kernels' fp16 hi / lo operand images in their epilogue (no fp32 q | k | v, no split pass)
+        fuse = E == 256 and self.n_head == 8 and L % 128 == 0 and ops.SPLIT_FUSE and ops.USE_MH_F16 and ops.USE_TF32X3 and self._split_ok and (name + '.pos_qkv') in W
+        a = None
+        if fuse:
+            u, _ = ops.layernorm(t, T[name + '.norm1.weight'], T[name + '.norm1.bias'])
+            ws = ops.attn_workspace(B, B, L, L, t.device)
+            try:
+                ops.linear(u, W[name + '.self_in'], res=W[name + '.pos_qkv'].unsqueeze(0).expand(B, -1, -1), fast=fast, attn_split=(ws, 32 ** -0.5))
+                a = ops.mha_presplit(ws, B, L, L, key_mask=key_mask)
+            except ops._lib.SmaError:
+                self._split_ok = False; fuse = False
+        if a is not None:
+            pass
+        elif (name + '.pos_qkv') in W:
             u, _ = ops.layernorm(t, T[name + '.norm1.weight'], T[name + '.norm1.bias'])
             qkv = ops.linear(u, W[name + '.self_in'], res=W[name + '.pos_qkv'].unsqueeze(0).expand(B, -1, -1), fast=fast)
         else:       # (a pack cache written before the positional term was folded)
@@ -504,16 +528,24 @@ class AppMotionCompFormer(ParamModule):
             qkv = torch.empty((B, L, 3 * E), device=t.device, dtype=torch.float32)
             ops.linear(uq, W[name + '.self_in'].cols(0, 2 * E), out=qkv[..., :2 * E], fast=fast)
             ops.linear(u, W[name + '.self_in'].cols(2 * E, E), out=qkv[..., 2 * E:], fast=fast)
-        a = ops.mha(qkv[..., :E], qkv[..., E:2 * E], qkv[..., 2 * E:], heads=self.n_head, key_mask=key_mask, fast=fast)
+        if a is None:
+            a = ops.mha(qkv[..., :E], qkv[..., E:2 * E], qkv[..., 2 * E:], heads=self.n_head, key_mask=key_mask, fast=fast)
         t = ops.linear(a, W[name + '.self_out'], res=t, fast=fast)
-        if (name + '.pos_q2') in W:
+        kv = W[name + '.ctx_kv']
+        a = None
+        if fuse and n_ctx % 64 == 0:
+            u2, _ = ops.layernorm(t, T[name + '.norm2.weight'], T[name + '.norm2.bias'])
+            ws = ops.attn_workspace(B, 1, L, n_ctx, t.device)
+            ops.linear(u2, W[name + '.cross_in'].cols(0, E), res=W[name + '.pos_q2'].unsqueeze(0).expand(B, -1, -1), fast=fast, attn_split=(ws, 32 ** -0.5))
+            a = ops.mha_presplit(ws, B, L, n_ctx, k=kv[:n_ctx, :E], v=kv[:n_ctx, E:])
+        elif (name + '.pos_q2') in W:
             u2, _ = ops.layernorm(t, T[name + '.norm2.weight'], T[name + '.norm2.bias'])
             qc = ops.linear(u2, W[name + '.cross_in'].cols(0, E), res=W[name + '.pos_q2'].unsqueeze(0).expand(B, -1, -1), fast=fast)
         else:
             _, uq = ops.layernorm(t, T[name + '.norm2.weight'], T[name + '.norm2.bias'], pos, want_y=False)
             qc = ops.linear(uq, W[name + '.cross_in'].cols(0, E), fast=fast)
-        kv = W[name + '.ctx_kv']
-        a = ops.mha(qc, kv[:n_ctx, :E], kv[:n_ctx, E:], heads=self.n_head, fast=fast)
+        if a is None:
+            a = ops.mha(qc, kv[:n_ctx, :E], kv[:n_ctx, E:], heads=self.n_head, fast=fast)
         t = ops.linear(a, W[name + '.cross_out'], res=t, fast=fast)
         u, _ = ops.layernorm(t, T[name + '.norm3.weight'], T[name + '.norm3.bias'])
         f = ops.conv2d(u.view(B, tg, tg, E), W[name + '.conv1'], pad=1, act='gelu', fast=fast)

@@ -44,7 +44,7 @@ __device__ __forceinline__ void a2_mma_ts(uint32_t d, uint32_t a_tmem, uint64_t 
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void attn256_split_kernel(const float* __restrict__ q, int ldq, const float* __restrict__ k, int ldk, const float* __restrict__ v, int ldv,
                                      long long bs_q, long long bs_kv, int B, int kvB, int L, int S, float qscale, uint16_t* __restrict__ ws) {
-  const long long nq = (long long)B * L * 32, nk = (long long)kvB * S * 32;
+  const long long nq = q ? (long long)B * L * 32 : 0, nk = (long long)kvB * S * 32;      // q == nullptr: the q images are already in the workspace
   const long long img_q = (long long)B * L * A2_D, img_k = (long long)kvB * S * A2_D;     // halfs per image
   uint16_t* qh = ws; uint16_t* ql = qh + img_q; uint16_t* kh = ql + img_q; uint16_t* kl = kh + img_k; uint16_t* vh = kl + img_k; uint16_t* vl = vh + img_k;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nq + 2 * nk; i += (long long)gridDim.x * blockDim.x) {
@@ -285,7 +285,7 @@ __global__ void __launch_bounds__(A2_THREADS, 1) attn256_kernel(const A2P p) {
 // shared with attn_mh.cu: fp16 hi / lo tile images of q (B frames, pre-scaled by qscale), k and v (kvB frames: 1 = shared by all frames)
 int sma_attn_split_launch(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv, long long q_bs, long long kv_bs, int B, int kvB,
                           int L, int S, float qscale, void* workspace, cudaStream_t st) {
-  const long long items = (long long)B * L * 32 + 2LL * kvB * S * 32;
+  const long long items = (q ? (long long)B * L * 32 : 0) + 2LL * kvB * S * 32;
   int blocks = (int)((items + 255) / 256); if (blocks > 148 * 16) blocks = 148 * 16;
   attn256_split_kernel<<<blocks, 256, 0, st>>>(q, ldq, k, ldk, v, ldv, q_bs, kv_bs, B, kvB, L, S, qscale, reinterpret_cast<uint16_t*>(workspace));
   SMA_LAUNCH_CHECK();
@@ -298,16 +298,20 @@ extern "C" int64_t sma_attn256_workspace_bytes(int B, int L, int S) {
 }
 
 extern "C" int sma_attn256_fwd(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv, int64_t q_bstride, int64_t kv_bstride,
-                               int B, int L, int S, float scale, void* workspace, float* out, int ldo, sma_stream_t stream) {
-  if (!q || !k || !v || !out || !workspace || B <= 0 || L <= 0 || S <= 0) return SMA_ERR_BAD_ARG;
+                               int B, int L, int S, float scale, void* workspace, float* out, int ldo, int presplit, sma_stream_t stream) {
+  // presplit != 0: the q | k | v projection's epilogue has written the operand images into `workspace` (sma_conv_desc.split_ws); q, k, v are then unused
+  if (!out || !workspace || B <= 0 || L <= 0 || S <= 0 || (!presplit && (!q || !k || !v))) return SMA_ERR_BAD_ARG;
+  if (presplit) { q = k = v = out; if (S != L) return SMA_ERR_BAD_ARG; }
   if ((L % A2_BQ) || (S % A2_BKV) || B > 65535) return SMA_ERR_UNSUPPORTED;
   if (((ldq | ldk | ldv | ldo) & 3) || ((q_bstride | kv_bstride) & 3)) return SMA_ERR_UNSUPPORTED;
   if ((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(v) | reinterpret_cast<uintptr_t>(out) |
        reinterpret_cast<uintptr_t>(workspace)) & 15)
     return SMA_ERR_BAD_ARG;
   cudaStream_t st = as_stream(stream);
-  int rs = sma_attn_split_launch(q, ldq, k, ldk, v, ldv, q_bstride, kv_bstride, B, B, L, S, scale * 1.4426950408889634f, workspace, st);
-  if (rs != SMA_OK) return rs;
+  if (!presplit) {
+    int rs = sma_attn_split_launch(q, ldq, k, ldk, v, ldv, q_bstride, kv_bstride, B, B, L, S, scale * 1.4426950408889634f, workspace, st);
+    if (rs != SMA_OK) return rs;
+  }
   static SmaDevOnce once;
   if (int rc = sma_opt_in_smem(once, attn256_kernel, (int)A2_SMEM + 1024)) return rc;
   A2P p; p.ws = reinterpret_cast<const uint16_t*>(workspace); p.out = out; p.ldo = ldo; p.B = B; p.L = L; p.S = S;

@@ -248,8 +248,12 @@ extern "C" int64_t sma_mha_e256_workspace_bytes(int B, int kvB, int L, int S) {
 }
 
 extern "C" int sma_mha_e256_fwd(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv, int64_t q_bstride, int64_t kv_bstride,
-                                int B, int L, int S, float scale, const uint8_t* key_mask, void* workspace, float* out, int ldo, sma_stream_t stream) {
-  if (!q || !k || !v || !out || !workspace || B <= 0 || L <= 0 || S <= 0) return SMA_ERR_BAD_ARG;
+                                int B, int L, int S, float scale, const uint8_t* key_mask, void* workspace, float* out, int ldo, int presplit, sma_stream_t stream) {
+  // presplit: 0 = q, k, v are fp32 tensors, split here; 1 = the q images were written into `workspace` by the projection's epilogue (sma_conv_desc.split_ws),
+  // k and v are split here; 2 = q, k and v images are all there already (q / k / v pointers are then unused)
+  if (presplit < 0 || presplit > 2 || !out || !workspace || B <= 0 || L <= 0 || S <= 0) return SMA_ERR_BAD_ARG;
+  if ((presplit == 0 && !q) || (presplit < 2 && (!k || !v))) return SMA_ERR_BAD_ARG;
+  if (presplit) { if (!q) q = out; if (!k) { k = out; v = out; } }         // (only their alignment is looked at below)
   if ((L % MH_BQ) || (S % MH_BKV) || B > 65535) return SMA_ERR_UNSUPPORTED;
   if (((ldq | ldk | ldv | ldo) & 3) || ((q_bstride | kv_bstride) & 3)) return SMA_ERR_UNSUPPORTED;
   if ((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(v) | reinterpret_cast<uintptr_t>(out) |
@@ -258,8 +262,10 @@ extern "C" int sma_mha_e256_fwd(const float* q, int ldq, const float* k, int ldk
   if (key_mask && ((reinterpret_cast<uintptr_t>(key_mask) & 15) || (S & 15))) return SMA_ERR_UNSUPPORTED;
   cudaStream_t st = as_stream(stream);
   const int kvB = kv_bstride ? B : 1;
-  int rs = sma_attn_split_launch(q, ldq, k, ldk, v, ldv, q_bstride, kv_bstride, B, kvB, L, S, scale * 1.4426950408889634f, workspace, st);
-  if (rs != SMA_OK) return rs;
+  if (presplit < 2) {
+    int rs = sma_attn_split_launch(presplit ? nullptr : q, ldq, k, ldk, v, ldv, q_bstride, kv_bstride, B, kvB, L, S, scale * 1.4426950408889634f, workspace, st);
+    if (rs != SMA_OK) return rs;
+  }
   static SmaDevOnce once;
   if (int rc = sma_opt_in_smem(once, attn_mh_kernel, (int)MH_SMEM + 1024)) return rc;
   MhP p; p.ws = reinterpret_cast<const uint16_t*>(workspace); p.mask = key_mask; p.out = out; p.ldo = ldo; p.B = B; p.kvB = kvB; p.L = L; p.S = S;

@@ -262,7 +262,7 @@ extern "C" int sma_conv2d_fwd(sma_conv_desc* d, sma_stream_t stream) {
   }
   d->kernel_used = 0;
   if (d->plan_only) return SMA_OK;
-  if (d->aux || d->x2) return SMA_ERR_UNSUPPORTED;           // the SFT epilogue / the two-tensor input live in the persistent tensor-core kernel only: callers fall back to sma_sft_combine
+  if (d->aux || d->x2 || d->split_ws) return SMA_ERR_UNSUPPORTED;           // the SFT epilogue / the two-tensor input live in the persistent tensor-core kernel only: callers fall back to sma_sft_combine
   ConvP p;
   p.x = d->x; p.w = d->w; p.bias = d->bias; p.pre_scale = d->pre_scale; p.pre_shift = d->pre_shift; p.res = d->res; p.y = d->y;
   p.in_bs = d->in_bstride; p.out_bs = d->out_bstride; p.res_bs = d->res_bstride;

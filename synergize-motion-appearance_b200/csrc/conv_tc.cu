@@ -241,6 +241,28 @@ __global__ void __launch_bounds__(192, 1) conv_tc_kernel(const TcP p) {
 
 
 
+// The q | k | v projection written straight into the attention kernels' operand images (attn256.cu / attn_mh.cu): the 8 consecutive columns a thread holds per
+// 256-bit store are exactly one 16-byte piece of a 128-byte tile row - the granularity of the split pass this replaces (which re-read 4.6 GB of
+// fp32 q / k / v per step to write the same bytes).  q is pre-scaled by scale * log2 e; hi = rn(x), lo = rn(x - hi); SWIZZLE_128B rows; q_lo piece-major.
+__device__ __forceinline__ void store_attn_split(uint16_t* ws, long long img_q, long long img_k, float qscale, int L, const float (&o)[8], int b, int r, int n) {
+  const int which = n >> 8, e = n & 255, g = e >> 3, c4 = g >> 3, ch = g & 7;
+  const float s = which == 0 ? qscale : 1.f;
+  uint4 hi, lo;
+  split_f16x2(o[0] * s, o[1] * s, hi.x, lo.x); split_f16x2(o[2] * s, o[3] * s, hi.y, lo.y);
+  split_f16x2(o[4] * s, o[5] * s, hi.z, lo.z); split_f16x2(o[6] * s, o[7] * s, hi.w, lo.w);
+  const int RB = which == 0 ? 128 : 64;                                // rows per tile: 128 queries / 64 keys
+  const int rb = r / RB, rr = r - rb * RB;
+  const long long tile = ((long long)b * (L / RB) + rb) * (4LL * RB * 64);
+  const long long off = tile + (long long)c4 * RB * 64 + (((uint32_t)rr * 128u + (uint32_t)((ch ^ (rr & 7)) << 4)) >> 1);
+  if (which == 0) {
+    *reinterpret_cast<uint4*>(ws + off) = hi;
+    *reinterpret_cast<uint4*>(ws + img_q + tile + ((long long)(c4 * 8 + ch) * 128 + rr) * 8) = lo;       // piece-major for the TMEM loaders
+  } else {
+    uint16_t* kh = ws + 2 * img_q + (which == 2 ? 2 * img_k : 0);
+    *reinterpret_cast<uint4*>(kh + off) = hi; *reinterpret_cast<uint4*>(kh + img_k + off) = lo;
+  }
+}
+
 // GroupNorm statistics of the tile a convolution has just computed (fused producer-side: the standalone statistics pass re-reads every normalised
 // tensor from HBM, 15 GB per 64-frame step).  The 8 consecutive channels o[0..7] of this lane's pixel row (zero for rows outside the image) are
 // reduced over the warp's 32 rows as 4 channel PAIRS x {sum, sum of squares}: a transposing butterfly - three rounds that halve the number of
@@ -314,6 +336,8 @@ struct Tc2P {
   int fuse;                   // 3-pass, NT <= 128: the hi and lo weight images (adjacent in the ring) are read as ONE B tile of 2*NT rows, so
                               // a_hi*[b_hi | b_lo] is one MMA; its lo half lands in accumulator columns [NT, 2NT) and is added in the epilogue
   int acc_cols;               // TMEM columns per accumulator (NT or 2*NT)
+  uint16_t* split_ws; long long split_img_q, split_img_k; float split_qscale;   // != nullptr: the output is written as the attention kernels' fp16 hi / lo tile images
+                              // (q | k | v of E = 256: columns [0,256) q, [256,512) k, [512,768) v; attn256.cu attn256_split_kernel's layout) instead of fp32 rows
   float* gnp; int gn_chunks;  // fused GroupNorm partial sums: [frame][chunk = 4 * tile-in-image + lane quarter][Cout / 2 pairs][sum, sum of squares]; nullptr: off
   int dbg;                    // timing experiments (results invalid): bit 2 = epilogue skips its residual loads and stores
   int flat, tiles_x, tiles_per_img, total_tiles;
@@ -514,10 +538,13 @@ __global__ void __launch_bounds__(TMA ? V2_THREADS_TMA : V2_THREADS, 1) conv_tc2
                 const long long pix = (long long)(oy * p.d2s + p1) * (p.Wo * p.d2s) + (ox * p.d2s + p2);
                 dst = p.y + (long long)b * p.out_bs + pix * p.out_ld + cval;
               }
-              if (mok)
-              asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst), "f"(o[0]), "f"(o[1]), "f"(o[2]), "f"(o[3]), "f"(o[4]), "f"(o[5]),
-                           "f"(o[6]), "f"(o[7])
-                           : "memory");
+              if (mok) {
+                if (p.split_ws) store_attn_split(p.split_ws, p.split_img_q, p.split_img_k, p.split_qscale, p.HoWo, o, b, r, n);
+                else
+                asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst), "f"(o[0]), "f"(o[1]), "f"(o[2]), "f"(o[3]), "f"(o[4]), "f"(o[5]),
+                             "f"(o[6]), "f"(o[7])
+                             : "memory");
+              }
             }
           }
         }
@@ -592,10 +619,13 @@ __global__ void __launch_bounds__(TMA ? V2_THREADS_TMA : V2_THREADS, 1) conv_tc2
                 const long long pix = (long long)(oy * p.d2s + p1) * (p.Wo * p.d2s) + (ox * p.d2s + p2);
                 dst = p.y + (long long)b * p.out_bs + pix * p.out_ld + cval;
               }
-              if (mok)
-              asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst), "f"(o[0]), "f"(o[1]), "f"(o[2]), "f"(o[3]), "f"(o[4]), "f"(o[5]),
-                           "f"(o[6]), "f"(o[7])
-                           : "memory");
+              if (mok) {
+                if (p.split_ws) store_attn_split(p.split_ws, p.split_img_q, p.split_img_k, p.split_qscale, p.HoWo, o, b, r, n);
+                else
+                asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst), "f"(o[0]), "f"(o[1]), "f"(o[2]), "f"(o[3]), "f"(o[4]), "f"(o[5]),
+                             "f"(o[6]), "f"(o[7])
+                             : "memory");
+              }
             }
           } else if (mok && !(p.dbg & 4)) {
   #pragma unroll
@@ -1220,6 +1250,16 @@ static int conv_tc2_try(sma_conv_desc* d, cudaStream_t st, bool f16) {
   const int main_adds = p.nblob * 4 * (p.fuse ? 1 : p.passes);
   p.acc_corr = (d->tc_variant & 256) ? 1.f : 1.f + 1.6e-8f * (float)main_adds;
   p.dbg = (d->tc_variant >> 1) & 7;
+  p.split_ws = nullptr; p.split_img_q = p.split_img_k = 0; p.split_qscale = 1.f;
+  if (d->split_ws) {      // attention operand images instead of fp32 rows: flat 1x1 layers producing q (256 columns) or q | k | v (768) of E = 256, whole 128-row tiles
+    const bool v8 = (d->out_ld & 7) == 0 && (d->out_bstride & 7) == 0 && (reinterpret_cast<uintptr_t>(d->y) & 31) == 0 && (!d->res || ((d->res_ld & 7) == 0 && (d->res_bstride & 7) == 0 && (reinterpret_cast<uintptr_t>(d->res) & 31) == 0));
+    if (!flat || patch || d->d2s > 1 || d->out_nchw || (d->Cout != 256 && d->Cout != 768) || (p.HoWo % 128) || !v8 || d->act != SMA_ACT_NONE ||
+        (reinterpret_cast<uintptr_t>(d->split_ws) & 15) || d->gn_want)
+      return SMA_ERR_UNSUPPORTED;
+    p.split_ws = reinterpret_cast<uint16_t*>(d->split_ws);
+    p.split_img_q = (long long)d->B * p.HoWo * 256; p.split_img_k = d->Cout == 768 ? p.split_img_q : 0;
+    p.split_qscale = d->split_qscale;
+  }
   // fused GroupNorm partial sums: only where the 256-bit epilogue runs (every lane then walks the same column blocks) and the output is the whole
   // normalised tensor (no depth-to-space); the caller learns through gn_chunks (0 = not produced: it runs sma_groupnorm_stats instead)
   {
@@ -1299,7 +1339,7 @@ int sma_conv2d_tc_try(sma_conv_desc* d, cudaStream_t st) {
     int r2 = conv_tc2_try(d, st, false);
     if (r2 != SMA_ERR_UNSUPPORTED) { d->kernel_used = 2; if (d->plan_only) d->w_tc_nt = nt_default; return r2; }
   }
-  if (d->aux || d->x2) return SMA_ERR_UNSUPPORTED;
+  if (d->aux || d->x2 || d->split_ws) return SMA_ERR_UNSUPPORTED;
   // gather kernel: one CTA per (128 rows, NT columns).  Few rows (tiny feature maps: the hourglass bottlenecks) would leave most SMs idle
   // with the widest tile, so the image may be packed with a narrower NT (more CTAs, each streaming a quarter of the weights).
   int NTg = d->w_tc_nt ? d->w_tc_nt : nt_default;

@@ -547,7 +547,7 @@ extern "C" int sma_pack_conv_weight_ts(const float* w_packed, int ldw, int Cout,
 // returns SMA_ERR_UNSUPPORTED when the shape / layout is not eligible (the caller then tries the shared-memory-operand kernels)
 int sma_conv2d_ts_try(sma_conv_desc* d, cudaStream_t st) {
   if (d->aux || d->plan_only) return SMA_ERR_UNSUPPORTED;      // (the tensor-memory-operand kernel is an opt-in experiment: never planned)
-  if (!d->w_ts || d->x2 || d->out_nchw || (d->precision != SMA_PREC_F16X3 && d->precision != SMA_PREC_F16) || (d->tc_variant & 1)) return SMA_ERR_UNSUPPORTED;
+  if (!d->w_ts || d->x2 || d->split_ws || d->out_nchw || (d->precision != SMA_PREC_F16X3 && d->precision != SMA_PREC_F16) || (d->tc_variant & 1)) return SMA_ERR_UNSUPPORTED;
   if ((d->Cin % 64) || (d->in_ld & 3) || (d->in_bstride & 3) || (reinterpret_cast<uintptr_t>(d->x) & 15) || (reinterpret_cast<uintptr_t>(d->w_ts) & 15))
     return SMA_ERR_UNSUPPORTED;
   if (d->pre_scale && ((reinterpret_cast<uintptr_t>(d->pre_scale) | reinterpret_cast<uintptr_t>(d->pre_shift)) & 15)) return SMA_ERR_UNSUPPORTED;

@@ -235,6 +235,7 @@ USE_TF32X3 = True        # let sma_conv2d_fwd pick a tcgen05 kernel where the sh
 ALLOW_TF32_1PASS = True  # honour `fast=True` requests (single pass)
 USE_TS = False           # weights as the tensor-memory A operand (csrc/conv_ts.cu) where they fit in tensor memory; False: shared-memory-operand kernels
 USE_MH_F16 = True        # 8-head E=256 attention: fp16-split kernel with pre-split tile images (csrc/attn_mh.cu); False: tf32 kernel (attn_tc.cu)
+SPLIT_FUSE = os.environ.get('SMA_NO_SPLITFUSE', '0') != '1'      # q | k | v projections write the attention operand images in their epilogue (conv2d(attn_split=))
 MHA_D4_MMA = os.environ.get('SMA_NO_D4_MMA', '0') != '1'      # head-dim-4 attention of single-pass stages (S3m) as register-level mma with P in fp16 (csrc/attn.cu)
 VQ_TILED = True          # large-N VQ lookups as the register-tiled exact-fp32 GEMM (bit-identical); False: warp-per-row kernel
 FUSE_GN = os.environ.get('SMA_NO_FUSE_GN', '0') != '1'           # (env: A/B on one box) GroupNorm partial sums of a conv's output from its own epilogue (conv2d(gn=...)); False: always the standalone statistics pass
@@ -262,13 +263,15 @@ def conv2d(x: torch.Tensor, cw: ConvW, *, stride: int = 1, pad: int = 0, pad_tl:
            pre: Optional[Tuple[torch.Tensor, torch.Tensor, str]] = None, res: Optional[torch.Tensor] = None,
            upsample2: bool = False, d2s: int = 0, out_nchw: bool = False, exact: bool = False, fast: bool = False,
            sft: Optional[Tuple[torch.Tensor, float]] = None, gn: Optional[Tuple[torch.Tensor, torch.Tensor]] = None,
-           x2: Optional[torch.Tensor] = None, x2_1x1: bool = False):
+           x2: Optional[torch.Tensor] = None, x2_1x1: bool = False, attn_split: Optional[Tuple[torch.Tensor, float]] = None):
     """`exact`: force the CUDA-core fp32 kernel; `fast`: allow single-pass TF32 on the tensor cores (layers whose
     contribution to the output error budget was measured to be negligible); default: 3xTF32 (fp32-faithful).
     `sft=(scale, w)`: Fuse_sft_block tail, y = res + w*(res*scale + conv(x)) (needs `res`): fused into the epilogue of the persistent
     tensor-core kernel; launches that cannot run there (exact mode, odd shapes) do conv -> sma_sft_combine instead.
     `gn=(gamma, beta)`: also return the GroupNorm(32, eps 1e-6) scale / shift of the OUTPUT, `(y, (scale, shift))`: the partial sums come out of the
     convolution's epilogue where the persistent tensor-core kernel runs (no second pass over y), else from groupnorm_stats(y).
+    `attn_split=(workspace, softmax_scale)`: a flat 1x1 layer producing q (256 columns) or q | k | v (768) of an E = 256 attention writes the attention
+    kernels' fp16 hi / lo operand images into `workspace` instead of fp32 rows (returns None; then mha(..., presplit=)); SmaError(unsupported) otherwise.
     `x2`: second input tensor of the same geometry; `cw` holds the weights of both (input channels of x first): conv(x, w1) + conv(x2, w2) in one
     accumulator (staged-input fp16 kernel only; raises SmaError(unsupported) otherwise - callers keep a two-convolution form)."""
     lib = _lib.load()
@@ -307,6 +310,10 @@ def conv2d(x: torch.Tensor, cw: ConvW, *, stride: int = 1, pad: int = 0, pad_tl:
         oB, oH, oW, oC, obs, old = _nhwc(out)
         assert (oB, oH, oW, oC) == (B, Ho * d2s, Wo * d2s, Cq), (out.shape, (B, Ho * d2s, Wo * d2s, Cq))
         d.y, d.out_bstride, d.out_ld = out.data_ptr(), obs, old
+    elif attn_split is not None:
+        out = attn_split[0]                               # (y is not written: the images go to the workspace; any aligned address satisfies the ABI's checks)
+        d.y, d.out_bstride, d.out_ld = out.data_ptr(), Ho * Wo * cw.Cout, cw.Cout
+        d.split_ws, d.split_qscale = attn_split[0].data_ptr(), float(attn_split[1]) * 1.4426950408889634
     else:
         if out is None:
             out = torch.empty((B, Ho, Wo, cw.Cout), device=x.device, dtype=torch.float32)
@@ -342,7 +349,7 @@ def conv2d(x: torch.Tensor, cw: ConvW, *, stride: int = 1, pad: int = 0, pad_tl:
             key = (B, Hi, Wi, stride, pt, pl, upsample2, Ho, Wo, out_nchw, d2s, d.precision, TC_VARIANT, x.data_ptr() & 15, ild & 3, ibs & 3,
                    pre is not None, sft is not None, 0 if res is None else (d.res_ld & 7, d.res_bstride & 7), d.out_ld & 7, d.out_bstride & 7,
                    d.gn_want, out.data_ptr() & 31, 0 if res is None else res.data_ptr() & 31,
-                   None if x2 is None else (Cin1, ild2 & 3, ibs2 & 3, x2.data_ptr() & 15, x2_1x1))
+                   None if x2 is None else (Cin1, ild2 & 3, ibs2 & 3, x2.data_ptr() & 15, x2_1x1), attn_split is not None)
             if cw.plans is None:
                 cw.plans = {}
             planned = cw.plans.get(key)
@@ -361,6 +368,8 @@ def conv2d(x: torch.Tensor, cw: ConvW, *, stride: int = 1, pad: int = 0, pad_tl:
                 d.gn_partial = gn_partial.data_ptr()
             else:
                 d.gn_want = 0
+    if attn_split is not None and (planned is None or planned[0] != 3):
+        raise _lib.SmaError('conv2d(attn_split=...): needs the persistent fp16 kernel (unsupported shape / layout): write fp32 rows and let the attention split them')
     if x2 is not None and (planned is None or planned[0] != 3):
         raise _lib.SmaError('conv2d(x2=...): the two-tensor input needs the staged-input fp16 kernel (unsupported shape / layout): run the two convolutions')
     if sft is not None and (planned is None or planned[0] not in (2, 3)):
@@ -379,6 +388,8 @@ def conv2d(x: torch.Tensor, cw: ConvW, *, stride: int = 1, pad: int = 0, pad_tl:
         raise _lib.SmaError(f'conv2d ran on kernel {d.kernel_used} but was planned on {planned[0]} (Cin={Cin} Cout={cw.Cout} k={cw.kh}): binding bug')
     global LAST_CONV_KERNEL
     LAST_CONV_KERNEL = d.kernel_used
+    if attn_split is not None:
+        return None
     if gn is not None:
         # gn = (gamma, beta[, groups[, scale_out, shift_out]]): the optional outputs are (B, C) column slices of wider buffers (the two halves of a
         # concatenated tensor are normalised with separate statistics: GroupNorm's groups do not straddle them)
@@ -400,7 +411,7 @@ def conv2d(x: torch.Tensor, cw: ConvW, *, stride: int = 1, pad: int = 0, pad_tl:
 def linear(x: torch.Tensor, cw: ConvW, **kw) -> torch.Tensor:
     """Linear over the last dim of a (B,L,E) token tensor == 1x1 conv over (B,1,L,E)."""
     y = conv2d(x.unsqueeze(1), cw, **{k: (v.unsqueeze(1) if isinstance(v, torch.Tensor) else v) for k, v in kw.items()})
-    return y.squeeze(1)
+    return None if y is None else y.squeeze(1)
 
 
 def groupnorm_stats(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, groups: int = 32, eps: float = 1e-6):
@@ -512,6 +523,35 @@ def blend_bil4(g: torch.Tensor, src_hw: Tuple[int, int], out: Optional[torch.Ten
 def mha(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, key_mask: Optional[torch.Tensor] = None,
         scale: Optional[float] = None, out: Optional[torch.Tensor] = None, exact: bool = False, fast: bool = False) -> torch.Tensor:
     """q (B,L,E-view) ; k,v (B,S,E-view) or (S,E-view) shared by all frames.  Views may be column slices."""
+    return _mha(q, k, v, heads, key_mask, scale, out, exact, fast)
+
+
+def attn_workspace(B: int, kvB: int, L: int, S: int, device) -> torch.Tensor:
+    """Workspace of the E = 256 attention kernels (fp16 hi / lo operand images of q, k, v): conv2d(attn_split=) writes into it, mha_presplit reads it."""
+    return torch.empty((_lib.load().sma_mha_e256_workspace_bytes(B, kvB, L, S),), device=device, dtype=torch.uint8)
+
+
+def mha_presplit(ws: torch.Tensor, B: int, L: int, S: int, k: Optional[torch.Tensor] = None, v: Optional[torch.Tensor] = None,
+                 key_mask: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """8-head E = 256 attention whose q images (k, v given: shared (S,E) codebook projections, split here) or q, k and v images (k = v = None:
+    self-attention, S = L) were written into `ws` by the projection's epilogue."""
+    lib = _lib.load()
+    E = 256
+    if out is None:
+        out = torch.empty((B, L, E), device=ws.device, dtype=torch.float32)
+    if key_mask is not None:
+        assert key_mask.dtype == torch.uint8 and key_mask.is_contiguous() and key_mask.numel() == B * S
+    shared = k is not None
+    if shared:
+        assert k.dim() == 2 and v.dim() == 2 and k.stride(-1) == 1 and v.stride(-1) == 1
+    with _Prof('mha', 4.0 * B * L * S * E, 4.0 * (2 * B * L * E + 2 * (1 if shared else B) * S * E), f'mha-f16 B{B} L{L} S{S} h8 D32'):
+        check(lib.sma_mha_e256_fwd(None, E, _ptr(k), k.stride(0) if shared else E, _ptr(v), v.stride(0) if shared else E, L * E, 0 if shared else S * E,
+                                   B, L, S, 32 ** -0.5, _ptr(key_mask), ws.data_ptr(), out.data_ptr(), out.stride(1), 1 if shared else 2, _stream()),
+              'sma_mha_e256_fwd(presplit)')
+    return out
+
+
+def _mha(q, k, v, heads, key_mask=None, scale=None, out=None, exact=False, fast=False):
     lib = _lib.load()
     B, L, E = q.shape
     D = E // heads
@@ -535,7 +575,7 @@ def mha(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, key_mask:
         ws = torch.empty((lib.sma_mha_e256_workspace_bytes(B, B if kvbs else 1, L, S),), device=q.device, dtype=torch.uint8)
         with _Prof('mha', 4.0 * B * L * S * E, 4.0 * (2 * B * L * E + 2 * (B if kvbs else 1) * S * E), f'mha-f16 B{B} L{L} S{S} h{heads} D{D}'):
             check(lib.sma_mha_e256_fwd(q.data_ptr(), q.stride(1), k.data_ptr(), ldk, v.data_ptr(), ldv, q.stride(0), kvbs, B, L, S, scale,
-                                       _ptr(key_mask), ws.data_ptr(), out.data_ptr(), out.stride(1), _stream()), 'sma_mha_e256_fwd')
+                                       _ptr(key_mask), ws.data_ptr(), out.data_ptr(), out.stride(1), 0, _stream()), 'sma_mha_e256_fwd')
         return out
     with _Prof('mha', 4.0 * B * L * S * E, 4.0 * (2 * B * L * E + 2 * (B if kvbs else 1) * S * E), f'mha B{B} L{L} S{S} h{heads} D{D}'):
         check(lib.sma_mha_fwd(q.data_ptr(), q.stride(1), k.data_ptr(), ldk, v.data_ptr(), ldv, kvbs, B, L, S, heads, D, scale,
@@ -555,7 +595,22 @@ def attn256(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, scale: float, out
     ws = torch.empty((lib.sma_attn256_workspace_bytes(B, L, S),), device=q.device, dtype=torch.uint8)
     with _Prof('mha', 4.0 * B * L * S * D, 4.0 * (2 * B * L * D + 2 * B * S * D), f'attn256 B{B} L{L} S{S}'):
         check(lib.sma_attn256_fwd(q.data_ptr(), q.stride(1), k.data_ptr(), k.stride(1), v.data_ptr(), v.stride(1), q.stride(0), k.stride(0),
-                                  B, L, S, scale, ws.data_ptr(), out.data_ptr(), out.stride(1), _stream()), 'sma_attn256_fwd')
+                                  B, L, S, scale, ws.data_ptr(), out.data_ptr(), out.stride(1), 0, _stream()), 'sma_attn256_fwd')
+    return out
+
+
+def attn256_workspace(B: int, L: int, device) -> torch.Tensor:
+    return torch.empty((_lib.load().sma_attn256_workspace_bytes(B, L, L),), device=device, dtype=torch.uint8)
+
+
+def attn256_presplit(ws: torch.Tensor, B: int, L: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """AttnBlock attention whose q | k | v operand images were written into `ws` by the qkv conv's epilogue (conv2d(attn_split=(ws, 256 ** -0.5)))."""
+    lib = _lib.load()
+    if out is None:
+        out = torch.empty((B, L, 256), device=ws.device, dtype=torch.float32)
+    with _Prof('mha', 4.0 * B * L * L * 256, 4.0 * 4 * B * L * 256, f'attn256 B{B} L{L} S{L}'):
+        check(lib.sma_attn256_fwd(None, 256, None, 256, None, 256, L * 256, L * 256, B, L, L, 1.0, ws.data_ptr(), out.data_ptr(), out.stride(1), 1, _stream()),
+              'sma_attn256_fwd(presplit)')
     return out
 
 

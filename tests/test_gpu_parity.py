@@ -518,6 +518,50 @@ def test_attn256_tensor_core_kernel(S, B, L, S_kv, qs):
         S.ops.attn256(dev[:, :100, :256], dev[:, :S_kv, 256:512], dev[:, :S_kv, 512:], 1.0)
 
 
+def test_projection_epilogue_writes_attention_operand_images(S):
+    """The q | k | v projection (self-attention) and the q projection (cross-attention onto shared codebook keys) of the E = 256 transformer layers
+    write the attention kernels' fp16 hi / lo images in their epilogue: same arithmetic as fp32 rows followed by the split pass -> bit-identical
+    attention output, one launch fewer each."""
+    B, L, E = 2, 1024, 256
+    w = rnd(3 * E, E, 1, 1, seed=1) * E ** -0.5
+    bias = rnd(3 * E, seed=2) * 0.1
+    cw = S.ops.pack_conv(w.cuda(), bias.cuda())
+    x = rnd(B, L, E, seed=3).cuda()
+    pos = (rnd(L, 3 * E, seed=4) * 0.1).cuda()
+    mask = (torch.rand(B, L, generator=torch.Generator().manual_seed(5)) < 0.1).to(torch.uint8).cuda()
+    qkv = S.ops.linear(x, cw, res=pos.unsqueeze(0).expand(B, -1, -1))
+    n0 = S.ops.launch_count()
+    ref = S.ops.mha(qkv[..., :E], qkv[..., E:2 * E], qkv[..., 2 * E:], 8, mask)
+    n_ref = S.ops.launch_count() - n0
+    ws = S.ops.attn_workspace(B, B, L, L, x.device)
+    assert S.ops.linear(x, cw, res=pos.unsqueeze(0).expand(B, -1, -1), attn_split=(ws, 32 ** -0.5)) is None
+    n0 = S.ops.launch_count()
+    got = S.ops.mha_presplit(ws, B, L, L, key_mask=mask)
+    assert S.ops.launch_count() - n0 == n_ref - 1
+    assert torch.equal(got, ref)
+    # cross-attention: q from the epilogue, shared k / v split by the attention call
+    for n_ctx in (256, 768):
+        kv = rnd(n_ctx, 2 * E, seed=6).cuda()
+        cq = cw.cols(0, E)
+        qc = S.ops.linear(x, cq, res=pos[:, :E].unsqueeze(0).expand(B, -1, -1))
+        ref = S.ops.mha(qc, kv[:, :E], kv[:, E:], 8)
+        ws = S.ops.attn_workspace(B, 1, L, n_ctx, x.device)
+        S.ops.linear(x, cq, res=pos[:, :E].unsqueeze(0).expand(B, -1, -1), attn_split=(ws, 32 ** -0.5))
+        got = S.ops.mha_presplit(ws, B, L, n_ctx, k=kv[:, :E], v=kv[:, E:])
+        assert torch.equal(got, ref)
+    # AttnBlock: single head of 256, the q | k | v conv with its GroupNorm prologue
+    xi = x.view(B, 32, 32, E)
+    sc, sh = (rnd(B, E, seed=8) * 0.2 + 1).cuda(), (rnd(B, E, seed=9) * 0.1).cuda()
+    qkv = S.ops.conv2d(xi, cw, pre=(sc, sh, 'none')).view(B, L, 3 * E)
+    ref = S.ops.mha(qkv[..., :E], qkv[..., E:2 * E], qkv[..., 2 * E:], 1, scale=E ** -0.5)
+    ws = S.ops.attn256_workspace(B, L, x.device)
+    S.ops.conv2d(xi, cw, pre=(sc, sh, 'none'), attn_split=(ws, E ** -0.5))
+    assert torch.equal(S.ops.attn256_presplit(ws, B, L), ref)
+    # shapes the epilogue cannot serve are refused (the caller writes fp32 rows instead)
+    with pytest.raises(RuntimeError):
+        S.ops.linear(x[:, :100], cw, attn_split=(ws, 1.0))
+
+
 def test_mha_all_keys_masked_gives_nan_like_reference(S):
     q, k, v = rnd(1, 1024, 256, seed=1).cuda(), rnd(1, 1024, 256, seed=2).cuda(), rnd(1, 1024, 256, seed=3).cuda()
     mask = torch.ones(1, 1024, dtype=torch.uint8, device='cuda')
