@@ -268,6 +268,10 @@ int sma_dense_motion_head(const float* logits, int ld, int h, int w, const float
  * the image and for columns >= k*k*C; turns the 7x7 conv over the 2-channel flow (archs/appmotioncodebook_arch.py:136,142) into one 1x1 conv of
  * depth Kp = 128 instead of 49 taps of a zero-padded 32-channel chunk. */
 int sma_im2col_small(const float* x, int B, int H, int W, int ld, int C, int k, int pad, float* out, int Kp, sma_stream_t stream);
+/* A k x k convolution with C <= 4 outputs (the image head, archs/vqgan_arch.py:349-352 last block; RefineFlow's conv2 / convo2, archs/appmotioncodebook_arch.py:163-175) as a
+ * pointwise layer whose k*k*C columns are (tap, c) - run by sma_conv2d_fwd over the un-shifted input - followed by this gather-sum:
+ * out[b,y,x,c] = bias[c] + sum_taps P[b, y+ky-pad, x+kx-pad, (ky*k+kx)*C + c], taps outside the map skipped (the conv's zero padding). */
+int sma_conv_tapsum(const float* P, int ldp, int B, int H, int W, int C, int k, int pad, const float* bias, float* out, int out_ld, sma_stream_t stream);
 /* flow glue of AppMotionCompFormer.forward (archs/appmotioncodebook_arch.py:562-601,689-710) */
 int sma_flow_to_px(const float* m, int B, int h, int w, float* flow_px, int out_ld, sma_stream_t stream);
 /* res: (B,h,w,res_ld) with columns 0,1 = delta-flow in pixels, 2 = delta-occlusion logit */

@@ -73,6 +73,7 @@ SIGNATURES = {
     'sma_dense_motion_head': ([_V, _I, _I, _I, _V, _V, _V, _V, _I, _I, _V, _V, _V, _V], C.c_int),
     'sma_im2col_small': ([_V, _I, _I, _I, _I, _I, _I, _I, _V, _I, _V], C.c_int),
     'sma_flow_to_px': ([_V, _I, _I, _I, _V, _I, _V], C.c_int),
+    'sma_conv_tapsum': ([_V, _I, _I, _I, _I, _I, _I, _I, _V, _V, _I, _V], C.c_int),
     'sma_flow_update': ([_V, _V, _V, _I, _I, _I, _I, _V, _V, _V], C.c_int),
     'sma_motion_ignore_mask': ([_V, _I, _I, _I, _I, _I, _V, _V], C.c_int),
     'sma_sft_combine': ([_V, _V, _V, _F, _L, _V, _V], C.c_int),

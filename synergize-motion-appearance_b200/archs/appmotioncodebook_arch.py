@@ -251,6 +251,8 @@ class AppMotionCompFormer(ParamModule):
                 n = f'{prefix}.blocks.{i}'
                 if kind == 'conv':
                     pc(n)
+                    if cout <= 4 and cin % 64 == 0 and T[n + '.weight'].shape[-1] == 3:      # the image head: its 9 taps as columns of a pointwise layer (ops.conv_tapsum)
+                        W[n + '.tap'] = ops.pack_conv_tapcols(T[n + '.weight'])
                 elif kind == 'res':
                     pres(n, cin, cout)
                 elif kind == 'attn':
@@ -287,6 +289,9 @@ class AppMotionCompFormer(ParamModule):
         # the two 3x3 output convs of RefineFlow read different halves of one buffer: one block-diagonal launch
         W['refine.conv2o2'] = ops.pack_conv_blockdiag([T['refine.conv2.weight'], T['refine.convo2.weight']],
                                                       [T['refine.conv2.bias'], T['refine.convo2.bias']])
+        big = torch.zeros((3, 256, 3, 3), device=T['refine.conv2.weight'].device, dtype=torch.float32)
+        big[0:2, :128] = T['refine.conv2.weight'].float(); big[2:3, 128:] = T['refine.convo2.weight'].float()
+        W['refine.conv2o2.tap'] = ops.pack_conv_tapcols(big)
         W['refine.conv1o1'] = ops.pack_conv_cat([T['refine.conv1.weight'], T['refine.convo1.weight']],
                                                 [T['refine.conv1.bias'], T['refine.convo1.bias']])
         for i, s in enumerate(self.SCALES):
@@ -372,6 +377,8 @@ class AppMotionCompFormer(ParamModule):
             if i > 0 and layout[i - 1][0] == 'norm':          # GroupNorm (no activation) feeding the last conv
                 s, h = stats if stats is not None else self._gn(f'{prefix}.blocks.{i - 1}', x)
                 pre = (s, h, 'none')
+            if (n + '.tap') in W and ops.TAPSUM and want is None and cout <= 4:
+                return ops.conv_tapsum(ops.conv2d(x, W[n + '.tap'], pre=pre, fast=fast), W[n].bias, cout, 3, 1, out=out)
             return ops.conv2d(x, W[n], pad=1, pre=pre, out=out, fast=fast, gn=want)
         if kind == 'res':
             return self._res(n, x, cin, cout, out=out, fast=fast, stats=stats, want=want)
@@ -593,7 +600,10 @@ class AppMotionCompFormer(ParamModule):
         ops.conv2d(ctx, W['refine.convc1'], pad=1, act='relu', out=z[..., 128:], fast=fs)
         f = ops.conv2d(z, W['refine.conv1o1'], pad=1, act='relu', fast=fs)                 # [flow branch 128 | occlusion branch 128]
         r = torch.empty((B, fg, fg, 4), device=dev, dtype=torch.float32)
-        ops.conv2d(f, W['refine.conv2o2'], pad=1, out=r[..., 0:3], fast=fs)                # [delta-flow 2 | delta-occlusion 1]
+        if ops.TAPSUM:         # 3 outputs: the 9 taps as 27 columns of a pointwise layer + a gather-sum (9x fewer tensor-core instructions)
+            ops.conv_tapsum(ops.conv2d(f, W['refine.conv2o2.tap'], fast=fs), W['refine.conv2o2'].bias, 3, 3, 1, out=r[..., 0:3])
+        else:
+            ops.conv2d(f, W['refine.conv2o2'], pad=1, out=r[..., 0:3], fast=fs)            # [delta-flow 2 | delta-occlusion 1]
         return ops.flow_update(m_prev, occ_prev, r) + (r,)
 
     # ------------------------------------------------------------------------------------------

@@ -432,7 +432,7 @@ __global__ void __launch_bounds__(TMA ? V2_THREADS_TMA : V2_THREADS, 1) conv_tc2
           int n = nt * p.NT + i; s_bias[i] = (p.bias && n < p.Cout) ? __ldg(p.bias + n) : 0.f;
           if (F16) s_scale[i] = __ldg(p.wscale + n) * p.acc_corr;
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"r"(32 * EPW) : "memory");      // (every epilogue warp: a count of 128 let four of the eight warps of the staged-input instantiations run ahead of the other four's writes)
         cur_nt = nt;
       }
       int oy, ox, r; bool mok;

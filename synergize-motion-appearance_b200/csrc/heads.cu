@@ -388,6 +388,35 @@ __global__ void __launch_bounds__(256) im2col_small_kernel(const float* __restri
     *reinterpret_cast<float4*>(out + (((long long)b * H + oy) * W + ox) * Kp + q * 4) = v;
   }
 }
+// A k x k convolution with very few output channels (the 3-channel image / [delta-flow | delta-occlusion] heads) as a pointwise layer + this sum:
+// the tensor-core kernel pays the same fixed cost per MMA whether it produces 8 or 256 columns, so the k*k taps are made COLUMNS of a 1x1 conv
+// (P[pixel][tap * C + c] = sum_ci w[c][ci][tap] x[pixel][ci], k*k times fewer MMAs) and the taps are gathered here:
+// out[y][x][c] = bias[c] + sum_tap P[y + ky - pad][x + kx - pad][tap * C + c]; taps outside the map are skipped (= the conv's zero padding).
+template <int C>
+__global__ void tapsum_kernel(const float* __restrict__ P, int ldp, int B, int H, int W, int k, int pad, const float* __restrict__ bias,
+                              float* __restrict__ out, int ldo) {
+  const long long n = (long long)B * H * W;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(i % W), y = (int)((i / W) % H);
+    const long long b = i / ((long long)W * H);
+    float acc[C];
+#pragma unroll
+    for (int c = 0; c < C; c++) acc[c] = bias ? __ldg(bias + c) : 0.f;
+    for (int ky = 0; ky < k; ky++) {
+      const int yy = y + ky - pad;
+      if (yy < 0 || yy >= H) continue;
+      for (int kx = 0; kx < k; kx++) {
+        const int xx = x + kx - pad;
+        if (xx < 0 || xx >= W) continue;
+        const float* src = P + ((b * H + yy) * W + xx) * ldp + (ky * k + kx) * C;
+#pragma unroll
+        for (int c = 0; c < C; c++) acc[c] += __ldg(src + c);
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < C; c++) out[i * ldo + c] = acc[c];
+  }
+}
 extern "C" int sma_im2col_small(const float* x, int B, int H, int W, int ld, int C, int k, int pad, float* out, int Kp, sma_stream_t s) {
   if (!x || !out || B <= 0 || H <= 0 || W <= 0 || C <= 0 || k <= 0 || pad < 0 || ld < C || (Kp & 3) || Kp < k * k * C) return SMA_ERR_BAD_ARG;
   if (reinterpret_cast<uintptr_t>(out) & 15) return SMA_ERR_BAD_ARG;
@@ -395,6 +424,18 @@ extern "C" int sma_im2col_small(const float* x, int B, int H, int W, int ld, int
   if (smem > 40 * 1024 || Kp > 256) return SMA_ERR_UNSUPPORTED;
   const int tiles_x = (W + 31) / 32, tiles_y = (H + 7) / 8;
   im2col_small_kernel<<<B * tiles_x * tiles_y, 256, smem, as_stream(s)>>>(x, B, H, W, ld, C, k, pad, out, Kp, tiles_x, tiles_y);
+  SMA_LAUNCH_CHECK(); return SMA_OK;
+}
+extern "C" int sma_conv_tapsum(const float* P, int ldp, int B, int H, int W, int C, int k, int pad, const float* bias, float* out, int ldo, sma_stream_t s) {
+  if (!P || !out || B <= 0 || H <= 0 || W <= 0 || k <= 0 || pad < 0 || C <= 0 || ldp < k * k * C || ldo < C) return SMA_ERR_BAD_ARG;
+  if (C > 4) return SMA_ERR_UNSUPPORTED;
+  const long long n = (long long)B * H * W;
+  switch (C) {
+    case 1: tapsum_kernel<1><<<nblocks(n), 256, 0, as_stream(s)>>>(P, ldp, B, H, W, k, pad, bias, out, ldo); break;
+    case 2: tapsum_kernel<2><<<nblocks(n), 256, 0, as_stream(s)>>>(P, ldp, B, H, W, k, pad, bias, out, ldo); break;
+    case 3: tapsum_kernel<3><<<nblocks(n), 256, 0, as_stream(s)>>>(P, ldp, B, H, W, k, pad, bias, out, ldo); break;
+    default: tapsum_kernel<4><<<nblocks(n), 256, 0, as_stream(s)>>>(P, ldp, B, H, W, k, pad, bias, out, ldo); break;
+  }
   SMA_LAUNCH_CHECK(); return SMA_OK;
 }
 extern "C" int sma_flow_to_px(const float* m, int B, int h, int w, float* o, int ld, sma_stream_t s) {

@@ -384,6 +384,16 @@ def conv2d(x: torch.Tensor, cw: ConvW, *, stride: int = 1, pad: int = 0, pad_tl:
                f'conv B{B} {Hi}x{Wi} Cin{Cin} Cout{cw.Cout} k{cw.kh} s{stride}{" up" if upsample2 else ""}{" pre" if pre is not None else ""}') as pr:
         check(lib.sma_conv2d_fwd(C.byref(d), _stream()), f'sma_conv2d_fwd Cin={Cin} Cout={cw.Cout} k={cw.kh}x{cw.kw}')
         pr.label += (' simt', ' tc-gather', ' tc-halo', ' tc-halo-f16', ' ts-f16')[d.kernel_used] + (' 1pass' if d.precision in (2, 4) else (' x2' if d.precision == 5 and d.kernel_used == 3 else ''))
+    if DET_CHECK and attn_split is None and d.res != d.y and d.x != d.y:
+        # debugging aid (SMA_DET_CHECK=1): launch every convolution twice and compare the outputs bit for bit
+        first = out.clone()
+        gp1 = None if gn_partial_dbg(locals()) is None else gn_partial_dbg(locals()).clone()
+        check(lib.sma_conv2d_fwd(C.byref(d), _stream()), 'sma_conv2d_fwd(det)')
+        same = torch.equal(first, out) and (gp1 is None or torch.equal(gp1, gn_partial_dbg(locals())))
+        if not same:
+            nd = int((first != out).sum())
+            print(f'DET_CHECK: conv B{B} {Hi}x{Wi} Cin{Cin} Cout{cw.Cout} k{cw.kh} s{stride} up{upsample2} pre{pre is not None} res{res is not None} kernel{d.kernel_used} '
+                  f'prec{d.precision} gn{d.gn_want} x2{x2 is not None}: {nd} differing outputs, first at {(first != out).nonzero()[0].tolist() if nd else None}', flush=True)
     if planned is not None and d.kernel_used != planned[0]:
         raise _lib.SmaError(f'conv2d ran on kernel {d.kernel_used} but was planned on {planned[0]} (Cin={Cin} Cout={cw.Cout} k={cw.kh}): binding bug')
     global LAST_CONV_KERNEL
@@ -766,6 +776,39 @@ def pack_conv_unfolded(weight: torch.Tensor, bias: Optional[torch.Tensor], Kp: i
     w2 = torch.zeros((O, Kp), device=weight.device, dtype=torch.float32)
     w2[:, :kh * kw * Cc] = weight.detach().float().permute(0, 2, 3, 1).reshape(O, kh * kw * Cc)
     return pack_conv(w2, bias)
+
+
+DET_CHECK = os.environ.get('SMA_DET_CHECK', '0') == '1'
+
+
+def gn_partial_dbg(loc):
+    return loc.get('gn_partial')
+
+
+TAPSUM = os.environ.get('SMA_NO_TAPSUM', '0') != '1'      # 3x3 convs with <= 4 outputs as a pointwise layer over (tap, c) columns + a gather-sum (conv_tapsum)
+
+
+def pack_conv_tapcols(weight: torch.Tensor) -> 'ConvW':
+    """OIHW weight of a k x k conv with few outputs -> the (k*k*O padded to 8, Cin) pointwise weight whose column (ky*k+kx)*O + o is tap (ky,kx) of output o
+    (the bias is added by conv_tapsum)."""
+    O, Cc, kh, kw = weight.shape
+    n = kh * kw * O
+    w2 = torch.zeros(((n + 7) // 8 * 8, Cc), device=weight.device, dtype=torch.float32)
+    w2[:n] = weight.detach().float().permute(2, 3, 0, 1).reshape(n, Cc)
+    return pack_conv(w2, None)
+
+
+def conv_tapsum(P: torch.Tensor, bias: Optional[torch.Tensor], C_out: int, k: int, pad: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """P (B,H,W,>=k*k*C) from the pointwise layer of pack_conv_tapcols -> the k x k conv's output (B,H,W,C) (`out` may be a column slice)."""
+    lib = _lib.load()
+    B, H, W, Cp, bs, ld = _nhwc(P)
+    assert bs == H * W * ld
+    if out is None:
+        out = torch.empty((B, H, W, C_out), device=P.device, dtype=torch.float32)
+    oB, oH, oW, oC, obs, old = _nhwc(out)
+    assert (oB, oH, oW, oC) == (B, H, W, C_out) and obs == H * W * old
+    check(lib.sma_conv_tapsum(P.data_ptr(), ld, B, H, W, C_out, k, pad, _ptr(bias), out.data_ptr(), old, _stream()), 'sma_conv_tapsum')
+    return out
 
 
 def flow_update(m_prev: torch.Tensor, occ_prev: torch.Tensor, res: torch.Tensor):

@@ -562,6 +562,46 @@ def test_projection_epilogue_writes_attention_operand_images(S):
         S.ops.linear(x[:, :100], cw, attn_split=(ws, 1.0))
 
 
+@pytest.mark.parametrize('Cin,H,fast,pre', [(256, 64, True, False), (64, 128, False, True), (64, 32, False, False)])
+def test_few_output_conv_as_tap_columns_plus_gather_sum(S, Cin, H, fast, pre):
+    """3x3 convs with 3 outputs (image head, RefineFlow's [delta-flow | delta-occlusion]) run as a pointwise layer over (tap, c) columns + sma_conv_tapsum:
+    against an fp64 convolution (zero padding = skipped taps at the border), with and without the GroupNorm prologue."""
+    B = 2
+    w = rnd(3, Cin, 3, 3, seed=1) * (9 * Cin) ** -0.5
+    bias = rnd(3, seed=2) * 0.1
+    x = rnd(B, Cin, H, H, seed=3)
+    sc, sh = rnd(B, Cin, seed=4) * 0.2 + 1, rnd(B, Cin, seed=5) * 0.1
+    xin = x * sc[:, :, None, None] + sh[:, :, None, None] if pre else x
+    ref = F.conv2d(xin.double(), w.double(), bias.double(), padding=1)
+    cw = S.ops.pack_conv_tapcols(w.cuda())
+    P = S.ops.conv2d(nhwc(x).cuda(), cw, pre=(sc.cuda(), sh.cuda(), 'none') if pre else None, fast=fast)
+    buf = torch.zeros(B, H, H, 4, device='cuda')
+    S.ops.conv_tapsum(P, bias.cuda(), 3, 3, 1, out=buf[..., :3])
+    assert float(buf[..., 3].abs().max()) == 0.0
+    err = float((nchw(buf[..., :3].contiguous()).double().cpu() - ref).abs().max())
+    assert err < (2e-3 if fast else 2e-5), err
+    direct = S.ops.conv2d(nhwc(x).cuda(), S.ops.pack_conv(w.cuda(), bias.cuda()), pad=1, pre=(sc.cuda(), sh.cuda(), 'none') if pre else None, fast=fast)
+    assert float((direct - buf[..., :3]).abs().max()) < (2e-3 if fast else 2e-5)
+
+
+def test_conv_many_column_tiles_is_deterministic_run_to_run(S):
+    """Regression: the epilogue warps re-stage the bias / column-scale slice whenever the N tile changes, between two named barriers; the second one
+    counted 128 threads while the staged-input instantiations run 256 epilogue threads, so four warps could read the previous tile's slice
+    (one 32 x 32 block wrong in ~1e-3 of the launches of the 16-N-tile un-patchify linear).  100 launches must be bit-identical."""
+    B = 64
+    w = rnd(4096, 256, 1, 1, seed=1) * 256 ** -0.5
+    w *= torch.exp2(torch.randint(-3, 4, (4096, 1, 1, 1), generator=torch.Generator().manual_seed(2)).float())     # distinct column scales per N tile
+    cw = S.ops.pack_conv(w.cuda(), (rnd(4096, seed=3)).cuda())
+    x = rnd(B, 32, 32, 256, seed=4).cuda()
+    first = S.ops.conv2d(x, cw, d2s=8)
+    out = torch.empty_like(first)
+    bad = 0
+    for _ in range(100):
+        S.ops.conv2d(x, cw, d2s=8, out=out)
+        bad += int(not torch.equal(out, first))
+    assert bad == 0, bad
+
+
 def test_mha_all_keys_masked_gives_nan_like_reference(S):
     q, k, v = rnd(1, 1024, 256, seed=1).cuda(), rnd(1, 1024, 256, seed=2).cuda(), rnd(1, 1024, 256, seed=3).cuda()
     mask = torch.ones(1, 1024, dtype=torch.uint8, device='cuda')
