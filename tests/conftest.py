@@ -29,6 +29,23 @@ def pytest_configure(config):
     config.addinivalue_line('markers', 'gpu: needs a CUDA device (run on the B200 box)')
 
 
+def _poison_device_memory():
+    """SMA_POISON=1: fill what the caching allocator will hand out with 0xFF bytes (NaN as fp32 / fp16) before any test runs, so that a kernel
+    that reads memory nobody wrote (and multiplies it by zero) shows up as NaN instead of passing on a box whose stale memory happens to be finite."""
+    free, _ = torch.cuda.mem_get_info()
+    big = [torch.empty(int(free * 0.2), dtype=torch.uint8, device='cuda').fill_(0xFF) for _ in range(3)]
+    small = [torch.empty(sz, dtype=torch.uint8, device='cuda').fill_(0xFF) for sz in (512, 4096, 65536, 524288) for _ in range(512)]
+    torch.cuda.synchronize()
+    del big, small
+
+
+@pytest.fixture(scope='session', autouse=True)
+def _poison():
+    if os.environ.get('SMA_POISON', '0') == '1' and torch.cuda.is_available():
+        _poison_device_memory()
+    yield
+
+
 @pytest.fixture(scope='session')
 def inventory():
     return json.load(open(os.path.join(GOLD, 'state_keys.json')))

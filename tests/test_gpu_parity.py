@@ -112,7 +112,7 @@ def test_conv2d_matches_torch(S, case, mode):
     saved = (S.ops.TC_VARIANT, S.ops.USE_F16, S.ops.USE_TS)
     S.ops.TC_VARIANT = {'gather': 1, 'ts': 32, 'ts-stream': 48, 'ts-stream128': 112, 'f16x3-3mma': 128}.get(mode, 0)
     S.ops.USE_F16 = mode in ('f16x3', 'f16x3-3mma', 'ts', 'ts-stream', 'ts-stream128', 'default')
-    S.ops.USE_TS = mode in ('ts', 'ts-stream', 'ts-stream128', 'default')
+    S.ops.USE_TS = saved[2] if mode == 'default' else mode in ('ts', 'ts-stream', 'ts-stream128')      # ('default' = the product's own configuration)
     try:
         y = S.ops.conv2d(nhwc(x), cw, stride=stride, pad=pad, act=ex.get('act', 'none'), pre=pre, res=res,
                          out_nchw=bool(ex.get('nchw')), exact=mode == 'exact', **kw)
