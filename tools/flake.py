@@ -13,7 +13,8 @@ wg, wm = O.synthetic_state_dict(inv['net_g'], seed=0), O.synthetic_state_dict(in
 g = S.build_network(CFG['network_g']); me = S.build_network(CFG['network_motion_estimator'])
 g.load_state_dict(wg, strict=True); me.load_state_dict(wm, strict=True)
 g, me = g.eval().cuda(), me.eval().cuda()
-src, drv = O.synthetic_frames(64, seed=77)
+NF = int(os.environ.get('FLAKE_FRAMES', '64'))
+src, drv = O.synthetic_frames(NF, seed=77)
 src8, drv8 = O.to_uint8(src), [O.to_uint8(f) for f in drv]
 f32 = [(torch.from_numpy(f.astype(np.float32) / 255.).permute(2, 0, 1) - 0.5) / 0.5 for f in drv8]
 s32 = (torch.from_numpy(src8.astype(np.float32) / 255.).permute(2, 0, 1) - 0.5) / 0.5
@@ -23,10 +24,10 @@ bad = 0
 for it in range(n):
     for kind in (sys.argv[2].split(',') if len(sys.argv) > 2 else ('u8', 'f32', 'dev')):
         if kind == 'u8':
-            p, _ = S.make_animation(src8, drv8, g, me, relative=True, adapt_movement_scale=True, batch=64)
+            p, _ = S.make_animation(src8, drv8, g, me, relative=True, adapt_movement_scale=True, batch=NF)
             p = np.stack(p)
         elif kind == 'f32':
-            p, _ = S.make_animation(s32, f32, g, me, relative=True, adapt_movement_scale=True, batch=64)
+            p, _ = S.make_animation(s32, f32, g, me, relative=True, adapt_movement_scale=True, batch=NF)
             p = np.stack(p)
         else:
             g.clear_source_cache(); me.dense_motion_network.clear_source_cache()
@@ -37,6 +38,6 @@ for it in range(n):
         d = (p != first)
         if d.any():
             bad += 1
-            fr = np.nonzero(d.reshape(64, -1).any(1))[0]
+            fr = np.nonzero(d.reshape(NF, -1).any(1))[0]
             print(f'iteration {it} {kind}: {int(d.sum())} differing values in frames {fr.tolist()[:16]} max level diff {int(np.abs(p.astype(int) - first.astype(int)).max())}', flush=True)
 print('iterations', n, 'mismatching runs', bad, {k: v for k, v in os.environ.items() if k.startswith('SMA_')})
