@@ -219,8 +219,12 @@ int sma_attn256_fwd(const float* q, int ldq, const float* k, int ldk, const floa
 int64_t sma_mha_e256_workspace_bytes(int B, int kvB, int L, int S);
 int sma_mha_e256_fwd(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv, int64_t q_bstride, int64_t kv_bstride,
                      int B, int L, int S, float scale, const uint8_t* key_mask, void* workspace, float* out, int ldo,
-                     int presplit /* 0: split q,k,v here; 1: q images already in workspace (sma_conv_desc.split_ws); 2: q,k,v images already there */,
+                     int presplit /* 0: split q,k,v here; 1: q images already in workspace (sma_conv_desc.split_ws); 2: q,k,v images already there;
+                                     3: q images in workspace and `k` = the images sma_attn_split_kv wrote for k, v shared by all frames (kv_bstride 0) */,
                      sma_stream_t stream);
+/* The operand images [k hi | k lo | v hi | v lo] (4 * S * 256 fp16) of k, v (S,256) shared by every frame - the frame-invariant codebook projections of the
+ * cross-attention (archs/appmotioncodebook_arch.py:109-116) - written once per weight load; S % 64 == 0. */
+int sma_attn_split_kv(const float* k, int ldk, const float* v, int ldv, int S, void* images, sma_stream_t stream);
 
 /* VectorQuantizer lookup (archs/vqgan_arch.py:33-73): d = fl(fl(|z|^2+|e|^2) - 2 z.e), argmin with
  * lowest-index ties -> idx (int64), zq = e[idx].  z:(N,E) row-major, codebook (n_codes,E).  workspace: n_codes floats (|e|^2) or NULL; with it,

@@ -56,6 +56,7 @@ SIGNATURES = {
     'sma_gather_bilinear4': ([_V, _I, _I, _I, _I, _L, _I, _V, _I, _I, _V], C.c_int),
     'sma_blend_bilinear4': ([_V, _I, _I, _I, _I, _V, _I, _I, _L, _I, _V], C.c_int),
     'sma_mha_fwd': ([_V, _I, _V, _I, _V, _I, _L, _I, _I, _I, _I, _I, _F, _V, _V, _I, _I, _V], C.c_int),
+    'sma_attn_split_kv': ([_V, _I, _V, _I, _I, _V, _V], C.c_int),
     'sma_attn256_workspace_bytes': ([_I, _I, _I], C.c_int64),
     'sma_attn256_fwd': ([_V, _I, _V, _I, _V, _I, _L, _L, _I, _I, _I, _F, _V, _V, _I, _I, _V], C.c_int),
     'sma_mha_e256_workspace_bytes': ([_I, _I, _I, _I], C.c_int64),

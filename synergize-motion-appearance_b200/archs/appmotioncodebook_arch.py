@@ -318,6 +318,9 @@ class AppMotionCompFormer(ParamModule):
                 # codebook keys/values are frame-invariant: project all rows once (prefix-sliceable for the split)
                 kv = ops.linear(codes.view(1, -1, E), W[n + '.cross_in'].cols(E, 2 * E), exact=True)
                 W[n + '.ctx_kv'] = kv[0]                              # (n_codes, 2E): K | V
+                if E == 256 and codes.shape[0] % 256 == 0:            # ... and, for the tensor-core attention, their fp16 hi / lo operand images per prefix length
+                    for n_ctx in range(codes.shape[0] // 4, codes.shape[0] + 1, codes.shape[0] // 4):
+                        W[n + f'.ctx_kvimg.{n_ctx}'] = ops.attn_kv_images(kv[0][:n_ctx, :E], kv[0][:n_ctx, E:])
         self._packed = W
         self._T = T
         self._src_cache = None
@@ -547,7 +550,11 @@ class AppMotionCompFormer(ParamModule):
             u2, _ = ops.layernorm(t, T[name + '.norm2.weight'], T[name + '.norm2.bias'])
             ws = ops.attn_workspace(B, 1, L, n_ctx, t.device)
             ops.linear(u2, W[name + '.cross_in'].cols(0, E), res=W[name + '.pos_q2'].unsqueeze(0).expand(B, -1, -1), fast=fast, attn_split=(ws, 32 ** -0.5))
-            a = ops.mha_presplit(ws, B, L, n_ctx, k=kv[:n_ctx, :E], v=kv[:n_ctx, E:])
+            img = W.get(name + f'.ctx_kvimg.{n_ctx}')              # the codebook k / v operand images are frame-invariant: split once per weight load
+            if img is not None:
+                a = ops.mha_presplit(ws, B, L, n_ctx, kv_images=img)
+            else:
+                a = ops.mha_presplit(ws, B, L, n_ctx, k=kv[:n_ctx, :E], v=kv[:n_ctx, E:])
         elif (name + '.pos_q2') in W:
             u2, _ = ops.layernorm(t, T[name + '.norm2.weight'], T[name + '.norm2.bias'])
             qc = ops.linear(u2, W[name + '.cross_in'].cols(0, E), res=W[name + '.pos_q2'].unsqueeze(0).expand(B, -1, -1), fast=fast)

@@ -3,7 +3,7 @@
 
 std::atomic<int> g_sma_launches{0};
 
-extern "C" int sma_abi_version(void) { return 10; }
+extern "C" int sma_abi_version(void) { return 11; }
 
 extern "C" const char* sma_status_string(int s) {
   switch (s) {

@@ -32,7 +32,7 @@ __device__ __forceinline__ void mh_mma_ts(uint32_t d, uint32_t a_tmem, uint64_t 
                : "memory");
 }
 
-struct MhP { const uint16_t* ws; const uint8_t* mask; float* out; int ldo, B, kvB, L, S; };
+struct MhP { const uint16_t* ws; const uint16_t* kv; const uint8_t* mask; float* out; int ldo, B, kvB, L, S; };      // kv != nullptr: the k / v images live there, not behind the q images
 
 // Two CTAs per SM (80 KB of shared memory, 256 tensor-memory columns each): the softmax of one CTA overlaps the MMA waits of the other.  The two
 // heads of the pair run one after the other over the same K / V tile stream (block index g = head * nblk + j drives every barrier phase).
@@ -50,7 +50,7 @@ __global__ void __launch_bounds__(MH_THREADS, 2) attn_mh_kernel(const MhP p) {
   auto k_full = [&](int s) { return bar0 + 8u * (5 + s); };   auto k_empty = [&](int s) { return bar0 + 8u * (7 + s); };
   auto v_full = [&](int s) { return bar0 + 8u * (9 + s); };   auto v_empty = [&](int s) { return bar0 + 8u * (11 + s); };
   const long long img_q = (long long)p.B * p.L * MH_E, img_k = (long long)p.kvB * p.S * MH_E;
-  const uint16_t* qh = p.ws; const uint16_t* ql = qh + img_q; const uint16_t* kh = ql + img_q; const uint16_t* kl = kh + img_k;
+  const uint16_t* qh = p.ws; const uint16_t* ql = qh + img_q; const uint16_t* kh = p.kv ? p.kv : ql + img_q; const uint16_t* kl = kh + img_k;
   const uint16_t* vh = kl + img_k; const uint16_t* vl = vh + img_k;
   const int kvb = p.kvB == 1 ? 0 : b;
 
@@ -242,6 +242,15 @@ __global__ void __launch_bounds__(MH_THREADS, 2) attn_mh_kernel(const MhP p) {
 
 }  // namespace
 
+// the four operand images [k hi | k lo | v hi | v lo] (fp16, tile layout) of k, v (S, 256) shared by every frame: 4 * S * 256 halfs
+extern "C" int sma_attn_split_kv(const float* k, int ldk, const float* v, int ldv, int S, void* images, sma_stream_t stream) {
+  if (!k || !v || !images || S <= 0) return SMA_ERR_BAD_ARG;
+  if ((S % MH_BKV) || ((ldk | ldv) & 3)) return SMA_ERR_UNSUPPORTED;
+  if ((reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(v) | reinterpret_cast<uintptr_t>(images)) & 15) return SMA_ERR_BAD_ARG;
+  // (no q: with B * L = 0 query rows the split kernel's q images are empty and the k images start at `images`)
+  return sma_attn_split_launch(nullptr, 0, k, ldk, v, ldv, 0, 0, 0, 1, 0, S, 1.f, images, as_stream(stream));
+}
+
 extern "C" int64_t sma_mha_e256_workspace_bytes(int B, int kvB, int L, int S) {
   if (B <= 0 || kvB <= 0 || L <= 0 || S <= 0) return 0;
   return 2LL * MH_E * 2 * ((long long)B * L + 2LL * kvB * S);      // fp16 hi + lo images of q, k, v
@@ -251,8 +260,12 @@ extern "C" int sma_mha_e256_fwd(const float* q, int ldq, const float* k, int ldk
                                 int B, int L, int S, float scale, const uint8_t* key_mask, void* workspace, float* out, int ldo, int presplit, sma_stream_t stream) {
   // presplit: 0 = q, k, v are fp32 tensors, split here; 1 = the q images were written into `workspace` by the projection's epilogue (sma_conv_desc.split_ws),
   // k and v are split here; 2 = q, k and v images are all there already (q / k / v pointers are then unused)
-  if (presplit < 0 || presplit > 2 || !out || !workspace || B <= 0 || L <= 0 || S <= 0) return SMA_ERR_BAD_ARG;
-  if ((presplit == 0 && !q) || (presplit < 2 && (!k || !v))) return SMA_ERR_BAD_ARG;
+  // 3 = q images in `workspace`, and `k` points at the operand images [k hi | k lo | v hi | v lo] of k, v shared by all frames (kv_bstride = 0), written once by
+  // sma_attn_split_kv (frame-invariant codebook projections: nothing is split per call)
+  if (presplit < 0 || presplit > 3 || !out || !workspace || B <= 0 || L <= 0 || S <= 0) return SMA_ERR_BAD_ARG;
+  if ((presplit == 0 && !q) || (presplit < 2 && (!k || !v)) || (presplit == 3 && (!k || kv_bstride != 0))) return SMA_ERR_BAD_ARG;
+  const uint16_t* kv_images = presplit == 3 ? reinterpret_cast<const uint16_t*>(k) : nullptr;
+  if (presplit == 3) v = k;
   if (presplit) { if (!q) q = out; if (!k) { k = out; v = out; } }         // (only their alignment is looked at below)
   if ((L % MH_BQ) || (S % MH_BKV) || B > 65535) return SMA_ERR_UNSUPPORTED;
   if (((ldq | ldk | ldv | ldo) & 3) || ((q_bstride | kv_bstride) & 3)) return SMA_ERR_UNSUPPORTED;
@@ -268,7 +281,7 @@ extern "C" int sma_mha_e256_fwd(const float* q, int ldq, const float* k, int ldk
   }
   static SmaDevOnce once;
   if (int rc = sma_opt_in_smem(once, attn_mh_kernel, (int)MH_SMEM + 1024)) return rc;
-  MhP p; p.ws = reinterpret_cast<const uint16_t*>(workspace); p.mask = key_mask; p.out = out; p.ldo = ldo; p.B = B; p.kvB = kvB; p.L = L; p.S = S;
+  MhP p; p.ws = reinterpret_cast<const uint16_t*>(workspace); p.kv = kv_images; p.mask = key_mask; p.out = out; p.ldo = ldo; p.B = B; p.kvB = kvB; p.L = L; p.S = S;
   attn_mh_kernel<<<dim3(L / MH_BQ, 4, B), MH_THREADS, MH_SMEM + 1024, st>>>(p);
   SMA_LAUNCH_CHECK();
   return SMA_OK;

@@ -541,8 +541,18 @@ def attn_workspace(B: int, kvB: int, L: int, S: int, device) -> torch.Tensor:
     return torch.empty((_lib.load().sma_mha_e256_workspace_bytes(B, kvB, L, S),), device=device, dtype=torch.uint8)
 
 
+def attn_kv_images(k: torch.Tensor, v: torch.Tensor) -> torch.Tensor:
+    """fp16 hi / lo operand images of k, v (S,256) shared by every frame (the cached codebook projections): split once, then mha_presplit(kv_images=)."""
+    lib = _lib.load()
+    S = k.shape[0]
+    assert k.dim() == 2 and v.dim() == 2 and k.shape[1] == 256 and k.stride(1) == 1 and v.stride(1) == 1
+    img = torch.empty((8 * S * 256,), device=k.device, dtype=torch.uint8)
+    check(lib.sma_attn_split_kv(k.data_ptr(), k.stride(0), v.data_ptr(), v.stride(0), S, img.data_ptr(), _stream()), 'sma_attn_split_kv')
+    return img
+
+
 def mha_presplit(ws: torch.Tensor, B: int, L: int, S: int, k: Optional[torch.Tensor] = None, v: Optional[torch.Tensor] = None,
-                 key_mask: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+                 key_mask: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None, kv_images: Optional[torch.Tensor] = None) -> torch.Tensor:
     """8-head E = 256 attention whose q images (k, v given: shared (S,E) codebook projections, split here) or q, k and v images (k = v = None:
     self-attention, S = L) were written into `ws` by the projection's epilogue."""
     lib = _lib.load()
@@ -551,7 +561,13 @@ def mha_presplit(ws: torch.Tensor, B: int, L: int, S: int, k: Optional[torch.Ten
         out = torch.empty((B, L, E), device=ws.device, dtype=torch.float32)
     if key_mask is not None:
         assert key_mask.dtype == torch.uint8 and key_mask.is_contiguous() and key_mask.numel() == B * S
-    shared = k is not None
+    shared = k is not None or kv_images is not None
+    if kv_images is not None:
+        assert kv_images.numel() == 8 * S * 256
+        with _Prof('mha', 4.0 * B * L * S * E, 4.0 * (2 * B * L * E + 2 * S * E), f'mha-f16 B{B} L{L} S{S} h8 D32'):
+            check(lib.sma_mha_e256_fwd(None, E, kv_images.data_ptr(), E, None, E, L * E, 0, B, L, S, 32 ** -0.5, _ptr(key_mask), ws.data_ptr(), out.data_ptr(),
+                                       out.stride(1), 3, _stream()), 'sma_mha_e256_fwd(presplit 3)')
+        return out
     if shared:
         assert k.dim() == 2 and v.dim() == 2 and k.stride(-1) == 1 and v.stride(-1) == 1
     with _Prof('mha', 4.0 * B * L * S * E, 4.0 * (2 * B * L * E + 2 * (1 if shared else B) * S * E), f'mha-f16 B{B} L{L} S{S} h8 D32'):

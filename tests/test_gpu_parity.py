@@ -549,6 +549,11 @@ def test_projection_epilogue_writes_attention_operand_images(S):
         S.ops.linear(x, cq, res=pos[:, :E].unsqueeze(0).expand(B, -1, -1), attn_split=(ws, 32 ** -0.5))
         got = S.ops.mha_presplit(ws, B, L, n_ctx, k=kv[:, :E], v=kv[:, E:])
         assert torch.equal(got, ref)
+        # ... and with the shared k / v images split once (what the generator caches per weight load): one launch, same bits
+        img = S.ops.attn_kv_images(kv[:, :E], kv[:, E:])
+        n0 = S.ops.launch_count()
+        got = S.ops.mha_presplit(ws, B, L, n_ctx, kv_images=img)
+        assert S.ops.launch_count() - n0 == 1 and torch.equal(got, ref)
     # AttnBlock: single head of 256, the q | k | v conv with its GroupNorm prologue
     xi = x.view(B, 32, 32, E)
     sc, sh = (rnd(B, E, seed=8) * 0.2 + 1).cuda(), (rnd(B, E, seed=9) * 0.1).cuda()

@@ -84,7 +84,7 @@ def test_c_abi_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), n
     lib.sma_abi_version.restype = ctypes.c_int
-    assert lib.sma_abi_version() == 10
+    assert lib.sma_abi_version() == 11
     from importlib import import_module
     _lib = import_module('synergize-motion-appearance_b200._lib')
     assert sorted(_lib.SIGNATURES) == names       # the ctypes table binds exactly the declared ABI
