@@ -334,6 +334,7 @@ def conv2d(x: torch.Tensor, cw: ConvW, *, stride: int = 1, pad: int = 0, pad_tl:
     d.tc_variant = TC_VARIANT
     d.kernel_used = -1
     planned = None
+    gn_partial = None
     if exact or not USE_TF32X3 or Cin % 32:
         d.precision = PREC['exact']
     else:
@@ -387,9 +388,9 @@ def conv2d(x: torch.Tensor, cw: ConvW, *, stride: int = 1, pad: int = 0, pad_tl:
     if DET_CHECK and attn_split is None and d.res != d.y and d.x != d.y:
         # debugging aid (SMA_DET_CHECK=1): launch every convolution twice and compare the outputs bit for bit
         first = out.clone()
-        gp1 = None if gn_partial_dbg(locals()) is None else gn_partial_dbg(locals()).clone()
+        gp1 = None if gn_partial is None else gn_partial.clone()
         check(lib.sma_conv2d_fwd(C.byref(d), _stream()), 'sma_conv2d_fwd(det)')
-        same = torch.equal(first, out) and (gp1 is None or torch.equal(gp1, gn_partial_dbg(locals())))
+        same = torch.equal(first, out) and (gp1 is None or torch.equal(gp1, gn_partial))
         if not same:
             nd = int((first != out).sum())
             print(f'DET_CHECK: conv B{B} {Hi}x{Wi} Cin{Cin} Cout{cw.Cout} k{cw.kh} s{stride} up{upsample2} pre{pre is not None} res{res is not None} kernel{d.kernel_used} '
@@ -794,13 +795,7 @@ def pack_conv_unfolded(weight: torch.Tensor, bias: Optional[torch.Tensor], Kp: i
     return pack_conv(w2, bias)
 
 
-DET_CHECK = os.environ.get('SMA_DET_CHECK', '0') == '1'
-
-
-def gn_partial_dbg(loc):
-    return loc.get('gn_partial')
-
-
+DET_CHECK = os.environ.get('SMA_DET_CHECK', '0') == '1'      # debugging aid: every convolution is launched twice and the two outputs compared bit for bit
 TAPSUM = os.environ.get('SMA_NO_TAPSUM', '0') != '1'      # 3x3 convs with <= 4 outputs as a pointwise layer over (tap, c) columns + a gather-sum (conv_tapsum)
 
 
