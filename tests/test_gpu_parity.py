@@ -589,6 +589,22 @@ def test_few_output_conv_as_tap_columns_plus_gather_sum(S, Cin, H, fast, pre):
     assert float((direct - buf[..., :3]).abs().max()) < (2e-3 if fast else 2e-5)
 
 
+@pytest.mark.parametrize('C,H,W', [(3, 45, 27), (2, 8, 32), (1, 9, 70), (3, 64, 64)])
+def test_conv_tapsum_ragged_sizes_bit_exact(S, C, H, W):
+    """sma_conv_tapsum's shared-memory tile form (8 x 32 outputs per block) at sizes that are not tile multiples: bit-exact against the same sum written in
+    torch in the same order (bias, then the taps row by row; a tap outside the map contributes 0), for 1-3 outputs."""
+    B = 2
+    P = rnd(B, H, W, 32, seed=11).cuda()
+    bias = rnd(C, seed=12).cuda()
+    out = S.ops.conv_tapsum(P, bias, C, 3, 1)
+    Pp = F.pad(P, (0, 0, 1, 1, 1, 1))
+    acc = bias.view(1, 1, 1, C).expand(B, H, W, C).clone()
+    for ky in range(3):
+        for kx in range(3):
+            acc = acc + Pp[:, ky:ky + H, kx:kx + W, (ky * 3 + kx) * C:(ky * 3 + kx) * C + C]
+    assert torch.equal(out, acc)
+
+
 def test_conv_many_column_tiles_is_deterministic_run_to_run(S):
     """Regression: the epilogue warps re-stage the bias / column-scale slice whenever the N tile changes, between two named barriers; the second one
     counted 128 threads while the staged-input instantiations run 256 epilogue threads, so four warps could read the previous tile's slice
