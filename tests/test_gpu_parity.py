@@ -387,6 +387,20 @@ def test_layernorm(S, E):
     assert float((yq.cpu().double() - (ref + pos.double())).abs().max()) < 1e-5
 
 
+@pytest.mark.parametrize('want_y,with_pos', [(True, True), (False, True), (True, False)])
+def test_layernorm_e32_ragged_rows(S, want_y, with_pos):
+    """The E = 32 kernel (eight lanes per row, 64 rows per block) with a row count that is not a block multiple, either output skipped, pos broadcast over frames."""
+    x = rnd(3, 37, 32, seed=1) * 3
+    g, b, pos = 1 + 0.1 * rnd(32, seed=2), 0.1 * rnd(32, seed=3), rnd(37, 32, seed=4, scale=0.02)
+    ref = F.layer_norm(x.double(), (32,), g.double(), b.double())
+    y, yq = S.ops.layernorm(x.cuda(), g.cuda(), b.cuda(), pos.cuda() if with_pos else None, want_y=want_y)
+    assert (y is not None) == want_y and (yq is not None) == with_pos
+    if y is not None:
+        assert float((y.cpu().double() - ref).abs().max()) < 1e-5
+    if yq is not None:
+        assert float((yq.cpu().double() - (ref + pos.double())).abs().max()) < 1e-5
+
+
 # ---------------------------------------------------------------------------------------------------
 # stage 2: warp + occlude, resize
 # ---------------------------------------------------------------------------------------------------
