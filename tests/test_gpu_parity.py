@@ -826,7 +826,7 @@ def test_vq_quantize_forward_values_bit_exact_indices(S, weights):
 def test_make_animation_matches_reference_clip(S, nets, golden, clip):
     g, me = nets
     src, drv = clip
-    for batch in (1, 3):
+    for batch in (1, 2, 3):          # 2: ragged last micro-batch
         preds, drvs = S.make_animation(src, drv, g, me, relative=True, adapt_movement_scale=True, batch=batch)
         assert len(preds) == 3 and preds[0].shape == (256, 256, 3) and preds[0].dtype == np.uint8
         for p, r in zip(preds, golden['pred_uint8']):
