@@ -92,6 +92,24 @@ def test_c_abi_exports_every_declared_symbol():
     assert bound.sma_sizeof_conv_desc() == ctypes.sizeof(_lib.ConvDesc)      # the struct mirror matches the compiled layout
 
 
+def test_library_sass_carries_tcgen05_tmem_and_tma_instructions():
+    """The built sm_100a library really is the Blackwell path: tcgen05 MMAs (UTCHMMA) with their commit barriers (UTCBAR), tensor-memory loads / stores
+    (LDTM / STTM), tensor-map TMA loads (UTMALDG) and bulk copies (UBLKCP) in the SASS; no GPU needed (cuobjdump disassembles the cubin)."""
+    import shutil
+    import subprocess
+    cuobjdump = shutil.which('cuobjdump') or '/usr/local/cuda/bin/cuobjdump'
+    if not os.path.exists(cuobjdump):
+        pytest.skip('cuobjdump not available')
+    lib_path = os.path.join(ROOT, 'synergize-motion-appearance_b200', 'csrc', 'libsma_b200.so')
+    r = subprocess.run([cuobjdump, '-sass', lib_path], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-500:]
+    assert 'sm_100a' in r.stdout
+    count = {k: r.stdout.count(k + ' ') + r.stdout.count(k + '.') for k in ('UTCHMMA', 'UTCBAR', 'LDTM', 'STTM', 'UTMALDG', 'UBLKCP')}
+    assert count['UTCHMMA'] > 1000 and count['UTCBAR'] > 100 and count['LDTM'] > 50 and count['STTM'] > 50 and count['UTMALDG'] > 10 and count['UBLKCP'] > 10, count
+    for kernel in ('conv_tc2_kernel', 'attn_mh_kernel', 'attn256_kernel', 'warp_occlude_kernel', 'vq_lookup_tiled_kernel', 'tapsum3_tiled_kernel', 'layernorm32_kernel'):
+        assert kernel in r.stdout, kernel
+
+
 def test_cpu_tensors_fail_loudly(weights):
     me = S.build_network(CFG['network_motion_estimator'])
     me.load_state_dict(weights[1])
