@@ -41,7 +41,7 @@ sys.path.insert(0, ROOT)
 
 H = W = 256
 CFG_KEYS = json.load(open(os.path.join(ROOT, 'tests', 'golden', 'state_keys.json')))
-DTYPE = 'f32 (fp32 storage; contractions as error-compensated fp16x3 splits on tcgen05 kind::f16, fp32 accumulate in TMEM; KP / S1 / S3m convs single-pass)'
+DTYPE = 'f32 (fp32 storage; contractions as error-compensated fp16x3 splits on tcgen05 kind::f16, fp32 accumulate in TMEM; dense-motion (S1) and motion-codebook (S3m) convs single-pass, key-point detector and generator three-pass)'
 
 
 def net_cfg():
